@@ -1,0 +1,207 @@
+/*
+ * particular_cuda.h — C ABI of libparticular_cuda.so, the B200 (sm_100a) compute backend for the
+ * `particular` N-body crate.
+ *
+ * This is the drop-in boundary: exactly what a `particular-cuda` Rust crate binds through
+ * `extern "C"` (see INTEGRATION.md and rust/particular-cuda/src/ffi.rs) so that its
+ * `cuda::BruteForce` / `cuda::BarnesHut` types can implement the crate's operator trait
+ *     Interaction<Between<&[P1], &[P2]>>           (reference particular/src/lib.rs:364-370)
+ * the same way the existing wgpu operator does     (reference particular/src/gpu/mod.rs:179-208).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary;
+ *   - every entry point returns a pcuda_status (0 = ok, < 0 = error) and never aborts; the message
+ *     of the last failure is available from pcuda_last_error();
+ *   - there is NO CPU fallback: without a usable sm_100 device pcuda_create() fails;
+ *   - a context is bound to one device, owns one stream and grow-only device/pinned buffers, and
+ *     allows one call in flight (the Rust wrapper holds `&mut CudaContext`, as the reference holds
+ *     `&mut GpuResources`, gpu/mod.rs:149-159);
+ *   - wire layout follows `GravitationalField<V, S>` (#[repr(C)] {position, m},
+ *     reference particular/src/gravity/mod.rs:12-18), densely packed, native endianness:
+ *         affecting (sources):  f32x3: float[4]  {x,y,z,mu}    f32x2: float[3] {x,y,mu}
+ *                               f64x3: double[4] {x,y,z,mu}
+ *         affected  (targets):  bare positions, float[3] / float[2] / double[3];
+ *                               NULL means "affected == affecting" (the `&[P]` storage,
+ *                               reference storage.rs:231-241) and saves one upload;
+ *         out:                  accelerations, same shape/type as the affected positions,
+ *                               in affected order.
+ *   - semantics of one call = reference `sequential::BruteForce` / `sequential::BarnesHut` over
+ *     `Between(affected, affecting)` with `Acceleration<CHECKED>` (softening = 0) or
+ *     `AccelerationSoftened<S, CHECKED>` (reference gravity/newtonian/acceleration*.rs):
+ *         d = p2 - p1;  n = |d|^2;  CHECKED && n == 0 -> contributes nothing;
+ *         otherwise a += d * mu2 / ((n + eps^2) * sqrt(n + eps^2))
+ *     Empty affected -> nothing written; empty affecting -> zeros (the CPU paths' behaviour;
+ *     the wgpu path panics on empty input, gpu/resources.rs:24).
+ */
+#ifndef PARTICULAR_CUDA_H
+#define PARTICULAR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCUDA_ABI_VERSION 1
+
+typedef enum pcuda_status {
+    PCUDA_OK = 0,
+    PCUDA_ERR_INVALID_ARGUMENT = -1,
+    PCUDA_ERR_NO_DEVICE = -2,        /* no CUDA device / not compute capability 10.x */
+    PCUDA_ERR_CUDA = -3,             /* a CUDA runtime call failed (see pcuda_last_error) */
+    PCUDA_ERR_OUT_OF_MEMORY = -4,
+    PCUDA_ERR_NCCL = -5,             /* NCCL missing or a collective failed */
+    PCUDA_ERR_TREE_OVERFLOW = -6,    /* traversal stack / node capacity exceeded */
+    PCUDA_ERR_NOT_INITIALISED = -7
+} pcuda_status;
+
+typedef struct pcuda_ctx pcuda_ctx;   /* opaque: device, stream, buffers, (optional) NCCL comm */
+typedef struct pcuda_tree pcuda_tree; /* opaque: a built Barnes-Hut tree living on the device  */
+
+typedef struct pcuda_config {
+    int32_t device;        /* CUDA ordinal */
+    uint32_t flags;        /* PCUDA_FLAG_* */
+    uint32_t leaf_size;    /* max particles per Barnes-Hut leaf; 0 = default (16) */
+    uint32_t reserved;
+} pcuda_config;
+
+#define PCUDA_FLAG_NONE 0u
+
+/* Per-phase device times of the LAST call on the context, in milliseconds (CUDA events on the
+ * context stream).  Phases that did not run are 0.  Replaces nothing in the reference (it has no
+ * metrics); used by bench.py. */
+typedef struct pcuda_timings {
+    float upload_ms;    /* host -> device copies                      */
+    float comm_ms;      /* NCCL all-gather of sources (multi-GPU)     */
+    float build_ms;     /* bbox + keys + sort + tree + centre of mass */
+    float compute_ms;   /* brute-force kernel(s) or theta-traversal   */
+    float download_ms;  /* device -> host copy of the result          */
+    uint32_t kernel_launches; /* kernels of this library launched by the call */
+    uint32_t reserved;
+} pcuda_timings;
+
+typedef struct pcuda_tree_info {
+    uint64_t n_particles;
+    uint64_t n_nodes;
+    uint32_t n_levels;     /* root = level 0 */
+    uint32_t leaf_size;
+    uint32_t dim;
+    uint32_t bits;         /* quantisation bits per axis: 21 (3-D) / 31 (2-D) */
+    float origin[3];       /* min corner of the root cube (reference square_with) */
+    float extent;          /* edge of the root cube */
+    float inv;             /* 2^bits / extent */
+    uint32_t reserved;
+} pcuda_tree_info;
+
+typedef enum pcuda_tree_array {
+    PCUDA_TREE_KEYS = 0,        /* uint64[n]   sorted Morton keys                      */
+    PCUDA_TREE_PERM = 1,        /* uint32[n]   sorted position -> original index       */
+    PCUDA_TREE_NODE_BEGIN = 2,  /* uint32[m]   first sorted particle of the node       */
+    PCUDA_TREE_NODE_COUNT = 3,  /* uint32[m]   particles in the node                   */
+    PCUDA_TREE_NODE_LEVEL = 4,  /* uint32[m]                                           */
+    PCUDA_TREE_NODE_FIRST_CHILD = 5, /* uint32[m] (0 for leaves)                       */
+    PCUDA_TREE_NODE_NUM_CHILDREN = 6,/* uint32[m] (0 for leaves)                       */
+    PCUDA_TREE_NODE_COM_MASS = 7     /* float[m][dim+1] {centre of mass, total mu}     */
+} pcuda_tree_array;
+
+/* ---- library / context ---------------------------------------------------------------------- */
+int pcuda_abi_version(void);
+const char *pcuda_status_string(int status);
+int pcuda_device_count(int *count);
+
+/* Replaces GpuResources::new + lazy WgpuResources::new (gpu/mod.rs:85-143, resources.rs:126-233):
+ * create once, reuse across calls. */
+int pcuda_create(const pcuda_config *config, pcuda_ctx **out);
+void pcuda_destroy(pcuda_ctx *ctx);
+/* Message of the last failed call on ctx (ctx == NULL: last failed pcuda_create on this thread). */
+const char *pcuda_last_error(const pcuda_ctx *ctx);
+int pcuda_get_timings(const pcuda_ctx *ctx, pcuda_timings *out);
+/* cudaStream_t of the context (as void*), for interop with the *_dev entry points. */
+void *pcuda_stream(pcuda_ctx *ctx);
+int pcuda_sync(pcuda_ctx *ctx);
+/* Device properties the roofline needs: SM count, max SM clock (kHz). */
+int pcuda_device_info(const pcuda_ctx *ctx, int *sm_count, int *sm_clock_khz, char *name,
+                      size_t name_len);
+
+/* Pinned host staging memory.  The reference packs particles straight into a mapped staging view
+ * (T::write_affected(affected, view), gpu/mod.rs:187-195); the Rust wrapper packs into these
+ * buffers so that uploads are true asynchronous DMA. */
+int pcuda_host_alloc(pcuda_ctx *ctx, size_t bytes, void **out);
+int pcuda_host_free(pcuda_ctx *ctx, void *p);
+
+/* ---- brute force: replaces gpu::BruteForce::compute (gpu/mod.rs:179-208) ----------------------
+ * HOST buffers in, HOST buffer out; blocking (the reference blocks too: pollster::block_on +
+ * device.poll(Wait), gpu/mod.rs:200, resources.rs:340).  Upload, kernel, download. */
+int pcuda_bruteforce_f32x3(pcuda_ctx *ctx, const float *affected_xyz, size_t n_affected,
+                           const float *affecting_xyzm, size_t n_affecting, float softening,
+                           int checked, float *out_xyz);
+int pcuda_bruteforce_f32x2(pcuda_ctx *ctx, const float *affected_xy, size_t n_affected,
+                           const float *affecting_xym, size_t n_affecting, float softening,
+                           int checked, float *out_xy);
+int pcuda_bruteforce_f64x3(pcuda_ctx *ctx, const double *affected_xyz, size_t n_affected,
+                           const double *affecting_xyzm, size_t n_affecting, double softening,
+                           int checked, double *out_xyz);
+
+/* DEVICE buffers in/out, enqueued on the context stream, returns without synchronising.
+ * The device-resident stepping path and the multi-GPU driver use these. */
+int pcuda_bruteforce_f32x3_dev(pcuda_ctx *ctx, const float *d_affected_xyz, size_t n_affected,
+                               const float *d_affecting_xyzm, size_t n_affecting, float softening,
+                               int checked, float *d_out_xyz);
+int pcuda_bruteforce_f32x2_dev(pcuda_ctx *ctx, const float *d_affected_xy, size_t n_affected,
+                               const float *d_affecting_xym, size_t n_affecting, float softening,
+                               int checked, float *d_out_xy);
+int pcuda_bruteforce_f64x3_dev(pcuda_ctx *ctx, const double *d_affected_xyz, size_t n_affected,
+                               const double *d_affecting_xyzm, size_t n_affecting,
+                               double softening, int checked, double *d_out_xyz);
+
+/* ---- Barnes-Hut: new on the GPU (the reference has sequential/parallel CPU versions only:
+ * sequential.rs:439-543, parallel.rs:297-367).  One call = build the tree over `affecting`
+ * (rebuilt every call like the reference, sequential.rs:539-541), then theta-traverse for every
+ * affected particle. */
+int pcuda_barneshut_f32x3(pcuda_ctx *ctx, const float *affected_xyz, size_t n_affected,
+                          const float *affecting_xyzm, size_t n_affecting, float theta,
+                          float softening, int checked, float *out_xyz);
+int pcuda_barneshut_f32x2(pcuda_ctx *ctx, const float *affected_xy, size_t n_affected,
+                          const float *affecting_xym, size_t n_affecting, float theta,
+                          float softening, int checked, float *out_xy);
+int pcuda_barneshut_f32x3_dev(pcuda_ctx *ctx, const float *d_affected_xyz, size_t n_affected,
+                              const float *d_affecting_xyzm, size_t n_affecting, float theta,
+                              float softening, int checked, float *d_out_xyz);
+int pcuda_barneshut_f32x2_dev(pcuda_ctx *ctx, const float *d_affected_xy, size_t n_affected,
+                              const float *d_affecting_xym, size_t n_affecting, float theta,
+                              float softening, int checked, float *d_out_xy);
+
+/* Split phase (replaces RootedOrthtree::new, storage.rs:20-33, and
+ * BarnesHut::compute(Between<&[P1], &RootedOrthtree>), sequential.rs:508-524): build once,
+ * traverse many times, inspect the arrays for parity tests. HOST buffers. `dim` is 2 or 3. */
+int pcuda_tree_build_f32(pcuda_ctx *ctx, uint32_t dim, const float *affecting, size_t n_affecting,
+                         pcuda_tree **out);
+int pcuda_tree_info_get(const pcuda_tree *tree, pcuda_tree_info *out);
+int pcuda_tree_read(pcuda_ctx *ctx, const pcuda_tree *tree, int which /* pcuda_tree_array */,
+                    void *dst, size_t dst_bytes);
+int pcuda_tree_traverse_f32(pcuda_ctx *ctx, const pcuda_tree *tree, const float *affected,
+                            size_t n_affected, float theta, float softening, int checked,
+                            float *out);
+/* interactions[0] = accepted node interactions, [1] = direct particle interactions,
+ * [2] = node tests, summed over all targets of the LAST traversal (instrumentation). */
+int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[3]);
+void pcuda_tree_destroy(pcuda_ctx *ctx, pcuda_tree *tree);
+
+/* ---- multi-GPU (one process per GPU; new — the reference is single-device) --------------------
+ * Targets are sharded by the caller; sources are replicated with an all-gather over NVLink each
+ * step.  NCCL is dlopen()ed on first use.  id is the 128-byte ncclUniqueId made by rank 0 and
+ * distributed by the host side (torch.distributed / MPI / a socket). */
+#define PCUDA_UNIQUE_ID_BYTES 128
+int pcuda_comm_unique_id(pcuda_ctx *ctx, uint8_t id[PCUDA_UNIQUE_ID_BYTES]);
+int pcuda_comm_init(pcuda_ctx *ctx, const uint8_t id[PCUDA_UNIQUE_ID_BYTES], int world_size,
+                    int rank);
+int pcuda_comm_destroy(pcuda_ctx *ctx);
+/* All-gather equally sized shards of `bytes_per_rank` bytes (device pointers, context stream). */
+int pcuda_comm_allgather_dev(pcuda_ctx *ctx, const void *d_send, void *d_recv,
+                             size_t bytes_per_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARTICULAR_CUDA_H */

@@ -1,0 +1,79 @@
+"""Builds particular_b200/libparticular_cuda.so with nvcc for sm_100a (in-tree, no JIT cache).
+
+The Rust crate's build.rs (rust/particular-cuda/build.rs) runs the same nvcc command; this script
+stands in for it here because the image has no cargo.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(PKG, "libparticular_cuda.so")
+
+SOURCES = ["context.cu", "bruteforce.cu", "barneshut.cu", "comm.cu", "probe.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-Wall",
+    # never --use_fast_math: fast intrinsics are chosen per kernel so f64 / tree build stay IEEE
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libparticular_cuda.so")
+
+
+def _host_cxx() -> list[str]:
+    # /opt/gcc wrappers in this image lack some spec files; prefer the distro compiler.
+    return ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(PKG, "..", "include", "particular_cuda.h"))
+    headers.append(os.path.abspath(__file__))
+    nvcc = _nvcc()
+
+    def compile_one(src: str) -> str:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _stale(o, [s] + headers):
+            cmd = [nvcc] + _host_cxx() + NVCC_FLAGS + ["-c", s, "-o", o]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return o
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    if force or _stale(LIB, objs):
+        cmd = [nvcc] + _host_cxx() + ["-shared", "-o", LIB] + objs + ["-ldl"]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,596 @@
+// bruteforce.cu — K1: softened pairwise gravity, O(n_affected * n_affecting), sm_100a.
+//
+// Replaces the reference's wgpu operator gpu::BruteForce (particular/src/gpu/mod.rs:179-208 and
+// the two WGSL templates gpu/bruteforce*.wgsl); the arithmetic follows the scalar pair kernel
+// gravity/impls/mod.rs:151-166 evaluated per (affected, affecting) pair as sequential::BruteForce
+// does (sequential.rs:181-194).  It is a new design, not a translation of the shaders:
+//
+//   * sources are streamed as 16-byte {x,y,z,mu} records in tiles that the TMA engine bulk-copies
+//     (cp.async.bulk + mbarrier complete_tx) into a 4-stage shared-memory ring; consumers read a
+//     record with one broadcast LDS.128;
+//   * every thread owns 2*TP targets held in registers as packed pairs, and all pair arithmetic
+//     is issued as packed FP32 (FADD2 / FFMA2 / FMUL2): 12 packed instructions + 2 MUFU.RSQ per
+//     two pairs, so the FP32 pipe (not the issue slots) is the limiter;
+//   * the grid is (target tiles) x (source splits) so that tens of waves of equal-cost CTAs cover
+//     the 148 SMs; split partial sums are reduced in a fixed order (deterministic results).
+//
+// FP32 work: 20 flop / pair by the GPU-Gems-3 convention the reference cites
+// (gpu/resources.rs:76-77).  Bytes are irrelevant: the source set lives in L2.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace pcuda {
+namespace bf {
+
+constexpr int STAGES = 4;
+constexpr int PREFETCH = 2;     // tiles in flight ahead of the consumers
+constexpr int TILE_MAX = 256;   // source records per stage
+constexpr float TINY_R2 = 1e-18f;  // CHECKED && eps == 0: r2 clamp that keeps mu * r^-3 finite
+constexpr float PAD_POS = 1e18f;   // zero-mass padding records sit here: they contribute exactly 0
+
+// ------------------------------------------------------------------------------------------------
+// f32 kernel.  Source record: DIM 3 -> {x,y,z,mu}; DIM 2 -> {x,y,mu,0}.
+// CLAMP = (checked && eps*eps == 0): a coincident pair must contribute nothing
+// (impls/mod.rs:160-161); with r2 clamped to TINY_R2 its term is d * finite = 0 exactly.
+// Without CLAMP either eps2 > 0 (d = 0 gives 0 without any test) or the caller asked for the
+// unchecked reference behaviour (coincident pair -> NaN, as in the reference).
+template <int DIM, int TP, int BLOCK, int MINB, bool CLAMP>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    pair_kernel_f32(const float *__restrict__ tgt, int tgt_stride, int n_tgt,
+                    const float4 *__restrict__ src, int n_src, int src_chunk, int tile, float eps2,
+                    float *__restrict__ out, float *__restrict__ partial, size_t n_pad) {
+    __shared__ __align__(128) float4 tiles[STAGES][TILE_MAX];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    // ---- targets: 2*TP per thread, negated, packed as (even, odd) pairs ----
+    const int tbase = blockIdx.x * (BLOCK * 2 * TP) + tid;
+    float2 ntx[TP], nty[TP], ntz[TP];
+#pragma unroll
+    for (int p = 0; p < TP; ++p) {
+        int i0 = min(tbase + (2 * p) * BLOCK, n_tgt - 1);
+        int i1 = min(tbase + (2 * p + 1) * BLOCK, n_tgt - 1);
+        const float *a = tgt + (size_t)i0 * tgt_stride;
+        const float *b = tgt + (size_t)i1 * tgt_stride;
+        ntx[p] = make_float2(-a[0], -b[0]);
+        nty[p] = make_float2(-a[1], -b[1]);
+        if (DIM == 3) ntz[p] = make_float2(-a[2], -b[2]);
+    }
+    float2 ax[TP], ay[TP], az[TP];
+#pragma unroll
+    for (int p = 0; p < TP; ++p) ax[p] = ay[p] = az[p] = make_float2(0.f, 0.f);
+
+    const int s_begin = blockIdx.y * src_chunk;
+    const int s_end = min(n_src, s_begin + src_chunk);
+    const int ntiles = (s_end - s_begin + tile - 1) / tile;
+
+    auto issue = [&](int t) {  // executed by thread 0 only
+        const int st = t % STAGES;
+        const int first = s_begin + t * tile;
+        const int cnt = min(tile, s_end - first);
+        const int cnt4 = (cnt + 3) & ~3;
+        for (int i = cnt; i < cnt4; ++i)
+            tiles[st][i] = DIM == 3 ? make_float4(PAD_POS, PAD_POS, PAD_POS, 0.f)
+                                    : make_float4(PAD_POS, PAD_POS, 0.f, 0.f);
+        ptx::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)cnt * 16u);
+        ptx::bulk_g2s(&tiles[st][0], src + first, (uint32_t)cnt * 16u, &full_bar[st]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], BLOCK / 32);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int t = 0; t < PREFETCH && t < ntiles; ++t) issue(t);
+
+    const float2 eps2p = make_float2(eps2, eps2);
+
+    for (int t = 0; t < ntiles; ++t) {
+        if (tid == 0 && t + PREFETCH < ntiles) {
+            const int tn = t + PREFETCH;
+            if (tn >= STAGES) ptx::mbar_wait(&empty_bar[tn % STAGES], ((tn / STAGES) - 1) & 1);
+            issue(tn);
+        }
+        const int st = t % STAGES;
+        ptx::mbar_wait(&full_bar[st], (t / STAGES) & 1);
+
+        const int cnt4 = (min(tile, s_end - (s_begin + t * tile)) + 3) & ~3;
+        const float4 *sp = tiles[st];
+#pragma unroll 1
+        for (int j = 0; j < cnt4; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 s = sp[j + u];
+                const float sm = DIM == 3 ? s.w : s.z;
+#pragma unroll
+                for (int p = 0; p < TP; ++p) {
+                    const float2 dx = ptx::add2(ntx[p], ptx::splat(s.x));
+                    const float2 dy = ptx::add2(nty[p], ptx::splat(s.y));
+                    float2 r2 = ptx::fma2(dx, dx, eps2p);
+                    r2 = ptx::fma2(dy, dy, r2);
+                    float2 dz;
+                    if (DIM == 3) {
+                        dz = ptx::add2(ntz[p], ptx::splat(s.z));
+                        r2 = ptx::fma2(dz, dz, r2);
+                    }
+                    if (CLAMP) {
+                        r2.x = fmaxf(r2.x, TINY_R2);
+                        r2.y = fmaxf(r2.y, TINY_R2);
+                    }
+                    float2 ri;
+                    ri.x = ptx::rsqrt_approx(r2.x);
+                    ri.y = ptx::rsqrt_approx(r2.y);
+                    const float2 ri2 = ptx::mul2(ri, ri);
+                    const float2 mri = ptx::mul2(ri, ptx::splat(sm));
+                    const float2 sc = ptx::mul2(ri2, mri);
+                    ax[p] = ptx::fma2(dx, sc, ax[p]);
+                    ay[p] = ptx::fma2(dy, sc, ay[p]);
+                    if (DIM == 3) az[p] = ptx::fma2(dz, sc, az[p]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty_bar[st]);
+    }
+
+    // ---- results ----
+    const bool direct = gridDim.y == 1;
+#pragma unroll
+    for (int p = 0; p < TP; ++p) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = tbase + (2 * p + h) * BLOCK;
+            if (i >= n_tgt) continue;
+            const float vx = h ? ax[p].y : ax[p].x;
+            const float vy = h ? ay[p].y : ay[p].x;
+            const float vz = DIM == 3 ? (h ? az[p].y : az[p].x) : 0.f;
+            if (direct) {
+                out[(size_t)i * DIM + 0] = vx;
+                out[(size_t)i * DIM + 1] = vy;
+                if (DIM == 3) out[(size_t)i * DIM + 2] = vz;
+            } else {
+                float *pp = partial + (size_t)blockIdx.y * DIM * n_pad + i;
+                pp[0] = vx;
+                pp[n_pad] = vy;
+                if (DIM == 3) pp[2 * n_pad] = vz;
+            }
+        }
+    }
+}
+
+// Fixed-order reduction of the source-split partial sums: out[i][c] = sum_y partial[y][c][i].
+template <typename T, int DIM>
+__global__ void reduce_partials(const T *__restrict__ partial, int splits, size_t n_pad, int n_tgt,
+                                T *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tgt) return;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+        T acc = 0;
+        for (int y = 0; y < splits; ++y) acc += partial[((size_t)y * DIM + c) * n_pad + i];
+        out[(size_t)i * DIM + c] = acc;
+    }
+}
+
+// DIM 2 sources arrive as {x,y,mu} (12 B); the kernel wants 16-byte {x,y,mu,0} records.
+__global__ void pack_sources_2d(const float *__restrict__ in, int n, float4 *__restrict__ outp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) outp[i] = make_float4(in[3 * (size_t)i], in[3 * (size_t)i + 1], in[3 * (size_t)i + 2], 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// f64 kernel (the "precision path", BASELINE config 5a).  Scalar DFMA arithmetic, T targets per
+// thread, same TMA ring with 32-byte {x,y,z,mu} records.  rsqrt(double) is CUDA's <= 1 ulp
+// implementation (MUFU.RSQ64H + Newton steps); per-term error is a few 1e-16, far inside the
+// 1e-12 parity bound.
+constexpr int TILE64 = 128;
+constexpr double TINY_R2_64 = 1e-200;
+constexpr double PAD_POS_64 = 1e100;
+
+template <int T, int BLOCK, bool CLAMP>
+__global__ void __launch_bounds__(BLOCK)
+    pair_kernel_f64(const double *__restrict__ tgt, int tgt_stride, int n_tgt,
+                    const double4 *__restrict__ src, int n_src, int src_chunk, int tile,
+                    double eps2, double *__restrict__ out, double *__restrict__ partial,
+                    size_t n_pad) {
+    __shared__ __align__(128) double4 tiles[STAGES][TILE64];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int tbase = blockIdx.x * (BLOCK * T) + tid;
+    double tx[T], ty[T], tz[T], ax[T], ay[T], az[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        const int i = min(tbase + k * BLOCK, n_tgt - 1);
+        const double *a = tgt + (size_t)i * tgt_stride;
+        tx[k] = a[0];
+        ty[k] = a[1];
+        tz[k] = a[2];
+        ax[k] = ay[k] = az[k] = 0.0;
+    }
+
+    const int s_begin = blockIdx.y * src_chunk;
+    const int s_end = min(n_src, s_begin + src_chunk);
+    const int ntiles = (s_end - s_begin + tile - 1) / tile;
+
+    auto issue = [&](int t) {
+        const int st = t % STAGES;
+        const int first = s_begin + t * tile;
+        const int cnt = min(tile, s_end - first);
+        const int cnt2 = (cnt + 1) & ~1;
+        for (int i = cnt; i < cnt2; ++i)
+            tiles[st][i] = make_double4(PAD_POS_64, PAD_POS_64, PAD_POS_64, 0.0);
+        ptx::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)cnt * 32u);
+        ptx::bulk_g2s(&tiles[st][0], src + first, (uint32_t)cnt * 32u, &full_bar[st]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], BLOCK / 32);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int t = 0; t < PREFETCH && t < ntiles; ++t) issue(t);
+
+    for (int t = 0; t < ntiles; ++t) {
+        if (tid == 0 && t + PREFETCH < ntiles) {
+            const int tn = t + PREFETCH;
+            if (tn >= STAGES) ptx::mbar_wait(&empty_bar[tn % STAGES], ((tn / STAGES) - 1) & 1);
+            issue(tn);
+        }
+        const int st = t % STAGES;
+        ptx::mbar_wait(&full_bar[st], (t / STAGES) & 1);
+        const int cnt2 = (min(tile, s_end - (s_begin + t * tile)) + 1) & ~1;
+        const double4 *sp = tiles[st];
+#pragma unroll 1
+        for (int j = 0; j < cnt2; j += 2) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const double4 s = sp[j + u];
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    const double dx = s.x - tx[k], dy = s.y - ty[k], dz = s.z - tz[k];
+                    double r2 = fma(dx, dx, eps2);
+                    r2 = fma(dy, dy, r2);
+                    r2 = fma(dz, dz, r2);
+                    if (CLAMP) r2 = fmax(r2, TINY_R2_64);
+                    const double ri = rsqrt(r2);
+                    const double sc = (ri * ri) * (ri * s.w);
+                    ax[k] = fma(dx, sc, ax[k]);
+                    ay[k] = fma(dy, sc, ay[k]);
+                    az[k] = fma(dz, sc, az[k]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty_bar[st]);
+    }
+
+    const bool direct = gridDim.y == 1;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        const int i = tbase + k * BLOCK;
+        if (i >= n_tgt) continue;
+        if (direct) {
+            out[(size_t)i * 3 + 0] = ax[k];
+            out[(size_t)i * 3 + 1] = ay[k];
+            out[(size_t)i * 3 + 2] = az[k];
+        } else {
+            double *pp = partial + (size_t)blockIdx.y * 3 * n_pad + i;
+            pp[0] = ax[k];
+            pp[n_pad] = ay[k];
+            pp[2 * n_pad] = az[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch planning.  A CTA covers `tile_t` targets and one chunk of sources; we want enough
+// equal-cost CTAs for >= ~16 waves over SMs x resident CTAs (tail < 6 %), but chunks of at least
+// a few tiles so the pipeline prologue is amortised.
+struct Plan {
+    int tp, block, minb;
+    int n_tb, splits, chunk, tile;
+};
+
+static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
+    Plan pl{};
+    if (force_tp > 0) pl.tp = force_tp;
+    else if (na >= (size_t)sm_count * 2 * 2048) pl.tp = 4;
+    else if (na >= (size_t)sm_count * 3 * 512) pl.tp = 2;
+    else pl.tp = 1;
+    pl.block = pl.tp == 1 ? 128 : 256;
+    pl.minb = pl.tp == 4 ? 2 : (pl.tp == 2 ? 3 : 4);
+    const int tile_t = pl.block * 2 * pl.tp;
+    pl.n_tb = (int)((na + tile_t - 1) / tile_t);
+    pl.tile = nb >= 4096 ? TILE_MAX : 64;
+    const long slots = (long)sm_count * pl.minb;
+    const long want = slots * 16;
+    long splits = (want + pl.n_tb - 1) / pl.n_tb;
+    const long max_splits = std::max<long>(1, (long)(nb / ((size_t)pl.tile * 4)));
+    splits = std::max<long>(1, std::min(splits, max_splits));
+    if (splits > 1 && pl.n_tb >= want) splits = 1;
+    long chunk = ((long)nb + splits - 1) / splits;
+    chunk = ((chunk + pl.tile - 1) / pl.tile) * pl.tile;
+    splits = ((long)nb + chunk - 1) / chunk;
+    pl.splits = (int)std::max<long>(1, splits);
+    pl.chunk = (int)chunk;
+    return pl;
+}
+
+template <int DIM, int TP, int BLOCK, int MINB>
+static cudaError_t launch_f32(const Plan &pl, bool clamp, cudaStream_t stream, const float *tgt,
+                              int tgt_stride, int na, const float4 *src, int nb, float eps2,
+                              float *out, float *partial, size_t n_pad) {
+    dim3 grid(pl.n_tb, pl.splits);
+    if (clamp)
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, true><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
+    else
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, false><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
+    return cudaGetLastError();
+}
+
+static int g_force_tp = 0;  // test / tuning hook (pcuda_debug_set)
+
+// Enqueues the brute-force evaluation on ctx->stream.  All pointers are device pointers.
+// src4: 16-byte records (DIM 3: {x,y,z,mu}; DIM 2: {x,y,mu,0}); tgt rows have tgt_stride floats.
+template <int DIM>
+static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na,
+                   const float4 *d_src4, size_t nb, float softening, int checked, float *d_out) {
+    if (na == 0) return PCUDA_OK;
+    if (nb == 0) {
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * DIM * sizeof(float), ctx->stream));
+        return PCUDA_OK;
+    }
+    if (na > 0x7fffffffull || nb > 0x7fffffffull)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    const float eps2 = softening * softening;
+    const bool clamp = checked && eps2 == 0.0f;
+    const Plan pl = make_plan(ctx->sm_count, na, nb, g_force_tp);
+    const size_t n_pad = (na + 63) & ~size_t(63);
+    float *partial = nullptr;
+    if (pl.splits > 1) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_partial.ensure((size_t)pl.splits * DIM * n_pad * sizeof(float)));
+        partial = ctx->d_partial.as<float>();
+    }
+    cudaError_t e;
+    if (pl.tp == 4)
+        e = launch_f32<DIM, 4, 256, 2>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                       (int)nb, eps2, d_out, partial, n_pad);
+    else if (pl.tp == 2)
+        e = launch_f32<DIM, 2, 256, 3>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                       (int)nb, eps2, d_out, partial, n_pad);
+    else
+        e = launch_f32<DIM, 1, 128, 4>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                       (int)nb, eps2, d_out, partial, n_pad);
+    PCUDA_CUDA_TRY(ctx, e);
+    ctx->launches++;
+    if (pl.splits > 1) {
+        reduce_partials<float, DIM><<<(unsigned)((na + 255) / 256), 256, 0, ctx->stream>>>(
+            partial, pl.splits, n_pad, (int)na, d_out);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return PCUDA_OK;
+}
+
+static int run_f64(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t na,
+                   const double4 *d_src4, size_t nb, double softening, int checked,
+                   double *d_out) {
+    if (na == 0) return PCUDA_OK;
+    if (nb == 0) {
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * 3 * sizeof(double), ctx->stream));
+        return PCUDA_OK;
+    }
+    if (na > 0x7fffffffull || nb > 0x7fffffffull)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    const double eps2 = softening * softening;
+    const bool clamp = checked && eps2 == 0.0;
+    constexpr int T = 2, BLOCK = 128;
+    const int tile_t = T * BLOCK;
+    const int n_tb = (int)((na + tile_t - 1) / tile_t);
+    const int tile = nb >= 2048 ? TILE64 : 32;
+    const long want = (long)ctx->sm_count * 4 * 16;
+    long splits = std::max<long>(1, std::min<long>((want + n_tb - 1) / n_tb,
+                                                   std::max<long>(1, (long)(nb / ((size_t)tile * 4)))));
+    if (n_tb >= want) splits = 1;
+    long chunk = ((long)nb + splits - 1) / splits;
+    chunk = ((chunk + tile - 1) / tile) * tile;
+    splits = ((long)nb + chunk - 1) / chunk;
+    const size_t n_pad = (na + 63) & ~size_t(63);
+    double *partial = nullptr;
+    if (splits > 1) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_partial.ensure((size_t)splits * 3 * n_pad * sizeof(double)));
+        partial = ctx->d_partial.as<double>();
+    }
+    dim3 grid(n_tb, (unsigned)splits);
+    if (clamp)
+        pair_kernel_f64<T, BLOCK, true><<<grid, BLOCK, 0, ctx->stream>>>(
+            d_tgt, tgt_stride, (int)na, d_src4, (int)nb, (int)chunk, tile, eps2, d_out, partial, n_pad);
+    else
+        pair_kernel_f64<T, BLOCK, false><<<grid, BLOCK, 0, ctx->stream>>>(
+            d_tgt, tgt_stride, (int)na, d_src4, (int)nb, (int)chunk, tile, eps2, d_out, partial, n_pad);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (splits > 1) {
+        reduce_partials<double, 3><<<(unsigned)((na + 255) / 256), 256, 0, ctx->stream>>>(
+            partial, (int)splits, n_pad, (int)na, d_out);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return PCUDA_OK;
+}
+
+static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// Device-pointer entry: DIM 3.
+static int dev_f32x3(pcuda_ctx *ctx, const float *d_aff, size_t na, const float *d_src, size_t nb,
+                     float eps, int checked, float *d_out) {
+    if (nb && !aligned(d_src, 16))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "affecting must be 16-byte aligned");
+    const float *tgt = d_aff ? d_aff : d_src;
+    const int stride = d_aff ? 3 : 4;
+    return run_f32<3>(ctx, tgt, stride, na, reinterpret_cast<const float4 *>(d_src), nb, eps,
+                      checked, d_out);
+}
+
+static int dev_f32x2(pcuda_ctx *ctx, const float *d_aff, size_t na, const float *d_src, size_t nb,
+                     float eps, int checked, float *d_out) {
+    float4 *packed = nullptr;
+    if (nb) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_packed_src.ensure(nb * sizeof(float4)));
+        packed = ctx->d_packed_src.as<float4>();
+        pack_sources_2d<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(d_src, (int)nb, packed);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    const float *tgt = d_aff ? d_aff : d_src;
+    const int stride = d_aff ? 2 : 3;
+    return run_f32<2>(ctx, tgt, stride, na, packed, nb, eps, checked, d_out);
+}
+
+static int dev_f64x3(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src, size_t nb,
+                     double eps, int checked, double *d_out) {
+    if (nb && !aligned(d_src, 16))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "affecting must be 16-byte aligned");
+    const double *tgt = d_aff ? d_aff : d_src;
+    const int stride = d_aff ? 3 : 4;
+    return run_f64(ctx, tgt, stride, na, reinterpret_cast<const double4 *>(d_src), nb, eps, checked,
+                   d_out);
+}
+
+// Host-pointer wrapper shared by the three precisions: upload, run, download, collect timings.
+template <typename S, typename RunFn>
+static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, const S *affecting,
+                     size_t nb, S *out, RunFn run) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if ((na && !out) || (nb && !affecting))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    if (!affected && na != nb)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
+                    "affected == NULL means affected == affecting, but n_affected != n_affecting");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    if (na == 0) return PCUDA_OK;
+    const size_t src_bytes = nb * (dim + 1) * sizeof(S), tgt_bytes = na * dim * sizeof(S);
+    phase_begin(ctx, PH_UPLOAD);
+    S *d_src = nullptr, *d_tgt = nullptr;
+    if (nb) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(src_bytes));
+        d_src = ctx->d_affecting.as<S>();
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_src, affecting, src_bytes, cudaMemcpyHostToDevice,
+                                            ctx->stream));
+    }
+    if (affected) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_affected.ensure(tgt_bytes));
+        d_tgt = ctx->d_affected.as<S>();
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_tgt, affected, tgt_bytes, cudaMemcpyHostToDevice,
+                                            ctx->stream));
+    }
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(tgt_bytes));
+    phase_end(ctx, PH_UPLOAD);
+    phase_begin(ctx, PH_COMPUTE);
+    PCUDA_TRY(run(d_tgt, d_src, ctx->d_out.as<S>()));
+    phase_end(ctx, PH_COMPUTE);
+    phase_begin(ctx, PH_DOWNLOAD);
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out.p, tgt_bytes, cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+    phase_end(ctx, PH_DOWNLOAD);
+    return timings_collect(ctx);
+}
+
+template <typename RunFn>
+static int dev_call(pcuda_ctx *ctx, RunFn run) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    ctx->launches = 0;
+    int s = run();
+    ctx->timings.kernel_launches = ctx->launches;
+    return s;
+}
+
+}  // namespace bf
+}  // namespace pcuda
+
+using namespace pcuda;
+
+extern "C" {
+
+int pcuda_bruteforce_f32x3(pcuda_ctx *ctx, const float *affected, size_t na, const float *affecting,
+                           size_t nb, float softening, int checked, float *out) {
+    return bf::host_call<float>(ctx, affected, na, 3, affecting, nb, out,
+                                [&](float *dt, float *ds, float *dout) {
+                                    return bf::dev_f32x3(ctx, dt, na, ds, nb, softening, checked, dout);
+                                });
+}
+
+int pcuda_bruteforce_f32x2(pcuda_ctx *ctx, const float *affected, size_t na, const float *affecting,
+                           size_t nb, float softening, int checked, float *out) {
+    return bf::host_call<float>(ctx, affected, na, 2, affecting, nb, out,
+                                [&](float *dt, float *ds, float *dout) {
+                                    return bf::dev_f32x2(ctx, dt, na, ds, nb, softening, checked, dout);
+                                });
+}
+
+int pcuda_bruteforce_f64x3(pcuda_ctx *ctx, const double *affected, size_t na,
+                           const double *affecting, size_t nb, double softening, int checked,
+                           double *out) {
+    return bf::host_call<double>(ctx, affected, na, 3, affecting, nb, out,
+                                 [&](double *dt, double *ds, double *dout) {
+                                     return bf::dev_f64x3(ctx, dt, na, ds, nb, softening, checked, dout);
+                                 });
+}
+
+int pcuda_bruteforce_f32x3_dev(pcuda_ctx *ctx, const float *d_affected, size_t na,
+                               const float *d_affecting, size_t nb, float softening, int checked,
+                               float *d_out) {
+    return bf::dev_call(ctx, [&] {
+        return bf::dev_f32x3(ctx, d_affected, na, d_affecting, nb, softening, checked, d_out);
+    });
+}
+
+int pcuda_bruteforce_f32x2_dev(pcuda_ctx *ctx, const float *d_affected, size_t na,
+                               const float *d_affecting, size_t nb, float softening, int checked,
+                               float *d_out) {
+    return bf::dev_call(ctx, [&] {
+        return bf::dev_f32x2(ctx, d_affected, na, d_affecting, nb, softening, checked, d_out);
+    });
+}
+
+int pcuda_bruteforce_f64x3_dev(pcuda_ctx *ctx, const double *d_affected, size_t na,
+                               const double *d_affecting, size_t nb, double softening, int checked,
+                               double *d_out) {
+    return bf::dev_call(ctx, [&] {
+        return bf::dev_f64x3(ctx, d_affected, na, d_affecting, nb, softening, checked, d_out);
+    });
+}
+
+// Tuning hook: force the targets-per-thread variant (0 = automatic).  Not part of the stable ABI.
+int pcuda_debug_set(const char *key, int value) {
+    if (key && std::string(key) == "bf_tp") {
+        bf::g_force_tp = value;
+        return PCUDA_OK;
+    }
+    return PCUDA_ERR_INVALID_ARGUMENT;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// common.cuh — internal declarations shared by the translation units of libparticular_cuda.so.
+// Not part of the C ABI (that is include/particular_cuda.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/particular_cuda.h"
+
+namespace pcuda {
+
+// Grow-only device buffer (the reference re-creates its wgpu buffers on any size change,
+// gpu/resources.rs:26-34; we only ever grow).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return static_cast<T *>(p);
+    }
+};
+
+struct Nccl;  // comm.cu
+
+enum Phase { PH_UPLOAD = 0, PH_COMM, PH_BUILD, PH_COMPUTE, PH_DOWNLOAD, PH_COUNT };
+
+}  // namespace pcuda
+
+struct pcuda_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int sm_clock_khz = 0;
+    size_t smem_optin = 0;
+    char name[128] = {0};
+    uint32_t leaf_size = 16;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // phase timing: start/stop event per phase, recorded lazily
+    cudaEvent_t ev0[pcuda::PH_COUNT] = {}, ev1[pcuda::PH_COUNT] = {};
+    bool ev_used[pcuda::PH_COUNT] = {};
+    pcuda_timings timings = {};
+    uint32_t launches = 0;
+
+    // brute force scratch
+    pcuda::DevBuf d_affected, d_affecting, d_out, d_partial, d_packed_src, d_packed_tgt;
+    // Barnes-Hut scratch (barneshut.cu owns the layout)
+    pcuda::DevBuf d_stack, d_counters, d_tgt_keys, d_tgt_keys_alt, d_tgt_perm, d_tgt_perm_alt,
+        d_tgt_sorted, d_cub_tmp, d_misc;
+    uint64_t last_counters[3] = {0, 0, 0};
+    pcuda_tree *call_tree = nullptr;  // tree reused by the one-shot Barnes-Hut entry points
+
+    pcuda::Nccl *nccl = nullptr;
+};
+
+namespace pcuda {
+
+int fail(pcuda_ctx *ctx, int status, const char *fmt, ...);
+void set_thread_error(const char *msg);
+
+void phase_begin(pcuda_ctx *ctx, Phase p);
+void phase_end(pcuda_ctx *ctx, Phase p);
+void timings_reset(pcuda_ctx *ctx);
+// Synchronises the stream and folds event times into ctx->timings.
+int timings_collect(pcuda_ctx *ctx);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void tree_free(pcuda_ctx *ctx, pcuda_tree *t);
+void nccl_free(pcuda_ctx *ctx);
+
+}  // namespace pcuda
+
+#define PCUDA_CUDA_TRY(ctx, expr)                                                              \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return pcuda::fail((ctx),                                                          \
+                               _e == cudaErrorMemoryAllocation ? PCUDA_ERR_OUT_OF_MEMORY       \
+                                                               : PCUDA_ERR_CUDA,               \
+                               "%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,              \
+                               cudaGetErrorString(_e));                                        \
+    } while (0)
+
+#define PCUDA_TRY(expr)                 \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != PCUDA_OK) return _s;  \
+    } while (0)

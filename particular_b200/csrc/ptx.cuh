@@ -1,0 +1,81 @@
+// ptx.cuh — thin inline-PTX wrappers for the sm_100a features the kernels use:
+// mbarrier producer/consumer pipeline, 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP),
+// approximate reciprocal square root (MUFU.RSQ) and packed FP32 pairs (FFMA2 / FADD2 / FMUL2).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace pcuda {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+// Makes freshly initialised mbarriers visible to the async (TMA) proxy.
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// Orders prior generic-proxy shared-memory writes before later async-proxy accesses.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PCUDA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PCUDA_DONE;\n"
+        "bra PCUDA_WAIT;\n"
+        "PCUDA_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D bulk tensor-memory-accelerator copy global -> shared, completion signalled on `bar`
+// (complete_tx::bytes).  bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// MUFU.RSQ: max relative error 2^-22.9 (PTX ISA, rsqrt.approx.f32), denormals flushed.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Packed FP32 pairs (sm_100+: fma.rn.f32x2 etc.).  One issue slot does two lanes of work, which
+// is what lets MUFU / LDS / loop overhead hide under the FMA pipe in the pair kernel.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
+
+}  // namespace ptx
+}  // namespace pcuda

@@ -1,0 +1,403 @@
+"""Host-side mirror of particular's operator interface for the CUDA backend.
+
+Same names, argument meaning and error behaviour as the reference (paths relative to
+/root/reference/particular/src):
+
+  Between(affected, affecting)              lib.rs:299-300
+  Interaction.compute(storage)              lib.rs:364-370
+  Ordered / Reordered / &[P] storages       storage.rs:48-241
+  Acceleration / AccelerationSoftened       gravity/newtonian/acceleration.rs:17-58,
+                                            gravity/newtonian/acceleration_softened.rs:17-63
+  BruteForce(resources.., interaction)      gpu/mod.rs:149-208   (the existing GPU operator)
+  BarnesHut(theta, interaction)             sequential.rs:439-543
+  RootedOrthtree                            storage.rs:11-46
+  GpuCompute extension sugar                gpu/mod.rs:13-37     -> cuda_brute_force / cuda_barnes_hut
+
+A "slice of particles" is a C-contiguous numpy array of shape (n, D+1): one
+``GravitationalField {position, m}`` row per particle (gravity/mod.rs:12-18); dtype float32 with
+D in {2, 3} or float64 with D == 3.  Results are (n_affected, D) arrays in affected order (the
+reference yields an iterator of vectors in the same order).
+
+All arithmetic happens in libparticular_cuda.so; nothing here computes an interaction on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Callable, Optional
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import CudaError, check, lib
+
+__all__ = [
+    "Between", "Ordered", "Reordered", "Acceleration", "AccelerationSoftened", "CudaContext",
+    "BruteForce", "BarnesHut", "RootedOrthtree", "cuda_brute_force", "cuda_barnes_hut",
+    "is_affecting", "CudaError",
+]
+
+
+# ---- storages -------------------------------------------------------------------------------------
+@dataclass
+class Between:
+    """``Between(affected, affecting)``: the first is acted upon, the second acts (lib.rs:299-300)."""
+    affected: Any
+    affecting: Any
+
+
+def is_affecting(particles: np.ndarray) -> np.ndarray:
+    """``GravitationalField::is_affecting`` (gravity/mod.rs:29-34): m != 0, vectorised."""
+    return particles[:, -1] != 0
+
+
+def _as_particles(p) -> np.ndarray:
+    a = np.ascontiguousarray(p)
+    if a.ndim != 2 or a.shape[1] not in (3, 4) or a.dtype not in (np.float32, np.float64):
+        raise TypeError(f"particles must be (n, D+1) float32/float64 with D in (2, 3); got "
+                        f"{a.shape} {a.dtype}")
+    return a
+
+
+class Ordered:
+    """Affecting particles first (storage.rs:48-138)."""
+
+    def __init__(self, particles: np.ndarray, affecting_len: int):
+        self._particles = particles
+        self._affecting_len = affecting_len
+
+    @classmethod
+    def with_(cls, affecting, non_affecting, is_affecting_fn: Callable = is_affecting):
+        """storage.rs:61-80: chain, then affecting_len = first index failing the predicate."""
+        a, b = _as_particles(affecting), _as_particles(non_affecting)
+        particles = np.ascontiguousarray(np.concatenate([a, b.astype(a.dtype, copy=False)]))
+        mask = np.asarray(is_affecting_fn(particles), dtype=bool)
+        fails = np.flatnonzero(~mask)
+        return cls(particles, int(fails[0]) if len(fails) else len(particles))
+
+    @classmethod
+    def new(cls, unordered, is_affecting_fn: Callable = is_affecting):
+        """storage.rs:85-95: two stable filter passes."""
+        p = _as_particles(unordered)
+        mask = np.asarray(is_affecting_fn(p), dtype=bool)
+        return cls.with_(p[mask], p[~mask], is_affecting_fn)
+
+    def affecting_len(self) -> int:
+        return self._affecting_len
+
+    def affecting(self) -> np.ndarray:
+        return self._particles[: self._affecting_len]
+
+    def non_affecting(self) -> np.ndarray:
+        return self._particles[self._affecting_len:]
+
+    def particles(self) -> np.ndarray:
+        return self._particles
+
+
+class Reordered:
+    """Borrow of the original slice plus an ``Ordered`` copy (storage.rs:141-205)."""
+
+    def __init__(self, unordered, is_affecting_fn: Callable = is_affecting):
+        self.unordered = _as_particles(unordered)
+        self._ordered = Ordered.new(self.unordered, is_affecting_fn)
+        self._fn = is_affecting_fn
+
+    new = classmethod(lambda cls, unordered, fn=is_affecting: cls(unordered, fn))
+
+    def ordered(self) -> Ordered:
+        return self._ordered
+
+    def affecting_len(self) -> int:
+        return self._ordered.affecting_len()
+
+    def affecting(self) -> np.ndarray:
+        return self._ordered.affecting()
+
+    def non_affecting(self) -> np.ndarray:
+        return self._ordered.non_affecting()
+
+    def reordered(self) -> np.ndarray:
+        return self._ordered.particles()
+
+    def is_affecting_fn(self):
+        return self._fn
+
+
+def _resolve(storage):
+    """The storage blanket impls (storage.rs:207-241) -> (affected_positions | None, affecting).
+    ``None`` for affected means "the affecting slice itself" (&[P] => Between(slice, slice))."""
+    if isinstance(storage, Between):
+        aff, src = storage.affected, storage.affecting
+        if isinstance(src, RootedOrthtree):
+            return aff, src
+        src = _as_particles(src)
+        if aff is src:
+            return None, src
+        aff = np.asarray(aff)
+        d = src.shape[1] - 1
+        if aff.ndim == 1:  # Between(&P1, &[P2]): a single affected particle
+            aff = aff[None, :]
+        if aff.shape[1] == d + 1:  # affected given as particles: only their positions matter
+            aff = aff[:, :d]
+        if aff.shape[1] != d:
+            raise TypeError(f"affected has dimension {aff.shape[1]}, affecting has {d}")
+        return np.ascontiguousarray(aff, dtype=src.dtype), src
+    if isinstance(storage, Ordered):  # storage.rs:207-217
+        p = storage.particles()
+        return np.ascontiguousarray(p[:, :-1]), np.ascontiguousarray(storage.affecting())
+    if isinstance(storage, Reordered):  # storage.rs:219-229
+        return (np.ascontiguousarray(storage.unordered[:, :-1]),
+                np.ascontiguousarray(storage.affecting()))
+    return None, _as_particles(storage)  # storage.rs:231-241
+
+
+# ---- interactions ---------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Acceleration:
+    """Newtonian acceleration, no softening (acceleration.rs:17-58)."""
+    is_checked: bool = True
+    softening = 0.0
+
+    @staticmethod
+    def checked():
+        return Acceleration(True)
+
+    @staticmethod
+    def unchecked():
+        return Acceleration(False)
+
+
+@dataclass(frozen=True)
+class AccelerationSoftened:
+    """Newtonian acceleration with softening (acceleration_softened.rs:17-63)."""
+    softening: float = 0.0
+    is_checked: bool = True
+
+    @staticmethod
+    def checked(softening):
+        return AccelerationSoftened(float(softening), True)
+
+    @staticmethod
+    def unchecked(softening):
+        return AccelerationSoftened(float(softening), False)
+
+
+# ---- context (the analogue of GpuResources + wgpu::Device + wgpu::Queue, gpu/mod.rs:85-159) -------
+class CudaContext:
+    """Owns one device, one stream, grow-only buffers and (optionally) an NCCL communicator.
+    Create once and reuse across calls ("should not be recreated for every iteration",
+    gpu/mod.rs:150-151)."""
+
+    def __init__(self, device: int = 0, leaf_size: int = 0):
+        cfg = _ffi.Config(device, 0, leaf_size, 0)
+        h = C.c_void_p()
+        check(lib.pcuda_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.device = device
+        sm, khz = C.c_int(), C.c_int()
+        name = C.create_string_buffer(128)
+        check(lib.pcuda_device_info(h, C.byref(sm), C.byref(khz), name, 128), h)
+        self.sm_count, self.sm_clock_khz, self.name = sm.value, khz.value, name.value.decode()
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise CudaError(_ffi.ERR_NOT_INITIALISED, "context destroyed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib.pcuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def timings(self) -> dict:
+        t = _ffi.Timings()
+        check(lib.pcuda_get_timings(self.handle, C.byref(t)), self.handle)
+        return t.as_dict()
+
+    def sync(self):
+        check(lib.pcuda_sync(self.handle), self.handle)
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(lib.pcuda_stream(self.handle) or 0)
+
+    def probe_fp32(self, packed: bool = True, iters: int = 4096, repeats: int = 5):
+        tf, ms = C.c_double(), C.c_float()
+        check(lib.pcuda_probe_fp32(self.handle, int(packed), iters, repeats, C.byref(tf),
+                                   C.byref(ms)), self.handle)
+        return tf.value, ms.value
+
+    # -- NCCL (multi-GPU, one process per GPU) --
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * _ffi.UNIQUE_ID_BYTES)()
+        check(lib.pcuda_comm_unique_id(self.handle, C.byref(buf)), self.handle)
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, world_size: int, rank: int):
+        buf = (C.c_uint8 * _ffi.UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        check(lib.pcuda_comm_init(self.handle, C.byref(buf), world_size, rank), self.handle)
+
+    def allgather_dev(self, send_ptr: int, recv_ptr: int, bytes_per_rank: int):
+        check(lib.pcuda_comm_allgather_dev(self.handle, send_ptr, recv_ptr, bytes_per_rank),
+              self.handle)
+
+
+def _suffix(src: np.ndarray) -> str:
+    d = src.shape[1] - 1
+    key = (src.dtype.type, d)
+    table = {(np.float32, 3): "f32x3", (np.float32, 2): "f32x2", (np.float64, 3): "f64x3"}
+    if key not in table:
+        # the reference does the same for shader dimensions it lacks: unimplemented!()
+        # (gravity/impls/mod.rs:362, 374)
+        raise NotImplementedError(f"no CUDA kernel for {src.dtype} in {d} dimensions")
+    return table[key]
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RootedOrthtree:
+    """A tree built on the device over the affecting particles (storage.rs:11-46).  f32 only."""
+
+    def __init__(self, ctx: CudaContext, particles):
+        p = _as_particles(particles)
+        if p.dtype != np.float32:
+            raise NotImplementedError("device trees are f32")
+        self.ctx, self.dim, self.n = ctx, p.shape[1] - 1, len(p)
+        h = C.c_void_p()
+        check(lib.pcuda_tree_build_f32(ctx.handle, self.dim, _ptr(p), len(p), C.byref(h)),
+              ctx.handle)
+        self._h = h
+        info = _ffi.TreeInfo()
+        check(lib.pcuda_tree_info_get(h, C.byref(info)), ctx.handle)
+        self.info = info
+        self.n_nodes, self.n_levels = int(info.n_nodes), int(info.n_levels)
+
+    new = classmethod(lambda cls, ctx, particles: cls(ctx, particles))
+
+    def read(self, which: int) -> np.ndarray:
+        n, m, d = self.n, self.n_nodes, self.dim
+        shape, dt = {
+            _ffi.TREE_KEYS: ((n,), np.uint64), _ffi.TREE_PERM: ((n,), np.uint32),
+            _ffi.TREE_NODE_BEGIN: ((m,), np.uint32), _ffi.TREE_NODE_COUNT: ((m,), np.uint32),
+            _ffi.TREE_NODE_LEVEL: ((m,), np.uint32), _ffi.TREE_NODE_FIRST_CHILD: ((m,), np.uint32),
+            _ffi.TREE_NODE_NUM_CHILDREN: ((m,), np.uint32),
+            _ffi.TREE_NODE_COM_MASS: ((m, d + 1), np.float32)}[which]
+        out = np.zeros(shape, dtype=dt)
+        check(lib.pcuda_tree_read(self.ctx.handle, self._h, which, _ptr(out), out.nbytes),
+              self.ctx.handle)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self.ctx._h is not None:
+            lib.pcuda_tree_destroy(self.ctx.handle, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- algorithms -----------------------------------------------------------------------------------
+class BruteForce:
+    """Brute-force algorithm on the GPU (the CUDA counterpart of gpu::BruteForce,
+    gpu/mod.rs:149-208): ``BruteForce(ctx, interaction).compute(storage)``."""
+
+    def __init__(self, ctx: CudaContext, interaction):
+        self.ctx, self.interaction = ctx, interaction
+
+    def compute(self, storage) -> np.ndarray:
+        aff, src = _resolve(storage)
+        sfx = _suffix(src)
+        d = src.shape[1] - 1
+        na = len(src) if aff is None else len(aff)
+        out = np.zeros((na, d), dtype=src.dtype)
+        fn = getattr(lib, f"pcuda_bruteforce_{sfx}")
+        check(fn(self.ctx.handle, _ptr(aff), na, _ptr(src), len(src),
+                 self.interaction.softening, int(self.interaction.is_checked), _ptr(out)),
+              self.ctx.handle)
+        return out
+
+    def compute_device(self, affected_ptr: Optional[int], n_affected: int, affecting_ptr: int,
+                       n_affecting: int, out_ptr: int, suffix: str = "f32x3") -> None:
+        """Device-resident variant: raw device pointers, enqueued on the context stream."""
+        fn = getattr(lib, f"pcuda_bruteforce_{suffix}_dev")
+        check(fn(self.ctx.handle, affected_ptr, n_affected, affecting_ptr, n_affecting,
+                 self.interaction.softening, int(self.interaction.is_checked), out_ptr),
+              self.ctx.handle)
+
+
+class BarnesHut:
+    """Barnes-Hut on the GPU: ``BarnesHut(ctx, theta, interaction).compute(storage)``
+    (sequential.rs:439-543 semantics: the tree is rebuilt on every call unless the storage is
+    ``Between(affected, RootedOrthtree)``)."""
+
+    def __init__(self, ctx: CudaContext, theta: float, interaction):
+        self.ctx, self.theta, self.interaction = ctx, float(theta), interaction
+
+    new = classmethod(lambda cls, ctx, theta, interaction: cls(ctx, theta, interaction))
+
+    def compute(self, storage) -> np.ndarray:
+        aff, src = _resolve(storage)
+        it = self.interaction
+        if isinstance(src, RootedOrthtree):
+            aff = np.asarray(aff)
+            if aff.ndim == 1:
+                aff = aff[None, :]
+            if aff.shape[1] == src.dim + 1:
+                aff = aff[:, : src.dim]
+            aff = np.ascontiguousarray(aff, dtype=np.float32)
+            out = np.zeros((len(aff), src.dim), dtype=np.float32)
+            check(lib.pcuda_tree_traverse_f32(self.ctx.handle, src._h, _ptr(aff), len(aff),
+                                              self.theta, it.softening, int(it.is_checked),
+                                              _ptr(out)), self.ctx.handle)
+            return out
+        sfx = _suffix(src)
+        if sfx == "f64x3":
+            raise NotImplementedError("Barnes-Hut on the device is f32 (2-D / 3-D)")
+        d = src.shape[1] - 1
+        na = len(src) if aff is None else len(aff)
+        out = np.zeros((na, d), dtype=np.float32)
+        fn = getattr(lib, f"pcuda_barneshut_{sfx}")
+        check(fn(self.ctx.handle, _ptr(aff), na, _ptr(src), len(src), self.theta, it.softening,
+                 int(it.is_checked), _ptr(out)), self.ctx.handle)
+        return out
+
+    def compute_device(self, affected_ptr: Optional[int], n_affected: int, affecting_ptr: int,
+                       n_affecting: int, out_ptr: int, suffix: str = "f32x3") -> None:
+        it = self.interaction
+        fn = getattr(lib, f"pcuda_barneshut_{suffix}_dev")
+        check(fn(self.ctx.handle, affected_ptr, n_affected, affecting_ptr, n_affecting, self.theta,
+                 it.softening, int(it.is_checked), out_ptr), self.ctx.handle)
+
+    def last_counters(self) -> dict:
+        c = (C.c_uint64 * 3)()
+        check(lib.pcuda_tree_last_counters(self.ctx.handle, C.byref(c)), self.ctx.handle)
+        return {"node_interactions": int(c[0]), "particle_interactions": int(c[1]),
+                "node_tests": int(c[2])}
+
+
+# ---- extension-trait sugar (GpuCompute, gpu/mod.rs:13-37) -------------------------------------------
+def cuda_brute_force(storage, ctx: CudaContext, interaction) -> np.ndarray:
+    return BruteForce(ctx, interaction).compute(storage)
+
+
+def cuda_barnes_hut(storage, ctx: CudaContext, theta: float, interaction) -> np.ndarray:
+    return BarnesHut(ctx, theta, interaction).compute(storage)

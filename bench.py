@@ -1,0 +1,495 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 backend for particular's hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload bruteforce|barneshut] [--n N] [--no-extra]
+
+Default workload (BASELINE.json configs[1]): brute force, 3-D f32, N = 1,000,000 massive particles
+drawn like the reference's criterion bench (benches/benchmark.rs:22-37: positions U[-5e3,5e3)^3,
+mu U[1e3,1e9), seed 1808), `Acceleration::checked()`; one "step" = one full evaluation of all N x N
+pair interactions (self pairs counted, as the reference evaluates them).  Metric: Gpair-interactions/s.
+
+  value   device-resident: the particles live in HBM; every step = pad/copy into the gather slot,
+          (N > 1 GPUs) in-place NCCL all-gather of the source records, pair kernel, fixed-order
+          reduction of the source-split partial sums.  N > 1: strong scaling — the N particles are
+          sharded over the ranks (targets), sources replicated by the all-gather.
+  e2e     the same evaluation through the public API with HOST buffers (pinned upload of the
+          rank's records, step, download of its accelerations inside the timed region).
+  roofline  FP32 pipe: 20 flop / pair (the GPU-Gems-3 convention the reference cites,
+          gpu/resources.rs:76-77) over the pair kernel's CUDA-event time.
+  cpu_baseline  the restated `parallel::BruteForceSimd<8>` (oracle/baseline_simd.c; AVX2 + OpenMP)
+          on the box's host cores, on a bounded target sample of the same workload.
+
+`--impl reference` times that CPU restatement as the reference arm (the Rust crate cannot be built
+here: no cargo/rustc in the image — DESIGN.md).  `--workload barneshut` makes Barnes-Hut
+(theta = 0.5, Plummer sphere, N = 10M) the headline line instead; by default its number rides along
+in the "barnes_hut" key of the brute-force line at N = 1 GPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 20.0
+SEED = 1808
+
+
+# ---- synthetic workloads -----------------------------------------------------------
+def uniform_cloud(n, seed=SEED):
+    rng = np.random.default_rng(seed)
+    p = np.empty((n, 4), dtype=np.float32)
+    p[:, :3] = rng.uniform(-5e3, 5e3, (n, 3))
+    p[:, 3] = rng.uniform(1e3, 1e9, n)
+    return p
+
+
+def plummer_cloud(n, seed=SEED):
+    rng = np.random.default_rng(seed)
+    r = np.empty(0)
+    while len(r) < n:
+        u = rng.uniform(1e-12, 1.0, n)
+        rr = 1.0 / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+        r = np.concatenate([r, rr[rr < 50.0]])
+    r = r[:n]
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    p = np.empty((n, 4), dtype=np.float32)
+    p[:, :3] = v * r[:, None]
+    p[:, 3] = 1.0 / n
+    return p
+
+
+# ---- clocks during the timed region (NVML; B200_PROFILING.md "clocks line") -------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # NVML missing: report nothing rather than invent numbers
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": self.err}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "sm_mhz_min": s[0] if s else None, "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None, "samples": len(s)}
+
+
+# ---- CPU arms ----------------------------------------------------------------------------------------
+def cpu_bruteforce_rate(P, seconds, steps=1):
+    """Restated parallel::BruteForceSimd<8> on a bounded target sample x all sources.
+    Returns (Gpairs/s, sample description, cores, per-step seconds list)."""
+    import oracle
+    n = len(P)
+    cores = oracle.baseline_threads()
+    probe = min(n, 256 * cores)
+    t0 = time.perf_counter()
+    oracle.brute_force_simd8_parallel(P[:probe, :3], P)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(n, max(probe, probe * seconds / dt)))
+    sample = max(64, sample - sample % 64)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle.brute_force_simd8_parallel(P[:sample, :3], P)
+        times.append(time.perf_counter() - t0)
+    rate = sample * n / (sum(times) / len(times)) / 1e9
+    return rate, f"first {sample} targets x all {n} sources, scaled linearly", cores, times
+
+
+def cpu_barneshut_rate(P, theta, seconds):
+    """Restated parallel::BarnesHut: single-thread build of the full tree + OpenMP traversal of a
+    bounded target sample; the per-evaluation time is build + traversal scaled to all targets."""
+    import oracle
+    n = len(P)
+    cores = oracle.baseline_threads()
+    t0 = time.perf_counter()
+    tree = oracle.Tree(P)
+    t_build = time.perf_counter() - t0
+    probe = min(n, 512 * cores)
+    idx = np.linspace(0, n - 1, probe).astype(np.int64)
+    t0 = time.perf_counter()
+    tree.traverse(P[idx, :3], theta, parallel=True)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(n, max(probe, probe * seconds / dt)))
+    idx = np.linspace(0, n - 1, sample).astype(np.int64)
+    t0 = time.perf_counter()
+    tree.traverse(P[idx, :3], theta, parallel=True)
+    t_trav = time.perf_counter() - t0
+    total = t_build + t_trav * n / sample
+    return (n / total, f"full single-thread build ({t_build:.1f} s) + traversal of {sample} evenly "
+            f"spaced targets of {n}, scaled linearly", cores, t_build, t_trav * n / sample)
+
+
+# ---- main ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bruteforce", choices=["bruteforce", "barneshut"])
+    ap.add_argument("--n", type=int, default=0, help="particle count (default: BASELINE config)")
+    ap.add_argument("--theta", type=float, default=0.5)
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the cpu_baseline leg and the ride-along Barnes-Hut number")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n = args.n or (1_000_000 if args.workload == "bruteforce" else 10_000_000)
+
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args, n, world)
+        return 0
+    if args.workload == "bruteforce":
+        return bench_bruteforce(args, n, rank, world, local_rank)
+    return bench_barneshut(args, n, rank, world, local_rank)
+
+
+def reference_arm(args, n, world):
+    """The reference's CPU implementation of the path (restated; kind "port") on all host cores."""
+    if args.workload == "bruteforce":
+        P = uniform_cloud(n)
+        per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+        rate, sample, cores, times = cpu_bruteforce_rate(P, per_step, steps=args.steps + args.warmup)
+        times = times[args.warmup:] or times
+        sample_n = int(sample.split()[1])
+        value = sample_n * n / (sum(times) / len(times)) / 1e9
+        line = {"impl": "reference", "metric": "brute-force pair interactions per second",
+                "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": bruteforce_config(n, world, "cpu"),
+                "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": "port",
+                                 "sample": sample + "; restated parallel::BruteForceSimd<8> "
+                                 "(AVX2 rsqrt + OpenMP), oracle/baseline_simd.c"},
+                "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    else:
+        P = plummer_cloud(n)
+        value, sample, cores, tb, tt = cpu_barneshut_rate(P, args.theta, 20.0)
+        line = {"impl": "reference", "metric": "Barnes-Hut particles per second (build + traversal)",
+                "value": value, "unit": "particles/s", "n_gpus": world, "steps": 1, "warmup": 0,
+                "ms_per_step": 1e3 * (tb + tt), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": barneshut_config(n, world, args.theta, "cpu"),
+                "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores,
+                                 "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def bruteforce_config(n, world, where):
+    return {"workload": f"brute force 3-D f32, N={n} massive particles, all pairs "
+                        f"(BASELINE configs[1]); uniform cube, mu U[1e3,1e9), seed {SEED}; "
+                        f"Acceleration::checked(), softening 0",
+            "n_particles": n, "pairs_per_step": n * n,
+            "parallelism": f"targets sharded over {world} GPU(s), sources all-gathered (NCCL)"
+            if where == "gpu" else "host threads over targets",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); the 16 MB source set "
+                  "is re-read from L2 by design" if where == "gpu" else "n/a"}
+
+
+def barneshut_config(n, world, theta, where):
+    return {"workload": f"Barnes-Hut 3-D f32 octree, theta={theta}, N={n} Plummer sphere (a=1, "
+                        f"r<50a, equal mu=1/N, seed {SEED}); tree rebuilt every step "
+                        f"(BASELINE configs[3]); Acceleration::checked()",
+            "n_particles": n, "theta": theta,
+            "parallelism": f"{world} GPU(s)" if where == "gpu" else "host threads over targets",
+            "l2": "inputs + tree exceed L2 at N=10M; 256 MiB buffer written between timed steps"
+            if where == "gpu" else "n/a"}
+
+
+def _dist_setup(world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return dist
+
+
+def _max_over_ranks(x, world, dist):
+    import torch
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(x, world, dist):
+    import torch
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def _barrier(world, dist):
+    import torch
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def bench_bruteforce(args, n, rank, world, local_rank):
+    import torch
+
+    import particular_b200 as pb
+    dist = _dist_setup(world, local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = pb.CudaContext(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    inter = pb.Acceleration.checked()
+    sh = pb.ShardedBruteForce(ctx, inter)
+    P = uniform_cloud(n)
+    lo, hi = pb.shard_bounds(n, world, rank)
+    n_local = hi - lo
+    d_local = torch.from_numpy(P[lo:hi]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+
+    def timed_steps(step_fn, k):
+        """Each step bracketed by events on the context stream; L2 flushed between steps."""
+        times, kernel_ms, launches = [], [], 0
+        for _ in range(k):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn()
+            e1.record(stream)
+            ctx.sync()
+            times.append(e0.elapsed_time(e1))
+            t = ctx.timings()
+            kernel_ms.append(t["compute_ms"])
+            launches += t["kernel_launches"]
+        return times, kernel_ms, launches
+
+    # ---- device-resident value ----
+    dev_step = lambda: sh.step_device(d_local, n)  # noqa: E731
+    for _ in range(args.warmup):
+        dev_step()
+    _barrier(world, dist)
+    sampler.start()
+    times, kernel_ms, launches = timed_steps(dev_step, args.steps)
+    _barrier(world, dist)
+    sampler.stop()
+    total_ms = _max_over_ranks(sum(times), world, dist)
+    ms_per_step = total_ms / args.steps
+    value = n * float(n) / (ms_per_step * 1e-3) / 1e9
+    total_launches = int(_sum_over_ranks(launches, world, dist))
+
+    # ---- end to end through the public API, host buffers ----
+    h_local = ctx.pinned_empty((n_local, 4), np.float32)
+    h_local[:] = P[lo:hi]
+    h_out = ctx.pinned_empty((n_local, 3), np.float32)
+    e2e_step = lambda: sh.compute_local(h_local, n, out=h_out)  # noqa: E731
+    for _ in range(2):
+        e2e_step()
+    _barrier(world, dist)
+    e2e_times, _, _ = timed_steps(e2e_step, args.steps)
+    _barrier(world, dist)
+    e2e_ms = _max_over_ranks(sum(e2e_times), world, dist) / args.steps
+    e2e_value = n * float(n) / (e2e_ms * 1e-3) / 1e9
+
+    # ---- roofline of the pair kernel (this rank's launch) ----
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    achieved = FLOP_PER_PAIR * n_local * float(n) / (k_ms * 1e-3) / 1e12
+    sm_max_mhz = (sampler.max_mhz or ctx.sm_clock_khz / 1e3)
+    peak_nominal = ctx.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    probe_tf, _ = ctx.probe_fp32(True, 8192, 3)
+    roofline = {"bound": "fp32", "kernel": "pcuda::bf::pair_kernel_f32<3,...>",
+                "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
+                "frac": achieved / peak_nominal,
+                "peak_source": f"{ctx.sm_count} SMs x 128 FP32 lanes x 2 flop x {sm_max_mhz:.0f} MHz "
+                               "(clocks.max.sm; MEASURED_PEAKS.json carries no FP32 figure)",
+                "peak_probe_ffma2": probe_tf, "frac_of_probe": achieved / probe_tf,
+                "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": n_local * n,
+                "kernel_ms": k_ms, "traffic": None}
+
+    line = {"metric": "brute-force pair interactions per second", "value": value,
+            "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": bruteforce_config(n, world, "gpu"),
+            "e2e": {"value": e2e_value, "unit": "Gpairs/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(n_local * 12),
+                    "bytes_are": "per rank"},
+            "gpu_launches": total_launches, "roofline": roofline, "clocks": sampler.summary(),
+            "device": ctx.name}
+
+    if rank == 0 and world == 1 and not args.no_extra:
+        rate, sample, cores, _ = cpu_bruteforce_rate(P, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": rate, "unit": "Gpairs/s", "cores": cores, "kind": "port",
+                                "sample": sample + "; restated parallel::BruteForceSimd<8> (AVX2 "
+                                "rsqrt + OpenMP), oracle/baseline_simd.c"}
+        try:
+            line["barnes_hut"] = barneshut_numbers(args, ctx, stream, flush, 10_000_000, args.theta,
+                                                   steps=3, warmup=2, cpu_seconds=args.cpu_seconds)
+        except Exception as e:  # keep the headline line even if the ride-along fails
+            line["barnes_hut"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_seconds):
+    """Single-GPU Barnes-Hut: device-resident particles/s (build + traversal every step), e2e
+    through the host API, HBM roofline of the traversal, CPU restatement beside it."""
+    import torch
+
+    import particular_b200 as pb
+    P = plummer_cloud(n)
+    dev = torch.device("cuda", ctx.device)
+    bh = pb.BarnesHut(ctx, theta, pb.Acceleration.checked())
+    d_src = torch.from_numpy(P).to(dev)
+    d_out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+
+    def run(step_fn, k):
+        times, tm, launches = [], [], 0
+        for _ in range(k):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn()
+            e1.record(stream)
+            ctx.sync()
+            times.append(e0.elapsed_time(e1))
+            t = ctx.timings()
+            tm.append(t)
+            launches += t["kernel_launches"]
+        return times, tm, launches
+
+    dev_step = lambda: bh.compute_device(None, n, d_src.data_ptr(), n, d_out.data_ptr())  # noqa: E731
+    for _ in range(warmup):
+        dev_step()
+    ctx.sync()
+    times, tm, launches = run(dev_step, steps)
+    ms = sum(times) / len(times)
+    build_ms = sum(t["build_ms"] for t in tm) / len(tm)
+    trav_ms = sum(t["compute_ms"] for t in tm) / len(tm)
+    counters = bh.last_counters()
+    h_in = ctx.pinned_empty((n, 4), np.float32)
+    h_in[:] = P
+    h_out = ctx.pinned_empty((n, 3), np.float32)
+    e2e_step = lambda: bh.compute(h_in, out=h_out)  # noqa: E731
+    e2e_step()
+    e2e_times, _, _ = run(e2e_step, steps)
+    e2e_ms = sum(e2e_times) / len(e2e_times)
+    inter = counters["node_interactions"] + counters["particle_interactions"]
+    out = {"metric": "Barnes-Hut particles per second (build + traversal)",
+           "value": n / (ms * 1e-3), "unit": "particles/s", "ms_per_step": ms,
+           "build_ms": build_ms, "traverse_ms": trav_ms, "steps": steps, "warmup": warmup,
+           "config": barneshut_config(n, 1, theta, "gpu"),
+           "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 12},
+           "gpu_launches": launches, "counters_last_step": counters,
+           "traversal_fp32": {"achieved": FLOP_PER_PAIR * inter / (trav_ms * 1e-3) / 1e12,
+                              "unit": "TFLOP/s", "interactions_per_target": inter / n}}
+    if not args.no_extra:
+        rate, sample, cores, tb, tt = cpu_barneshut_rate(P, theta, cpu_seconds)
+        out["cpu_baseline"] = {"value": rate, "unit": "particles/s", "cores": cores, "kind": "port",
+                               "sample": sample + "; restated parallel::BarnesHut",
+                               "build_s": tb, "traverse_s": tt}
+    del d_src, d_out
+    return out
+
+
+def bench_barneshut(args, n, rank, world, local_rank):
+    import torch
+
+    import particular_b200 as pb
+    dist = _dist_setup(world, local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = pb.CudaContext(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        raise SystemExit("multi-GPU Barnes-Hut is not wired into bench.py yet")
+    sampler.start()
+    res = barneshut_numbers(args, ctx, stream, flush, n, args.theta, args.steps, args.warmup,
+                            args.cpu_seconds)
+    sampler.stop()
+    line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": res["config"], "e2e": res["e2e"],
+            "gpu_launches": res["gpu_launches"], "clocks": sampler.summary(), "device": ctx.name,
+            "build_ms": res["build_ms"], "traverse_ms": res["traverse_ms"],
+            "counters_last_step": res["counters_last_step"],
+            "traversal_fp32": res["traversal_fp32"]}
+    if "cpu_baseline" in res:
+        line["cpu_baseline"] = res["cpu_baseline"]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

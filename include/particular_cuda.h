@@ -119,6 +119,8 @@ const char *pcuda_last_error(const pcuda_ctx *ctx);
 int pcuda_get_timings(const pcuda_ctx *ctx, pcuda_timings *out);
 /* cudaStream_t of the context (as void*), for interop with the *_dev entry points. */
 void *pcuda_stream(pcuda_ctx *ctx);
+/* Waits for the context stream; also folds the phase events of the last *_dev call into the
+ * timings returned by pcuda_get_timings(). */
 int pcuda_sync(pcuda_ctx *ctx);
 /* Device properties the roofline needs: SM count, max SM clock (kHz). */
 int pcuda_device_info(const pcuda_ctx *ctx, int *sm_count, int *sm_clock_khz, char *name,
@@ -200,6 +202,25 @@ int pcuda_comm_destroy(pcuda_ctx *ctx);
 /* All-gather equally sized shards of `bytes_per_rank` bytes (device pointers, context stream). */
 int pcuda_comm_allgather_dev(pcuda_ctx *ctx, const void *d_send, void *d_recv,
                              size_t bytes_per_rank);
+
+/* One multi-GPU brute-force step, device-resident (new).  Every rank passes the
+ * {x,y,z,mu} records of the particles it owns (n_local <= shard_capacity; shard_capacity must be
+ * the same on all ranks).  The records are placed in this rank's slot of d_gathered_xyzm
+ * (world_size * shard_capacity records; unused slots are padded with zero-mass records that
+ * contribute exactly 0), all-gathered in place, and the local particles are evaluated against
+ * all of them: d_out_xyz[i] = acceleration of local particle i (n_local x 3).  Without a
+ * communicator (pcuda_comm_init not called) this is the single-GPU all-pairs evaluation.
+ * Enqueued on the context stream; does not synchronise; pcuda_get_timings() after pcuda_sync()
+ * does not include this call's phases (use events on pcuda_stream()). */
+int pcuda_bruteforce_f32x3_sharded_dev(pcuda_ctx *ctx, const float *d_local_xyzm, size_t n_local,
+                                       size_t shard_capacity, float softening, int checked,
+                                       float *d_gathered_xyzm, float *d_out_xyz);
+
+/* The same step with HOST buffers (upload of the local records, step, download of the local
+ * accelerations); blocking; fills pcuda_get_timings() including comm_ms. */
+int pcuda_bruteforce_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_t n_local,
+                                   size_t shard_capacity, float softening, int checked,
+                                   float *out_xyz);
 
 #ifdef __cplusplus
 }

@@ -478,6 +478,44 @@ static int dev_f64x3(pcuda_ctx *ctx, const double *d_aff, size_t na, const doubl
                    d_out);
 }
 
+// Multi-GPU step (one process per GPU): every rank owns `n_local` particles.  The local records
+// are copied into this rank's slot of `d_gathered` (capacity `cap` records per rank; unused slots
+// are filled with zero-mass records at PAD_POS, which contribute exactly 0), the slots are
+// all-gathered in place over NVLink, and the local targets (aliasing the gathered records,
+// stride 4) are evaluated against all world * cap sources.
+__global__ void fill_slot_f32x3(const float4 *__restrict__ local, int n_local, int cap,
+                                float4 *__restrict__ slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) slot[i] = i < n_local ? local[i] : make_float4(PAD_POS, PAD_POS, PAD_POS, 0.f);
+}
+
+static int sharded_f32x3(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t cap,
+                         float eps, int checked, float *d_gathered, float *d_out) {
+    int world = 1, rank = 0;
+    nccl_world(ctx, &world, &rank);
+    if (cap == 0 || n_local > cap)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "n_local (%zu) exceeds shard capacity (%zu)",
+                    n_local, cap);
+    if (!aligned(d_local, 16) || !aligned(d_gathered, 16))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "records must be 16-byte aligned");
+    if ((size_t)world * cap > 0x7fffffffull)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    float4 *all = reinterpret_cast<float4 *>(d_gathered);
+    float4 *slot = all + (size_t)rank * cap;
+    phase_begin(ctx, PH_COMM);
+    fill_slot_f32x3<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const float4 *>(d_local), (int)n_local, (int)cap, slot);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (world > 1) PCUDA_TRY(pcuda_comm_allgather_dev(ctx, slot, all, cap * sizeof(float4)));
+    phase_end(ctx, PH_COMM);
+    phase_begin(ctx, PH_COMPUTE);
+    PCUDA_TRY(run_f32<3>(ctx, reinterpret_cast<const float *>(slot), 4, n_local, all,
+                         (size_t)world * cap, eps, checked, d_out));
+    phase_end(ctx, PH_COMPUTE);
+    return PCUDA_OK;
+}
+
 // Host-pointer wrapper shared by the three precisions: upload, run, download, collect timings.
 template <typename S, typename RunFn>
 static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, const S *affecting,
@@ -582,6 +620,51 @@ int pcuda_bruteforce_f64x3_dev(pcuda_ctx *ctx, const double *d_affected, size_t 
     return bf::dev_call(ctx, [&] {
         return bf::dev_f64x3(ctx, d_affected, na, d_affecting, nb, softening, checked, d_out);
     });
+}
+
+int pcuda_bruteforce_f32x3_sharded_dev(pcuda_ctx *ctx, const float *d_local_xyzm, size_t n_local,
+                                       size_t shard_capacity, float softening, int checked,
+                                       float *d_gathered_xyzm, float *d_out_xyz) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    int s = bf::sharded_f32x3(ctx, d_local_xyzm, n_local, shard_capacity, softening, checked,
+                              d_gathered_xyzm, d_out_xyz);
+    ctx->timings.kernel_launches = ctx->launches;
+    return s;
+}
+
+int pcuda_bruteforce_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_t n_local,
+                                   size_t shard_capacity, float softening, int checked,
+                                   float *out_xyz) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n_local && (!local_xyzm || !out_xyz))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    int world = 1, rank = 0;
+    nccl_world(ctx, &world, &rank);
+    const size_t cap = shard_capacity;
+    if (cap == 0 || n_local > cap)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "n_local (%zu) exceeds shard capacity (%zu)",
+                    n_local, cap);
+    phase_begin(ctx, PH_UPLOAD);
+    PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(cap * 16));
+    PCUDA_CUDA_TRY(ctx, ctx->d_packed_src.ensure((size_t)world * cap * 16));
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(cap * 12));
+    if (n_local)
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_affecting.p, local_xyzm, n_local * 16,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+    phase_end(ctx, PH_UPLOAD);
+    // every rank must enter the collective, even one that owns no particles
+    PCUDA_TRY(bf::sharded_f32x3(ctx, ctx->d_affecting.as<float>(), n_local, cap, softening,
+                                checked, ctx->d_packed_src.as<float>(), ctx->d_out.as<float>()));
+    phase_begin(ctx, PH_DOWNLOAD);
+    if (n_local)
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out_xyz, ctx->d_out.p, n_local * 12,
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+    phase_end(ctx, PH_DOWNLOAD);
+    return timings_collect(ctx);
 }
 
 // Tuning hook: force the targets-per-thread variant (0 = automatic).  Not part of the stable ABI.

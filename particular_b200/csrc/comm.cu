@@ -60,6 +60,12 @@ void nccl_free(pcuda_ctx *ctx) {
     ctx->nccl = nullptr;
 }
 
+void nccl_world(const pcuda_ctx *ctx, int *world, int *rank) {
+    const bool on = ctx->nccl && ctx->nccl->comm;
+    *world = on ? ctx->nccl->world : 1;
+    *rank = on ? ctx->nccl->rank : 0;
+}
+
 static int nccl_fail(pcuda_ctx *ctx, const char *what, ncclResult_t r) {
     return fail(ctx, PCUDA_ERR_NCCL, "%s failed: %s (%d)", what,
                 ctx->nccl && ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?", r);

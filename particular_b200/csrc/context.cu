@@ -167,8 +167,7 @@ void *pcuda_stream(pcuda_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr;
 int pcuda_sync(pcuda_ctx *ctx) {
     if (!ctx) return PCUDA_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(ctx->device);
-    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return PCUDA_OK;
+    return timings_collect(ctx);
 }
 
 int pcuda_device_info(const pcuda_ctx *ctx, int *sm_count, int *sm_clock_khz, char *name,

@@ -194,6 +194,7 @@ class CudaContext:
         h = C.c_void_p()
         check(lib.pcuda_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        self._pinned = []
         self.device = device
         sm, khz = C.c_int(), C.c_int()
         name = C.create_string_buffer(128)
@@ -208,6 +209,9 @@ class CudaContext:
 
     def close(self):
         if getattr(self, "_h", None) is not None:
+            for p in self._pinned:
+                lib.pcuda_host_free(self._h, p)
+            self._pinned = []
             lib.pcuda_destroy(self._h)
             self._h = None
 
@@ -234,6 +238,19 @@ class CudaContext:
     @property
     def stream_ptr(self) -> int:
         return int(lib.pcuda_stream(self.handle) or 0)
+
+    def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """A numpy array backed by page-locked host memory (pcuda_host_alloc): the analogue of
+        the mapped staging view the reference packs particles into (gpu/mod.rs:187-195).
+        Arrays handed to compute() from here are copied by true asynchronous DMA."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        check(lib.pcuda_host_alloc(self.handle, max(n, 1), C.byref(p)), self.handle)
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned.append(p)
+        return arr
 
     def probe_fp32(self, packed: bool = True, iters: int = 4096, repeats: int = 5):
         tf, ms = C.c_double(), C.c_float()
@@ -265,6 +282,14 @@ def _suffix(src: np.ndarray) -> str:
         # (gravity/impls/mod.rs:362, 374)
         raise NotImplementedError(f"no CUDA kernel for {src.dtype} in {d} dimensions")
     return table[key]
+
+
+def _out_array(out, shape, dtype) -> np.ndarray:
+    if out is None:
+        return np.zeros(shape, dtype=dtype)
+    if out.shape != shape or out.dtype != dtype or not out.flags.c_contiguous:
+        raise TypeError(f"out must be a C-contiguous {shape} {np.dtype(dtype)} array")
+    return out
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -323,12 +348,15 @@ class BruteForce:
     def __init__(self, ctx: CudaContext, interaction):
         self.ctx, self.interaction = ctx, interaction
 
-    def compute(self, storage) -> np.ndarray:
+    def compute(self, storage, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`out`: optional preallocated (n_affected, D) result array (e.g. from
+        ``ctx.pinned_empty``); by default a fresh array is returned, as the reference returns a
+        fresh Vec (gpu/mod.rs:184, 205)."""
         aff, src = _resolve(storage)
         sfx = _suffix(src)
         d = src.shape[1] - 1
         na = len(src) if aff is None else len(aff)
-        out = np.zeros((na, d), dtype=src.dtype)
+        out = _out_array(out, (na, d), src.dtype)
         fn = getattr(lib, f"pcuda_bruteforce_{sfx}")
         check(fn(self.ctx.handle, _ptr(aff), na, _ptr(src), len(src),
                  self.interaction.softening, int(self.interaction.is_checked), _ptr(out)),
@@ -354,7 +382,7 @@ class BarnesHut:
 
     new = classmethod(lambda cls, ctx, theta, interaction: cls(ctx, theta, interaction))
 
-    def compute(self, storage) -> np.ndarray:
+    def compute(self, storage, out: Optional[np.ndarray] = None) -> np.ndarray:
         aff, src = _resolve(storage)
         it = self.interaction
         if isinstance(src, RootedOrthtree):
@@ -364,7 +392,7 @@ class BarnesHut:
             if aff.shape[1] == src.dim + 1:
                 aff = aff[:, : src.dim]
             aff = np.ascontiguousarray(aff, dtype=np.float32)
-            out = np.zeros((len(aff), src.dim), dtype=np.float32)
+            out = _out_array(out, (len(aff), src.dim), np.float32)
             check(lib.pcuda_tree_traverse_f32(self.ctx.handle, src._h, _ptr(aff), len(aff),
                                               self.theta, it.softening, int(it.is_checked),
                                               _ptr(out)), self.ctx.handle)
@@ -374,7 +402,7 @@ class BarnesHut:
             raise NotImplementedError("Barnes-Hut on the device is f32 (2-D / 3-D)")
         d = src.shape[1] - 1
         na = len(src) if aff is None else len(aff)
-        out = np.zeros((na, d), dtype=np.float32)
+        out = _out_array(out, (na, d), np.float32)
         fn = getattr(lib, f"pcuda_barneshut_{sfx}")
         check(fn(self.ctx.handle, _ptr(aff), na, _ptr(src), len(src), self.theta, it.softening,
                  int(it.is_checked), _ptr(out)), self.ctx.handle)

@@ -1,0 +1,110 @@
+"""Multi-GPU brute force: one process per GPU, targets sharded, sources all-gathered over NVLink.
+
+New functionality (the reference is single-device).  Each rank owns a
+contiguous block of the particle slice (input order is preserved, so concatenating the ranks'
+outputs in rank order gives the reference's output order, sequential.rs:101-106).  Per step:
+
+    local {x,y,z,mu} records --(pcuda: pad + in-place ncclAllGather on the context stream)-->
+    all records on every GPU --(pair kernel, local targets x all sources)--> local accelerations
+
+PyTorch is plumbing only: device memory for the shards and ``torch.distributed`` to hand rank 0's
+ncclUniqueId to the other ranks (and, in ``compute``, to collect the shards' results on the host).
+The all-gather on the data path is issued by libparticular_cuda.so on its own communicator and
+stream, not by torch.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+__all__ = ["shard_bounds", "shard_capacity", "ShardedBruteForce"]
+
+
+def shard_capacity(n: int, world: int) -> int:
+    """Records per rank slot: ceil(n / world), at least 1 (NCCL needs equal, non-empty slots)."""
+    return max(1, -(-n // world))
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of the particle slice owned by `rank`."""
+    cap = shard_capacity(n, world)
+    lo = min(n, rank * cap)
+    return lo, min(n, lo + cap)
+
+
+class ShardedBruteForce:
+    """``ShardedBruteForce(ctx, interaction).compute(particles)``: the multi-GPU counterpart of
+    ``BruteForce(ctx, interaction).compute(particles)`` for the ``&[P]`` storage (all particles
+    affect all particles, storage.rs:231-241).  f32 3-D."""
+
+    def __init__(self, ctx, interaction, group=None, init_comm: bool = True):
+        import torch.distributed as dist
+        self.ctx, self.interaction, self.group = ctx, interaction, group
+        self.dist = dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._gathered = None
+        self._out = None
+        if init_comm and self.world > 1:
+            self._init_comm()
+
+    # -- communicator bootstrap: rank 0 makes the ncclUniqueId, torch.distributed carries it --
+    def _init_comm(self):
+        import torch
+        uid = [self.ctx.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(uid, src=0, group=self.group)
+        self.ctx.comm_init(uid[0], self.world, self.rank)
+        torch.cuda.synchronize()
+
+    # -- device-resident step ------------------------------------------------------------------
+    def step_device(self, local, n_total: int):
+        """`local`: this rank's (n_local, 4) float32 CUDA tensor of {x,y,z,mu}; `n_total`: particle
+        count over all ranks.  Returns the (n_local, 3) CUDA tensor of accelerations (owned by this
+        object, overwritten by the next call).  Enqueued on the context stream; not synchronised."""
+        import torch
+        from ._ffi import check, lib
+        cap = shard_capacity(n_total, self.world)
+        n_local = int(local.shape[0])
+        if self._gathered is None or self._gathered.shape[0] < self.world * cap:
+            self._gathered = torch.empty((self.world * cap, 4), dtype=torch.float32,
+                                         device=local.device)
+        if self._out is None or self._out.shape[0] < max(n_local, 1):
+            self._out = torch.empty((max(n_local, 1), 3), dtype=torch.float32, device=local.device)
+        it = self.interaction
+        check(lib.pcuda_bruteforce_f32x3_sharded_dev(
+            self.ctx.handle, local.data_ptr(), n_local, cap, it.softening, int(it.is_checked),
+            self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
+        return self._out[:n_local]
+
+    # -- host API --------------------------------------------------------------------------------
+    def compute_local(self, local_records: np.ndarray, n_total: int,
+                      out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Upload this rank's records, run one sharded step, download the local accelerations
+        (pcuda_bruteforce_f32x3_sharded: blocking, host buffers)."""
+        import ctypes as C
+
+        from ._ffi import check, lib
+        it = self.interaction
+        if out is None:
+            out = np.zeros((len(local_records), 3), dtype=np.float32)
+        check(lib.pcuda_bruteforce_f32x3_sharded(
+            self.ctx.handle, local_records.ctypes.data_as(C.c_void_p), len(local_records),
+            shard_capacity(n_total, self.world), it.softening, int(it.is_checked),
+            out.ctypes.data_as(C.c_void_p)), self.ctx.handle)
+        return out
+
+    def compute(self, particles, gather: bool = True) -> Optional[np.ndarray]:
+        """Every rank passes the same full (n, 4) slice.  Returns all accelerations in slice
+        order on every rank (gather=True) or only this rank's block."""
+        p = np.ascontiguousarray(particles, dtype=np.float32)
+        if p.ndim != 2 or p.shape[1] != 4:
+            raise NotImplementedError("sharded brute force is f32 3-D: particles must be (n, 4)")
+        n = len(p)
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        local = self.compute_local(np.ascontiguousarray(p[lo:hi]), n)
+        if not gather or self.world == 1:
+            return local
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, local, group=self.group)
+        return np.concatenate(parts, axis=0)

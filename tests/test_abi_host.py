@@ -1,0 +1,115 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the
+header declares, refuses to run without a B200 (no CPU fallback), and the host-side mirror of the
+reference's storages resolves to the same Between(affected, affecting) as the oracle's statement of
+storage.rs:207-241.  No compute calls happen here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, uniform_cloud
+
+HEADER = os.path.join(ROOT, "include", "particular_cuda.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcuda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from particular_b200 import _ffi
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(_ffi.lib, s), f"libparticular_cuda.so does not export {s}"
+        assert s in _ffi.SIGNATURES, f"{s} is declared in the header but not bound in _ffi.py"
+    assert _ffi.lib.pcuda_abi_version() == 1
+
+
+def test_header_compiles_as_c():
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import particular_b200 as pb
+    from particular_b200 import _ffi
+    with pytest.raises(pb.CudaError) as e:
+        pb.CudaContext(0)
+    assert e.value.status == _ffi.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+    n = C.c_int(-1)
+    assert _ffi.lib.pcuda_device_count(C.byref(n)) != 0 and n.value == 0
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "particular_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_status_strings():
+    from particular_b200 import _ffi
+    assert _ffi.lib.pcuda_status_string(0) == b"ok"
+    assert b"sm_100" in _ffi.lib.pcuda_status_string(_ffi.ERR_NO_DEVICE)
+
+
+def test_storage_resolution_matches_reference_semantics():
+    import oracle
+    import particular_b200.interface as pi
+    p = uniform_cloud(40, massive_ratio=0.3)
+    p = p[np.random.default_rng(1).permutation(40)]
+    # &[P]  => Between(slice, slice); affected None means "alias of affecting"
+    aff, src = pi._resolve(p)
+    assert aff is None and np.array_equal(src, p)
+    # &Reordered => Between(unordered, affecting copy)
+    ro = pi.Reordered.new(p)
+    aff, src = pi._resolve(ro)
+    a2, s2 = oracle.between_of_reordered(p)
+    assert np.array_equal(aff, a2) and np.array_equal(src, s2)
+    assert ro.affecting_len() == 12 and len(ro.non_affecting()) == 28
+    assert np.array_equal(ro.reordered()[:12], s2)
+    # &Ordered => Between(ordered_all, affecting prefix)
+    od = pi.Ordered.new(p)
+    aff, src = pi._resolve(od)
+    a3, s3 = oracle.between_of_ordered(p)
+    assert np.array_equal(aff, a3) and np.array_equal(src, s3)
+    # Ordered::with: affecting_len = first index failing the predicate (storage.rs:71-74)
+    od2 = pi.Ordered.with_(p[:5], p[5:])
+    first_massless = int(np.flatnonzero(p[:, 3] == 0)[0])
+    assert od2.affecting_len() == first_massless
+    # Between(&P1, &[P2]) and particles given as affected
+    aff, src = pi._resolve(pi.Between(p[3], p))
+    assert aff.shape == (1, 3) and np.array_equal(aff[0], p[3, :3])
+    aff, src = pi._resolve(pi.Between(p[:7], p[7:]))
+    assert aff.shape == (7, 3)
+
+
+def test_interactions_mirror_reference_constructors():
+    import particular_b200 as pb
+    assert pb.Acceleration.checked().is_checked and pb.Acceleration.checked().softening == 0.0
+    assert not pb.Acceleration.unchecked().is_checked
+    s = pb.AccelerationSoftened.checked(100.0)
+    assert s.softening == 100.0 and s.is_checked
+    assert not pb.AccelerationSoftened.unchecked(1.0).is_checked
+
+
+def test_unsupported_shapes_raise():
+    import particular_b200.interface as pi
+    with pytest.raises(TypeError):
+        pi._as_particles(np.zeros((4, 6), np.float32))
+    with pytest.raises(NotImplementedError):
+        pi._suffix(np.zeros((4, 3), np.float64))  # f64 2-D: no kernel, like unimplemented!()

@@ -185,8 +185,9 @@ int pcuda_tree_read(pcuda_ctx *ctx, const pcuda_tree *tree, int which /* pcuda_t
 int pcuda_tree_traverse_f32(pcuda_ctx *ctx, const pcuda_tree *tree, const float *affected,
                             size_t n_affected, float theta, float softening, int checked,
                             float *out);
-/* interactions[0] = accepted node interactions, [1] = direct particle interactions,
- * [2] = node tests, summed over all targets of the LAST traversal (instrumentation). */
+/* Instrumentation of the LAST traversal: counters[0] = accepted node (centre-of-mass)
+ * interactions and [1] = direct particle interactions, both summed over all targets;
+ * [2] = node tests, summed over the 32-target groups that walk the tree together. */
 int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[3]);
 void pcuda_tree_destroy(pcuda_ctx *ctx, pcuda_tree *tree);
 

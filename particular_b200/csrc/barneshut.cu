@@ -1,19 +1,1057 @@
-// barneshut.cu — placeholder while the tree kernels land (replaced in the next commit).
+// barneshut.cu — K2..K5: Barnes-Hut on the GPU (new: the reference has only CPU versions,
+// particular/src/sequential.rs:439-543 and parallel.rs:297-367, whose tree is the recursive
+// bucket partition of tree/mod.rs:91-138).
+//
+// Build (K2-K4), every call, like the reference (sequential.rs:539-541):
+//   K2  root cube = BoundingBox::square_with (tree/partition.rs:136-153): min/max reduction, then
+//       origin/extent/scale;  Morton (3-D, 21 bits/axis) / Z-order (2-D, 31 bits/axis) keys
+//   K3  stable LSD radix sort of (key, index) pairs (cub::DeviceRadixSort), gather of the
+//       particles into key order as float4 {x, y, z|0, mu}
+//   K4  linear orthtree over the sorted keys, level by level (a cell with more than `leaf_size`
+//       particles splits into the distinct next-level digits found by binary search in its key
+//       range); nodes are stored breadth-first, children of a node contiguous; centre of mass
+//       bottom-up in double precision, in a fixed order
+//   The resulting arrays are bit-identical to the CPU statement of the same specification
+//   (oracle/oracle_octree.inc) — keys, permutation, node ranges, levels, children and {com, mass}.
+//
+// Traversal (K5), warp-cooperative: a warp owns 32 consecutive targets in key order and walks the
+// tree ONCE for the group with a shared stack: every lane tests one node per step against the
+// group's bounding box (opening rule of sequential.rs:490-494 with the group's minimum distance,
+// so a node is opened whenever ANY member would open it), children are pushed with a warp scan,
+// accepted nodes and the particles of opened leaves are appended to a shared interaction list with
+// ballot/popc compaction, and whenever 32 entries are ready every lane evaluates all of them for
+// its own target (the pair term of gravity/impls/mod.rs:151-166).  A pair at zero distance
+// contributes nothing (sequential.rs:485-487 skips a node at the target's position).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
+#include "ptx.cuh"
+
 namespace pcuda {
-void tree_free(pcuda_ctx *, pcuda_tree *) {}
+namespace bh {
+
+// One tree node: 32 bytes = one DRAM sector.
+struct __align__(32) NodeRec {
+    float4 cm;             // centre of mass {x, y, z (0 in 2-D)}, w = total mu
+    uint32_t first_child;  // index of the first child (children are contiguous); 0 for leaves
+    uint32_t nchild_level; // n_children | level << 8
+    uint32_t begin;        // first sorted particle of the cell
+    uint32_t count;        // particles in the cell
+};
+
+struct Frame {  // quantisation frame == the reference's root cube
+    float origin[3];
+    float ext;
+    float inv;
+};
+
+template <int DIM>
+struct Dims {
+    static constexpr int BITS = DIM == 3 ? 21 : 31;
+    static constexpr int X = 1 << DIM;
+};
+
+}  // namespace bh
 }  // namespace pcuda
-using namespace pcuda;
-#define NI(ctx) return fail(ctx, PCUDA_ERR_NOT_INITIALISED, "Barnes-Hut not built yet")
-extern "C" {
-int pcuda_barneshut_f32x3(pcuda_ctx *c, const float *, size_t, const float *, size_t, float, float, int, float *) { NI(c); }
-int pcuda_barneshut_f32x2(pcuda_ctx *c, const float *, size_t, const float *, size_t, float, float, int, float *) { NI(c); }
-int pcuda_barneshut_f32x3_dev(pcuda_ctx *c, const float *, size_t, const float *, size_t, float, float, int, float *) { NI(c); }
-int pcuda_barneshut_f32x2_dev(pcuda_ctx *c, const float *, size_t, const float *, size_t, float, float, int, float *) { NI(c); }
-int pcuda_tree_build_f32(pcuda_ctx *c, uint32_t, const float *, size_t, pcuda_tree **) { NI(c); }
-int pcuda_tree_info_get(const pcuda_tree *, pcuda_tree_info *) { return PCUDA_ERR_NOT_INITIALISED; }
-int pcuda_tree_read(pcuda_ctx *c, const pcuda_tree *, int, void *, size_t) { NI(c); }
-int pcuda_tree_traverse_f32(pcuda_ctx *c, const pcuda_tree *, const float *, size_t, float, float, int, float *) { NI(c); }
-int pcuda_tree_last_counters(pcuda_ctx *c, uint64_t *) { NI(c); }
-void pcuda_tree_destroy(pcuda_ctx *, pcuda_tree *) {}
+
+struct pcuda_tree {
+    int dim = 3, bits = 21;
+    size_t n = 0, n_nodes = 0;
+    int n_levels = 0;
+    uint32_t leaf_size = 16;
+    std::vector<uint32_t> level_begin;  // n_levels + 1 entries
+    pcuda::bh::Frame frame = {};
+    pcuda::DevBuf keys[2], perm[2], sorted, nodes, moments, d_frame, scan_in, scan_out, cub_tmp,
+        partial;
+    int cur = 0;  // which of keys[]/perm[] holds the sorted data
+    uint64_t *d_keys() const { return keys[cur].as<uint64_t>(); }
+    uint32_t *d_perm() const { return perm[cur].as<uint32_t>(); }
+};
+
+namespace pcuda {
+namespace bh {
+
+// ------------------------------------------------------------------------------------------------
+// K2a: per-axis min / max.  min/max are exact and associative, so any reduction order gives the
+// bits of the sequential fold in tree/partition.rs:109-132.  NaNs are ignored (as `v < lo` does).
+template <int DIM>
+__global__ void __launch_bounds__(256) bbox_partial(const float *__restrict__ p, int stride, int n,
+                                                    float *__restrict__ partial) {
+    float lo[DIM], hi[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        lo[k] = INFINITY;
+        hi[k] = -INFINITY;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            const float v = p[(size_t)i * stride + k];
+            lo[k] = fminf(lo[k], v);
+            hi[k] = fmaxf(hi[k], v);
+        }
+    }
+    __shared__ float s[8][2 * DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            s[w][k] = lo[k];
+            s[w][DIM + k] = hi[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * DIM) {
+        const bool is_hi = threadIdx.x >= DIM;
+        float v = s[0][threadIdx.x];
+        for (int j = 1; j < 8; ++j) v = is_hi ? fmaxf(v, s[j][threadIdx.x]) : fminf(v, s[j][threadIdx.x]);
+        partial[blockIdx.x * 2 * DIM + threadIdx.x] = v;
+    }
 }
+
+// K2b: final reduction + frame.  ext = max_k(hi-lo) folded from 0; half = ext/2;
+// origin_k = (lo_k+hi_k)/2 - half; inv = 2^BITS/ext (0 when ext == 0).  Explicit _rn intrinsics:
+// no contraction, IEEE division — the same bits as oracle_octree.inc quant_frame.
+template <int DIM>
+__global__ void frame_kernel(const float *__restrict__ partial, int nblocks, Frame *out) {
+    __shared__ float s[2 * DIM];
+    if (threadIdx.x < 2 * DIM) {
+        const bool is_hi = threadIdx.x >= DIM;
+        float v = is_hi ? -INFINITY : INFINITY;
+        for (int j = 0; j < nblocks; ++j) {
+            const float q = partial[j * 2 * DIM + threadIdx.x];
+            v = is_hi ? fmaxf(v, q) : fminf(v, q);
+        }
+        s[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ext = 0.0f;
+        for (int k = 0; k < DIM; ++k) {
+            const float e = __fsub_rn(s[DIM + k], s[k]);
+            ext = e > ext ? e : ext;
+        }
+        const float half = __fdiv_rn(ext, 2.0f);
+        for (int k = 0; k < 3; ++k)
+            out->origin[k] = k < DIM ? __fsub_rn(__fdiv_rn(__fadd_rn(s[k], s[DIM + k]), 2.0f), half) : 0.f;
+        out->ext = ext;
+        out->inv = ext > 0.0f ? __fdiv_rn((float)(1ull << Dims<DIM>::BITS), ext) : 0.0f;
+    }
+}
+
+__device__ __forceinline__ uint64_t spread3(uint32_t q) {  // 21 bits -> every third bit
+    uint64_t x = q & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__device__ __forceinline__ uint64_t spread2(uint32_t q) {  // 31 bits -> every second bit
+    uint64_t x = q & 0x7fffffffu;
+    x = (x | x << 16) & 0x0000ffff0000ffffull;
+    x = (x | x << 8) & 0x00ff00ff00ff00ffull;
+    x = (x | x << 4) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | x << 2) & 0x3333333333333333ull;
+    x = (x | x << 1) & 0x5555555555555555ull;
+    return x;
+}
+
+template <int DIM>
+__device__ __forceinline__ uint64_t encode(const float *pos, const Frame &f) {
+    constexpr int BITS = Dims<DIM>::BITS;
+    const float top = (float)(1ull << BITS);
+    uint32_t q[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        float t = __fmul_rn(__fsub_rn(pos[k], f.origin[k]), f.inv);
+        t = t > 0.0f ? t : 0.0f;  // also maps NaN to 0
+        q[k] = t >= top ? (uint32_t)((1ull << BITS) - 1) : (uint32_t)t;
+    }
+    if (DIM == 3) return spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[DIM - 1]) << 2;
+    return spread2(q[0]) | spread2(q[1]) << 1;
+}
+
+// K2c: keys in input order + identity permutation.
+template <int DIM>
+__global__ void __launch_bounds__(256) encode_kernel(const float *__restrict__ p, int stride, int n,
+                                                     const Frame *__restrict__ frame,
+                                                     uint64_t *__restrict__ keys,
+                                                     uint32_t *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Frame f = *frame;
+    float pos[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) pos[k] = p[(size_t)i * stride + k];
+    keys[i] = encode<DIM>(pos, f);
+    idx[i] = (uint32_t)i;
+}
+
+// K3b: gather into key order as {x, y, z|0, mu}.  has_mass == false: bare positions (targets).
+template <int DIM>
+__global__ void __launch_bounds__(256) gather_kernel(const float *__restrict__ p, int stride,
+                                                     bool has_mass, int n,
+                                                     const uint32_t *__restrict__ perm,
+                                                     float4 *__restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *q = p + (size_t)perm[i] * stride;
+    sorted[i] = make_float4(q[0], q[1], DIM == 3 ? q[2] : 0.f, has_mass ? q[DIM] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a: number of children of every node of one level (0 for leaves).  A cell splits when it
+// holds more than `nleaf` particles and is above the last level.
+template <int DIM>
+__device__ __forceinline__ uint32_t next_digit_start(const uint64_t *__restrict__ keys, uint32_t pos,
+                                                     uint32_t end, int shift) {
+    // first index in (pos, end] whose digit prefix differs from keys[pos] (keys are sorted)
+    const uint64_t pre = keys[pos] >> shift;
+    uint32_t lo = pos + 1, hi = end;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((keys[mid] >> shift) > pre) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) count_children(const NodeRec *__restrict__ nodes,
+                                                      const uint64_t *__restrict__ keys,
+                                                      uint32_t lvl_begin, uint32_t lvl_count,
+                                                      int level, uint32_t nleaf,
+                                                      uint32_t *__restrict__ nchild) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > lvl_count) return;
+    if (t == lvl_count) {  // sentinel so that the exclusive scan yields the total
+        nchild[t] = 0;
+        return;
+    }
+    const NodeRec nd = nodes[lvl_begin + t];
+    uint32_t c = 0;
+    if (nd.count > nleaf && level < Dims<DIM>::BITS) {
+        const int shift = DIM * (Dims<DIM>::BITS - level - 1);
+        uint32_t pos = nd.begin;
+        const uint32_t end = nd.begin + nd.count;
+        while (pos < end) {
+            pos = next_digit_start<DIM>(keys, pos, end, shift);
+            ++c;
+        }
+    }
+    nchild[t] = c;
+}
+
+// K4b: writes the children of one level's nodes at next_begin + offset (breadth-first order).
+template <int DIM>
+__global__ void __launch_bounds__(128) emit_children(NodeRec *__restrict__ nodes,
+                                                     const uint64_t *__restrict__ keys,
+                                                     uint32_t lvl_begin, uint32_t lvl_count,
+                                                     int level, const uint32_t *__restrict__ nchild,
+                                                     const uint32_t *__restrict__ offset,
+                                                     uint32_t next_begin) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= lvl_count) return;
+    const uint32_t c = nchild[t];
+    NodeRec &nd = nodes[lvl_begin + t];
+    if (c == 0) {
+        nd.first_child = 0;
+        nd.nchild_level = (uint32_t)level << 8;
+        return;
+    }
+    const uint32_t first = next_begin + offset[t];
+    nd.first_child = first;
+    nd.nchild_level = c | (uint32_t)level << 8;
+    const int shift = DIM * (Dims<DIM>::BITS - level - 1);
+    uint32_t pos = nd.begin;
+    const uint32_t end = nd.begin + nd.count;
+    for (uint32_t k = 0; k < c; ++k) {
+        const uint32_t nxt = next_digit_start<DIM>(keys, pos, end, shift);
+        NodeRec ch;
+        ch.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+        ch.first_child = 0;
+        ch.nchild_level = (uint32_t)(level + 1) << 8;
+        ch.begin = pos;
+        ch.count = nxt - pos;
+        nodes[first + k] = ch;
+        pos = nxt;
+    }
+}
+
+__global__ void init_root(NodeRec *nodes, uint32_t n) {
+    NodeRec r;
+    r.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.first_child = 0;
+    r.nchild_level = 0;
+    r.begin = 0;
+    r.count = n;
+    nodes[0] = r;
+}
+
+// K4c: moments of one level, deepest level first.  Double precision, fixed order, unfused
+// (__dmul_rn / __dadd_rn), identical to oracle_octree.inc:
+//   leaf:      M = sum m_i, Mx_k = sum m_i * x_ik over the cell's particles in key order
+//   internal:  sums of the children's moments in child order
+//   com_k = (float)(Mx_k / M), mass = (float)M;  M == 0 => com = position of the first particle.
+template <int DIM>
+__global__ void __launch_bounds__(128) moments_kernel(NodeRec *__restrict__ nodes,
+                                                      double *__restrict__ mom,
+                                                      const float4 *__restrict__ sorted,
+                                                      uint32_t lvl_begin, uint32_t lvl_count) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= lvl_count) return;
+    const uint32_t j = lvl_begin + t;
+    NodeRec nd = nodes[j];
+    const uint32_t nc = nd.nchild_level & 0xffu;
+    double m[4] = {0.0, 0.0, 0.0, 0.0};  // x, y, z, M
+    if (nc == 0) {
+        for (uint32_t i = nd.begin; i < nd.begin + nd.count; ++i) {
+            const float4 p = sorted[i];
+            const double mi = (double)p.w;
+            m[0] = __dadd_rn(m[0], __dmul_rn(mi, (double)p.x));
+            m[1] = __dadd_rn(m[1], __dmul_rn(mi, (double)p.y));
+            if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(mi, (double)p.z));
+            m[3] = __dadd_rn(m[3], mi);
+        }
+    } else {
+        for (uint32_t c = nd.first_child; c < nd.first_child + nc; ++c) {
+            const double4 q = reinterpret_cast<const double4 *>(mom)[c];
+            m[0] = __dadd_rn(m[0], q.x);
+            m[1] = __dadd_rn(m[1], q.y);
+            if (DIM == 3) m[2] = __dadd_rn(m[2], q.z);
+            m[3] = __dadd_rn(m[3], q.w);
+        }
+    }
+    reinterpret_cast<double4 *>(mom)[j] = make_double4(m[0], m[1], m[2], m[3]);
+    float4 cm;
+    if (m[3] == 0.0) {
+        const float4 p = sorted[nd.begin];
+        cm = make_float4(p.x, p.y, DIM == 3 ? p.z : 0.f, 0.f);
+    } else {
+        cm.x = (float)__ddiv_rn(m[0], m[3]);
+        cm.y = (float)__ddiv_rn(m[1], m[3]);
+        cm.z = DIM == 3 ? (float)__ddiv_rn(m[2], m[3]) : 0.f;
+        cm.w = (float)m[3];
+    }
+    nodes[j].cm = cm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: warp-cooperative theta-traversal.
+constexpr int TRAV_WARPS = 8;      // warps per block
+constexpr int STACK_CAP = 1024;    // node indices per warp (shared memory)
+constexpr int STACK_RESERVE = 8 * 32;  // room a depth-first descent may still need (7 per level)
+constexpr int LIST_CAP = 64;       // interaction ring per warp (float4 entries)
+constexpr float TINY_R2 = 1e-30f;
+
+struct TravArgs {
+    const NodeRec *nodes;
+    const float4 *src;    // sorted sources {x,y,z,mu}
+    const float4 *tgt;    // targets in traversal order {x,y,z,_}
+    const uint32_t *tgt_perm;  // traversal order -> output row (nullptr: identity)
+    float *out;
+    unsigned long long *counters;  // [0] node interactions, [1] particle interactions, [2] node tests
+    int n_tgt;
+    int dim;
+    float ext;
+    float theta2;
+    float eps2;
+};
+
+// Evaluates `cnt` (<= 32) ring entries starting at `head` for this lane's target.
+__device__ __forceinline__ void eval_entries(const float4 *ring, int head, int cnt, float px,
+                                             float py, float pz, float eps2, float &ax, float &ay,
+                                             float &az) {
+    if (cnt == 32) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const float4 e = ring[(head + j) & (LIST_CAP - 1)];
+            const float dx = e.x - px, dy = e.y - py, dz = e.z - pz;
+            float r2 = fmaf(dx, dx, eps2);
+            r2 = fmaf(dy, dy, r2);
+            r2 = fmaf(dz, dz, r2);
+            r2 = r2 == 0.f ? __int_as_float(0x7f800000) : r2;  // zero distance contributes nothing
+            const float ri = ptx::rsqrt_approx(r2);
+            const float s = (ri * ri) * (ri * e.w);
+            ax = fmaf(dx, s, ax);
+            ay = fmaf(dy, s, ay);
+            az = fmaf(dz, s, az);
+        }
+    } else {
+        for (int j = 0; j < cnt; ++j) {
+            const float4 e = ring[(head + j) & (LIST_CAP - 1)];
+            const float dx = e.x - px, dy = e.y - py, dz = e.z - pz;
+            float r2 = fmaf(dx, dx, eps2);
+            r2 = fmaf(dy, dy, r2);
+            r2 = fmaf(dz, dz, r2);
+            r2 = r2 == 0.f ? __int_as_float(0x7f800000) : r2;
+            const float ri = ptx::rsqrt_approx(r2);
+            const float s = (ri * ri) * (ri * e.w);
+            ax = fmaf(dx, s, ax);
+            ay = fmaf(dy, s, ay);
+            az = fmaf(dz, s, az);
+        }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_WARPS * 32) traverse_kernel(TravArgs a) {
+    __shared__ uint32_t s_stack[TRAV_WARPS][STACK_CAP];
+    __shared__ __align__(16) float4 s_ring[TRAV_WARPS][LIST_CAP];
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = blockIdx.x * TRAV_WARPS + warp;
+    const int t0 = group * 32;
+    if (t0 >= a.n_tgt) return;
+    uint32_t *stack = s_stack[warp];
+    float4 *ring = s_ring[warp];
+
+    const int ti = min(t0 + lane, a.n_tgt - 1);
+    const bool live = t0 + lane < a.n_tgt;
+    const float4 tp = a.tgt[ti];
+    const float px = tp.x, py = tp.y, pz = tp.z;
+
+    // group bounding box -> centre and half extent
+    float lox = px, hix = px, loy = py, hiy = py, loz = pz, hiz = pz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(FULL, lox, o));
+        hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(FULL, loy, o));
+        hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, o));
+        loz = fminf(loz, __shfl_xor_sync(FULL, loz, o));
+        hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, o));
+    }
+    const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+    const float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
+
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    unsigned long long c_node = 0, c_part = 0, c_test = 0;
+
+    int sp = 1;          // stack size (uniform across the warp)
+    int head = 0, fill = 0;  // interaction ring (uniform)
+    if (lane == 0) stack[0] = 0;
+    __syncwarp();
+
+    auto flush_full = [&]() {  // evaluate while at least 32 entries are ready
+        while (fill >= 32) {
+            __syncwarp();
+            eval_entries(ring, head, 32, px, py, pz, a.eps2, ax, ay, az);
+            head = (head + 32) & (LIST_CAP - 1);
+            fill -= 32;
+            __syncwarp();
+        }
+    };
+
+    while (sp > 0) {
+        // pop up to 32 nodes, but never so many that their children could overflow the stack
+        int room = (STACK_CAP - STACK_RESERVE - sp) / 7;
+        int k = min(min(32, sp), max(room, 1));
+        const bool has = lane < k;
+        NodeRec nd;
+        nd.count = 0;
+        nd.nchild_level = 0;
+        if (has) {
+            const uint32_t id = stack[sp - 1 - lane];
+            const uint4 *q = reinterpret_cast<const uint4 *>(a.nodes + id);
+            const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+            nd.cm = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z),
+                                __uint_as_float(q0.w));
+            nd.first_child = q1.x;
+            nd.nchild_level = q1.y;
+            nd.begin = q1.z;
+            nd.count = q1.w;
+        }
+        sp -= k;
+        __syncwarp();
+
+        // opening rule for the group: (theta^2) * dmin^2 < width^2, dmin = distance from the
+        // centre of mass to the group's bounding box
+        bool open = false;
+        if (has) {
+            const float ddx = fmaxf(fabsf(nd.cm.x - cx) - hx, 0.f);
+            const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
+            const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
+            const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+            const int level = (int)(nd.nchild_level >> 8);
+            const float w = a.ext * __int_as_float((127 - level) << 23);
+            open = a.theta2 * d2 < w * w;
+        }
+        const uint32_t nc = nd.nchild_level & 0xffu;
+        const bool open_internal = has && open && nc > 0;
+        const bool open_leaf = has && open && nc == 0;
+        const bool accept = has && !open && nd.cm.w != 0.f;
+        if (COUNT) c_test += __popc(__ballot_sync(FULL, has));
+
+        // push the children of opened internal nodes (warp scan of the child counts)
+        {
+            int c = open_internal ? (int)nc : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int base = sp + incl - c;
+            for (int j = 0; j < c; ++j) stack[base + j] = nd.first_child + j;
+            sp += total;
+        }
+
+        // accepted nodes -> interaction ring
+        {
+            const unsigned m = __ballot_sync(FULL, accept);
+            if (m) {
+                if (accept) ring[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] = nd.cm;
+                const int cnt = __popc(m);
+                if (COUNT) c_node += cnt;
+                fill += cnt;
+                flush_full();
+            }
+        }
+
+        // particles of opened leaves -> interaction ring, one particle per leaf per round
+        {
+            int remaining = open_leaf ? (int)nd.count : 0;
+            uint32_t pidx = nd.begin;
+            unsigned m = __ballot_sync(FULL, remaining > 0);
+            while (m) {
+                if (remaining > 0) {
+                    ring[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] =
+                        __ldg(a.src + pidx);
+                    ++pidx;
+                    --remaining;
+                }
+                const int cnt = __popc(m);
+                if (COUNT) c_part += cnt;
+                fill += cnt;
+                flush_full();
+                m = __ballot_sync(FULL, remaining > 0);
+            }
+        }
+        __syncwarp();
+    }
+    if (fill > 0) {
+        __syncwarp();
+        eval_entries(ring, head, fill, px, py, pz, a.eps2, ax, ay, az);
+    }
+
+    if (live) {
+        const uint32_t row = a.tgt_perm ? a.tgt_perm[ti] : (uint32_t)ti;
+        float *o = a.out + (size_t)row * a.dim;
+        o[0] = ax;
+        o[1] = ay;
+        if (a.dim == 3) o[2] = az;
+    }
+    if (COUNT) {
+        // per-target counts: every live lane evaluated every list entry of its group
+        const unsigned long long lanes = __popc(__ballot_sync(FULL, live));
+        if (lane == 0) {
+            atomicAdd(a.counters + 0, c_node * lanes);
+            atomicAdd(a.counters + 1, c_part * lanes);
+            atomicAdd(a.counters + 2, c_test);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side.
+static cudaError_t grow_keep(DevBuf &b, size_t bytes, size_t keep, cudaStream_t stream) {
+    if (bytes <= b.cap) return cudaSuccess;
+    void *np = nullptr;
+    const size_t want = bytes + bytes / 2 + 256;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) return e;
+    if (b.p && keep) {
+        e = cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
+    if (b.p) cudaFree(b.p);
+    b.p = np;
+    b.cap = want;
+    return e;
+}
+
+template <int DIM>
+static int sort_by_key(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n, const Frame *d_frame,
+                       DevBuf keys[2], DevBuf perm[2], int *cur, DevBuf &cub_tmp) {
+    for (int i = 0; i < 2; ++i) {
+        PCUDA_CUDA_TRY(ctx, keys[i].ensure(n * sizeof(uint64_t)));
+        PCUDA_CUDA_TRY(ctx, perm[i].ensure(n * sizeof(uint32_t)));
+    }
+    encode_kernel<DIM><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        d_pos, stride, (int)n, d_frame, keys[0].as<uint64_t>(), perm[0].as<uint32_t>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    cub::DoubleBuffer<uint64_t> kb(keys[0].as<uint64_t>(), keys[1].as<uint64_t>());
+    cub::DoubleBuffer<uint32_t> vb(perm[0].as<uint32_t>(), perm[1].as<uint32_t>());
+    size_t tmp = 0;
+    const int end_bit = DIM * Dims<DIM>::BITS;
+    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)n, 0, end_bit,
+                                                        ctx->stream));
+    PCUDA_CUDA_TRY(ctx, cub_tmp.ensure(tmp));
+    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, kb, vb, (int)n, 0, end_bit,
+                                                        ctx->stream));
+    ctx->launches += 1 + (end_bit + 7) / 8;  // histogram + one onesweep pass per 8 bits
+    *cur = kb.selector;
+    return PCUDA_OK;
+}
+
+template <int DIM>
+static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n) {
+    constexpr int BITS = Dims<DIM>::BITS;
+    const int stride = DIM + 1;
+    t->dim = DIM;
+    t->bits = BITS;
+    t->n = n;
+    t->n_nodes = 0;
+    t->n_levels = 0;
+    t->leaf_size = ctx->leaf_size;
+    t->level_begin.clear();
+    t->frame = Frame{};
+    if (n == 0) return PCUDA_OK;
+    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    cudaStream_t st = ctx->stream;
+
+    // K2: root cube + keys
+    const int nb = (int)std::min<size_t>(ctx->sm_count * 8, (n + 255) / 256);
+    PCUDA_CUDA_TRY(ctx, t->partial.ensure((size_t)nb * 2 * DIM * sizeof(float)));
+    PCUDA_CUDA_TRY(ctx, t->d_frame.ensure(sizeof(Frame)));
+    bbox_partial<DIM><<<nb, 256, 0, st>>>(d_particles, stride, (int)n, t->partial.as<float>());
+    frame_kernel<DIM><<<1, 32, 0, st>>>(t->partial.as<float>(), nb, t->d_frame.as<Frame>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    // K3: sort + gather
+    PCUDA_TRY(sort_by_key<DIM>(ctx, d_particles, stride, n, t->d_frame.as<Frame>(), t->keys, t->perm,
+                               &t->cur, t->cub_tmp));
+    PCUDA_CUDA_TRY(ctx, t->sorted.ensure(n * sizeof(float4)));
+    gather_kernel<DIM><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        d_particles, stride, true, (int)n, t->d_perm(), t->sorted.as<float4>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(&t->frame, t->d_frame.p, sizeof(Frame), cudaMemcpyDeviceToHost, st));
+
+    // K4: level-by-level linear orthtree
+    size_t cap_nodes = std::max<size_t>(1024, n / 2 + 64);
+    PCUDA_CUDA_TRY(ctx, t->nodes.ensure(cap_nodes * sizeof(NodeRec)));
+    cap_nodes = t->nodes.cap / sizeof(NodeRec);
+    init_root<<<1, 1, 0, st>>>(t->nodes.as<NodeRec>(), (uint32_t)n);
+    ctx->launches++;
+    t->level_begin.push_back(0);
+    uint32_t lvl_begin = 0, lvl_count = 1;
+    size_t total = 1;
+    uint32_t *h_total = nullptr;
+    PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&h_total, sizeof(uint32_t), cudaHostAllocDefault));
+    int status = PCUDA_OK;
+    for (int level = 0;; ++level) {
+        const size_t m = lvl_count;
+        cudaError_t e = t->scan_in.ensure((m + 1) * 4);
+        if (e == cudaSuccess) e = t->scan_out.ensure((m + 1) * 4);
+        size_t tmp = 0;
+        if (e == cudaSuccess)
+            e = cub::DeviceScan::ExclusiveSum(nullptr, tmp, t->scan_in.as<uint32_t>(),
+                                              t->scan_out.as<uint32_t>(), (int)(m + 1), st);
+        if (e == cudaSuccess) e = t->cub_tmp.ensure(tmp);
+        if (e != cudaSuccess) {
+            status = fail(ctx, PCUDA_ERR_CUDA, "tree level scratch: %s", cudaGetErrorString(e));
+            break;
+        }
+        count_children<DIM><<<(unsigned)((m + 1 + 127) / 128), 128, 0, st>>>(
+            t->nodes.as<NodeRec>(), t->d_keys(), lvl_begin, lvl_count, level, t->leaf_size,
+            t->scan_in.as<uint32_t>());
+        cub::DeviceScan::ExclusiveSum(t->cub_tmp.p, tmp, t->scan_in.as<uint32_t>(),
+                                      t->scan_out.as<uint32_t>(), (int)(m + 1), st);
+        cudaMemcpyAsync(h_total, t->scan_out.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+        ctx->launches += 3;
+        if (e != cudaSuccess) {
+            status = fail(ctx, PCUDA_ERR_CUDA, "tree level %d: %s", level, cudaGetErrorString(e));
+            break;
+        }
+        const uint32_t children = *h_total;
+        if (total + children > 0xfffffff0ull) {
+            status = fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "more than 2^32 tree nodes");
+            break;
+        }
+        if (children) {
+            e = grow_keep(t->nodes, (total + children) * sizeof(NodeRec), total * sizeof(NodeRec), st);
+            if (e != cudaSuccess) {
+                status = fail(ctx, e == cudaErrorMemoryAllocation ? PCUDA_ERR_OUT_OF_MEMORY : PCUDA_ERR_CUDA,
+                              "tree node storage: %s", cudaGetErrorString(e));
+                break;
+            }
+        }
+        emit_children<DIM><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
+            t->nodes.as<NodeRec>(), t->d_keys(), lvl_begin, lvl_count, level,
+            t->scan_in.as<uint32_t>(), t->scan_out.as<uint32_t>(), (uint32_t)total);
+        ctx->launches++;
+        t->level_begin.push_back((uint32_t)total);
+        if (children == 0) break;
+        lvl_begin = (uint32_t)total;
+        lvl_count = children;
+        total += children;
+    }
+    cudaFreeHost(h_total);
+    if (status != PCUDA_OK) return status;
+    t->n_nodes = total;
+    t->n_levels = (int)t->level_begin.size() - 1;
+
+    // K4c: centre of mass, deepest level first
+    PCUDA_CUDA_TRY(ctx, t->moments.ensure(total * 4 * sizeof(double)));
+    for (int l = t->n_levels - 1; l >= 0; --l) {
+        const uint32_t b = t->level_begin[l], c = t->level_begin[l + 1] - b;
+        moments_kernel<DIM><<<(c + 127) / 128, 128, 0, st>>>(t->nodes.as<NodeRec>(),
+                                                              t->moments.as<double>(),
+                                                              t->sorted.as<float4>(), b, c);
+        ctx->launches++;
+    }
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    return PCUDA_OK;
+}
+
+static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d_particles, size_t n) {
+    if (dim == 3) return build<3>(ctx, t, d_particles, n);
+    if (dim == 2) return build<2>(ctx, t, d_particles, n);
+    return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+}
+
+static bool g_count = true;  // instrumentation of the traversal (pcuda_tree_last_counters)
+
+// d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
+static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na, float theta,
+                    float eps, float *d_out) {
+    const int dim = t->dim;
+    if (na == 0) return PCUDA_OK;
+    if (t->n == 0) {
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * dim * sizeof(float), ctx->stream));
+        return PCUDA_OK;
+    }
+    if (na > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    if (!d_tgt && na != t->n)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "affected == NULL but n_affected != tree size");
+    cudaStream_t st = ctx->stream;
+    const float4 *tgt_sorted;
+    const uint32_t *tgt_perm;
+    if (!d_tgt) {
+        tgt_sorted = t->sorted.as<float4>();
+        tgt_perm = t->d_perm();
+    } else {
+        // key the targets in the tree's frame and process them in key order (coherent groups)
+        DevBuf keys[2] = {ctx->d_tgt_keys, ctx->d_tgt_keys_alt};
+        DevBuf perm[2] = {ctx->d_tgt_perm, ctx->d_tgt_perm_alt};
+        int cur = 0;
+        int s = dim == 3 ? sort_by_key<3>(ctx, d_tgt, 3, na, t->d_frame.as<Frame>(), keys, perm, &cur, ctx->d_cub_tmp)
+                         : sort_by_key<2>(ctx, d_tgt, 2, na, t->d_frame.as<Frame>(), keys, perm, &cur, ctx->d_cub_tmp);
+        ctx->d_tgt_keys = keys[0];
+        ctx->d_tgt_keys_alt = keys[1];
+        ctx->d_tgt_perm = perm[0];
+        ctx->d_tgt_perm_alt = perm[1];
+        PCUDA_TRY(s);
+        PCUDA_CUDA_TRY(ctx, ctx->d_tgt_sorted.ensure(na * sizeof(float4)));
+        const uint32_t *p = perm[cur].as<uint32_t>();
+        if (dim == 3)
+            gather_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, 3, false, (int)na, p,
+                                                                           ctx->d_tgt_sorted.as<float4>());
+        else
+            gather_kernel<2><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, 2, false, (int)na, p,
+                                                                           ctx->d_tgt_sorted.as<float4>());
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+        tgt_sorted = ctx->d_tgt_sorted.as<float4>();
+        tgt_perm = p;
+    }
+    PCUDA_CUDA_TRY(ctx, ctx->d_counters.ensure(3 * sizeof(unsigned long long)));
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 3 * sizeof(unsigned long long), st));
+    TravArgs a;
+    a.nodes = t->nodes.as<NodeRec>();
+    a.src = t->sorted.as<float4>();
+    a.tgt = tgt_sorted;
+    a.tgt_perm = tgt_perm;
+    a.out = d_out;
+    a.counters = ctx->d_counters.as<unsigned long long>();
+    a.n_tgt = (int)na;
+    a.dim = dim;
+    a.ext = t->frame.ext;
+    a.theta2 = theta * theta;
+    a.eps2 = eps * eps;
+    const size_t groups = (na + 31) / 32;
+    const unsigned blocks = (unsigned)((groups + TRAV_WARPS - 1) / TRAV_WARPS);
+    if (g_count)
+        traverse_kernel<true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+    else
+        traverse_kernel<false><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PCUDA_OK;
+}
+
+static int read_counters(pcuda_ctx *ctx) {
+    if (!ctx->d_counters.p) return PCUDA_OK;
+    unsigned long long h[3];
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) ctx->last_counters[i] = h[i];
+    return PCUDA_OK;
+}
+
+// One-shot Barnes-Hut with device pointers: build over `affecting`, traverse for `affected`.
+static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t na, const float *d_src,
+                       size_t nb, float theta, float eps, float *d_out) {
+    if (!d_aff && na != nb)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
+                    "affected == NULL means affected == affecting, but n_affected != n_affecting");
+    if (!ctx->call_tree) ctx->call_tree = new pcuda_tree();
+    phase_begin(ctx, PH_BUILD);
+    PCUDA_TRY(build_dim(ctx, ctx->call_tree, dim, d_src, nb));
+    phase_end(ctx, PH_BUILD);
+    phase_begin(ctx, PH_COMPUTE);
+    PCUDA_TRY(traverse(ctx, ctx->call_tree, d_aff, na, theta, eps, d_out));
+    phase_end(ctx, PH_COMPUTE);
+    return PCUDA_OK;
+}
+
+static int oneshot_host(pcuda_ctx *ctx, uint32_t dim, const float *aff, size_t na, const float *src,
+                        size_t nb, float theta, float eps, float *out) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if ((na && !out) || (nb && !src))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    if (!aff && na != nb)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
+                    "affected == NULL means affected == affecting, but n_affected != n_affecting");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    if (na == 0) return PCUDA_OK;
+    const size_t src_bytes = nb * (dim + 1) * sizeof(float), tgt_bytes = na * dim * sizeof(float);
+    phase_begin(ctx, PH_UPLOAD);
+    float *d_src = nullptr, *d_tgt = nullptr;
+    if (nb) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(src_bytes));
+        d_src = ctx->d_affecting.as<float>();
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (aff) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_affected.ensure(tgt_bytes));
+        d_tgt = ctx->d_affected.as<float>();
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_tgt, aff, tgt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(tgt_bytes));
+    phase_end(ctx, PH_UPLOAD);
+    PCUDA_TRY(oneshot_dev(ctx, dim, d_tgt, na, d_src, nb, theta, eps, ctx->d_out.as<float>()));
+    phase_begin(ctx, PH_DOWNLOAD);
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out.p, tgt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    phase_end(ctx, PH_DOWNLOAD);
+    PCUDA_TRY(timings_collect(ctx));
+    return read_counters(ctx);
+}
+
+}  // namespace bh
+
+void tree_free(pcuda_ctx *ctx, pcuda_tree *t) {
+    if (!t) return;
+    (void)ctx;
+    DevBuf *bufs[] = {&t->keys[0], &t->keys[1], &t->perm[0], &t->perm[1], &t->sorted, &t->nodes,
+                      &t->moments, &t->d_frame, &t->scan_in, &t->scan_out, &t->cub_tmp, &t->partial};
+    for (DevBuf *b : bufs) b->release();
+    delete t;
+}
+
+}  // namespace pcuda
+
+using namespace pcuda;
+
+extern "C" {
+
+int pcuda_barneshut_f32x3(pcuda_ctx *ctx, const float *aff, size_t na, const float *src, size_t nb,
+                          float theta, float softening, int checked, float *out) {
+    (void)checked;  // a zero-distance pair never contributes in Barnes-Hut (sequential.rs:485-487)
+    return bh::oneshot_host(ctx, 3, aff, na, src, nb, theta, softening, out);
+}
+
+int pcuda_barneshut_f32x2(pcuda_ctx *ctx, const float *aff, size_t na, const float *src, size_t nb,
+                          float theta, float softening, int checked, float *out) {
+    (void)checked;
+    return bh::oneshot_host(ctx, 2, aff, na, src, nb, theta, softening, out);
+}
+
+static int bh_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t na, const float *d_src,
+                  size_t nb, float theta, float softening, float *d_out) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    int s = bh::oneshot_dev(ctx, dim, d_aff, na, d_src, nb, theta, softening, d_out);
+    ctx->timings.kernel_launches = ctx->launches;
+    return s;
+}
+
+int pcuda_barneshut_f32x3_dev(pcuda_ctx *ctx, const float *d_aff, size_t na, const float *d_src,
+                              size_t nb, float theta, float softening, int checked, float *d_out) {
+    (void)checked;
+    return bh_dev(ctx, 3, d_aff, na, d_src, nb, theta, softening, d_out);
+}
+
+int pcuda_barneshut_f32x2_dev(pcuda_ctx *ctx, const float *d_aff, size_t na, const float *d_src,
+                              size_t nb, float theta, float softening, int checked, float *d_out) {
+    (void)checked;
+    return bh_dev(ctx, 2, d_aff, na, d_src, nb, theta, softening, d_out);
+}
+
+int pcuda_tree_build_f32(pcuda_ctx *ctx, uint32_t dim, const float *affecting, size_t n,
+                         pcuda_tree **out) {
+    if (!ctx || !out) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    if (dim != 2 && dim != 3) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+    if (n && !affecting) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    const size_t bytes = n * (dim + 1) * sizeof(float);
+    phase_begin(ctx, PH_UPLOAD);
+    if (n) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(bytes));
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_affecting.p, affecting, bytes, cudaMemcpyHostToDevice,
+                                            ctx->stream));
+    }
+    phase_end(ctx, PH_UPLOAD);
+    pcuda_tree *t = new pcuda_tree();
+    phase_begin(ctx, PH_BUILD);
+    int s = bh::build_dim(ctx, t, dim, ctx->d_affecting.as<float>(), n);
+    if (s != PCUDA_OK) {
+        tree_free(ctx, t);
+        return s;
+    }
+    phase_end(ctx, PH_BUILD);
+    s = timings_collect(ctx);
+    if (s != PCUDA_OK) {
+        tree_free(ctx, t);
+        return s;
+    }
+    *out = t;
+    return PCUDA_OK;
+}
+
+int pcuda_tree_info_get(const pcuda_tree *t, pcuda_tree_info *out) {
+    if (!t || !out) return PCUDA_ERR_INVALID_ARGUMENT;
+    memset(out, 0, sizeof *out);
+    out->n_particles = t->n;
+    out->n_nodes = t->n_nodes;
+    out->n_levels = (uint32_t)t->n_levels;
+    out->leaf_size = t->leaf_size;
+    out->dim = (uint32_t)t->dim;
+    out->bits = (uint32_t)t->bits;
+    for (int k = 0; k < 3; ++k) out->origin[k] = t->frame.origin[k];
+    out->extent = t->frame.ext;
+    out->inv = t->frame.inv;
+    return PCUDA_OK;
+}
+
+int pcuda_tree_read(pcuda_ctx *ctx, const pcuda_tree *t, int which, void *dst, size_t dst_bytes) {
+    if (!ctx || !t || (!dst && dst_bytes))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL argument");
+    DeviceGuard guard(ctx->device);
+    const size_t n = t->n, m = t->n_nodes;
+    size_t need = 0;
+    switch (which) {
+        case PCUDA_TREE_KEYS: need = n * 8; break;
+        case PCUDA_TREE_PERM: need = n * 4; break;
+        case PCUDA_TREE_NODE_BEGIN:
+        case PCUDA_TREE_NODE_COUNT:
+        case PCUDA_TREE_NODE_LEVEL:
+        case PCUDA_TREE_NODE_FIRST_CHILD:
+        case PCUDA_TREE_NODE_NUM_CHILDREN: need = m * 4; break;
+        case PCUDA_TREE_NODE_COM_MASS: need = m * (t->dim + 1) * 4; break;
+        default: return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "unknown tree array %d", which);
+    }
+    if (dst_bytes < need)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "destination holds %zu bytes, %zu needed", dst_bytes, need);
+    if (need == 0) return PCUDA_OK;
+    if (which == PCUDA_TREE_KEYS || which == PCUDA_TREE_PERM) {
+        const void *src = which == PCUDA_TREE_KEYS ? (const void *)t->d_keys() : (const void *)t->d_perm();
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+        PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return PCUDA_OK;
+    }
+    std::vector<bh::NodeRec> h(m);
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), t->nodes.p, m * sizeof(bh::NodeRec), cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t *u = static_cast<uint32_t *>(dst);
+    float *f = static_cast<float *>(dst);
+    for (size_t j = 0; j < m; ++j) {
+        const bh::NodeRec &r = h[j];
+        switch (which) {
+            case PCUDA_TREE_NODE_BEGIN: u[j] = r.begin; break;
+            case PCUDA_TREE_NODE_COUNT: u[j] = r.count; break;
+            case PCUDA_TREE_NODE_LEVEL: u[j] = r.nchild_level >> 8; break;
+            case PCUDA_TREE_NODE_FIRST_CHILD: u[j] = r.first_child; break;
+            case PCUDA_TREE_NODE_NUM_CHILDREN: u[j] = r.nchild_level & 0xffu; break;
+            default:
+                if (t->dim == 3) {
+                    f[4 * j + 0] = r.cm.x; f[4 * j + 1] = r.cm.y; f[4 * j + 2] = r.cm.z; f[4 * j + 3] = r.cm.w;
+                } else {
+                    f[3 * j + 0] = r.cm.x; f[3 * j + 1] = r.cm.y; f[3 * j + 2] = r.cm.w;
+                }
+        }
+    }
+    return PCUDA_OK;
+}
+
+int pcuda_tree_traverse_f32(pcuda_ctx *ctx, const pcuda_tree *t, const float *affected, size_t na,
+                            float theta, float softening, int checked, float *out) {
+    (void)checked;
+    if (!ctx || !t) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (na && (!affected || !out)) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    if (na == 0) return PCUDA_OK;
+    const size_t bytes = na * t->dim * sizeof(float);
+    phase_begin(ctx, PH_UPLOAD);
+    PCUDA_CUDA_TRY(ctx, ctx->d_affected.ensure(bytes));
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(bytes));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_affected.p, affected, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    phase_end(ctx, PH_UPLOAD);
+    phase_begin(ctx, PH_COMPUTE);
+    PCUDA_TRY(bh::traverse(ctx, t, ctx->d_affected.as<float>(), na, theta, softening, ctx->d_out.as<float>()));
+    phase_end(ctx, PH_COMPUTE);
+    phase_begin(ctx, PH_DOWNLOAD);
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    phase_end(ctx, PH_DOWNLOAD);
+    PCUDA_TRY(timings_collect(ctx));
+    return bh::read_counters(ctx);
+}
+
+int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[3]) {
+    if (!ctx || !counters) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL argument");
+    DeviceGuard guard(ctx->device);
+    PCUDA_TRY(bh::read_counters(ctx));
+    for (int i = 0; i < 3; ++i) counters[i] = ctx->last_counters[i];
+    return PCUDA_OK;
+}
+
+void pcuda_tree_destroy(pcuda_ctx *ctx, pcuda_tree *t) {
+    if (!t) return;
+    if (ctx) {
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        tree_free(ctx, t);
+    } else {
+        tree_free(nullptr, t);
+    }
+}
+
+}  // extern "C"

@@ -28,16 +28,19 @@ namespace bf {
 constexpr int STAGES = 4;
 constexpr int PREFETCH = 2;     // tiles in flight ahead of the consumers
 constexpr int TILE_MAX = 256;   // source records per stage
-constexpr float TINY_R2 = 1e-18f;  // CHECKED && eps == 0: r2 clamp that keeps mu * r^-3 finite
+constexpr float TINY_R2 = 1e-18f;  // clamp variant of CHECKED && eps == 0 (tuning only)
 constexpr float PAD_POS = 1e18f;   // zero-mass padding records sit here: they contribute exactly 0
 
 // ------------------------------------------------------------------------------------------------
 // f32 kernel.  Source record: DIM 3 -> {x,y,z,mu}; DIM 2 -> {x,y,mu,0}.
-// CLAMP = (checked && eps*eps == 0): a coincident pair must contribute nothing
-// (impls/mod.rs:160-161); with r2 clamped to TINY_R2 its term is d * finite = 0 exactly.
-// Without CLAMP either eps2 > 0 (d = 0 gives 0 without any test) or the caller asked for the
+// CLAMP != 0 <=> (checked && eps*eps == 0): a coincident pair must contribute nothing
+// (impls/mod.rs:160-161).  CLAMP == 1 (default): r2 == 0 is replaced by +inf, so rsqrt gives 0
+// and the term is d * 0 = 0 for any finite mu (two ALU-pipe instructions, FSETP + FSEL, that
+// issue in slots the FMA pipe leaves free).  CLAMP == 2 (tuning alternative): r2 is clamped to
+// TINY_R2 with one FMNMX; exact only while mu * 1e27 stays finite.
+// CLAMP == 0: either eps2 > 0 (d = 0 gives 0 without any test) or the caller asked for the
 // unchecked reference behaviour (coincident pair -> NaN, as in the reference).
-template <int DIM, int TP, int BLOCK, int MINB, bool CLAMP>
+template <int DIM, int TP, int BLOCK, int MINB, int CLAMP>
 __global__ void __launch_bounds__(BLOCK, MINB)
     pair_kernel_f32(const float *__restrict__ tgt, int tgt_stride, int n_tgt,
                     const float4 *__restrict__ src, int n_src, int src_chunk, int tile, float eps2,
@@ -124,7 +127,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                         dz = ptx::add2(ntz[p], ptx::splat(s.z));
                         r2 = ptx::fma2(dz, dz, r2);
                     }
-                    if (CLAMP) {
+                    if (CLAMP == 1) {
+                        r2.x = r2.x == 0.f ? __int_as_float(0x7f800000) : r2.x;
+                        r2.y = r2.y == 0.f ? __int_as_float(0x7f800000) : r2.y;
+                    } else if (CLAMP == 2) {
                         r2.x = fmaxf(r2.x, TINY_R2);
                         r2.y = fmaxf(r2.y, TINY_R2);
                     }
@@ -195,7 +201,6 @@ __global__ void pack_sources_2d(const float *__restrict__ in, int n, float4 *__r
 // implementation (MUFU.RSQ64H + Newton steps); per-term error is a few 1e-16, far inside the
 // 1e-12 parity bound.
 constexpr int TILE64 = 128;
-constexpr double TINY_R2_64 = 1e-200;
 constexpr double PAD_POS_64 = 1e100;
 
 template <int T, int BLOCK, bool CLAMP>
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(BLOCK)
                     double r2 = fma(dx, dx, eps2);
                     r2 = fma(dy, dy, r2);
                     r2 = fma(dz, dz, r2);
-                    if (CLAMP) r2 = fmax(r2, TINY_R2_64);
+                    if (CLAMP) r2 = r2 == 0.0 ? __longlong_as_double(0x7ff0000000000000ll) : r2;
                     const double ri = rsqrt(r2);
                     const double sc = (ri * ri) * (ri * s.w);
                     ax[k] = fma(dx, sc, ax[k]);
@@ -335,21 +340,25 @@ static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
     return pl;
 }
 
+static int g_force_tp = 0;    // test / tuning hooks (pcuda_debug_set)
+static int g_clamp_mode = 1;
+
 template <int DIM, int TP, int BLOCK, int MINB>
 static cudaError_t launch_f32(const Plan &pl, bool clamp, cudaStream_t stream, const float *tgt,
                               int tgt_stride, int na, const float4 *src, int nb, float eps2,
                               float *out, float *partial, size_t n_pad) {
     dim3 grid(pl.n_tb, pl.splits);
-    if (clamp)
-        pair_kernel_f32<DIM, TP, BLOCK, MINB, true><<<grid, BLOCK, 0, stream>>>(
+    if (clamp && g_clamp_mode == 2)
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 2><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
+    else if (clamp)
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 1><<<grid, BLOCK, 0, stream>>>(
             tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
     else
-        pair_kernel_f32<DIM, TP, BLOCK, MINB, false><<<grid, BLOCK, 0, stream>>>(
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 0><<<grid, BLOCK, 0, stream>>>(
             tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
     return cudaGetLastError();
 }
-
-static int g_force_tp = 0;  // test / tuning hook (pcuda_debug_set)
 
 // Enqueues the brute-force evaluation on ctx->stream.  All pointers are device pointers.
 // src4: 16-byte records (DIM 3: {x,y,z,mu}; DIM 2: {x,y,mu,0}); tgt rows have tgt_stride floats.
@@ -671,6 +680,10 @@ int pcuda_bruteforce_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size
 int pcuda_debug_set(const char *key, int value) {
     if (key && std::string(key) == "bf_tp") {
         bf::g_force_tp = value;
+        return PCUDA_OK;
+    }
+    if (key && std::string(key) == "bf_clamp" && (value == 1 || value == 2)) {
+        bf::g_clamp_mode = value;
         return PCUDA_OK;
     }
     return PCUDA_ERR_INVALID_ARGUMENT;

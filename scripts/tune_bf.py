@@ -40,7 +40,8 @@ d_out = torch.zeros((N, 3), dtype=torch.float32, device="cuda")
 torch.cuda.synchronize()
 stream = torch.cuda.ExternalStream(ctx.stream_ptr)
 res = {}
-for eps, name in ((0.0, "checked"), (1.0, "softened")):
+for eps, name, clamp in ((0.0, "checked_select", 1), (0.0, "checked_fmnmx", 2), (1.0, "softened", 1)):
+    lib.pcuda_debug_set(b"bf_clamp", clamp)
     inter = pb.AccelerationSoftened.checked(eps) if eps else pb.Acceleration.checked()
     bf = pb.BruteForce(ctx, inter)
     for tp in (4, 2, 1):

@@ -88,6 +88,17 @@ def brute_force_exact(affected, affecting, softening=0.0, checked=True):
     return out
 
 
+def brute_force_abs(affected, affecting, softening=0.0):
+    """S_i = sum_j |term_ij| in extended precision: S_i / |a_i| is the condition number of the
+    summation, used to state the floating-point tolerance of a reordered f32 sum."""
+    affected, affecting, dt, d, sfx = _prep(affected, affecting)
+    out = np.zeros(affected.shape[0], dtype=np.float64)
+    getattr(lib(), f"oracle_bruteforce_abs_{sfx}")(
+        _ptr(affected), C.c_size_t(len(affected)), _ptr(affecting), C.c_size_t(len(affecting)),
+        _scalar(dt, softening), _ptr(out))
+    return out
+
+
 def brute_force_simd8_parallel(affected, affecting, softening=0.0, checked=True):
     """parallel::BruteForceSimd<8> restated with AVX2 + OpenMP (timing baseline, f32 3-D only)."""
     affected, affecting, dt, d, sfx = _prep(affected, affecting)

@@ -12,7 +12,7 @@
 //       range); nodes are stored breadth-first, children of a node contiguous; centre of mass
 //       bottom-up in double precision, in a fixed order
 //   The resulting arrays are bit-identical to the CPU statement of the same specification
-//   (oracle/oracle_octree.inc) — keys, permutation, node ranges, levels, children and {com, mass}.
+//   (the test oracle; DESIGN.md "Tree specification") — keys, permutation, node ranges, levels, children and {com, mass}.
 //
 // Traversal (K5), warp-cooperative: a warp owns 32 consecutive targets in key order and walks the
 // tree ONCE for the group with a shared stack: every lane tests one node per step against the
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) bbox_partial(const float *__restrict__ p,
 
 // K2b: final reduction + frame.  ext = max_k(hi-lo) folded from 0; half = ext/2;
 // origin_k = (lo_k+hi_k)/2 - half; inv = 2^BITS/ext (0 when ext == 0).  Explicit _rn intrinsics:
-// no contraction, IEEE division — the same bits as oracle_octree.inc quant_frame.
+// no contraction, IEEE division — the same bits as the CPU statement of the specification.
 template <int DIM>
 __global__ void frame_kernel(const float *__restrict__ partial, int nblocks, Frame *out) {
     __shared__ float s[2 * DIM];
@@ -305,7 +305,7 @@ __global__ void init_root(NodeRec *nodes, uint32_t n) {
 }
 
 // K4c: moments of one level, deepest level first.  Double precision, fixed order, unfused
-// (__dmul_rn / __dadd_rn), identical to oracle_octree.inc:
+// (__dmul_rn / __dadd_rn), identical to the CPU statement of the specification:
 //   leaf:      M = sum m_i, Mx_k = sum m_i * x_ik over the cell's particles in key order
 //   internal:  sums of the children's moments in child order
 //   com_k = (float)(Mx_k / M), mass = (float)M;  M == 0 => com = position of the first particle.
@@ -353,18 +353,117 @@ __global__ void __launch_bounds__(128) moments_kernel(NodeRec *__restrict__ node
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: warp-cooperative theta-traversal.
+// K5a: target groups.  The targets are walked in key order in groups of at most 32 that never
+// straddle a coarse cell boundary: a SEGMENT is a maximal cell (key prefix) holding at most
+// `seg_max` targets (found from the keys alone: adjacent keys first differ at digit L[i], and the
+// cell they share is counted by scanning L to both sides), and every segment is cut into equal
+// chunks of <= 32 consecutive targets.  Without this, 32 consecutive keys that cross e.g. the
+// centre of a Plummer sphere have a bounding box spanning the core and open millions of nodes.
+constexpr int GROUP_BLOCK = 256;
+constexpr int SEG_MAX_LIMIT = 256;
+
+template <int DIM>
+__global__ void __launch_bounds__(256) boundary_levels(const uint64_t *__restrict__ keys, int n,
+                                                       uint8_t *__restrict__ L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0) {
+        L[0] = 0;
+        return;
+    }
+    const uint64_t x = keys[i] ^ keys[i - 1];
+    L[i] = x == 0 ? (uint8_t)(Dims<DIM>::BITS + 1)
+                  : (uint8_t)(Dims<DIM>::BITS - (63 - __clzll((long long)x)) / DIM);
+}
+
+__global__ void __launch_bounds__(GROUP_BLOCK) group_flags(const uint8_t *__restrict__ L, int n,
+                                                           int bits, int T,
+                                                           uint32_t *__restrict__ flag) {
+    __shared__ uint8_t sL[GROUP_BLOCK + 4 * SEG_MAX_LIMIT + 2];
+    __shared__ uint8_t sH[GROUP_BLOCK + 2 * SEG_MAX_LIMIT];
+    const int base = blockIdx.x * GROUP_BLOCK;
+    const int l0 = base - 2 * T - 1;  // global index of sL[0]
+    const int nl = GROUP_BLOCK + 4 * T + 2;
+    for (int k = threadIdx.x; k < nl; k += GROUP_BLOCK) {
+        const int g = l0 + k;
+        sL[k] = (g <= 0 || g >= n) ? 0 : L[g];  // outside the array: a boundary at the root
+    }
+    __syncthreads();
+    const int h0 = base - T;  // global index of sH[0]
+    const int nh = GROUP_BLOCK + 2 * T;
+    for (int k = threadIdx.x; k < nh; k += GROUP_BLOCK) {
+        const int i = h0 + k;
+        bool hard;
+        if (i <= 0 || i >= n) hard = true;
+        else {
+            const int li = sL[i - l0];
+            if (li == bits + 1) hard = false;  // identical keys never separate
+            else {
+                const int l = li - 1;  // level of the smallest cell holding targets i-1 and i
+                int j = i - 1;         // walk left to the first target of that cell
+                while (j > 0 && i - j <= T && sL[j - l0] > l) --j;
+                if (i - j > T) hard = true;
+                else {
+                    int k2 = i + 1;    // walk right to the first target past that cell
+                    while (k2 < n && k2 - j <= T && sL[k2 - l0] > l) ++k2;
+                    hard = k2 - j > T;
+                }
+            }
+        }
+        sH[k] = hard;
+    }
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    if (i >= n) return;
+    int ss = i;  // segment start: nearest hard boundary at or before i
+    while (ss > 0 && i - ss < T && !sH[ss - h0]) --ss;
+    bool start;
+    if (!sH[ss - h0] && ss > 0) start = (i & 31) == 0;  // inside a long run of identical keys
+    else {
+        int se = i + 1;  // segment end: next hard boundary
+        while (se < n && se - ss <= T && !sH[se - h0]) ++se;
+        const int len = se - ss;
+        if (len <= T) {
+            const int chunks = (len + 31) / 32;
+            const int cs = (len + chunks - 1) / chunks;
+            start = (i - ss) % cs == 0;
+        } else {
+            start = i == ss || (i & 31) == 0;  // the head of a long run of identical keys
+        }
+    }
+    flag[i] = start ? 1u : 0u;
+}
+
+// Compaction of the group starts; the last thread also writes the sentinel and the group count.
+__global__ void __launch_bounds__(256) scatter_groups(const uint32_t *__restrict__ flag,
+                                                      const uint32_t *__restrict__ pos, int n,
+                                                      uint32_t *__restrict__ group_start,
+                                                      uint32_t *__restrict__ n_groups) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) group_start[pos[i]] = (uint32_t)i;
+    if (i == n - 1) {
+        const uint32_t g = pos[i] + flag[i];
+        group_start[g] = (uint32_t)n;
+        *n_groups = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b: warp-cooperative theta-traversal (persistent warps, groups handed out by an atomic counter).
 constexpr int TRAV_WARPS = 8;      // warps per block
 constexpr int STACK_CAP = 1024;    // node indices per warp (shared memory)
 constexpr int STACK_RESERVE = 8 * 32;  // room a depth-first descent may still need (7 per level)
 constexpr int LIST_CAP = 64;       // interaction ring per warp (float4 entries)
-constexpr float TINY_R2 = 1e-30f;
 
 struct TravArgs {
     const NodeRec *nodes;
     const float4 *src;    // sorted sources {x,y,z,mu}
     const float4 *tgt;    // targets in traversal order {x,y,z,_}
     const uint32_t *tgt_perm;  // traversal order -> output row (nullptr: identity)
+    const uint32_t *group_start;  // n_groups + 1 entries
+    const uint32_t *n_groups;
+    uint32_t *work;       // next group to hand out
     float *out;
     unsigned long long *counters;  // [0] node interactions, [1] particle interactions, [2] node tests
     int n_tgt;
@@ -374,200 +473,217 @@ struct TravArgs {
     float eps2;
 };
 
-// Evaluates `cnt` (<= 32) ring entries starting at `head` for this lane's target.
-__device__ __forceinline__ void eval_entries(const float4 *ring, int head, int cnt, float px,
-                                             float py, float pz, float eps2, float &ax, float &ay,
-                                             float &az) {
-    if (cnt == 32) {
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-            const float4 e = ring[(head + j) & (LIST_CAP - 1)];
-            const float dx = e.x - px, dy = e.y - py, dz = e.z - pz;
-            float r2 = fmaf(dx, dx, eps2);
-            r2 = fmaf(dy, dy, r2);
-            r2 = fmaf(dz, dz, r2);
-            r2 = r2 == 0.f ? __int_as_float(0x7f800000) : r2;  // zero distance contributes nothing
-            const float ri = ptx::rsqrt_approx(r2);
-            const float s = (ri * ri) * (ri * e.w);
-            ax = fmaf(dx, s, ax);
-            ay = fmaf(dy, s, ay);
-            az = fmaf(dz, s, az);
-        }
-    } else {
-        for (int j = 0; j < cnt; ++j) {
-            const float4 e = ring[(head + j) & (LIST_CAP - 1)];
-            const float dx = e.x - px, dy = e.y - py, dz = e.z - pz;
-            float r2 = fmaf(dx, dx, eps2);
-            r2 = fmaf(dy, dy, r2);
-            r2 = fmaf(dz, dz, r2);
-            r2 = r2 == 0.f ? __int_as_float(0x7f800000) : r2;
-            const float ri = ptx::rsqrt_approx(r2);
-            const float s = (ri * ri) * (ri * e.w);
-            ax = fmaf(dx, s, ax);
-            ay = fmaf(dy, s, ay);
-            az = fmaf(dz, s, az);
-        }
+// Evaluates ring entries head+first, head+first+step, ... < head+cnt for this lane's target.
+__device__ __forceinline__ void eval_entries(const float4 *ring, int head, int first, int step,
+                                             int cnt, float px, float py, float pz, float eps2,
+                                             float &ax, float &ay, float &az) {
+#pragma unroll 4
+    for (int j = first; j < cnt; j += step) {
+        const float4 e = ring[(head + j) & (LIST_CAP - 1)];
+        const float dx = e.x - px, dy = e.y - py, dz = e.z - pz;
+        float r2 = fmaf(dx, dx, eps2);
+        r2 = fmaf(dy, dy, r2);
+        r2 = fmaf(dz, dz, r2);
+        r2 = r2 == 0.f ? __int_as_float(0x7f800000) : r2;  // zero distance contributes nothing
+        const float ri = ptx::rsqrt_approx(r2);
+        const float s = (ri * ri) * (ri * e.w);
+        ax = fmaf(dx, s, ax);
+        ay = fmaf(dy, s, ay);
+        az = fmaf(dz, s, az);
     }
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(TRAV_WARPS * 32) traverse_kernel(TravArgs a) {
+__global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a) {
     __shared__ uint32_t s_stack[TRAV_WARPS][STACK_CAP];
     __shared__ __align__(16) float4 s_ring[TRAV_WARPS][LIST_CAP];
 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int group = blockIdx.x * TRAV_WARPS + warp;
-    const int t0 = group * 32;
-    if (t0 >= a.n_tgt) return;
     uint32_t *stack = s_stack[warp];
     float4 *ring = s_ring[warp];
-
-    const int ti = min(t0 + lane, a.n_tgt - 1);
-    const bool live = t0 + lane < a.n_tgt;
-    const float4 tp = a.tgt[ti];
-    const float px = tp.x, py = tp.y, pz = tp.z;
-
-    // group bounding box -> centre and half extent
-    float lox = px, hix = px, loy = py, hiy = py, loz = pz, hiz = pz;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lox = fminf(lox, __shfl_xor_sync(FULL, lox, o));
-        hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, o));
-        loy = fminf(loy, __shfl_xor_sync(FULL, loy, o));
-        hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, o));
-        loz = fminf(loz, __shfl_xor_sync(FULL, loz, o));
-        hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, o));
-    }
-    const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
-    const float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
-
-    float ax = 0.f, ay = 0.f, az = 0.f;
+    const uint32_t n_groups = *a.n_groups;
     unsigned long long c_node = 0, c_part = 0, c_test = 0;
 
-    int sp = 1;          // stack size (uniform across the warp)
-    int head = 0, fill = 0;  // interaction ring (uniform)
-    if (lane == 0) stack[0] = 0;
-    __syncwarp();
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(a.work, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= n_groups) break;
+        const int t0 = (int)a.group_start[g];
+        const int gcnt = (int)a.group_start[g + 1] - t0;  // 1..32 targets
+        // lanes = (target, slice): a group of <= 16 targets uses 32 / gpad lanes per target, each
+        // evaluating every (32 / gpad)-th interaction; partial sums are combined at the end
+        int gpad = 1;
+        while (gpad < gcnt) gpad <<= 1;
+        const int slices = 32 / gpad;
+        const int tl = lane & (gpad - 1), slice = lane / gpad;
+        const int ti = t0 + min(tl, gcnt - 1);
+        const float4 tp = a.tgt[ti];
+        const float px = tp.x, py = tp.y, pz = tp.z;
 
-    auto flush_full = [&]() {  // evaluate while at least 32 entries are ready
-        while (fill >= 32) {
-            __syncwarp();
-            eval_entries(ring, head, 32, px, py, pz, a.eps2, ax, ay, az);
-            head = (head + 32) & (LIST_CAP - 1);
-            fill -= 32;
-            __syncwarp();
-        }
-    };
-
-    while (sp > 0) {
-        // pop up to 32 nodes, but never so many that their children could overflow the stack
-        int room = (STACK_CAP - STACK_RESERVE - sp) / 7;
-        int k = min(min(32, sp), max(room, 1));
-        const bool has = lane < k;
-        NodeRec nd;
-        nd.count = 0;
-        nd.nchild_level = 0;
-        if (has) {
-            const uint32_t id = stack[sp - 1 - lane];
-            const uint4 *q = reinterpret_cast<const uint4 *>(a.nodes + id);
-            const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
-            nd.cm = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z),
-                                __uint_as_float(q0.w));
-            nd.first_child = q1.x;
-            nd.nchild_level = q1.y;
-            nd.begin = q1.z;
-            nd.count = q1.w;
-        }
-        sp -= k;
-        __syncwarp();
-
-        // opening rule for the group: (theta^2) * dmin^2 < width^2, dmin = distance from the
-        // centre of mass to the group's bounding box
-        bool open = false;
-        if (has) {
-            const float ddx = fmaxf(fabsf(nd.cm.x - cx) - hx, 0.f);
-            const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
-            const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
-            const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-            const int level = (int)(nd.nchild_level >> 8);
-            const float w = a.ext * __int_as_float((127 - level) << 23);
-            open = a.theta2 * d2 < w * w;
-        }
-        const uint32_t nc = nd.nchild_level & 0xffu;
-        const bool open_internal = has && open && nc > 0;
-        const bool open_leaf = has && open && nc == 0;
-        const bool accept = has && !open && nd.cm.w != 0.f;
-        if (COUNT) c_test += __popc(__ballot_sync(FULL, has));
-
-        // push the children of opened internal nodes (warp scan of the child counts)
-        {
-            int c = open_internal ? (int)nc : 0;
-            int incl = c;
+        // group bounding box -> centre and half extent
+        float lox = px, hix = px, loy = py, hiy = py, loz = pz, hiz = pz;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            const int base = sp + incl - c;
-            for (int j = 0; j < c; ++j) stack[base + j] = nd.first_child + j;
-            sp += total;
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(FULL, lox, o));
+            hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, o));
+            loy = fminf(loy, __shfl_xor_sync(FULL, loy, o));
+            hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, o));
+            loz = fminf(loz, __shfl_xor_sync(FULL, loz, o));
+            hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, o));
         }
+        const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+        const float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
 
-        // accepted nodes -> interaction ring
-        {
-            const unsigned m = __ballot_sync(FULL, accept);
-            if (m) {
-                if (accept) ring[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] = nd.cm;
-                const int cnt = __popc(m);
-                if (COUNT) c_node += cnt;
-                fill += cnt;
-                flush_full();
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        unsigned long long g_node = 0, g_part = 0;
+        int sp = 1;              // stack size (uniform across the warp)
+        int head = 0, fill = 0;  // interaction ring (uniform)
+        __syncwarp();
+        if (lane == 0) stack[0] = 0;
+        __syncwarp();
+
+        auto flush_full = [&]() {  // evaluate while at least 32 entries are ready
+            while (fill >= 32) {
+                __syncwarp();
+                eval_entries(ring, head, slice, slices, 32, px, py, pz, a.eps2, ax, ay, az);
+                head = (head + 32) & (LIST_CAP - 1);
+                fill -= 32;
+                __syncwarp();
             }
-        }
+        };
 
-        // particles of opened leaves -> interaction ring, one particle per leaf per round
-        {
-            int remaining = open_leaf ? (int)nd.count : 0;
-            uint32_t pidx = nd.begin;
-            unsigned m = __ballot_sync(FULL, remaining > 0);
-            while (m) {
-                if (remaining > 0) {
-                    ring[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] =
-                        __ldg(a.src + pidx);
-                    ++pidx;
-                    --remaining;
+        while (sp > 0) {
+            // pop up to 32 nodes, but never so many that their children could overflow the stack
+            const int room = (STACK_CAP - STACK_RESERVE - sp) / 7;
+            const int k = min(min(32, sp), max(room, 1));
+            const bool has = lane < k;
+            NodeRec nd;
+            nd.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+            nd.first_child = 0;
+            nd.begin = 0;
+            nd.count = 0;
+            nd.nchild_level = 0;
+            if (has) {
+                const uint32_t id = stack[sp - 1 - lane];
+                const uint4 *q = reinterpret_cast<const uint4 *>(a.nodes + id);
+                const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                nd.cm = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y),
+                                    __uint_as_float(q0.z), __uint_as_float(q0.w));
+                nd.first_child = q1.x;
+                nd.nchild_level = q1.y;
+                nd.begin = q1.z;
+                nd.count = q1.w;
+            }
+            sp -= k;
+            __syncwarp();
+
+            // opening rule for the group: (theta^2) * dmin^2 < width^2, dmin = distance from the
+            // centre of mass to the group's bounding box
+            bool open = false;
+            if (has) {
+                const float ddx = fmaxf(fabsf(nd.cm.x - cx) - hx, 0.f);
+                const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
+                const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
+                const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                const int level = (int)(nd.nchild_level >> 8);
+                const float w = a.ext * __int_as_float((127 - level) << 23);
+                open = a.theta2 * d2 < w * w;
+            }
+            const uint32_t nc = nd.nchild_level & 0xffu;
+            const bool open_internal = has && open && nc > 0;
+            const bool open_leaf = has && open && nc == 0;
+            const bool accept = has && !open && nd.cm.w != 0.f;
+            if (COUNT) c_test += k;
+
+            // push the children of opened internal nodes (warp scan of the child counts)
+            {
+                const int c = open_internal ? (int)nc : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
                 }
-                const int cnt = __popc(m);
-                if (COUNT) c_part += cnt;
-                fill += cnt;
-                flush_full();
-                m = __ballot_sync(FULL, remaining > 0);
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int base = sp + incl - c;
+                for (int j = 0; j < c; ++j) stack[base + j] = nd.first_child + j;
+                sp += total;
             }
-        }
-        __syncwarp();
-    }
-    if (fill > 0) {
-        __syncwarp();
-        eval_entries(ring, head, fill, px, py, pz, a.eps2, ax, ay, az);
-    }
 
-    if (live) {
-        const uint32_t row = a.tgt_perm ? a.tgt_perm[ti] : (uint32_t)ti;
-        float *o = a.out + (size_t)row * a.dim;
-        o[0] = ax;
-        o[1] = ay;
-        if (a.dim == 3) o[2] = az;
-    }
-    if (COUNT) {
-        // per-target counts: every live lane evaluated every list entry of its group
-        const unsigned long long lanes = __popc(__ballot_sync(FULL, live));
-        if (lane == 0) {
-            atomicAdd(a.counters + 0, c_node * lanes);
-            atomicAdd(a.counters + 1, c_part * lanes);
-            atomicAdd(a.counters + 2, c_test);
+            // accepted nodes -> interaction ring
+            {
+                const unsigned m = __ballot_sync(FULL, accept);
+                if (m) {
+                    if (accept)
+                        ring[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] = nd.cm;
+                    const int cnt = __popc(m);
+                    if (COUNT) g_node += cnt;
+                    fill += cnt;
+                    flush_full();
+                }
+            }
+
+            // particles of opened leaves -> interaction ring, 32 particles per round: lane f of a
+            // round finds the leaf that owns flat index f by a shuffle binary search over the
+            // inclusive scan of the leaf sizes, so every round is one coalesced-per-leaf load
+            {
+                const int c = open_leaf ? (int)nd.count : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int excl = incl - c;
+                for (int base = 0; base < total; base += 32) {
+                    const int f = base + lane;
+                    int owner = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, (owner + step - 1) & 31);
+                        if (v <= f) owner += step;
+                    }
+                    owner = min(owner, 31);
+                    const uint32_t ob = __shfl_sync(FULL, nd.begin, owner);
+                    const int oe = __shfl_sync(FULL, excl, owner);
+                    if (f < total)
+                        ring[(head + fill + lane) & (LIST_CAP - 1)] = __ldg(a.src + ob + (f - oe));
+                    const int cnt = min(32, total - base);
+                    if (COUNT) g_part += cnt;
+                    fill += cnt;
+                    flush_full();
+                }
+            }
+            __syncwarp();
         }
+        if (fill > 0) {
+            __syncwarp();
+            eval_entries(ring, head, slice, slices, fill, px, py, pz, a.eps2, ax, ay, az);
+        }
+        for (int o = gpad; o < 32; o <<= 1) {  // combine the slices of each target
+            ax += __shfl_xor_sync(FULL, ax, o);
+            ay += __shfl_xor_sync(FULL, ay, o);
+            az += __shfl_xor_sync(FULL, az, o);
+        }
+        if (slice == 0 && tl < gcnt) {
+            const uint32_t row = a.tgt_perm ? a.tgt_perm[ti] : (uint32_t)ti;
+            float *o = a.out + (size_t)row * a.dim;
+            o[0] = ax;
+            o[1] = ay;
+            if (a.dim == 3) o[2] = az;
+        }
+        if (COUNT) {  // per-target counts: every target of the group saw every list entry
+            c_node += g_node * gcnt;
+            c_part += g_part * gcnt;
+        }
+    }
+    if (COUNT && lane == 0) {
+        atomicAdd(a.counters + 0, c_node);
+        atomicAdd(a.counters + 1, c_part);
+        atomicAdd(a.counters + 2, c_test);
     }
 }
 
@@ -733,6 +849,7 @@ static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d
 }
 
 static bool g_count = true;  // instrumentation of the traversal (pcuda_tree_last_counters)
+static int g_seg_max = 128;  // largest cell (in targets) that is cut into groups (tuning hook)
 
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
 static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na, float theta,
@@ -749,9 +866,11 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
     cudaStream_t st = ctx->stream;
     const float4 *tgt_sorted;
     const uint32_t *tgt_perm;
+    const uint64_t *tgt_keys;
     if (!d_tgt) {
         tgt_sorted = t->sorted.as<float4>();
         tgt_perm = t->d_perm();
+        tgt_keys = t->d_keys();
     } else {
         // key the targets in the tree's frame and process them in key order (coherent groups)
         DevBuf keys[2] = {ctx->d_tgt_keys, ctx->d_tgt_keys_alt};
@@ -776,23 +895,52 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         ctx->launches++;
         tgt_sorted = ctx->d_tgt_sorted.as<float4>();
         tgt_perm = p;
+        tgt_keys = keys[cur].as<uint64_t>();
     }
-    PCUDA_CUDA_TRY(ctx, ctx->d_counters.ensure(3 * sizeof(unsigned long long)));
-    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 3 * sizeof(unsigned long long), st));
+    // K5a: groups from the target keys
+    const int n = (int)na;
+    PCUDA_CUDA_TRY(ctx, ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
+    uint32_t *d_work = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 3);
+    uint32_t *d_ngroups = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 4);
+    // d_stack layout: L (n bytes, padded) | flag (n u32) | pos (n u32) | group_start (n + 1 u32)
+    const size_t n4 = ((size_t)n + 3) & ~size_t(3);
+    PCUDA_CUDA_TRY(ctx, ctx->d_stack.ensure(n4 + (3 * (size_t)n + 1) * 4));
+    uint8_t *d_L = ctx->d_stack.as<uint8_t>();
+    uint32_t *d_flag = reinterpret_cast<uint32_t *>(d_L + n4);
+    uint32_t *d_pos = d_flag + n;
+    uint32_t *d_gstart = d_pos + n;
+    const unsigned nb256 = (unsigned)((n + 255) / 256);
+    if (dim == 3) boundary_levels<3><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
+    else boundary_levels<2><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
+    group_flags<<<(unsigned)((n + GROUP_BLOCK - 1) / GROUP_BLOCK), GROUP_BLOCK, 0, st>>>(
+        d_L, n, t->bits, g_seg_max, d_flag);
+    size_t tmp = 0;
+    PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_flag, d_pos, n, st));
+    PCUDA_CUDA_TRY(ctx, ctx->d_cub_tmp.ensure(tmp));
+    PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, tmp, d_flag, d_pos, n, st));
+    scatter_groups<<<nb256, 256, 0, st>>>(d_flag, d_pos, n, d_gstart, d_ngroups);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 5;
+
     TravArgs a;
     a.nodes = t->nodes.as<NodeRec>();
     a.src = t->sorted.as<float4>();
     a.tgt = tgt_sorted;
     a.tgt_perm = tgt_perm;
+    a.group_start = d_gstart;
+    a.n_groups = d_ngroups;
+    a.work = d_work;
     a.out = d_out;
     a.counters = ctx->d_counters.as<unsigned long long>();
-    a.n_tgt = (int)na;
+    a.n_tgt = n;
     a.dim = dim;
     a.ext = t->frame.ext;
     a.theta2 = theta * theta;
     a.eps2 = eps * eps;
-    const size_t groups = (na + 31) / 32;
-    const unsigned blocks = (unsigned)((groups + TRAV_WARPS - 1) / TRAV_WARPS);
+    const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
+                                                       (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
     if (g_count)
         traverse_kernel<true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
     else
@@ -862,6 +1010,19 @@ static int oneshot_host(pcuda_ctx *ctx, uint32_t dim, const float *aff, size_t n
 }
 
 }  // namespace bh
+
+int bh_debug_set(const char *key, int value) {
+    const std::string k = key ? key : "";
+    if (k == "bh_seg_max" && value >= 32 && value <= bh::SEG_MAX_LIMIT && value % 32 == 0) {
+        bh::g_seg_max = value;
+        return PCUDA_OK;
+    }
+    if (k == "bh_count") {
+        bh::g_count = value != 0;
+        return PCUDA_OK;
+    }
+    return PCUDA_ERR_INVALID_ARGUMENT;
+}
 
 void tree_free(pcuda_ctx *ctx, pcuda_tree *t) {
     if (!t) return;

@@ -686,7 +686,7 @@ int pcuda_debug_set(const char *key, int value) {
         bf::g_clamp_mode = value;
         return PCUDA_OK;
     }
-    return PCUDA_ERR_INVALID_ARGUMENT;
+    return pcuda::bh_debug_set(key, value);
 }
 
 }  // extern "C"

@@ -97,6 +97,7 @@ struct DeviceGuard {
 };
 
 void tree_free(pcuda_ctx *ctx, pcuda_tree *t);
+int bh_debug_set(const char *key, int value);  // barneshut.cu tuning hooks
 void nccl_free(pcuda_ctx *ctx);
 // comm.cu: world size / rank of the context's communicator (1 / 0 when none was initialised).
 void nccl_world(const pcuda_ctx *ctx, int *world, int *rank);

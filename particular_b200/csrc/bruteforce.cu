@@ -34,17 +34,22 @@ constexpr float PAD_POS = 1e18f;   // zero-mass padding records sit here: they c
 // ------------------------------------------------------------------------------------------------
 // f32 kernel.  Source record: DIM 3 -> {x,y,z,mu}; DIM 2 -> {x,y,mu,0}.
 // CLAMP != 0 <=> (checked && eps*eps == 0): a coincident pair must contribute nothing
-// (impls/mod.rs:160-161).  CLAMP == 1 (default): r2 == 0 is replaced by +inf, so rsqrt gives 0
-// and the term is d * 0 = 0 for any finite mu (two ALU-pipe instructions, FSETP + FSEL, that
-// issue in slots the FMA pipe leaves free).  CLAMP == 2 (tuning alternative): r2 is clamped to
-// TINY_R2 with one FMNMX; exact only while mu * 1e27 stays finite.
+// (impls/mod.rs:160-161).
+//   CLAMP == 1: r2 == 0 is replaced by +inf, so rsqrt gives 0 and the term is d * 0 = 0 for any
+//               finite mu.  Exact; two ALU-pipe instructions per pair (FSETP + FSEL), ~5 % slower.
+//   CLAMP == 2: r2 is clamped from below with one FMNMX to a threshold derived from the largest
+//               |mu| of the call (mass_max_kernel) such that mu * r^-3 stays finite; a coincident
+//               pair then gives d * finite = 0 exactly.  Differs from CLAMP == 1 only for pairs
+//               closer than ~1.4e-10 * (max|mu| / 1e9)^(1/3) — below the f32 spacing of any
+//               position with |x| > 1e-3.  Used for large problems where the kernel time matters.
 // CLAMP == 0: either eps2 > 0 (d = 0 gives 0 without any test) or the caller asked for the
 // unchecked reference behaviour (coincident pair -> NaN, as in the reference).
 template <int DIM, int TP, int BLOCK, int MINB, int CLAMP>
 __global__ void __launch_bounds__(BLOCK, MINB)
     pair_kernel_f32(const float *__restrict__ tgt, int tgt_stride, int n_tgt,
                     const float4 *__restrict__ src, int n_src, int src_chunk, int tile, float eps2,
-                    float *__restrict__ out, float *__restrict__ partial, size_t n_pad) {
+                    float *__restrict__ out, float *__restrict__ partial, size_t n_pad,
+                    const unsigned *__restrict__ mass_max_bits) {
     __shared__ __align__(128) float4 tiles[STAGES][TILE_MAX];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -98,6 +103,13 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         for (int t = 0; t < PREFETCH && t < ntiles; ++t) issue(t);
 
     const float2 eps2p = make_float2(eps2, eps2);
+    float tiny_r2 = TINY_R2;
+    if (CLAMP == 2) {
+        // smallest r2 for which max|mu| * r2^-1.5 < ~1e38:  r2 > (max|mu| * 1e-38)^(2/3)
+        const float mmax = __uint_as_float(*mass_max_bits);
+        const float c = cbrtf(fminf(mmax, 3e38f) * 1e-38f);
+        tiny_r2 = fmaxf(2.f * c * c, 1e-36f);
+    }
 
     for (int t = 0; t < ntiles; ++t) {
         if (tid == 0 && t + PREFETCH < ntiles) {
@@ -131,8 +143,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                         r2.x = r2.x == 0.f ? __int_as_float(0x7f800000) : r2.x;
                         r2.y = r2.y == 0.f ? __int_as_float(0x7f800000) : r2.y;
                     } else if (CLAMP == 2) {
-                        r2.x = fmaxf(r2.x, TINY_R2);
-                        r2.y = fmaxf(r2.y, TINY_R2);
+                        r2.x = fmaxf(r2.x, tiny_r2);
+                        r2.y = fmaxf(r2.y, tiny_r2);
                     }
                     float2 ri;
                     ri.x = ptx::rsqrt_approx(r2.x);
@@ -173,6 +185,19 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             }
         }
     }
+}
+
+// max |mu| over the source records (bit pattern of a non-negative float orders like an unsigned).
+__global__ void __launch_bounds__(256) mass_max_kernel(const float4 *__restrict__ src, int n, int dim,
+                                                       unsigned *__restrict__ out) {
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 s = src[i];
+        m = fmaxf(m, fabsf(dim == 3 ? s.w : s.z));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
 // Fixed-order reduction of the source-split partial sums: out[i][c] = sum_y partial[y][c][i].
@@ -341,22 +366,22 @@ static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
 }
 
 static int g_force_tp = 0;    // test / tuning hooks (pcuda_debug_set)
-static int g_clamp_mode = 1;
+static int g_clamp_mode = 0;   // 0 = automatic (by problem size), 1 = select, 2 = mass-aware clamp
 
 template <int DIM, int TP, int BLOCK, int MINB>
-static cudaError_t launch_f32(const Plan &pl, bool clamp, cudaStream_t stream, const float *tgt,
+static cudaError_t launch_f32(const Plan &pl, int clamp, cudaStream_t stream, const float *tgt,
                               int tgt_stride, int na, const float4 *src, int nb, float eps2,
-                              float *out, float *partial, size_t n_pad) {
+                              float *out, float *partial, size_t n_pad, const unsigned *mass_max) {
     dim3 grid(pl.n_tb, pl.splits);
-    if (clamp && g_clamp_mode == 2)
+    if (clamp == 2)
         pair_kernel_f32<DIM, TP, BLOCK, MINB, 2><<<grid, BLOCK, 0, stream>>>(
-            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
-    else if (clamp)
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
+    else if (clamp == 1)
         pair_kernel_f32<DIM, TP, BLOCK, MINB, 1><<<grid, BLOCK, 0, stream>>>(
-            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
     else
         pair_kernel_f32<DIM, TP, BLOCK, MINB, 0><<<grid, BLOCK, 0, stream>>>(
-            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad);
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
     return cudaGetLastError();
 }
 
@@ -373,8 +398,20 @@ static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na
     if (na > 0x7fffffffull || nb > 0x7fffffffull)
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     const float eps2 = softening * softening;
-    const bool clamp = checked && eps2 == 0.0f;
+    int clamp = 0;
+    if (checked && eps2 == 0.0f)
+        clamp = g_clamp_mode ? g_clamp_mode : ((double)na * (double)nb >= 2.5e8 ? 2 : 1);
     const Plan pl = make_plan(ctx->sm_count, na, nb, g_force_tp);
+    unsigned *mass_max = nullptr;
+    if (clamp == 2) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_massmax.ensure(sizeof(unsigned)));
+        mass_max = ctx->d_massmax.as<unsigned>();
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(mass_max, 0, sizeof(unsigned), ctx->stream));
+        const int blocks = (int)std::min<size_t>((size_t)ctx->sm_count * 4, (nb + 255) / 256);
+        mass_max_kernel<<<blocks, 256, 0, ctx->stream>>>(d_src4, (int)nb, DIM, mass_max);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     const size_t n_pad = (na + 63) & ~size_t(63);
     float *partial = nullptr;
     if (pl.splits > 1) {
@@ -384,13 +421,13 @@ static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na
     cudaError_t e;
     if (pl.tp == 4)
         e = launch_f32<DIM, 4, 256, 2>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
-                                       (int)nb, eps2, d_out, partial, n_pad);
+                                       (int)nb, eps2, d_out, partial, n_pad, mass_max);
     else if (pl.tp == 2)
         e = launch_f32<DIM, 2, 256, 3>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
-                                       (int)nb, eps2, d_out, partial, n_pad);
+                                       (int)nb, eps2, d_out, partial, n_pad, mass_max);
     else
         e = launch_f32<DIM, 1, 128, 4>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
-                                       (int)nb, eps2, d_out, partial, n_pad);
+                                       (int)nb, eps2, d_out, partial, n_pad, mass_max);
     PCUDA_CUDA_TRY(ctx, e);
     ctx->launches++;
     if (pl.splits > 1) {
@@ -682,7 +719,7 @@ int pcuda_debug_set(const char *key, int value) {
         bf::g_force_tp = value;
         return PCUDA_OK;
     }
-    if (key && std::string(key) == "bf_clamp" && (value == 1 || value == 2)) {
+    if (key && std::string(key) == "bf_clamp" && value >= 0 && value <= 2) {
         bf::g_clamp_mode = value;
         return PCUDA_OK;
     }

@@ -63,7 +63,7 @@ struct pcuda_ctx {
     uint32_t launches = 0;
 
     // brute force scratch
-    pcuda::DevBuf d_affected, d_affecting, d_out, d_partial, d_packed_src, d_packed_tgt;
+    pcuda::DevBuf d_affected, d_affecting, d_out, d_partial, d_packed_src, d_packed_tgt, d_massmax;
     // Barnes-Hut scratch (barneshut.cu owns the layout)
     pcuda::DevBuf d_stack, d_counters, d_tgt_keys, d_tgt_keys_alt, d_tgt_perm, d_tgt_perm_alt,
         d_tgt_sorted, d_cub_tmp, d_misc;

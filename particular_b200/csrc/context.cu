@@ -140,7 +140,7 @@ void pcuda_destroy(pcuda_ctx *ctx) {
     nccl_free(ctx);
     if (ctx->call_tree) tree_free(ctx, ctx->call_tree);
     DevBuf *bufs[] = {&ctx->d_affected, &ctx->d_affecting, &ctx->d_out, &ctx->d_partial,
-                      &ctx->d_packed_src, &ctx->d_packed_tgt, &ctx->d_stack, &ctx->d_counters,
+                      &ctx->d_packed_src, &ctx->d_packed_tgt, &ctx->d_massmax, &ctx->d_stack, &ctx->d_counters,
                       &ctx->d_tgt_keys, &ctx->d_tgt_keys_alt, &ctx->d_tgt_perm,
                       &ctx->d_tgt_perm_alt, &ctx->d_tgt_sorted, &ctx->d_cub_tmp, &ctx->d_misc};
     for (DevBuf *b : bufs) b->release();

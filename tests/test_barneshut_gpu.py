@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import oracle
-from tests.conftest import plummer_cloud, rel_err, uniform_cloud
+from tests.conftest import assert_bruteforce_parity, plummer_cloud, rel_err, uniform_cloud
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kat.json")))
@@ -117,8 +117,7 @@ def test_theta0_is_brute_force(pb, ctx, dim):
     exact = oracle.brute_force_exact(p[:, :dim], p)
     got = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).compute(p)
     ref32 = oracle.brute_force_parallel(p[:, :dim], p)
-    e_gpu, e_ref = rel_err(got, exact), rel_err(ref32, exact)
-    assert (e_gpu <= np.maximum(1e-5, e_ref)).all(), e_gpu.max()
+    assert_bruteforce_parity(got, ref32, p[:, :dim], p)
     c = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).last_counters()
     assert c["particle_interactions"] == 6000 * 6000 and c["node_interactions"] == 0
 

@@ -1,9 +1,10 @@
 """GPU parity of the brute-force path (K1) against the CPU oracle, through the C ABI.
 
-Tolerances: per-particle ||a_gpu - a_ref|| / ||a_ref|| <= 1e-5 (f32) / 1e-12 (f64)
-against the bit-faithful restatement of sequential::BruteForce for N <= 16384; for larger N both
-are compared with the extended-precision sum and the GPU must be no worse than
-max(1e-5, error of the reference's own f32 left fold)."""
+Tolerance (tests/conftest.py parity_tolerance, DESIGN.md "Parity"): per particle
+||a_gpu - a_ref|| / ||a_ref|| <= 1e-5 (f32) / 1e-12 (f64) + 4 sqrt(N) u kappa_i against the
+bit-faithful restatement of sequential::BruteForce, where the second term is the rounding noise of
+the reference's own left fold for an ill-conditioned sum; in aggregate the GPU must be no less
+accurate than that fold when both are compared with the extended-precision sum."""
 import ctypes as C
 import json
 import os
@@ -12,7 +13,7 @@ import numpy as np
 import pytest
 
 import oracle
-from tests.conftest import rel_err, uniform_cloud
+from tests.conftest import assert_bruteforce_parity, rel_err, uniform_cloud
 
 pytestmark = pytest.mark.gpu
 
@@ -57,10 +58,12 @@ def test_golden_cloud(pb, ctx, name):
     dt = np.float64 if name.startswith("f64") else np.float32
     tol = TOL64 if dt == np.float64 else TOL32
     p = np.array(r["particles"], dtype=dt)
+    d = p.shape[1] - 1
     got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(p)
-    assert rel_err(got, np.array(r["brute_force"])).max() <= tol
+    assert_bruteforce_parity(got, np.array(r["brute_force"], dtype=dt), p[:, :d], p)
+    assert rel_err(got, np.array(r["brute_force"])).max() <= 10 * tol
     got = pb.BruteForce(ctx, pb.AccelerationSoftened.checked(1.5)).compute(p)
-    assert rel_err(got, np.array(r["brute_force_softened_1.5"])).max() <= tol
+    assert_bruteforce_parity(got, np.array(r["brute_force_softened_1.5"], dtype=dt), p[:, :d], p, 1.5)
 
 
 @pytest.mark.parametrize("tp", [1, 2, 4])
@@ -74,7 +77,7 @@ def test_random_cloud_f32x3(pb, ctx, tp, n):
     if n == 1:
         assert not got.any() and not ref.any()
         return
-    assert rel_err(got, ref).max() <= TOL32
+    assert_bruteforce_parity(got, ref, p[:, :3], p)
 
 
 @pytest.mark.parametrize("soft,checked", [(0.0, True), (2.5, True), (2.5, False), (100.0, True)])
@@ -84,7 +87,7 @@ def test_interaction_variants_f32(pb, ctx, dim, soft, checked):
     it = pb.AccelerationSoftened(soft, checked) if soft else pb.Acceleration(checked)
     got = pb.BruteForce(ctx, it).compute(p)
     ref = oracle.brute_force_parallel(p[:, :dim], p, soft, checked)
-    assert rel_err(got, ref).max() <= TOL32
+    assert_bruteforce_parity(got, ref, p[:, :dim], p, soft)
 
 
 @pytest.mark.parametrize("n", [1, 5, 129, 1000, 4099])
@@ -94,9 +97,9 @@ def test_random_cloud_f64(pb, ctx, n):
     ref = oracle.brute_force_parallel(p[:, :3], p)
     assert got.dtype == np.float64
     if n > 1:
-        assert rel_err(got, ref).max() <= TOL64
+        assert_bruteforce_parity(got, ref, p[:, :3], p)
     got = pb.BruteForce(ctx, pb.AccelerationSoftened.checked(3.0)).compute(p)
-    assert rel_err(got, oracle.brute_force_parallel(p[:, :3], p, 3.0)).max() <= TOL64
+    assert_bruteforce_parity(got, oracle.brute_force_parallel(p[:, :3], p, 3.0), p[:, :3], p, 3.0)
 
 
 @pytest.mark.parametrize("na,nb", [(1, 1000), (1000, 1), (777, 1234), (5000, 33), (33, 5000)])
@@ -107,7 +110,24 @@ def test_rectangular_between(pb, ctx, na, nb, dim, dtype):
     aff = uniform_cloud(na, d=dim, dtype=dtype, seed=4)[:, :dim]
     got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(pb.Between(aff, src))
     ref = oracle.brute_force_parallel(aff, src)
-    assert rel_err(got, ref).max() <= (TOL64 if dtype == np.float64 else TOL32)
+    assert_bruteforce_parity(got, ref, aff, src)
+
+
+@pytest.mark.parametrize("scale", [1e-20, 1.0, 1.3e11])
+def test_mass_scale_with_coincident_pairs(pb, ctx, scale):
+    """Both `checked` variants (exact select for small problems, mass-aware clamp for large ones)
+    give 0 for coincident pairs at any mass scale (e.g. SI: mu_sun = 1.3e20)."""
+    from particular_b200._ffi import lib
+    p = uniform_cloud(3000, seed=31)
+    p[:, 3] *= scale
+    p[7, :3] = p[2000, :3]
+    ref = oracle.brute_force_parallel(p[:, :3], p)
+    for mode in (1, 2, 0):
+        assert lib.pcuda_debug_set(b"bf_clamp", mode) == 0
+        got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(p)
+        assert np.isfinite(got).all()
+        assert_bruteforce_parity(got, ref, p[:, :3], p)
+    lib.pcuda_debug_set(b"bf_clamp", 0)
 
 
 def test_coincident_particles_and_massless_sources(pb, ctx):
@@ -119,7 +139,7 @@ def test_coincident_particles_and_massless_sources(pb, ctx):
         got = pb.BruteForce(ctx, it).compute(p)
         ref = oracle.brute_force_parallel(p[:, :3], p, soft)
         assert np.isfinite(got).all()
-        assert rel_err(got, ref).max() <= TOL32
+        assert_bruteforce_parity(got, ref, p[:, :3], p, soft)
     # unchecked + no softening: a coincident pair is 0 * inf = NaN in the reference
     # (impls/mod.rs:160-165) and here
     got = pb.BruteForce(ctx, pb.Acceleration.unchecked()).compute(p)
@@ -139,7 +159,7 @@ def test_massive_massless_split(pb, ctx, storage):
         st, (aff, src) = pb.Ordered.new(p), oracle.between_of_ordered(p)
     assert len(src) == 100
     got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(st)
-    assert rel_err(got, oracle.brute_force_parallel(aff, src)).max() <= TOL32
+    assert_bruteforce_parity(got, oracle.brute_force_parallel(aff, src), aff, src)
 
 
 def test_empty_inputs(pb, ctx):
@@ -185,7 +205,7 @@ def test_sharded_entry_single_rank(pb, ctx):
     sh = pb.ShardedBruteForce(ctx, pb.Acceleration.checked())
     got = sh.compute(p)
     ref = oracle.brute_force_parallel(p[:, :3], p)
-    assert rel_err(got, ref).max() <= TOL32
+    assert_bruteforce_parity(got, ref, p[:, :3], p)
     t = ctx.timings()
     assert t["kernel_launches"] >= 2 and t["compute_ms"] > 0
 
@@ -196,7 +216,7 @@ def test_pinned_buffers(pb, ctx):
     out = ctx.pinned_empty((1500, 3), np.float32)
     got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(p, out=out)
     assert got is out
-    assert rel_err(got, oracle.brute_force_parallel(p[:, :3], p)).max() <= TOL32
+    assert_bruteforce_parity(got, oracle.brute_force_parallel(p[:, :3], p), p[:, :3], p)
 
 
 def test_circular_orbit(pb, ctx):
@@ -226,11 +246,10 @@ def test_full_size_properties(pb, ctx):
     assert np.isfinite(full).all()
     exact = oracle.brute_force_exact(p[idx, :3], p)
     ref32 = oracle.brute_force_parallel(p[idx, :3], p)
-    e_gpu, e_ref = rel_err(full[idx], exact), rel_err(ref32, exact)
-    assert (e_gpu <= np.maximum(TOL32, e_ref)).all(), (e_gpu.max(), e_ref.max())
+    assert_bruteforce_parity(full[idx], ref32, p[idx, :3], p)
     # rectangular call on the sample reproduces the same rows up to summation order
     part = bf.compute(pb.Between(p[idx, :3], p))
-    assert rel_err(part, exact).max() <= max(TOL32, e_ref.max())
+    assert_bruteforce_parity(part, ref32, p[idx, :3], p)
     p2 = p.copy()
     p2[:, 3] *= 2
     d_src2 = torch.from_numpy(p2).cuda()

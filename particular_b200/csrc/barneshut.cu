@@ -48,6 +48,7 @@ struct Frame {  // quantisation frame == the reference's root cube
     float origin[3];
     float ext;
     float inv;
+    float mass_bound;  // n * max|mu|: bounds the |mass| of every node (not part of the tree spec)
 };
 
 template <int DIM>
@@ -81,8 +82,9 @@ namespace bh {
 // bits of the sequential fold in tree/partition.rs:109-132.  NaNs are ignored (as `v < lo` does).
 template <int DIM>
 __global__ void __launch_bounds__(256) bbox_partial(const float *__restrict__ p, int stride, int n,
-                                                    float *__restrict__ partial) {
-    float lo[DIM], hi[DIM];
+                                                    float *__restrict__ partial,
+                                                    unsigned *__restrict__ mass_max_bits) {
+    float lo[DIM], hi[DIM], mmax = 0.f;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
         lo[k] = INFINITY;
@@ -95,7 +97,11 @@ __global__ void __launch_bounds__(256) bbox_partial(const float *__restrict__ p,
             lo[k] = fminf(lo[k], v);
             hi[k] = fmaxf(hi[k], v);
         }
+        mmax = fmaxf(mmax, fabsf(p[(size_t)i * stride + DIM]));
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(mass_max_bits, __float_as_uint(mmax));
     __shared__ float s[8][2 * DIM];
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
@@ -126,7 +132,8 @@ __global__ void __launch_bounds__(256) bbox_partial(const float *__restrict__ p,
 // origin_k = (lo_k+hi_k)/2 - half; inv = 2^BITS/ext (0 when ext == 0).  Explicit _rn intrinsics:
 // no contraction, IEEE division — the same bits as the CPU statement of the specification.
 template <int DIM>
-__global__ void frame_kernel(const float *__restrict__ partial, int nblocks, Frame *out) {
+__global__ void frame_kernel(const float *__restrict__ partial, int nblocks, int n,
+                             const unsigned *__restrict__ mass_max_bits, Frame *out) {
     __shared__ float s[2 * DIM];
     if (threadIdx.x < 2 * DIM) {
         const bool is_hi = threadIdx.x >= DIM;
@@ -149,6 +156,7 @@ __global__ void frame_kernel(const float *__restrict__ partial, int nblocks, Fra
             out->origin[k] = k < DIM ? __fsub_rn(__fdiv_rn(__fadd_rn(s[k], s[DIM + k]), 2.0f), half) : 0.f;
         out->ext = ext;
         out->inv = ext > 0.0f ? __fdiv_rn((float)(1ull << Dims<DIM>::BITS), ext) : 0.0f;
+        out->mass_bound = (float)n * __uint_as_float(*mass_max_bits);
     }
 }
 
@@ -466,43 +474,64 @@ struct TravArgs {
     uint32_t *work;       // next group to hand out
     float *out;
     unsigned long long *counters;  // [0] node interactions, [1] particle interactions, [2] node tests
+    const Frame *frame;   // root cube extent + mass bound
     int n_tgt;
     int dim;
-    float ext;
     float theta2;
     float eps2;
 };
 
-// Evaluates ring entries head+first, head+first+step, ... < head+cnt for this lane's target.
-__device__ __forceinline__ void eval_entries(const float4 *ring, int head, int first, int step,
-                                             int cnt, float px, float py, float pz, float eps2,
-                                             float &ax, float &ay, float &az) {
-#pragma unroll 4
-    for (int j = first; j < cnt; j += step) {
-        const float4 e = ring[(head + j) & (LIST_CAP - 1)];
-        const float dx = e.x - px, dy = e.y - py, dz = e.z - pz;
-        float r2 = fmaf(dx, dx, eps2);
-        r2 = fmaf(dy, dy, r2);
-        r2 = fmaf(dz, dz, r2);
-        r2 = r2 == 0.f ? __int_as_float(0x7f800000) : r2;  // zero distance contributes nothing
-        const float ri = ptx::rsqrt_approx(r2);
-        const float s = (ri * ri) * (ri * e.w);
-        ax = fmaf(dx, s, ax);
-        ay = fmaf(dy, s, ay);
-        az = fmaf(dz, s, az);
-    }
+// The interaction list of a warp lives in shared memory as PAIRS of entries laid out
+// {x0 x1 y0 y1}{z0 z1 m0 m1}, so that one lane evaluates two entries at a time with packed FP32
+// (FADD2 / FFMA2 / FMUL2): 12 packed + 2 MUFU + 2 FMNMX + 2 LDS.128 per two interactions.
+__device__ __forceinline__ void list_store(float *list, int i, const float4 e) {
+    float *q = list + (i >> 1) * 8 + (i & 1);
+    q[0] = e.x;
+    q[2] = e.y;
+    q[4] = e.z;
+    q[6] = e.w;
+}
+
+__device__ __forceinline__ void eval_pair(const float4 A, const float4 B, float2 npx, float2 npy,
+                                          float2 npz, float2 eps2p, float tiny, float2 &ax,
+                                          float2 &ay, float2 &az) {
+    const float2 dx = ptx::add2(make_float2(A.x, A.y), npx);
+    const float2 dy = ptx::add2(make_float2(A.z, A.w), npy);
+    const float2 dz = ptx::add2(make_float2(B.x, B.y), npz);
+    float2 r2 = ptx::fma2(dx, dx, eps2p);
+    r2 = ptx::fma2(dy, dy, r2);
+    r2 = ptx::fma2(dz, dz, r2);
+    // zero distance contributes nothing: r2 is clamped so that mu * r^-3 stays finite and the
+    // term is d * finite = 0 (the threshold is far below any separation of distinct f32 positions)
+    r2.x = fmaxf(r2.x, tiny);
+    r2.y = fmaxf(r2.y, tiny);
+    float2 ri;
+    ri.x = ptx::rsqrt_approx(r2.x);
+    ri.y = ptx::rsqrt_approx(r2.y);
+    const float2 ri2 = ptx::mul2(ri, ri);
+    const float2 mri = ptx::mul2(ri, make_float2(B.z, B.w));
+    const float2 sc = ptx::mul2(ri2, mri);
+    ax = ptx::fma2(dx, sc, ax);
+    ay = ptx::fma2(dy, sc, ay);
+    az = ptx::fma2(dz, sc, az);
 }
 
 template <bool COUNT>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a) {
     __shared__ uint32_t s_stack[TRAV_WARPS][STACK_CAP];
-    __shared__ __align__(16) float4 s_ring[TRAV_WARPS][LIST_CAP];
+    __shared__ __align__(16) float4 s_list[TRAV_WARPS][LIST_CAP];
 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *stack = s_stack[warp];
-    float4 *ring = s_ring[warp];
+    float4 *list4 = s_list[warp];
+    float *list = reinterpret_cast<float *>(list4);
     const uint32_t n_groups = *a.n_groups;
+    const float2 eps2p = make_float2(a.eps2, a.eps2);
+    const float ext = a.frame->ext;
+    // r2 floor such that (largest node mass) * r^-3 stays finite (see eval_pair)
+    const float cb = cbrtf(fminf(a.frame->mass_bound, 3e38f)) * 2.2e-13f;
+    const float tiny = fmaxf(2.f * cb * cb, 1e-36f);
     unsigned long long c_node = 0, c_part = 0, c_test = 0;
 
     for (;;) {
@@ -536,20 +565,34 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
         const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
         const float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
 
-        float ax = 0.f, ay = 0.f, az = 0.f;
+        const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py),
+                     npz = make_float2(-pz, -pz);
+        float2 ax2 = make_float2(0.f, 0.f), ay2 = ax2, az2 = ax2;
         unsigned long long g_node = 0, g_part = 0;
-        int sp = 1;              // stack size (uniform across the warp)
-        int head = 0, fill = 0;  // interaction ring (uniform)
+        int sp = 1;    // stack size (uniform across the warp)
+        int fill = 0;  // entries in the interaction list (uniform)
         __syncwarp();
         if (lane == 0) stack[0] = 0;
         __syncwarp();
 
-        auto flush_full = [&]() {  // evaluate while at least 32 entries are ready
-            while (fill >= 32) {
+        auto flush_full = [&]() {  // evaluate the first 32 entries once they are ready
+            if (fill >= 32) {
                 __syncwarp();
-                eval_entries(ring, head, slice, slices, 32, px, py, pz, a.eps2, ax, ay, az);
-                head = (head + 32) & (LIST_CAP - 1);
+                if (slices == 1) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, tiny, ax2, ay2, az2);
+                } else {
+                    for (int q = slice; q < 16; q += slices)
+                        eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, tiny, ax2, ay2, az2);
+                }
                 fill -= 32;
+                // move the remainder (< 32 entries = <= 16 pairs = <= 32 float4) to the front
+                const bool mv = lane < ((fill + 1) >> 1) * 2;
+                float4 v;
+                if (mv) v = list4[32 + lane];
+                __syncwarp();
+                if (mv) list4[lane] = v;
                 __syncwarp();
             }
         };
@@ -588,7 +631,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
                 const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
                 const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
                 const int level = (int)(nd.nchild_level >> 8);
-                const float w = a.ext * __int_as_float((127 - level) << 23);
+                const float w = ext * __int_as_float((127 - level) << 23);
                 open = a.theta2 * d2 < w * w;
             }
             const uint32_t nc = nd.nchild_level & 0xffu;
@@ -616,8 +659,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
             {
                 const unsigned m = __ballot_sync(FULL, accept);
                 if (m) {
-                    if (accept)
-                        ring[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] = nd.cm;
+                    if (accept) list_store(list, fill + __popc(m & ((1u << lane) - 1)), nd.cm);
                     const int cnt = __popc(m);
                     if (COUNT) g_node += cnt;
                     fill += cnt;
@@ -649,8 +691,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
                     owner = min(owner, 31);
                     const uint32_t ob = __shfl_sync(FULL, nd.begin, owner);
                     const int oe = __shfl_sync(FULL, excl, owner);
-                    if (f < total)
-                        ring[(head + fill + lane) & (LIST_CAP - 1)] = __ldg(a.src + ob + (f - oe));
+                    if (f < total) list_store(list, fill + lane, __ldg(a.src + ob + (f - oe)));
                     const int cnt = min(32, total - base);
                     if (COUNT) g_part += cnt;
                     fill += cnt;
@@ -660,9 +701,13 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
             __syncwarp();
         }
         if (fill > 0) {
+            if ((fill & 1) && lane == 0) list_store(list, fill, make_float4(0.f, 0.f, 0.f, 0.f));
             __syncwarp();
-            eval_entries(ring, head, slice, slices, fill, px, py, pz, a.eps2, ax, ay, az);
+            const int pairs = (fill + 1) >> 1;
+            for (int q = slice; q < pairs; q += slices)
+                eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, tiny, ax2, ay2, az2);
         }
+        float ax = ax2.x + ax2.y, ay = ay2.x + ay2.y, az = az2.x + az2.y;
         for (int o = gpad; o < 32; o <<= 1) {  // combine the slices of each target
             ax += __shfl_xor_sync(FULL, ax, o);
             ay += __shfl_xor_sync(FULL, ay, o);
@@ -749,9 +794,12 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
     // K2: root cube + keys
     const int nb = (int)std::min<size_t>(ctx->sm_count * 8, (n + 255) / 256);
     PCUDA_CUDA_TRY(ctx, t->partial.ensure((size_t)nb * 2 * DIM * sizeof(float)));
-    PCUDA_CUDA_TRY(ctx, t->d_frame.ensure(sizeof(Frame)));
-    bbox_partial<DIM><<<nb, 256, 0, st>>>(d_particles, stride, (int)n, t->partial.as<float>());
-    frame_kernel<DIM><<<1, 32, 0, st>>>(t->partial.as<float>(), nb, t->d_frame.as<Frame>());
+    PCUDA_CUDA_TRY(ctx, t->d_frame.ensure(sizeof(Frame) + sizeof(unsigned)));
+    unsigned *d_mmax = reinterpret_cast<unsigned *>(t->d_frame.as<Frame>() + 1);
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_mmax, 0, sizeof(unsigned), st));
+    bbox_partial<DIM><<<nb, 256, 0, st>>>(d_particles, stride, (int)n, t->partial.as<float>(), d_mmax);
+    frame_kernel<DIM><<<1, 32, 0, st>>>(t->partial.as<float>(), nb, (int)n, d_mmax,
+                                        t->d_frame.as<Frame>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 2;
     // K3: sort + gather
@@ -935,7 +983,7 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
     a.counters = ctx->d_counters.as<unsigned long long>();
     a.n_tgt = n;
     a.dim = dim;
-    a.ext = t->frame.ext;
+    a.frame = t->d_frame.as<Frame>();
     a.theta2 = theta * theta;
     a.eps2 = eps * eps;
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond

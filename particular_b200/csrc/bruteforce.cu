@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     if (CLAMP == 2) {
         // smallest r2 for which max|mu| * r2^-1.5 < ~1e38:  r2 > (max|mu| * 1e-38)^(2/3)
         const float mmax = __uint_as_float(*mass_max_bits);
-        const float c = cbrtf(fminf(mmax, 3e38f) * 1e-38f);
+        const float c = cbrtf(fminf(mmax, 3e38f)) * 2.2e-13f;  // 2.2e-13 ~ cbrt(1e-38)
         tiny_r2 = fmaxf(2.f * c * c, 1e-36f);
     }
 

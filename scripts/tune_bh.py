@@ -40,10 +40,10 @@ d_out = torch.zeros((N, 3), dtype=torch.float32, device="cuda")
 idx = np.sort(np.random.default_rng(1).choice(N, 2048, replace=False))
 exact = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(pb.Between(P[idx, :3], P))
 ctx.close()
-for leaf in (8, 16, 32):
+for leaf in (8, 16):
     ctx = pb.CudaContext(0, leaf_size=leaf)
     bh = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked())
-    for seg in (32, 64, 128, 256):
+    for seg in (64, 128, 256):
         lib.pcuda_debug_set(b"bh_seg_max", seg)
         for count in (1, 0):
             lib.pcuda_debug_set(b"bh_count", count)

@@ -69,7 +69,7 @@ def parity_tolerance(n_affecting, kappa, dtype=np.float32):
     return base + 4.0 * np.sqrt(max(n_affecting, 1)) * u * np.asarray(kappa)
 
 
-def assert_bruteforce_parity(got, ref, affected, affecting, softening=0.0):
+def assert_bruteforce_parity(got, ref, affected, affecting, softening=0.0, aggregate=True):
     """GPU vs the bit-faithful restatement of sequential::BruteForce, per particle."""
     import oracle
     exact = oracle.brute_force_exact(affected, affecting, softening)
@@ -81,9 +81,12 @@ def assert_bruteforce_parity(got, ref, affected, affecting, softening=0.0):
     bad = np.flatnonzero(err > tol)
     assert len(bad) == 0, (f"{len(bad)} particles out of tolerance; worst {err[bad].max():.3e} "
                            f"(tol {tol[bad][np.argmax(err[bad])]:.3e})")
-    # and, in aggregate, the kernel is no less accurate than the reference's own fold
-    e_gpu, e_ref = rel_err(got, exact), rel_err(ref, exact)
-    assert e_gpu.max() <= max(1.25 * e_ref.max(), tol.min()), (e_gpu.max(), e_ref.max())
+    if aggregate:
+        # in aggregate the kernel is no less accurate than the reference's own fold (errors against
+        # the extended-precision sum, normalised by the condition number; 99th percentile)
+        e_gpu, e_ref = rel_err(got, exact) / kappa, rel_err(ref, exact) / kappa
+        q_gpu, q_ref = np.percentile(e_gpu, 99), np.percentile(e_ref, 99)
+        assert q_gpu <= 1.25 * q_ref + 4 * (EPS32 if tol.min() > 1e-9 else EPS64), (q_gpu, q_ref)
     return err
 
 

@@ -131,6 +131,7 @@ def cpu_bruteforce_rate(P, seconds, steps=1):
     Returns (Gpairs/s, sample description, cores, per-step seconds list)."""
     import oracle
     n = len(P)
+    oracle.use_all_cores()
     cores = oracle.baseline_threads()
     probe = min(n, 256 * cores)
     t0 = time.perf_counter()
@@ -152,6 +153,7 @@ def cpu_barneshut_rate(P, theta, seconds):
     bounded target sample; the per-evaluation time is build + traversal scaled to all targets."""
     import oracle
     n = len(P)
+    oracle.use_all_cores()
     cores = oracle.baseline_threads()
     t0 = time.perf_counter()
     tree = oracle.Tree(P)

@@ -111,6 +111,13 @@ def brute_force_simd8_parallel(affected, affecting, softening=0.0, checked=True)
     return out
 
 
+def use_all_cores() -> int:
+    """Use every host core for the OpenMP legs (torchrun sets OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_threads(C.c_int(n))
+    return n
+
+
 def baseline_threads() -> int:
     return int(lib().oracle_baseline_threads())
 

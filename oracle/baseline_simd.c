@@ -26,6 +26,15 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1; the baseline legs ask for all host cores explicitly. */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_baseline_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

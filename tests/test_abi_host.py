@@ -113,3 +113,17 @@ def test_unsupported_shapes_raise():
         pi._as_particles(np.zeros((4, 6), np.float32))
     with pytest.raises(NotImplementedError):
         pi._suffix(np.zeros((4, 3), np.float64))  # f64 2-D: no kernel, like unimplemented!()
+
+
+def test_cpp_host_api_builds_and_refuses_without_gpu():
+    """include/particular_cuda.hpp (the C++ mirror of the reference's operator interface) compiles
+    against the C ABI; without a GPU its test program stops at context creation (exit 77)."""
+    import torch
+    import __graft_entry__ as ge
+    exe = ge.build_cpp_host_test()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)
+        assert "no CPU fallback" in r.stdout

@@ -258,3 +258,14 @@ def test_full_size_properties(pb, ctx):
     bf.compute_device(None, n, d_src2.data_ptr(), n, d_out2.data_ptr())
     ctx.sync()
     assert torch.equal(d_out2, 2 * d_out)
+
+
+def test_cpp_host_api(pb, ctx):
+    """The reference's acceleration_error! / circular_orbit! tests written in C++ against
+    include/particular_cuda.hpp with a user-defined particle type (tests/cpp/test_host_api.cpp)."""
+    import subprocess
+
+    import __graft_entry__ as ge
+    r = subprocess.run([ge.build_cpp_host_test()], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all host-API checks passed" in r.stdout

@@ -65,6 +65,7 @@ struct pcuda_tree {
     size_t n = 0, n_nodes = 0;
     int n_levels = 0;
     uint32_t leaf_size = 16;
+    double nodes_per_particle = 0.5;    // capacity guess; doubled when a build overflows
     std::vector<uint32_t> level_begin;  // n_levels + 1 entries
     pcuda::bh::Frame frame = {};
     pcuda::DevBuf keys[2], perm[2], sorted, nodes, moments, d_frame, scan_in, scan_out, cub_tmp,
@@ -224,8 +225,16 @@ __global__ void __launch_bounds__(256) gather_kernel(const float *__restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4a: number of children of every node of one level (0 for leaves).  A cell splits when it
-// holds more than `nleaf` particles and is above the last level.
+// K4: level-by-level linear orthtree WITHOUT host round trips.  The level bounds live in device
+// memory (BuildState); one kernel per level is enqueued for all BITS levels up front and a kernel
+// whose level turns out empty returns at once.
+struct BuildState {
+    uint32_t level_begin[36];  // level l = nodes [level_begin[l], level_begin[l+1])
+    uint32_t ticket[34];       // tile dispenser of each level's kernel
+    uint32_t overflow;         // a level did not fit into `capacity` nodes
+    uint32_t capacity;
+};
+
 template <int DIM>
 __device__ __forceinline__ uint32_t next_digit_start(const uint64_t *__restrict__ keys, uint32_t pos,
                                                      uint32_t end, int shift) {
@@ -240,69 +249,7 @@ __device__ __forceinline__ uint32_t next_digit_start(const uint64_t *__restrict_
     return lo;
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(128) count_children(const NodeRec *__restrict__ nodes,
-                                                      const uint64_t *__restrict__ keys,
-                                                      uint32_t lvl_begin, uint32_t lvl_count,
-                                                      int level, uint32_t nleaf,
-                                                      uint32_t *__restrict__ nchild) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > lvl_count) return;
-    if (t == lvl_count) {  // sentinel so that the exclusive scan yields the total
-        nchild[t] = 0;
-        return;
-    }
-    const NodeRec nd = nodes[lvl_begin + t];
-    uint32_t c = 0;
-    if (nd.count > nleaf && level < Dims<DIM>::BITS) {
-        const int shift = DIM * (Dims<DIM>::BITS - level - 1);
-        uint32_t pos = nd.begin;
-        const uint32_t end = nd.begin + nd.count;
-        while (pos < end) {
-            pos = next_digit_start<DIM>(keys, pos, end, shift);
-            ++c;
-        }
-    }
-    nchild[t] = c;
-}
-
-// K4b: writes the children of one level's nodes at next_begin + offset (breadth-first order).
-template <int DIM>
-__global__ void __launch_bounds__(128) emit_children(NodeRec *__restrict__ nodes,
-                                                     const uint64_t *__restrict__ keys,
-                                                     uint32_t lvl_begin, uint32_t lvl_count,
-                                                     int level, const uint32_t *__restrict__ nchild,
-                                                     const uint32_t *__restrict__ offset,
-                                                     uint32_t next_begin) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= lvl_count) return;
-    const uint32_t c = nchild[t];
-    NodeRec &nd = nodes[lvl_begin + t];
-    if (c == 0) {
-        nd.first_child = 0;
-        nd.nchild_level = (uint32_t)level << 8;
-        return;
-    }
-    const uint32_t first = next_begin + offset[t];
-    nd.first_child = first;
-    nd.nchild_level = c | (uint32_t)level << 8;
-    const int shift = DIM * (Dims<DIM>::BITS - level - 1);
-    uint32_t pos = nd.begin;
-    const uint32_t end = nd.begin + nd.count;
-    for (uint32_t k = 0; k < c; ++k) {
-        const uint32_t nxt = next_digit_start<DIM>(keys, pos, end, shift);
-        NodeRec ch;
-        ch.cm = make_float4(0.f, 0.f, 0.f, 0.f);
-        ch.first_child = 0;
-        ch.nchild_level = (uint32_t)(level + 1) << 8;
-        ch.begin = pos;
-        ch.count = nxt - pos;
-        nodes[first + k] = ch;
-        pos = nxt;
-    }
-}
-
-__global__ void init_root(NodeRec *nodes, uint32_t n) {
+__global__ void init_build(NodeRec *nodes, uint32_t n, BuildState *st, uint32_t capacity) {
     NodeRec r;
     r.cm = make_float4(0.f, 0.f, 0.f, 0.f);
     r.first_child = 0;
@@ -310,6 +257,125 @@ __global__ void init_root(NodeRec *nodes, uint32_t n) {
     r.begin = 0;
     r.count = n;
     nodes[0] = r;
+    for (int i = 0; i < 36; ++i) st->level_begin[i] = i == 0 ? 0u : 1u;
+    for (int i = 0; i < 34; ++i) st->ticket[i] = 0;
+    st->overflow = 0;
+    st->capacity = capacity;
+}
+
+constexpr int EXPAND_BLOCK = 128;
+
+// One level: every node with more than `nleaf` particles (and above the last level) is split into
+// the distinct next-level digits present in its key range (binary searches); the children of the
+// level are numbered in node order — breadth-first — by a single-pass scan: tiles of 128 nodes are
+// handed out by an atomic ticket, scanned in the block and chained with decoupled look-back
+// (tile_state word = tag << 32 | value, tag = 4 (level + 1) + {1: tile aggregate, 2: inclusive}).
+template <int DIM>
+__global__ void __launch_bounds__(EXPAND_BLOCK) expand_level(NodeRec *__restrict__ nodes,
+                                                             const uint64_t *__restrict__ keys,
+                                                             BuildState *st,
+                                                             unsigned long long *tile_state,
+                                                             int level, uint32_t nleaf) {
+    constexpr int X = Dims<DIM>::X;
+    const uint32_t lvl_begin = st->level_begin[level], lvl_end = st->level_begin[level + 1];
+    const uint32_t lvl_count = lvl_end - lvl_begin;
+    if (lvl_count == 0 || st->overflow) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->level_begin[level + 2] = lvl_end;
+        return;
+    }
+    const uint32_t n_tiles = (lvl_count + EXPAND_BLOCK - 1) / EXPAND_BLOCK;
+    const uint32_t capacity = st->capacity;
+    const int shift = DIM * (Dims<DIM>::BITS - level - 1);
+    typedef cub::BlockScan<uint32_t, EXPAND_BLOCK> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ uint32_t s_tile, s_prefix;
+    const unsigned long long tag = (unsigned long long)(level + 1) * 4;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[level], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const uint32_t t = tile * EXPAND_BLOCK + threadIdx.x;
+        uint32_t c = 0, cb[X + 1];
+        if (t < lvl_count) {
+            const uint32_t begin = nodes[lvl_begin + t].begin, count = nodes[lvl_begin + t].count;
+            if (count > nleaf && level < Dims<DIM>::BITS) {
+                uint32_t pos = begin;
+                const uint32_t end = begin + count;
+#pragma unroll
+                for (int k = 0; k < X; ++k) {
+                    if (pos < end) {
+                        cb[k] = pos;
+                        pos = next_digit_start<DIM>(keys, pos, end, shift);
+                        ++c;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k <= X; ++k)
+                    if (k == (int)c) cb[k] = end;
+            }
+        }
+        uint32_t off, total;
+        Scan(scan_tmp).ExclusiveSum(c, off, total);
+        if (threadIdx.x == 0) {
+            uint32_t excl = 0;
+            volatile unsigned long long *ts = tile_state;
+            if (tile > 0) {
+                ts[tile] = (tag + 1) << 32 | total;
+                __threadfence();
+                int p = (int)tile - 1;
+                for (;;) {
+                    const unsigned long long w = ts[p];
+                    const unsigned long long wt = w >> 32;
+                    if (wt == tag + 2) {
+                        excl += (uint32_t)w;
+                        break;
+                    }
+                    if (wt == tag + 1) {
+                        excl += (uint32_t)w;
+                        --p;
+                    }
+                }
+            }
+            ts[tile] = (tag + 2) << 32 | (excl + total);
+            __threadfence();
+            s_prefix = excl;
+            if (tile == n_tiles - 1) {
+                const unsigned long long next_end = (unsigned long long)lvl_end + excl + total;
+                if (next_end > capacity) {
+                    st->overflow = 1;
+                    st->level_begin[level + 2] = lvl_end;
+                } else {
+                    st->level_begin[level + 2] = (uint32_t)next_end;
+                }
+            }
+        }
+        __syncthreads();
+        if (t < lvl_count) {
+            NodeRec &nd = nodes[lvl_begin + t];
+            const unsigned long long first = (unsigned long long)lvl_end + s_prefix + off;
+            if (c == 0 || first + c > capacity) {
+                nd.first_child = 0;
+                nd.nchild_level = (uint32_t)level << 8;
+            } else {
+                nd.first_child = (uint32_t)first;
+                nd.nchild_level = c | (uint32_t)level << 8;
+#pragma unroll
+                for (int k = 0; k < X; ++k) {
+                    if (k < (int)c) {
+                        NodeRec ch;
+                        ch.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+                        ch.first_child = 0;
+                        ch.nchild_level = (uint32_t)(level + 1) << 8;
+                        ch.begin = cb[k];
+                        ch.count = cb[k + 1] - cb[k];
+                        nodes[first + k] = ch;
+                    }
+                }
+            }
+        }
+    }
 }
 
 // K4c: moments of one level, deepest level first.  Double precision, fixed order, unfused
@@ -321,43 +387,46 @@ template <int DIM>
 __global__ void __launch_bounds__(128) moments_kernel(NodeRec *__restrict__ nodes,
                                                       double *__restrict__ mom,
                                                       const float4 *__restrict__ sorted,
-                                                      uint32_t lvl_begin, uint32_t lvl_count) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= lvl_count) return;
-    const uint32_t j = lvl_begin + t;
-    NodeRec nd = nodes[j];
-    const uint32_t nc = nd.nchild_level & 0xffu;
-    double m[4] = {0.0, 0.0, 0.0, 0.0};  // x, y, z, M
-    if (nc == 0) {
-        for (uint32_t i = nd.begin; i < nd.begin + nd.count; ++i) {
-            const float4 p = sorted[i];
-            const double mi = (double)p.w;
-            m[0] = __dadd_rn(m[0], __dmul_rn(mi, (double)p.x));
-            m[1] = __dadd_rn(m[1], __dmul_rn(mi, (double)p.y));
-            if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(mi, (double)p.z));
-            m[3] = __dadd_rn(m[3], mi);
+                                                      const BuildState *__restrict__ st, int level) {
+    const uint32_t lvl_begin = st->level_begin[level];
+    const uint32_t lvl_count = st->level_begin[level + 1] - lvl_begin;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < lvl_count;
+         t += gridDim.x * blockDim.x) {
+        const uint32_t j = lvl_begin + t;
+        NodeRec nd = nodes[j];
+        const uint32_t nc = nd.nchild_level & 0xffu;
+        double m[4] = {0.0, 0.0, 0.0, 0.0};  // x, y, z, M
+        if (nc == 0) {
+            for (uint32_t i = nd.begin; i < nd.begin + nd.count; ++i) {
+                const float4 p = sorted[i];
+                const double mi = (double)p.w;
+                m[0] = __dadd_rn(m[0], __dmul_rn(mi, (double)p.x));
+                m[1] = __dadd_rn(m[1], __dmul_rn(mi, (double)p.y));
+                if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(mi, (double)p.z));
+                m[3] = __dadd_rn(m[3], mi);
+            }
+        } else {
+            for (uint32_t c = nd.first_child; c < nd.first_child + nc; ++c) {
+                const double4 q = reinterpret_cast<const double4 *>(mom)[c];
+                m[0] = __dadd_rn(m[0], q.x);
+                m[1] = __dadd_rn(m[1], q.y);
+                if (DIM == 3) m[2] = __dadd_rn(m[2], q.z);
+                m[3] = __dadd_rn(m[3], q.w);
+            }
         }
-    } else {
-        for (uint32_t c = nd.first_child; c < nd.first_child + nc; ++c) {
-            const double4 q = reinterpret_cast<const double4 *>(mom)[c];
-            m[0] = __dadd_rn(m[0], q.x);
-            m[1] = __dadd_rn(m[1], q.y);
-            if (DIM == 3) m[2] = __dadd_rn(m[2], q.z);
-            m[3] = __dadd_rn(m[3], q.w);
+        reinterpret_cast<double4 *>(mom)[j] = make_double4(m[0], m[1], m[2], m[3]);
+        float4 cm;
+        if (m[3] == 0.0) {
+            const float4 p = sorted[nd.begin];
+            cm = make_float4(p.x, p.y, DIM == 3 ? p.z : 0.f, 0.f);
+        } else {
+            cm.x = (float)__ddiv_rn(m[0], m[3]);
+            cm.y = (float)__ddiv_rn(m[1], m[3]);
+            cm.z = DIM == 3 ? (float)__ddiv_rn(m[2], m[3]) : 0.f;
+            cm.w = (float)m[3];
         }
+        nodes[j].cm = cm;
     }
-    reinterpret_cast<double4 *>(mom)[j] = make_double4(m[0], m[1], m[2], m[3]);
-    float4 cm;
-    if (m[3] == 0.0) {
-        const float4 p = sorted[nd.begin];
-        cm = make_float4(p.x, p.y, DIM == 3 ? p.z : 0.f, 0.f);
-    } else {
-        cm.x = (float)__ddiv_rn(m[0], m[3]);
-        cm.y = (float)__ddiv_rn(m[1], m[3]);
-        cm.z = DIM == 3 ? (float)__ddiv_rn(m[2], m[3]) : 0.f;
-        cm.w = (float)m[3];
-    }
-    nodes[j].cm = cm;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -734,22 +803,6 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
 
 // ------------------------------------------------------------------------------------------------
 // Host side.
-static cudaError_t grow_keep(DevBuf &b, size_t bytes, size_t keep, cudaStream_t stream) {
-    if (bytes <= b.cap) return cudaSuccess;
-    void *np = nullptr;
-    const size_t want = bytes + bytes / 2 + 256;
-    cudaError_t e = cudaMalloc(&np, want);
-    if (e != cudaSuccess) return e;
-    if (b.p && keep) {
-        e = cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    }
-    if (b.p) cudaFree(b.p);
-    b.p = np;
-    b.cap = want;
-    return e;
-}
-
 template <int DIM>
 static int sort_by_key(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n, const Frame *d_frame,
                        DevBuf keys[2], DevBuf perm[2], int *cur, DevBuf &cub_tmp) {
@@ -810,83 +863,51 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
         d_particles, stride, true, (int)n, t->d_perm(), t->sorted.as<float4>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
-    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(&t->frame, t->d_frame.p, sizeof(Frame), cudaMemcpyDeviceToHost, st));
 
-    // K4: level-by-level linear orthtree
-    size_t cap_nodes = std::max<size_t>(1024, n / 2 + 64);
-    PCUDA_CUDA_TRY(ctx, t->nodes.ensure(cap_nodes * sizeof(NodeRec)));
-    cap_nodes = t->nodes.cap / sizeof(NodeRec);
-    init_root<<<1, 1, 0, st>>>(t->nodes.as<NodeRec>(), (uint32_t)n);
-    ctx->launches++;
-    t->level_begin.push_back(0);
-    uint32_t lvl_begin = 0, lvl_count = 1;
-    size_t total = 1;
-    uint32_t *h_total = nullptr;
-    PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&h_total, sizeof(uint32_t), cudaHostAllocDefault));
-    int status = PCUDA_OK;
-    for (int level = 0;; ++level) {
-        const size_t m = lvl_count;
-        cudaError_t e = t->scan_in.ensure((m + 1) * 4);
-        if (e == cudaSuccess) e = t->scan_out.ensure((m + 1) * 4);
-        size_t tmp = 0;
-        if (e == cudaSuccess)
-            e = cub::DeviceScan::ExclusiveSum(nullptr, tmp, t->scan_in.as<uint32_t>(),
-                                              t->scan_out.as<uint32_t>(), (int)(m + 1), st);
-        if (e == cudaSuccess) e = t->cub_tmp.ensure(tmp);
-        if (e != cudaSuccess) {
-            status = fail(ctx, PCUDA_ERR_CUDA, "tree level scratch: %s", cudaGetErrorString(e));
-            break;
+    // K4: level-by-level linear orthtree, all levels enqueued without host round trips; one
+    // read-back of the level table at the end.  If the node capacity guess was too small the
+    // build is repeated with the capacity it asked for (grow-only, so this happens at most once
+    // per size class).
+    for (int attempt = 0;; ++attempt) {
+        size_t cap_nodes = std::max<size_t>(4096, (size_t)((double)n * t->nodes_per_particle) + 1024);
+        PCUDA_CUDA_TRY(ctx, t->nodes.ensure(cap_nodes * sizeof(NodeRec)));
+        cap_nodes = std::min<size_t>(t->nodes.cap / sizeof(NodeRec), 0xfffffff0ull);
+        PCUDA_CUDA_TRY(ctx, t->moments.ensure(cap_nodes * 4 * sizeof(double)));
+        const size_t max_tiles = (cap_nodes + EXPAND_BLOCK - 1) / EXPAND_BLOCK + 1;
+        PCUDA_CUDA_TRY(ctx, t->scan_in.ensure(sizeof(BuildState)));
+        PCUDA_CUDA_TRY(ctx, t->scan_out.ensure(max_tiles * sizeof(unsigned long long)));
+        BuildState *d_state = t->scan_in.as<BuildState>();
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(t->scan_out.p, 0, max_tiles * sizeof(unsigned long long), st));
+        init_build<<<1, 1, 0, st>>>(t->nodes.as<NodeRec>(), (uint32_t)n, d_state, (uint32_t)cap_nodes);
+        const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, max_tiles);
+        for (int level = 0; level <= BITS; ++level)
+            expand_level<DIM><<<grid, EXPAND_BLOCK, 0, st>>>(
+                t->nodes.as<NodeRec>(), t->d_keys(), d_state,
+                t->scan_out.as<unsigned long long>(), level, t->leaf_size);
+        const unsigned mgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (cap_nodes + 127) / 128);
+        for (int level = BITS; level >= 0; --level)
+            moments_kernel<DIM><<<mgrid, 128, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(),
+                                                       t->sorted.as<float4>(), d_state, level);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 1 + 2 * (BITS + 1);
+        BuildState h;
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(&t->frame, t->d_frame.p, sizeof(Frame), cudaMemcpyDeviceToHost, st));
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(&h, d_state, sizeof h, cudaMemcpyDeviceToHost, st));
+        PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (h.overflow) {
+            if (attempt >= 8 || cap_nodes >= 0xfffffff0ull)
+                return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "tree does not fit into %zu nodes", cap_nodes);
+            t->nodes_per_particle = std::max(2.0 * t->nodes_per_particle, 2.0 * (double)cap_nodes / (double)n);
+            continue;
         }
-        count_children<DIM><<<(unsigned)((m + 1 + 127) / 128), 128, 0, st>>>(
-            t->nodes.as<NodeRec>(), t->d_keys(), lvl_begin, lvl_count, level, t->leaf_size,
-            t->scan_in.as<uint32_t>());
-        cub::DeviceScan::ExclusiveSum(t->cub_tmp.p, tmp, t->scan_in.as<uint32_t>(),
-                                      t->scan_out.as<uint32_t>(), (int)(m + 1), st);
-        cudaMemcpyAsync(h_total, t->scan_out.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st);
-        e = cudaStreamSynchronize(st);
-        ctx->launches += 3;
-        if (e != cudaSuccess) {
-            status = fail(ctx, PCUDA_ERR_CUDA, "tree level %d: %s", level, cudaGetErrorString(e));
-            break;
-        }
-        const uint32_t children = *h_total;
-        if (total + children > 0xfffffff0ull) {
-            status = fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "more than 2^32 tree nodes");
-            break;
-        }
-        if (children) {
-            e = grow_keep(t->nodes, (total + children) * sizeof(NodeRec), total * sizeof(NodeRec), st);
-            if (e != cudaSuccess) {
-                status = fail(ctx, e == cudaErrorMemoryAllocation ? PCUDA_ERR_OUT_OF_MEMORY : PCUDA_ERR_CUDA,
-                              "tree node storage: %s", cudaGetErrorString(e));
-                break;
-            }
-        }
-        emit_children<DIM><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
-            t->nodes.as<NodeRec>(), t->d_keys(), lvl_begin, lvl_count, level,
-            t->scan_in.as<uint32_t>(), t->scan_out.as<uint32_t>(), (uint32_t)total);
-        ctx->launches++;
-        t->level_begin.push_back((uint32_t)total);
-        if (children == 0) break;
-        lvl_begin = (uint32_t)total;
-        lvl_count = children;
-        total += children;
+        t->level_begin.clear();
+        int levels = 0;
+        while (levels <= BITS && h.level_begin[levels + 1] > h.level_begin[levels]) ++levels;
+        for (int l = 0; l <= levels; ++l) t->level_begin.push_back(h.level_begin[l]);
+        t->n_levels = levels;
+        t->n_nodes = h.level_begin[levels];
+        break;
     }
-    cudaFreeHost(h_total);
-    if (status != PCUDA_OK) return status;
-    t->n_nodes = total;
-    t->n_levels = (int)t->level_begin.size() - 1;
-
-    // K4c: centre of mass, deepest level first
-    PCUDA_CUDA_TRY(ctx, t->moments.ensure(total * 4 * sizeof(double)));
-    for (int l = t->n_levels - 1; l >= 0; --l) {
-        const uint32_t b = t->level_begin[l], c = t->level_begin[l + 1] - b;
-        moments_kernel<DIM><<<(c + 127) / 128, 128, 0, st>>>(t->nodes.as<NodeRec>(),
-                                                              t->moments.as<double>(),
-                                                              t->sorted.as<float4>(), b, c);
-        ctx->launches++;
-    }
-    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     return PCUDA_OK;
 }
 

@@ -253,7 +253,9 @@ def barneshut_config(n, world, theta, where):
                         f"r<50a, equal mu=1/N, seed {SEED}); tree rebuilt every step "
                         f"(BASELINE configs[3]); Acceleration::checked()",
             "n_particles": n, "theta": theta,
-            "parallelism": f"{world} GPU(s)" if where == "gpu" else "host threads over targets",
+            "parallelism": (f"{world} GPU(s): particles all-gathered (NCCL), tree build replicated, "
+                            f"targets sharded" if world > 1 else "1 GPU") if where == "gpu"
+            else "host threads over targets",
             "l2": "inputs + tree exceed L2 at N=10M; 256 MiB buffer written between timed steps"
             if where == "gpu" else "n/a"}
 
@@ -398,17 +400,28 @@ def bench_bruteforce(args, n, rank, world, local_rank):
     return 0
 
 
-def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_seconds):
-    """Single-GPU Barnes-Hut: device-resident particles/s (build + traversal every step), e2e
-    through the host API, HBM roofline of the traversal, CPU restatement beside it."""
+def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_seconds, rank=0,
+                      world=1, dist=None):
+    """Barnes-Hut: device-resident particles/s (tree rebuilt + traversal every step), e2e through
+    the host API, work counters, CPU restatement beside it.  world > 1: every rank owns a block of
+    the particles, all-gathers the records, builds the identical tree and traverses its block."""
     import torch
 
     import particular_b200 as pb
     P = plummer_cloud(n)
     dev = torch.device("cuda", ctx.device)
-    bh = pb.BarnesHut(ctx, theta, pb.Acceleration.checked())
-    d_src = torch.from_numpy(P).to(dev)
-    d_out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    inter = pb.Acceleration.checked()
+    lo, hi = pb.shard_bounds(n, world, rank)
+    n_local = hi - lo
+    if world == 1:
+        bh = pb.BarnesHut(ctx, theta, inter)
+        d_src = torch.from_numpy(P).to(dev)
+        d_out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        dev_step = lambda: bh.compute_device(None, n, d_src.data_ptr(), n, d_out.data_ptr())  # noqa: E731
+    else:
+        bh = pb.ShardedBarnesHut(ctx, theta, inter)
+        d_src = torch.from_numpy(P[lo:hi]).to(dev)
+        dev_step = lambda: bh.step_device(d_src, n)  # noqa: E731
 
     def run(step_fn, k):
         times, tm, launches = [], [], 0
@@ -426,38 +439,53 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
             launches += t["kernel_launches"]
         return times, tm, launches
 
-    dev_step = lambda: bh.compute_device(None, n, d_src.data_ptr(), n, d_out.data_ptr())  # noqa: E731
     for _ in range(warmup):
         dev_step()
     ctx.sync()
+    if dist is not None:
+        _barrier(world, dist)
     times, tm, launches = run(dev_step, steps)
-    ms = sum(times) / len(times)
+    if dist is not None:
+        _barrier(world, dist)
+    ms = _max_over_ranks(sum(times), world, dist) / steps if dist is not None else sum(times) / steps
     build_ms = sum(t["build_ms"] for t in tm) / len(tm)
     trav_ms = sum(t["compute_ms"] for t in tm) / len(tm)
-    counters = bh.last_counters()
-    h_in = ctx.pinned_empty((n, 4), np.float32)
-    h_in[:] = P
-    h_out = ctx.pinned_empty((n, 3), np.float32)
-    e2e_step = lambda: bh.compute(h_in, out=h_out)  # noqa: E731
+    comm_ms = sum(t["comm_ms"] for t in tm) / len(tm)
+    plain = pb.BarnesHut(ctx, theta, inter)
+    counters = plain.last_counters()
+    h_in = ctx.pinned_empty((n_local, 4), np.float32)
+    h_in[:] = P[lo:hi]
+    h_out = ctx.pinned_empty((n_local, 3), np.float32)
+    if world == 1:
+        e2e_step = lambda: bh.compute(h_in, out=h_out)  # noqa: E731
+    else:
+        e2e_step = lambda: bh.compute_local(h_in, n, out=h_out)  # noqa: E731
     e2e_step()
+    if dist is not None:
+        _barrier(world, dist)
     e2e_times, _, _ = run(e2e_step, steps)
-    e2e_ms = sum(e2e_times) / len(e2e_times)
-    inter = counters["node_interactions"] + counters["particle_interactions"]
+    if dist is not None:
+        _barrier(world, dist)
+    e2e_ms = (_max_over_ranks(sum(e2e_times), world, dist) if dist is not None else sum(e2e_times)) / steps
+    inter_n = counters["node_interactions"] + counters["particle_interactions"]
+    total_launches = int(_sum_over_ranks(launches, world, dist)) if dist is not None else launches
     out = {"metric": "Barnes-Hut particles per second (build + traversal)",
            "value": n / (ms * 1e-3), "unit": "particles/s", "ms_per_step": ms,
-           "build_ms": build_ms, "traverse_ms": trav_ms, "steps": steps, "warmup": warmup,
-           "config": barneshut_config(n, 1, theta, "gpu"),
+           "comm_ms": comm_ms, "build_ms": build_ms, "traverse_ms": trav_ms, "steps": steps,
+           "warmup": warmup, "config": barneshut_config(n, world, theta, "gpu"),
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 12},
-           "gpu_launches": launches, "counters_last_step": counters,
-           "traversal_fp32": {"achieved": FLOP_PER_PAIR * inter / (trav_ms * 1e-3) / 1e12,
-                              "unit": "TFLOP/s", "interactions_per_target": inter / n}}
-    if not args.no_extra:
+                   "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 12,
+                   "bytes_are": "per rank"},
+           "gpu_launches": total_launches, "counters_last_step_rank0": counters,
+           "traversal_fp32": {"achieved": FLOP_PER_PAIR * inter_n / (trav_ms * 1e-3) / 1e12,
+                              "unit": "TFLOP/s", "interactions_per_target": inter_n / max(n_local, 1),
+                              "note": "20 flop per accepted interaction, this rank's targets"}}
+    if not args.no_extra and rank == 0 and world == 1:
         rate, sample, cores, tb, tt = cpu_barneshut_rate(P, theta, cpu_seconds)
         out["cpu_baseline"] = {"value": rate, "unit": "particles/s", "cores": cores, "kind": "port",
                                "sample": sample + "; restated parallel::BarnesHut",
                                "build_s": tb, "traverse_s": tt}
-    del d_src, d_out
+    del d_src
     return out
 
 
@@ -471,25 +499,25 @@ def bench_barneshut(args, n, rank, world, local_rank):
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local_rank)
-    if world > 1:
-        raise SystemExit("multi-GPU Barnes-Hut is not wired into bench.py yet")
     sampler.start()
     res = barneshut_numbers(args, ctx, stream, flush, n, args.theta, args.steps, args.warmup,
-                            args.cpu_seconds)
+                            args.cpu_seconds, rank, world, dist)
     sampler.stop()
     line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": res["config"], "e2e": res["e2e"],
             "gpu_launches": res["gpu_launches"], "clocks": sampler.summary(), "device": ctx.name,
-            "build_ms": res["build_ms"], "traverse_ms": res["traverse_ms"],
-            "counters_last_step": res["counters_last_step"],
+            "comm_ms": res["comm_ms"], "build_ms": res["build_ms"], "traverse_ms": res["traverse_ms"],
+            "counters_last_step_rank0": res["counters_last_step_rank0"],
             "traversal_fp32": res["traversal_fp32"]}
     if "cpu_baseline" in res:
         line["cpu_baseline"] = res["cpu_baseline"]
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

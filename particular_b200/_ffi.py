@@ -94,6 +94,8 @@ SIGNATURES = {
     "pcuda_comm_allgather_dev": (_i, [_vp, _vp, _vp, _sz]),
     "pcuda_bruteforce_f32x3_sharded": (_i, [_vp, _vp, _sz, _sz, _f, _i, _vp]),
     "pcuda_bruteforce_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _i, _vp, _vp]),
+    "pcuda_barneshut_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp, _vp]),
+    "pcuda_barneshut_f32x3_sharded": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp]),
     # not in the stable header: measurement / tuning hooks
     "pcuda_probe_fp32": (_i, [_vp, _i, _i, _i, C.POINTER(_d), C.POINTER(_f)]),
     "pcuda_debug_set": (_i, [C.c_char_p, _i]),

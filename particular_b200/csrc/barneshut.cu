@@ -501,9 +501,10 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_flags(const uint8_t *__rest
         while (se < n && se - ss <= T && !sH[se - h0]) ++se;
         const int len = se - ss;
         if (len <= T) {
-            const int chunks = (len + 31) / 32;
-            const int cs = (len + chunks - 1) / chunks;
-            start = (i - ss) % cs == 0;
+            // full groups of 32 first; the remainder forms one small group whose lanes are
+            // shared out over the interaction list (see traverse_kernel), which wastes fewer
+            // lanes than equal chunks of e.g. 20 + 20
+            start = ((i - ss) & 31) == 0;
         } else {
             start = i == ss || (i & 31) == 0;  // the head of a long run of identical keys
         }
@@ -709,19 +710,36 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
             const bool accept = has && !open && nd.cm.w != 0.f;
             if (COUNT) c_test += k;
 
-            // push the children of opened internal nodes (warp scan of the child counts)
+            // one warp scan serves both the children to push (low 10 bits, <= 256 in total) and
+            // the particles of opened leaves (high 22 bits); a leaf too large for the packing
+            // (only possible at the last level, many identical keys) takes a second scan
+            const int c_child = open_internal ? (int)nc : 0;
+            const int c_leaf = open_leaf ? (int)nd.count : 0;
+            const bool wide = __any_sync(FULL, c_leaf > 65535);
+            int leaf_incl;
             {
-                const int c = open_internal ? (int)nc : 0;
-                int incl = c;
+                unsigned packed = (unsigned)c_child | (wide ? 0u : (unsigned)c_leaf << 10);
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
+                    const unsigned v = __shfl_up_sync(FULL, packed, o);
+                    if (lane >= o) packed += v;
                 }
+                const int incl = (int)(packed & 1023u);
+                leaf_incl = (int)(packed >> 10);
                 const int total = __shfl_sync(FULL, incl, 31);
-                const int base = sp + incl - c;
-                for (int j = 0; j < c; ++j) stack[base + j] = nd.first_child + j;
+                const int base = sp + incl - c_child;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < c_child) stack[base + j] = nd.first_child + j;
                 sp += total;
+            }
+            if (wide) {
+                leaf_incl = c_leaf;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, leaf_incl, o);
+                    if (lane >= o) leaf_incl += v;
+                }
             }
 
             // accepted nodes -> interaction ring
@@ -740,15 +758,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
             // round finds the leaf that owns flat index f by a shuffle binary search over the
             // inclusive scan of the leaf sizes, so every round is one coalesced-per-leaf load
             {
-                const int c = open_leaf ? (int)nd.count : 0;
-                int incl = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
+                const int incl = leaf_incl;
                 const int total = __shfl_sync(FULL, incl, 31);
-                const int excl = incl - c;
+                const int excl = incl - c_leaf;
                 for (int base = 0; base < total; base += 32) {
                     const int f = base + lane;
                     int owner = 0;
@@ -921,9 +933,11 @@ static bool g_count = true;  // instrumentation of the traversal (pcuda_tree_las
 static int g_seg_max = 128;  // largest cell (in targets) that is cut into groups (tuning hook)
 
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
+// tgt_stride: floats per target row (0 = bare positions, i.e. `dim`).
 static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na, float theta,
-                    float eps, float *d_out) {
+                    float eps, float *d_out, int tgt_stride = 0) {
     const int dim = t->dim;
+    const int ts = tgt_stride ? tgt_stride : dim;
     if (na == 0) return PCUDA_OK;
     if (t->n == 0) {
         PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * dim * sizeof(float), ctx->stream));
@@ -945,8 +959,8 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         DevBuf keys[2] = {ctx->d_tgt_keys, ctx->d_tgt_keys_alt};
         DevBuf perm[2] = {ctx->d_tgt_perm, ctx->d_tgt_perm_alt};
         int cur = 0;
-        int s = dim == 3 ? sort_by_key<3>(ctx, d_tgt, 3, na, t->d_frame.as<Frame>(), keys, perm, &cur, ctx->d_cub_tmp)
-                         : sort_by_key<2>(ctx, d_tgt, 2, na, t->d_frame.as<Frame>(), keys, perm, &cur, ctx->d_cub_tmp);
+        int s = dim == 3 ? sort_by_key<3>(ctx, d_tgt, ts, na, t->d_frame.as<Frame>(), keys, perm, &cur, ctx->d_cub_tmp)
+                         : sort_by_key<2>(ctx, d_tgt, ts, na, t->d_frame.as<Frame>(), keys, perm, &cur, ctx->d_cub_tmp);
         ctx->d_tgt_keys = keys[0];
         ctx->d_tgt_keys_alt = keys[1];
         ctx->d_tgt_perm = perm[0];
@@ -955,10 +969,10 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         PCUDA_CUDA_TRY(ctx, ctx->d_tgt_sorted.ensure(na * sizeof(float4)));
         const uint32_t *p = perm[cur].as<uint32_t>();
         if (dim == 3)
-            gather_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, 3, false, (int)na, p,
+            gather_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, ts, false, (int)na, p,
                                                                            ctx->d_tgt_sorted.as<float4>());
         else
-            gather_kernel<2><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, 2, false, (int)na, p,
+            gather_kernel<2><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, ts, false, (int)na, p,
                                                                            ctx->d_tgt_sorted.as<float4>());
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
@@ -1040,6 +1054,37 @@ static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t 
     phase_end(ctx, PH_BUILD);
     phase_begin(ctx, PH_COMPUTE);
     PCUDA_TRY(traverse(ctx, ctx->call_tree, d_aff, na, theta, eps, d_out));
+    phase_end(ctx, PH_COMPUTE);
+    return PCUDA_OK;
+}
+
+// Multi-GPU step (one process per GPU), "replicated build": every rank owns the contiguous block
+// [rank * cap, rank * cap + n_local) of the n_total particles (cap = ceil(n_total / world)).  The
+// local records are all-gathered in place over NVLink, every GPU builds the identical tree over
+// all n_total particles, and only the local block is traversed.
+static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total,
+                       float theta, float eps, float *d_gathered, float *d_out) {
+    int world = 1, rank = 0;
+    nccl_world(ctx, &world, &rank);
+    const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
+    const size_t lo = std::min(n_total, (size_t)rank * cap), hi = std::min(n_total, lo + cap);
+    if (n_local != hi - lo)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
+                    "rank %d of %d must own %zu of %zu particles (contiguous blocks of %zu), got %zu",
+                    rank, world, hi - lo, n_total, cap, n_local);
+    float *slot = d_gathered + (size_t)rank * cap * 4;
+    phase_begin(ctx, PH_COMM);
+    if (n_local)
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(slot, d_local, n_local * 16, cudaMemcpyDeviceToDevice,
+                                            ctx->stream));
+    if (world > 1) PCUDA_TRY(pcuda_comm_allgather_dev(ctx, slot, d_gathered, cap * 16));
+    phase_end(ctx, PH_COMM);
+    if (!ctx->call_tree) ctx->call_tree = new pcuda_tree();
+    phase_begin(ctx, PH_BUILD);
+    PCUDA_TRY(build_dim(ctx, ctx->call_tree, 3, d_gathered, n_total));
+    phase_end(ctx, PH_BUILD);
+    phase_begin(ctx, PH_COMPUTE);
+    PCUDA_TRY(traverse(ctx, ctx->call_tree, slot, n_local, theta, eps, d_out, 4));
     phase_end(ctx, PH_COMPUTE);
     return PCUDA_OK;
 }
@@ -1140,6 +1185,50 @@ int pcuda_barneshut_f32x2_dev(pcuda_ctx *ctx, const float *d_aff, size_t na, con
                               size_t nb, float theta, float softening, int checked, float *d_out) {
     (void)checked;
     return bh_dev(ctx, 2, d_aff, na, d_src, nb, theta, softening, d_out);
+}
+
+int pcuda_barneshut_f32x3_sharded_dev(pcuda_ctx *ctx, const float *d_local_xyzm, size_t n_local,
+                                      size_t n_total, float theta, float softening, int checked,
+                                      float *d_gathered_xyzm, float *d_out_xyz) {
+    (void)checked;
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    int s = bh::sharded_dev(ctx, d_local_xyzm, n_local, n_total, theta, softening, d_gathered_xyzm,
+                            d_out_xyz);
+    ctx->timings.kernel_launches = ctx->launches;
+    return s;
+}
+
+int pcuda_barneshut_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_t n_local,
+                                  size_t n_total, float theta, float softening, int checked,
+                                  float *out_xyz) {
+    (void)checked;
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n_local && (!local_xyzm || !out_xyz))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    int world = 1, rank = 0;
+    nccl_world(ctx, &world, &rank);
+    const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
+    phase_begin(ctx, PH_UPLOAD);
+    PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(cap * 16));
+    PCUDA_CUDA_TRY(ctx, ctx->d_packed_src.ensure((size_t)world * cap * 16));
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(cap * 12));
+    if (n_local)
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_affecting.p, local_xyzm, n_local * 16,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+    phase_end(ctx, PH_UPLOAD);
+    PCUDA_TRY(bh::sharded_dev(ctx, ctx->d_affecting.as<float>(), n_local, n_total, theta, softening,
+                              ctx->d_packed_src.as<float>(), ctx->d_out.as<float>()));
+    phase_begin(ctx, PH_DOWNLOAD);
+    if (n_local)
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out_xyz, ctx->d_out.p, n_local * 12, cudaMemcpyDeviceToHost,
+                                            ctx->stream));
+    phase_end(ctx, PH_DOWNLOAD);
+    PCUDA_TRY(timings_collect(ctx));
+    return bh::read_counters(ctx);
 }
 
 int pcuda_tree_build_f32(pcuda_ctx *ctx, uint32_t dim, const float *affecting, size_t n,

@@ -1,4 +1,5 @@
-"""Multi-GPU brute force: one process per GPU, targets sharded, sources all-gathered over NVLink.
+"""Multi-GPU brute force and Barnes-Hut: one process per GPU, targets sharded, sources all-gathered
+over NVLink (Barnes-Hut: every GPU then builds the identical tree — "replicated build").
 
 New functionality (the reference is single-device).  Each rank owns a
 contiguous block of the particle slice (input order is preserved, so concatenating the ranks'
@@ -18,7 +19,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "shard_capacity", "ShardedBruteForce"]
+__all__ = ["shard_bounds", "shard_capacity", "ShardedBruteForce", "ShardedBarnesHut"]
 
 
 def shard_capacity(n: int, world: int) -> int:
@@ -108,3 +109,44 @@ class ShardedBruteForce:
         parts = [None] * self.world
         self.dist.all_gather_object(parts, local, group=self.group)
         return np.concatenate(parts, axis=0)
+
+
+class ShardedBarnesHut(ShardedBruteForce):
+    """``ShardedBarnesHut(ctx, theta, interaction).compute(particles)``: the multi-GPU counterpart
+    of ``BarnesHut(ctx, theta, interaction).compute(particles)`` for the ``&[P]`` storage.  Every
+    rank all-gathers the particle records, builds the identical tree over all of them (replicated
+    build) and traverses it for its own contiguous block of targets.  f32 3-D."""
+
+    def __init__(self, ctx, theta: float, interaction, group=None, init_comm: bool = True):
+        super().__init__(ctx, interaction, group, init_comm)
+        self.theta = float(theta)
+
+    def step_device(self, local, n_total: int):
+        import torch
+        from ._ffi import check, lib
+        cap = shard_capacity(n_total, self.world)
+        n_local = int(local.shape[0])
+        if self._gathered is None or self._gathered.shape[0] < self.world * cap:
+            self._gathered = torch.empty((self.world * cap, 4), dtype=torch.float32,
+                                         device=local.device)
+        if self._out is None or self._out.shape[0] < max(n_local, 1):
+            self._out = torch.empty((max(n_local, 1), 3), dtype=torch.float32, device=local.device)
+        it = self.interaction
+        check(lib.pcuda_barneshut_f32x3_sharded_dev(
+            self.ctx.handle, local.data_ptr(), n_local, n_total, self.theta, it.softening,
+            int(it.is_checked), self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
+        return self._out[:n_local]
+
+    def compute_local(self, local_records: np.ndarray, n_total: int,
+                      out: Optional[np.ndarray] = None) -> np.ndarray:
+        import ctypes as C
+
+        from ._ffi import check, lib
+        it = self.interaction
+        if out is None:
+            out = np.zeros((len(local_records), 3), dtype=np.float32)
+        check(lib.pcuda_barneshut_f32x3_sharded(
+            self.ctx.handle, local_records.ctypes.data_as(C.c_void_p), len(local_records), n_total,
+            self.theta, it.softening, int(it.is_checked), out.ctypes.data_as(C.c_void_p)),
+            self.ctx.handle)
+        return out

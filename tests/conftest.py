@@ -86,7 +86,10 @@ def assert_bruteforce_parity(got, ref, affected, affecting, softening=0.0, aggre
         # the extended-precision sum, normalised by the condition number; 99th percentile)
         e_gpu, e_ref = rel_err(got, exact) / kappa, rel_err(ref, exact) / kappa
         q_gpu, q_ref = np.percentile(e_gpu, 99), np.percentile(e_ref, 99)
-        assert q_gpu <= 1.25 * q_ref + 4 * (EPS32 if tol.min() > 1e-9 else EPS64), (q_gpu, q_ref)
+        # additive slack = the per-term error of the kernel itself: MUFU.RSQ is accurate to
+        # 2^-22.9 (PTX ISA, rsqrt.approx.f32) and enters cubed => ~4e-7; f64 rsqrt <= 1 ulp
+        slack = 6e-7 if tol.min() > 1e-9 else 16 * EPS64
+        assert q_gpu <= 1.25 * q_ref + slack, (q_gpu, q_ref)
     return err
 
 

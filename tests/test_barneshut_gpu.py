@@ -227,3 +227,17 @@ def test_full_size_plummer(pb, ctx):
     cm = t.read(_ffi.TREE_NODE_COM_MASS)
     assert np.isclose(cm[0, 3], p[:, 3].astype(np.float64).sum(), rtol=1e-6)
     t.close()
+
+
+def test_sharded_entry_single_rank(pb, ctx):
+    """The multi-GPU step degenerates to the plain evaluation without a communicator."""
+    p = plummer_cloud(10000, seed=14)
+    got = pb.ShardedBarnesHut(ctx, 0.5, pb.Acceleration.checked()).compute(p)
+    ref = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked()).compute(pb.Between(p[:, :3], p))
+    assert np.array_equal(got, ref)
+    from particular_b200 import _ffi
+    import ctypes as C
+    out = np.zeros((5, 3), np.float32)
+    st = _ffi.lib.pcuda_barneshut_f32x3_sharded(ctx.handle, p.ctypes.data_as(C.c_void_p), 5, 10000, 0.5,
+                                                0.0, 1, out.ctypes.data_as(C.c_void_p))
+    assert st == _ffi.ERR_INVALID_ARGUMENT  # a rank must own its whole block

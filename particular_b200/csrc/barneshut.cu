@@ -930,7 +930,7 @@ static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d
 }
 
 static bool g_count = true;  // instrumentation of the traversal (pcuda_tree_last_counters)
-static int g_seg_max = 128;  // largest cell (in targets) that is cut into groups (tuning hook)
+static int g_seg_max = 256;  // largest cell (in targets) that is cut into groups (tuning hook)
 
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
 // tgt_stride: floats per target row (0 = bare positions, i.e. `dim`).

@@ -37,11 +37,16 @@ constexpr float PAD_POS = 1e18f;   // zero-mass padding records sit here: they c
 // (impls/mod.rs:160-161).
 //   CLAMP == 1: r2 == 0 is replaced by +inf, so rsqrt gives 0 and the term is d * 0 = 0 for any
 //               finite mu.  Exact; two ALU-pipe instructions per pair (FSETP + FSEL), ~5 % slower.
-//   CLAMP == 2: r2 is clamped from below with one FMNMX to a threshold derived from the largest
-//               |mu| of the call (mass_max_kernel) such that mu * r^-3 stays finite; a coincident
-//               pair then gives d * finite = 0 exactly.  Differs from CLAMP == 1 only for pairs
-//               closer than ~1.4e-10 * (max|mu| / 1e9)^(1/3) — below the f32 spacing of any
-//               position with |x| > 1e-3.  Used for large problems where the kernel time matters.
+//   CLAMP == 2: r2 is clamped from below with one FMNMX to t = 2 (max|mu| * 1e-38)^(2/3), derived
+//               from the largest |mu| of the call (mass_max_kernel) so that mu * r^-3 stays
+//               finite; a coincident pair then gives d * finite = 0 exactly.  (Tuning only.)
+//   CLAMP == 3: the same threshold t is ADDED to r2 through the FMA chain that already adds
+//               eps^2 (zero extra instructions; every instruction issued next to the FMA pipe
+//               costs about one pipe cycle on sm_100).  Coincident pairs give
+//               exactly 0; r2 + t == r2 bit for bit whenever r2 >= 2^24 t, i.e. for separations
+//               above ~1.3e-6 * (max|mu| / 1e9)^(1/3), and t ~ 1e-19 is 9 orders of magnitude
+//               below the f32 resolution of positions of magnitude >= 1e-3.  Default for large
+//               problems.
 // CLAMP == 0: either eps2 > 0 (d = 0 gives 0 without any test) or the caller asked for the
 // unchecked reference behaviour (coincident pair -> NaN, as in the reference).
 template <int DIM, int TP, int BLOCK, int MINB, int CLAMP>
@@ -102,13 +107,14 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     if (tid == 0)
         for (int t = 0; t < PREFETCH && t < ntiles; ++t) issue(t);
 
-    const float2 eps2p = make_float2(eps2, eps2);
+    float2 eps2p = make_float2(eps2, eps2);
     float tiny_r2 = TINY_R2;
-    if (CLAMP == 2) {
+    if (CLAMP >= 2) {
         // smallest r2 for which max|mu| * r2^-1.5 < ~1e38:  r2 > (max|mu| * 1e-38)^(2/3)
         const float mmax = __uint_as_float(*mass_max_bits);
         const float c = cbrtf(fminf(mmax, 3e38f)) * 2.2e-13f;  // 2.2e-13 ~ cbrt(1e-38)
         tiny_r2 = fmaxf(2.f * c * c, 1e-36f);
+        if (CLAMP == 3) eps2p = make_float2(tiny_r2, tiny_r2);
     }
 
     for (int t = 0; t < ntiles; ++t) {
@@ -335,6 +341,10 @@ __global__ void __launch_bounds__(BLOCK)
 // Launch planning.  A CTA covers `tile_t` targets and one chunk of sources; we want enough
 // equal-cost CTAs for >= ~16 waves over SMs x resident CTAs (tail < 6 %), but chunks of at least
 // a few tiles so the pipeline prologue is amortised.
+static int g_force_tp = 0;    // test / tuning hooks (pcuda_debug_set)
+static int g_clamp_mode = 0;   // 0 = automatic (by problem size), 1 = select, 2 = clamp, 3 = additive
+static int g_waves = 48;       // equal-cost CTAs per resident slot (tail < 1 / g_waves)
+
 struct Plan {
     int tp, block, minb;
     int n_tb, splits, chunk, tile;
@@ -352,7 +362,7 @@ static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
     pl.n_tb = (int)((na + tile_t - 1) / tile_t);
     pl.tile = nb >= 4096 ? TILE_MAX : 64;
     const long slots = (long)sm_count * pl.minb;
-    const long want = slots * 16;
+    const long want = slots * g_waves;
     long splits = (want + pl.n_tb - 1) / pl.n_tb;
     const long max_splits = std::max<long>(1, (long)(nb / ((size_t)pl.tile * 4)));
     splits = std::max<long>(1, std::min(splits, max_splits));
@@ -365,15 +375,16 @@ static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
     return pl;
 }
 
-static int g_force_tp = 0;    // test / tuning hooks (pcuda_debug_set)
-static int g_clamp_mode = 0;   // 0 = automatic (by problem size), 1 = select, 2 = mass-aware clamp
 
 template <int DIM, int TP, int BLOCK, int MINB>
 static cudaError_t launch_f32(const Plan &pl, int clamp, cudaStream_t stream, const float *tgt,
                               int tgt_stride, int na, const float4 *src, int nb, float eps2,
                               float *out, float *partial, size_t n_pad, const unsigned *mass_max) {
     dim3 grid(pl.n_tb, pl.splits);
-    if (clamp == 2)
+    if (clamp == 3)
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 3><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
+    else if (clamp == 2)
         pair_kernel_f32<DIM, TP, BLOCK, MINB, 2><<<grid, BLOCK, 0, stream>>>(
             tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
     else if (clamp == 1)
@@ -400,10 +411,10 @@ static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na
     const float eps2 = softening * softening;
     int clamp = 0;
     if (checked && eps2 == 0.0f)
-        clamp = g_clamp_mode ? g_clamp_mode : ((double)na * (double)nb >= 2.5e8 ? 2 : 1);
+        clamp = g_clamp_mode ? g_clamp_mode : ((double)na * (double)nb >= 2.5e8 ? 3 : 1);
     const Plan pl = make_plan(ctx->sm_count, na, nb, g_force_tp);
     unsigned *mass_max = nullptr;
-    if (clamp == 2) {
+    if (clamp >= 2) {
         PCUDA_CUDA_TRY(ctx, ctx->d_massmax.ensure(sizeof(unsigned)));
         mass_max = ctx->d_massmax.as<unsigned>();
         PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(mass_max, 0, sizeof(unsigned), ctx->stream));
@@ -719,7 +730,11 @@ int pcuda_debug_set(const char *key, int value) {
         bf::g_force_tp = value;
         return PCUDA_OK;
     }
-    if (key && std::string(key) == "bf_clamp" && value >= 0 && value <= 2) {
+    if (key && std::string(key) == "bf_waves" && value >= 1 && value <= 1024) {
+        bf::g_waves = value;
+        return PCUDA_OK;
+    }
+    if (key && std::string(key) == "bf_clamp" && value >= 0 && value <= 3) {
         bf::g_clamp_mode = value;
         return PCUDA_OK;
     }

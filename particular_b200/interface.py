@@ -252,7 +252,8 @@ class CudaContext:
         self._pinned.append(p)
         return arr
 
-    def probe_fp32(self, packed: bool = True, iters: int = 4096, repeats: int = 5):
+    def probe_fp32(self, packed=True, iters: int = 4096, repeats: int = 5):
+        """FP32-pipe microbenchmark; `packed` is a mode 0..7 (see csrc/probe.cu; True = 1)."""
         tf, ms = C.c_double(), C.c_float()
         check(lib.pcuda_probe_fp32(self.handle, int(packed), iters, repeats, C.byref(tf),
                                    C.byref(ms)), self.handle)

@@ -40,11 +40,14 @@ d_out = torch.zeros((N, 3), dtype=torch.float32, device="cuda")
 torch.cuda.synchronize()
 stream = torch.cuda.ExternalStream(ctx.stream_ptr)
 res = {}
-for eps, name, clamp in ((0.0, "checked_select", 1), (0.0, "checked_fmnmx", 2), (1.0, "softened", 1)):
+for eps, name, clamp, waves in ((0.0, "checked_additive_w16", 3, 16), (0.0, "checked_additive_w48", 3, 48),
+                                (0.0, "checked_additive_w96", 3, 96), (0.0, "checked_fmnmx_w48", 2, 48),
+                                (0.0, "checked_select_w48", 1, 48), (1.0, "softened_w48", 1, 48)):
     lib.pcuda_debug_set(b"bf_clamp", clamp)
+    lib.pcuda_debug_set(b"bf_waves", waves)
     inter = pb.AccelerationSoftened.checked(eps) if eps else pb.Acceleration.checked()
     bf = pb.BruteForce(ctx, inter)
-    for tp in (4, 2, 1):
+    for tp in (4, 2):
         lib.pcuda_debug_set(b"bf_tp", tp)
         for _ in range(2):
             bf.compute_device(None, N, d_src.data_ptr(), N, d_out.data_ptr())

@@ -122,7 +122,7 @@ def test_mass_scale_with_coincident_pairs(pb, ctx, scale):
     p[:, 3] *= scale
     p[7, :3] = p[2000, :3]
     ref = oracle.brute_force_parallel(p[:, :3], p)
-    for mode in (1, 2, 0):
+    for mode in (1, 2, 3, 0):
         assert lib.pcuda_debug_set(b"bf_clamp", mode) == 0
         got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(p)
         assert np.isfinite(got).all()

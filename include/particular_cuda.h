@@ -187,8 +187,9 @@ int pcuda_tree_traverse_f32(pcuda_ctx *ctx, const pcuda_tree *tree, const float 
                             float *out);
 /* Instrumentation of the LAST traversal: counters[0] = accepted node (centre-of-mass)
  * interactions and [1] = direct particle interactions, both summed over all targets;
- * [2] = node tests, summed over the 32-target groups that walk the tree together. */
-int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[3]);
+ * [2] = node tests and [3] = interaction-list entries (nodes + particles), both summed over the
+ * <= 32-target groups that walk the tree together; [4] = number of groups. */
+int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[5]);
 void pcuda_tree_destroy(pcuda_ctx *ctx, pcuda_tree *tree);
 
 /* ---- multi-GPU (one process per GPU; new — the reference is single-device) --------------------

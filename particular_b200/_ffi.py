@@ -86,7 +86,7 @@ SIGNATURES = {
     "pcuda_tree_info_get": (_i, [_vp, C.POINTER(TreeInfo)]),
     "pcuda_tree_read": (_i, [_vp, _vp, _i, _vp, _sz]),
     "pcuda_tree_traverse_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _i, _vp]),
-    "pcuda_tree_last_counters": (_i, [_vp, C.POINTER(C.c_uint64 * 3)]),
+    "pcuda_tree_last_counters": (_i, [_vp, C.POINTER(C.c_uint64 * 5)]),
     "pcuda_tree_destroy": (None, [_vp, _vp]),
     "pcuda_comm_unique_id": (_i, [_vp, C.POINTER(C.c_uint8 * UNIQUE_ID_BYTES)]),
     "pcuda_comm_init": (_i, [_vp, C.POINTER(C.c_uint8 * UNIQUE_ID_BYTES), _i, _i]),

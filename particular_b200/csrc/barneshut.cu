@@ -543,7 +543,8 @@ struct TravArgs {
     const uint32_t *n_groups;
     uint32_t *work;       // next group to hand out
     float *out;
-    unsigned long long *counters;  // [0] node interactions, [1] particle interactions, [2] node tests
+    unsigned long long *counters;  // [0] node interactions, [1] particle interactions, [2] node tests,
+                                   // [3] list entries appended (nodes + particles, per group)
     const Frame *frame;   // root cube extent + mass bound
     int n_tgt;
     int dim;
@@ -553,7 +554,7 @@ struct TravArgs {
 
 // The interaction list of a warp lives in shared memory as PAIRS of entries laid out
 // {x0 x1 y0 y1}{z0 z1 m0 m1}, so that one lane evaluates two entries at a time with packed FP32
-// (FADD2 / FFMA2 / FMUL2): 12 packed + 2 MUFU + 2 FMNMX + 2 LDS.128 per two interactions.
+// (FADD2 / FFMA2 / FMUL2): 12 packed + 2 MUFU + 2 LDS.128 per two interactions.
 __device__ __forceinline__ void list_store(float *list, int i, const float4 e) {
     float *q = list + (i >> 1) * 8 + (i & 1);
     q[0] = e.x;
@@ -563,18 +564,17 @@ __device__ __forceinline__ void list_store(float *list, int i, const float4 e) {
 }
 
 __device__ __forceinline__ void eval_pair(const float4 A, const float4 B, float2 npx, float2 npy,
-                                          float2 npz, float2 eps2p, float tiny, float2 &ax,
-                                          float2 &ay, float2 &az) {
+                                          float2 npz, float2 eps2p, float2 &ax, float2 &ay,
+                                          float2 &az) {
     const float2 dx = ptx::add2(make_float2(A.x, A.y), npx);
     const float2 dy = ptx::add2(make_float2(A.z, A.w), npy);
     const float2 dz = ptx::add2(make_float2(B.x, B.y), npz);
     float2 r2 = ptx::fma2(dx, dx, eps2p);
     r2 = ptx::fma2(dy, dy, r2);
     r2 = ptx::fma2(dz, dz, r2);
-    // zero distance contributes nothing: r2 is clamped so that mu * r^-3 stays finite and the
-    // term is d * finite = 0 (the threshold is far below any separation of distinct f32 positions)
-    r2.x = fmaxf(r2.x, tiny);
-    r2.y = fmaxf(r2.y, tiny);
+    // zero distance contributes nothing: eps2p carries, on top of the softening, a floor t chosen
+    // so that (largest node mass) * r^-3 stays finite, hence the term is d * finite = 0; t is far
+    // below the resolution of distinct f32 positions (r2 + t == r2 bit for bit for r2 >= 2^24 t)
     float2 ri;
     ri.x = ptx::rsqrt_approx(r2.x);
     ri.y = ptx::rsqrt_approx(r2.y);
@@ -597,12 +597,12 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
     float4 *list4 = s_list[warp];
     float *list = reinterpret_cast<float *>(list4);
     const uint32_t n_groups = *a.n_groups;
-    const float2 eps2p = make_float2(a.eps2, a.eps2);
     const float ext = a.frame->ext;
     // r2 floor such that (largest node mass) * r^-3 stays finite (see eval_pair)
     const float cb = cbrtf(fminf(a.frame->mass_bound, 3e38f)) * 2.2e-13f;
     const float tiny = fmaxf(2.f * cb * cb, 1e-36f);
-    unsigned long long c_node = 0, c_part = 0, c_test = 0;
+    const float2 eps2p = make_float2(a.eps2 + tiny, a.eps2 + tiny);
+    unsigned long long c_node = 0, c_part = 0, c_test = 0, c_entries = 0;
 
     for (;;) {
         uint32_t g = 0;
@@ -651,10 +651,10 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
                 if (slices == 1) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
-                        eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, tiny, ax2, ay2, az2);
+                        eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, ax2, ay2, az2);
                 } else {
                     for (int q = slice; q < 16; q += slices)
-                        eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, tiny, ax2, ay2, az2);
+                        eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, ax2, ay2, az2);
                 }
                 fill -= 32;
                 // move the remainder (< 32 entries = <= 16 pairs = <= 32 float4) to the front
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
             __syncwarp();
             const int pairs = (fill + 1) >> 1;
             for (int q = slice; q < pairs; q += slices)
-                eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, tiny, ax2, ay2, az2);
+                eval_pair(list4[2 * q], list4[2 * q + 1], npx, npy, npz, eps2p, ax2, ay2, az2);
         }
         float ax = ax2.x + ax2.y, ay = ay2.x + ay2.y, az = az2.x + az2.y;
         for (int o = gpad; o < 32; o <<= 1) {  // combine the slices of each target
@@ -804,12 +804,14 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
         if (COUNT) {  // per-target counts: every target of the group saw every list entry
             c_node += g_node * gcnt;
             c_part += g_part * gcnt;
+            c_entries += g_node + g_part;
         }
     }
     if (COUNT && lane == 0) {
         atomicAdd(a.counters + 0, c_node);
         atomicAdd(a.counters + 1, c_part);
         atomicAdd(a.counters + 2, c_test);
+        atomicAdd(a.counters + 5, c_entries);
     }
 }
 
@@ -1035,10 +1037,12 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
 
 static int read_counters(pcuda_ctx *ctx) {
     if (!ctx->d_counters.p) return PCUDA_OK;
-    unsigned long long h[3];
+    unsigned long long h[6];  // [3], [4] hold the work dispenser and the group count
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 3; ++i) ctx->last_counters[i] = h[i];
+    ctx->last_counters[3] = h[5];
+    ctx->last_counters[4] = h[4] & 0xffffffffull;  // number of target groups
     return PCUDA_OK;
 }
 
@@ -1354,11 +1358,11 @@ int pcuda_tree_traverse_f32(pcuda_ctx *ctx, const pcuda_tree *t, const float *af
     return bh::read_counters(ctx);
 }
 
-int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[3]) {
+int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[5]) {
     if (!ctx || !counters) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL argument");
     DeviceGuard guard(ctx->device);
     PCUDA_TRY(bh::read_counters(ctx));
-    for (int i = 0; i < 3; ++i) counters[i] = ctx->last_counters[i];
+    for (int i = 0; i < 5; ++i) counters[i] = ctx->last_counters[i];
     return PCUDA_OK;
 }
 

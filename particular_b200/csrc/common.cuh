@@ -67,7 +67,7 @@ struct pcuda_ctx {
     // Barnes-Hut scratch (barneshut.cu owns the layout)
     pcuda::DevBuf d_stack, d_counters, d_tgt_keys, d_tgt_keys_alt, d_tgt_perm, d_tgt_perm_alt,
         d_tgt_sorted, d_cub_tmp, d_misc;
-    uint64_t last_counters[3] = {0, 0, 0};
+    uint64_t last_counters[5] = {0, 0, 0, 0, 0};
     pcuda_tree *call_tree = nullptr;  // tree reused by the one-shot Barnes-Hut entry points
 
     pcuda::Nccl *nccl = nullptr;

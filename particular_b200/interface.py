@@ -417,10 +417,10 @@ class BarnesHut:
                  it.softening, int(it.is_checked), out_ptr), self.ctx.handle)
 
     def last_counters(self) -> dict:
-        c = (C.c_uint64 * 3)()
+        c = (C.c_uint64 * 5)()
         check(lib.pcuda_tree_last_counters(self.ctx.handle, C.byref(c)), self.ctx.handle)
         return {"node_interactions": int(c[0]), "particle_interactions": int(c[1]),
-                "node_tests": int(c[2])}
+                "node_tests": int(c[2]), "list_entries": int(c[3]), "groups": int(c[4])}
 
 
 # ---- extension-trait sugar (GpuCompute, gpu/mod.rs:13-37) -------------------------------------------

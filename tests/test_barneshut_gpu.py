@@ -241,3 +241,20 @@ def test_sharded_entry_single_rank(pb, ctx):
     st = _ffi.lib.pcuda_barneshut_f32x3_sharded(ctx.handle, p.ctypes.data_as(C.c_void_p), 5, 10000, 0.5,
                                                 0.0, 1, out.ctypes.data_as(C.c_void_p))
     assert st == _ffi.ERR_INVALID_ARGUMENT  # a rank must own its whole block
+
+
+def test_full_size_2d_quadtree(pb, ctx):
+    """BASELINE configs[4b]: 2-D f32 Barnes-Hut quadtree, N = 4,194,304, theta = 0.5, softening 100
+    (the particle-toy shape, examples/particle-toy/src/nbody.rs:30).  Sampled error statistics
+    against the extended-precision sum and the reference algorithm."""
+    n = 4_194_304
+    p = uniform_cloud(n, d=2, seed=1808)
+    it = pb.AccelerationSoftened.checked(100.0)
+    bh = pb.BarnesHut(ctx, 0.5, it)
+    got = bh.compute(p)
+    assert got.shape == (n, 2) and np.isfinite(got).all()
+    idx = np.sort(np.random.default_rng(3).choice(n, 256, replace=False))
+    exact = oracle.brute_force_exact(p[idx, :2], p, 100.0)
+    tree = oracle.Tree(p)
+    ref = tree.traverse(p[idx, :2], 0.5, 100.0, parallel=True)
+    assert_same_theta_error(got[idx], ref, exact, slack=1.25)

@@ -269,3 +269,42 @@ def test_cpp_host_api(pb, ctx):
     r = subprocess.run([ge.build_cpp_host_test()], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all host-API checks passed" in r.stdout
+
+
+def test_full_size_massive_massless_split(pb, ctx):
+    """BASELINE configs[2]: 10k massive + 16M massless particles interleaved, split by mu != 0
+    through Reordered (storage.rs:153-163, 219-229): every particle is affected, only the massive
+    ones affect.  Sampled parity at full size + linearity in mu."""
+    n_massive, n = 10_000, 16_010_000
+    rng = np.random.default_rng(1808)
+    p = np.empty((n, 4), np.float32)
+    p[:, :3] = rng.uniform(-5e3, 5e3, (n, 3))
+    p[:, 3] = 0.0
+    massive_at = np.sort(rng.choice(n, n_massive, replace=False))
+    p[massive_at, 3] = rng.uniform(1e3, 1e9, n_massive)
+    st = pb.Reordered.new(p)
+    assert st.affecting_len() == n_massive
+    bf = pb.BruteForce(ctx, pb.Acceleration.checked())
+    got = bf.compute(st)
+    assert got.shape == (n, 3) and np.isfinite(got).all()
+    idx = np.sort(rng.choice(n, 2000, replace=False))
+    idx = np.concatenate([idx, massive_at[:200]])      # massive ones feel the other massive ones
+    aff, src = oracle.between_of_reordered(p)
+    ref = oracle.brute_force_parallel(aff[idx], src)
+    assert_bruteforce_parity(got[idx], ref, aff[idx], src)
+    p2 = p.copy()
+    p2[:, 3] *= 4
+    got2 = bf.compute(pb.Reordered.new(p2))
+    assert np.array_equal(got2, 4 * got)               # scaling mu by 4 is exact in binary
+
+
+def test_full_size_f64(pb, ctx):
+    """BASELINE configs[4a]: f64 brute force, N = 262144 (the precision path), <= 1e-12."""
+    n = 262_144
+    p = uniform_cloud(n, dtype=np.float64, seed=1808)
+    got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(p)
+    assert got.dtype == np.float64 and np.isfinite(got).all()
+    idx = np.sort(np.random.default_rng(2).choice(n, 1500, replace=False))
+    ref = oracle.brute_force_parallel(p[idx, :3], p)
+    assert_bruteforce_parity(got[idx], ref, p[idx, :3], p)
+    assert rel_err(got[idx], ref).max() < 1e-11

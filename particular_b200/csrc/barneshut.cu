@@ -136,14 +136,33 @@ template <int DIM>
 __global__ void frame_kernel(const float *__restrict__ partial, int nblocks, int n,
                              const unsigned *__restrict__ mass_max_bits, Frame *out) {
     __shared__ float s[2 * DIM];
+    __shared__ float sw[8][2 * DIM];
+    float v[2 * DIM];
+#pragma unroll
+    for (int c = 0; c < 2 * DIM; ++c) v[c] = c >= DIM ? -INFINITY : INFINITY;
+    for (int j = threadIdx.x; j < nblocks; j += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 2 * DIM; ++c) {
+            const float q = partial[j * 2 * DIM + c];
+            v[c] = c >= DIM ? fmaxf(v[c], q) : fminf(v[c], q);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 2 * DIM; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float q = __shfl_xor_sync(0xffffffffu, v[c], o);
+            v[c] = c >= DIM ? fmaxf(v[c], q) : fminf(v[c], q);
+        }
+        if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5][c] = v[c];
+    }
+    __syncthreads();
     if (threadIdx.x < 2 * DIM) {
         const bool is_hi = threadIdx.x >= DIM;
-        float v = is_hi ? -INFINITY : INFINITY;
-        for (int j = 0; j < nblocks; ++j) {
-            const float q = partial[j * 2 * DIM + threadIdx.x];
-            v = is_hi ? fmaxf(v, q) : fminf(v, q);
-        }
-        s[threadIdx.x] = v;
+        float r = sw[0][threadIdx.x];
+        for (int j = 1; j < (int)(blockDim.x >> 5); ++j)
+            r = is_hi ? fmaxf(r, sw[j][threadIdx.x]) : fminf(r, sw[j][threadIdx.x]);
+        s[threadIdx.x] = r;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -264,6 +283,7 @@ __global__ void init_build(NodeRec *nodes, uint32_t n, BuildState *st, uint32_t 
 }
 
 constexpr int EXPAND_BLOCK = 128;
+constexpr uint32_t SMALL_LEVEL = 8192;  // levels up to this many nodes take the node-x-digit path
 
 // One level: every node with more than `nleaf` particles (and above the last level) is split into
 // the distinct next-level digits present in its key range (binary searches); the children of the
@@ -283,12 +303,18 @@ __global__ void __launch_bounds__(EXPAND_BLOCK) expand_level(NodeRec *__restrict
         if (blockIdx.x == 0 && threadIdx.x == 0) st->level_begin[level + 2] = lvl_end;
         return;
     }
-    const uint32_t n_tiles = (lvl_count + EXPAND_BLOCK - 1) / EXPAND_BLOCK;
+    // A level with few nodes (the top of the tree: huge key ranges, hardly any parallelism) is
+    // latency bound, so there X threads serve one node: thread d finds where digit d starts by an
+    // independent binary search, instead of one thread walking from digit to digit.
+    const bool small = lvl_count <= SMALL_LEVEL;
+    const uint32_t tile_nodes = small ? EXPAND_BLOCK / X : EXPAND_BLOCK;
+    const uint32_t n_tiles = (lvl_count + tile_nodes - 1) / tile_nodes;
     const uint32_t capacity = st->capacity;
     const int shift = DIM * (Dims<DIM>::BITS - level - 1);
     typedef cub::BlockScan<uint32_t, EXPAND_BLOCK> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t s_b[EXPAND_BLOCK / X][X + 1];
     const unsigned long long tag = (unsigned long long)(level + 1) * 4;
     for (;;) {
         __syncthreads();
@@ -296,19 +322,51 @@ __global__ void __launch_bounds__(EXPAND_BLOCK) expand_level(NodeRec *__restrict
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= n_tiles) break;
-        const uint32_t t = tile * EXPAND_BLOCK + threadIdx.x;
+        if (small) {
+            const uint32_t tn = tile * tile_nodes + threadIdx.x / X;
+            const uint32_t d = threadIdx.x % X;
+            if (tn < lvl_count) {
+                const uint32_t begin = nodes[lvl_begin + tn].begin, count = nodes[lvl_begin + tn].count;
+                if (count > nleaf && level < Dims<DIM>::BITS) {
+                    const uint64_t want = ((keys[begin] >> shift) & ~(uint64_t)(X - 1)) | d;
+                    uint32_t lo = begin, hi = begin + count;
+                    while (d != 0 && lo < hi) {  // first key of the cell whose digit is >= d
+                        const uint32_t mid = lo + ((hi - lo) >> 1);
+                        if ((keys[mid] >> shift) < want) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    s_b[threadIdx.x / X][d] = lo;
+                    if (d == 0) s_b[threadIdx.x / X][X] = begin + count;
+                }
+            }
+            __syncthreads();
+        }
+        const uint32_t t = tile * tile_nodes + threadIdx.x;
+        const bool valid = threadIdx.x < tile_nodes && t < lvl_count;
         uint32_t c = 0, cb[X + 1];
-        if (t < lvl_count) {
+        if (valid) {
             const uint32_t begin = nodes[lvl_begin + t].begin, count = nodes[lvl_begin + t].count;
             if (count > nleaf && level < Dims<DIM>::BITS) {
-                uint32_t pos = begin;
                 const uint32_t end = begin + count;
+                if (small) {
 #pragma unroll
-                for (int k = 0; k < X; ++k) {
-                    if (pos < end) {
-                        cb[k] = pos;
-                        pos = next_digit_start<DIM>(keys, pos, end, shift);
-                        ++c;
+                    for (int k = 0; k < X; ++k) {
+                        const uint32_t bk = s_b[threadIdx.x][k];
+                        const bool present = s_b[threadIdx.x][k + 1] > bk;
+#pragma unroll
+                        for (int m = 0; m < X; ++m)
+                            if (present && m == (int)c) cb[m] = bk;
+                        c += present;
+                    }
+                } else {
+                    uint32_t pos = begin;
+#pragma unroll
+                    for (int k = 0; k < X; ++k) {
+                        if (pos < end) {
+                            cb[k] = pos;
+                            pos = next_digit_start<DIM>(keys, pos, end, shift);
+                            ++c;
+                        }
                     }
                 }
 #pragma unroll
@@ -352,7 +410,7 @@ __global__ void __launch_bounds__(EXPAND_BLOCK) expand_level(NodeRec *__restrict
             }
         }
         __syncthreads();
-        if (t < lvl_count) {
+        if (valid) {
             NodeRec &nd = nodes[lvl_begin + t];
             const unsigned long long first = (unsigned long long)lvl_end + s_prefix + off;
             if (c == 0 || first + c > capacity) {
@@ -453,61 +511,126 @@ __global__ void __launch_bounds__(256) boundary_levels(const uint64_t *__restric
                   : (uint8_t)(Dims<DIM>::BITS - (63 - __clzll((long long)x)) / DIM);
 }
 
-__global__ void __launch_bounds__(GROUP_BLOCK) group_flags(const uint8_t *__restrict__ L, int n,
-                                                           int bits, int T,
-                                                           uint32_t *__restrict__ flag) {
-    __shared__ uint8_t sL[GROUP_BLOCK + 4 * SEG_MAX_LIMIT + 2];
-    __shared__ uint8_t sH[GROUP_BLOCK + 2 * SEG_MAX_LIMIT];
+// Boundary i (between targets i-1 and i) is HARD when the smallest cell holding both targets has
+// more than T targets.  That cell spans from the nearest j < i with L[j] < L[i] to the nearest
+// k > i with L[k] < L[i] ("nearest smaller value" on both sides; L is 0 outside the array), so
+// hard <=> k - j > T.  The walk over L skips 16 entries at a time through a table of chunk
+// minima.  Output: one bit per boundary (bits at and past n are set).
+constexpr int HARD_CHUNK = 16;
+constexpr int HARD_HALO = SEG_MAX_LIMIT + 2 * HARD_CHUNK;
+
+__global__ void __launch_bounds__(GROUP_BLOCK) hard_flags(const uint8_t *__restrict__ L, int n,
+                                                          int bits, int T,
+                                                          uint32_t *__restrict__ hard_bits) {
+    __shared__ __align__(16) uint8_t sL[GROUP_BLOCK + 2 * HARD_HALO];
+    __shared__ uint8_t sM[(GROUP_BLOCK + 2 * HARD_HALO) / HARD_CHUNK];
     const int base = blockIdx.x * GROUP_BLOCK;
-    const int l0 = base - 2 * T - 1;  // global index of sL[0]
-    const int nl = GROUP_BLOCK + 4 * T + 2;
-    for (int k = threadIdx.x; k < nl; k += GROUP_BLOCK) {
+    const int l0 = base - HARD_HALO;  // global index of sL[0]; a multiple of HARD_CHUNK
+    constexpr int NL = GROUP_BLOCK + 2 * HARD_HALO;
+    for (int k = threadIdx.x; k < NL; k += GROUP_BLOCK) {
         const int g = l0 + k;
-        sL[k] = (g <= 0 || g >= n) ? 0 : L[g];  // outside the array: a boundary at the root
+        sL[k] = (g <= 0 || g >= n) ? 0 : L[g];
     }
     __syncthreads();
-    const int h0 = base - T;  // global index of sH[0]
-    const int nh = GROUP_BLOCK + 2 * T;
-    for (int k = threadIdx.x; k < nh; k += GROUP_BLOCK) {
-        const int i = h0 + k;
-        bool hard;
-        if (i <= 0 || i >= n) hard = true;
-        else {
-            const int li = sL[i - l0];
-            if (li == bits + 1) hard = false;  // identical keys never separate
-            else {
-                const int l = li - 1;  // level of the smallest cell holding targets i-1 and i
-                int j = i - 1;         // walk left to the first target of that cell
-                while (j > 0 && i - j <= T && sL[j - l0] > l) --j;
-                if (i - j > T) hard = true;
-                else {
-                    int k2 = i + 1;    // walk right to the first target past that cell
-                    while (k2 < n && k2 - j <= T && sL[k2 - l0] > l) ++k2;
-                    hard = k2 - j > T;
-                }
-            }
-        }
-        sH[k] = hard;
+    for (int c = threadIdx.x; c < NL / HARD_CHUNK; c += GROUP_BLOCK) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(sL + c * HARD_CHUNK);
+        uint32_t m = __vminu4(__vminu4(v.x, v.y), __vminu4(v.z, v.w));
+        m = __vminu4(m, m >> 16);
+        m = __vminu4(m, m >> 8);
+        sM[c] = (uint8_t)(m & 0xffu);
     }
     __syncthreads();
     const int i = base + threadIdx.x;
-    if (i >= n) return;
-    int ss = i;  // segment start: nearest hard boundary at or before i
-    while (ss > 0 && i - ss < T && !sH[ss - h0]) --ss;
-    bool start;
-    if (!sH[ss - h0] && ss > 0) start = (i & 31) == 0;  // inside a long run of identical keys
+    bool hard;
+    if (i <= 0 || i >= n) hard = true;
     else {
-        int se = i + 1;  // segment end: next hard boundary
-        while (se < n && se - ss <= T && !sH[se - h0]) ++se;
-        const int len = se - ss;
-        if (len <= T) {
-            // full groups of 32 first; the remainder forms one small group whose lanes are
-            // shared out over the interaction list (see traverse_kernel), which wastes fewer
-            // lanes than equal chunks of e.g. 20 + 20
-            start = ((i - ss) & 31) == 0;
-        } else {
-            start = i == ss || (i & 31) == 0;  // the head of a long run of identical keys
+        const int li = sL[i - l0];
+        if (li == bits + 1) hard = false;  // identical keys never separate
+        else {
+            int j = i - 1;  // nearest j < i with L[j] < li (first target of the shared cell)
+            const int jmin = i - T - 1;
+            while (j > jmin) {
+                const int q = j - l0;
+                if ((q & (HARD_CHUNK - 1)) == HARD_CHUNK - 1 && sM[q / HARD_CHUNK] >= li) {
+                    j -= HARD_CHUNK;
+                    continue;
+                }
+                if (sL[q] < li) break;
+                --j;
+            }
+            if (i - j > T) hard = true;
+            else {
+                int k = i + 1;  // nearest k > i with L[k] < li (first target past the cell)
+                const int kmax = j + T + 1;
+                while (k < kmax) {
+                    const int q = k - l0;
+                    if ((q & (HARD_CHUNK - 1)) == 0 && sM[q / HARD_CHUNK] >= li) {
+                        k += HARD_CHUNK;
+                        continue;
+                    }
+                    if (sL[q] < li) break;
+                    ++k;
+                }
+                hard = k - j > T;
+            }
         }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, hard);
+    if ((threadIdx.x & 31) == 0) hard_bits[i >> 5] = word;
+}
+
+// Group starts from the hard boundaries: a SEGMENT runs from one hard boundary to the next; a
+// segment of <= T targets is cut into full groups of 32 from its start (the remainder forms one
+// small group whose lanes are shared out over the interaction list, see traverse_kernel); longer
+// segments (runs of identical keys) are cut at multiples of 32.
+__device__ __forceinline__ uint32_t hard_word(const uint32_t *__restrict__ hb, int w, int nwords) {
+    return (w < 0 || w >= nwords) ? 0xffffffffu : __ldg(hb + w);
+}
+
+__global__ void __launch_bounds__(GROUP_BLOCK) group_flags(const uint32_t *__restrict__ hard_bits,
+                                                           int n, int T, int gsize,
+                                                           uint32_t *__restrict__ flag) {
+    const int i = blockIdx.x * GROUP_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const int nwords = (n + 31) >> 5;
+    // segment start: nearest hard boundary in [i - T, i]
+    int ss = -1;
+    {
+        int w = i >> 5;
+        uint32_t m = hard_word(hard_bits, w, nwords) & (0xffffffffu >> (31 - (i & 31)));
+        const int lim = max(i - T, 0);
+        for (;;) {
+            if (m) {
+                const int p = w * 32 + 31 - __clz((int)m);
+                if (p >= lim) ss = p;
+                break;
+            }
+            --w;
+            if (w * 32 + 31 < lim) break;
+            m = hard_word(hard_bits, w, nwords);
+        }
+    }
+    bool start;
+    const int gm = gsize - 1;  // gsize = targets per group: 32 or 64
+    if (ss < 0) start = (i & gm) == 0;  // inside a long run of identical keys
+    else {
+        // segment end: next hard boundary in (i, ss + T]
+        int se = -1;
+        int w = i >> 5;
+        uint32_t m = (i & 31) == 31 ? 0u : hard_word(hard_bits, w, nwords) & (0xffffffffu << ((i & 31) + 1));
+        const int lim = ss + T;
+        for (;;) {
+            if (m) {
+                const int p = w * 32 + __ffs((int)m) - 1;
+                if (p <= lim) se = p;
+                break;
+            }
+            ++w;
+            if (w * 32 > lim) break;
+            m = hard_word(hard_bits, w, nwords);
+        }
+        if (se >= 0) start = ((i - ss) & gm) == 0;
+        else start = i == ss || (i & gm) == 0;  // the head of a long run of identical keys
     }
     flag[i] = start ? 1u : 0u;
 }
@@ -816,6 +939,265 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse_kernel(TravArgs a
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5c: the same walk with TWO targets per lane (groups of up to 64 targets).  The packed FP32
+// lanes now hold two targets and an interaction-list entry is a scalar-broadcast operand
+// (FADD2 Rd, -Rtargets.F32x2, Rentry.F32), so the list is plain {x,y,z,mu} records: one
+// conflict-free STS.128 per appended entry, one broadcast LDS.128 per entry and pair of targets,
+// and the tree walk is shared by twice as many targets.  The list is a 64-entry ring that is
+// evaluated 32 entries at a time.
+__device__ __forceinline__ void eval_entry(const float4 e, float2 npx, float2 npy, float2 npz,
+                                           float2 eps2p, float2 &ax, float2 &ay, float2 &az) {
+    const float2 dx = ptx::add2(ptx::splat(e.x), npx);
+    const float2 dy = ptx::add2(ptx::splat(e.y), npy);
+    const float2 dz = ptx::add2(ptx::splat(e.z), npz);
+    float2 r2 = ptx::fma2(dx, dx, eps2p);
+    r2 = ptx::fma2(dy, dy, r2);
+    r2 = ptx::fma2(dz, dz, r2);
+    float2 ri;
+    ri.x = ptx::rsqrt_approx(r2.x);
+    ri.y = ptx::rsqrt_approx(r2.y);
+    const float2 ri2 = ptx::mul2(ri, ri);
+    const float2 mri = ptx::mul2(ri, ptx::splat(e.w));
+    const float2 sc = ptx::mul2(ri2, mri);
+    ax = ptx::fma2(dx, sc, ax);
+    ay = ptx::fma2(dy, sc, ay);
+    az = ptx::fma2(dz, sc, az);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs a) {
+    __shared__ uint32_t s_stack[TRAV_WARPS][STACK_CAP];
+    __shared__ __align__(16) float4 s_list[TRAV_WARPS][LIST_CAP];
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *stack = s_stack[warp];
+    float4 *list4 = s_list[warp];
+    const uint32_t n_groups = *a.n_groups;
+    const float ext = a.frame->ext;
+    const float cb = cbrtf(fminf(a.frame->mass_bound, 3e38f)) * 2.2e-13f;
+    const float tiny = fmaxf(2.f * cb * cb, 1e-36f);  // see eval_pair
+    const float2 eps2p = make_float2(a.eps2 + tiny, a.eps2 + tiny);
+    unsigned long long c_node = 0, c_part = 0, c_test = 0, c_entries = 0;
+
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(a.work, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= n_groups) break;
+        const int t0 = (int)a.group_start[g];
+        const int gcnt = (int)a.group_start[g + 1] - t0;  // 1..64 targets
+        // lanes = (pair of targets, slice): a group of <= 32 targets uses 64 / gpad lanes per
+        // pair, each evaluating every (64 / gpad)-th list entry; partial sums are combined at
+        // the end
+        int half = 1;  // lanes per slice = gpad / 2
+        while (2 * half < gcnt) half <<= 1;
+        const int slices = 32 / half;
+        const int tl = lane & (half - 1), slice = lane / half;
+        const int ia = t0 + min(tl, gcnt - 1), ib = t0 + min(tl + half, gcnt - 1);
+        // scalar loads on purpose: each (a, b) coordinate pair is then free to land in an aligned
+        // register pair, the operand form of FADD2; out of two LDG.128 quads ptxas re-packs the
+        // pair with two MOVs in front of every FADD2
+        float3 ta, tb;
+        ta.x = ptx::ldg_f32(&a.tgt[ia].x);
+        tb.x = ptx::ldg_f32(&a.tgt[ib].x);
+        ta.y = ptx::ldg_f32(&a.tgt[ia].y);
+        tb.y = ptx::ldg_f32(&a.tgt[ib].y);
+        ta.z = ptx::ldg_f32(&a.tgt[ia].z);
+        tb.z = ptx::ldg_f32(&a.tgt[ib].z);
+
+        float lox = fminf(ta.x, tb.x), hix = fmaxf(ta.x, tb.x);
+        float loy = fminf(ta.y, tb.y), hiy = fmaxf(ta.y, tb.y);
+        float loz = fminf(ta.z, tb.z), hiz = fmaxf(ta.z, tb.z);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(FULL, lox, o));
+            hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, o));
+            loy = fminf(loy, __shfl_xor_sync(FULL, loy, o));
+            hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, o));
+            loz = fminf(loz, __shfl_xor_sync(FULL, loz, o));
+            hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, o));
+        }
+        const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+        const float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
+
+        const float2 npx = make_float2(-ta.x, -tb.x), npy = make_float2(-ta.y, -tb.y),
+                     npz = make_float2(-ta.z, -tb.z);
+        float2 ax2 = make_float2(0.f, 0.f), ay2 = ax2, az2 = ax2;
+        unsigned long long g_node = 0, g_part = 0;
+        int sp = 1;    // stack size (uniform across the warp)
+        int head = 0;  // ring position of the oldest list entry: 0 or 32 (uniform)
+        int fill = 0;  // entries in the ring (uniform), < 32 between steps
+        __syncwarp();
+        if (lane == 0) stack[0] = 0;
+        __syncwarp();
+
+        auto flush_full = [&]() {  // evaluate the 32 oldest entries once they are ready
+            if (fill >= 32) {
+                __syncwarp();
+                const float4 *blk = list4 + head;
+                if (slices == 1) {
+#pragma unroll 16
+                    for (int q = 0; q < 32; ++q) eval_entry(blk[q], npx, npy, npz, eps2p, ax2, ay2, az2);
+                } else {
+                    for (int q = slice; q < 32; q += slices)
+                        eval_entry(blk[q], npx, npy, npz, eps2p, ax2, ay2, az2);
+                }
+                fill -= 32;
+                head ^= 32;
+                __syncwarp();
+            }
+        };
+
+        while (sp > 0) {
+            const int room = (STACK_CAP - STACK_RESERVE - sp) / 7;
+            const int k = min(min(32, sp), max(room, 1));
+            const bool has = lane < k;
+            NodeRec nd;
+            nd.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+            nd.first_child = 0;
+            nd.begin = 0;
+            nd.count = 0;
+            nd.nchild_level = 0;
+            if (has) {
+                const uint32_t id = stack[sp - 1 - lane];
+                const uint4 *q = reinterpret_cast<const uint4 *>(a.nodes + id);
+                const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                nd.cm = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y),
+                                    __uint_as_float(q0.z), __uint_as_float(q0.w));
+                nd.first_child = q1.x;
+                nd.nchild_level = q1.y;
+                nd.begin = q1.z;
+                nd.count = q1.w;
+            }
+            sp -= k;
+            __syncwarp();
+
+            bool open = false;
+            if (has) {
+                const float ddx = fmaxf(fabsf(nd.cm.x - cx) - hx, 0.f);
+                const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
+                const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
+                const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                const int level = (int)(nd.nchild_level >> 8);
+                const float w = ext * __int_as_float((127 - level) << 23);
+                open = a.theta2 * d2 < w * w;
+            }
+            const uint32_t nc = nd.nchild_level & 0xffu;
+            const bool open_internal = has && open && nc > 0;
+            const bool open_leaf = has && open && nc == 0;
+            const bool accept = has && !open && nd.cm.w != 0.f;
+            if (COUNT) c_test += k;
+
+            const int c_child = open_internal ? (int)nc : 0;
+            const int c_leaf = open_leaf ? (int)nd.count : 0;
+            const bool wide = __any_sync(FULL, c_leaf > 65535);
+            int leaf_incl;
+            {
+                unsigned packed = (unsigned)c_child | (wide ? 0u : (unsigned)c_leaf << 10);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(FULL, packed, o);
+                    if (lane >= o) packed += v;
+                }
+                const int incl = (int)(packed & 1023u);
+                leaf_incl = (int)(packed >> 10);
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int base = sp + incl - c_child;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < c_child) stack[base + j] = nd.first_child + j;
+                sp += total;
+            }
+            if (wide) {
+                leaf_incl = c_leaf;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, leaf_incl, o);
+                    if (lane >= o) leaf_incl += v;
+                }
+            }
+
+            {  // accepted nodes -> ring
+                const unsigned m = __ballot_sync(FULL, accept);
+                if (m) {
+                    if (accept)
+                        list4[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] = nd.cm;
+                    const int cnt = __popc(m);
+                    if (COUNT) g_node += cnt;
+                    fill += cnt;
+                    flush_full();
+                }
+            }
+
+            {  // particles of opened leaves -> ring, 32 per round (see traverse_kernel)
+                const int incl = leaf_incl;
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int excl = incl - c_leaf;
+                for (int base = 0; base < total; base += 32) {
+                    const int f = base + lane;
+                    int owner = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, (owner + step - 1) & 31);
+                        if (v <= f) owner += step;
+                    }
+                    owner = min(owner, 31);
+                    const uint32_t ob = __shfl_sync(FULL, nd.begin, owner);
+                    const int oe = __shfl_sync(FULL, excl, owner);
+                    if (f < total)
+                        list4[(head + fill + lane) & (LIST_CAP - 1)] = __ldg(a.src + ob + (f - oe));
+                    const int cnt = min(32, total - base);
+                    if (COUNT) g_part += cnt;
+                    fill += cnt;
+                    flush_full();
+                }
+            }
+            __syncwarp();
+        }
+        if (fill > 0) {
+            __syncwarp();
+            for (int q = slice; q < fill; q += slices)
+                eval_entry(list4[(head + q) & (LIST_CAP - 1)], npx, npy, npz, eps2p, ax2, ay2, az2);
+        }
+        float axa = ax2.x, aya = ay2.x, aza = az2.x, axb = ax2.y, ayb = ay2.y, azb = az2.y;
+        for (int o = half; o < 32; o <<= 1) {  // combine the slices of each target
+            axa += __shfl_xor_sync(FULL, axa, o);
+            aya += __shfl_xor_sync(FULL, aya, o);
+            aza += __shfl_xor_sync(FULL, aza, o);
+            axb += __shfl_xor_sync(FULL, axb, o);
+            ayb += __shfl_xor_sync(FULL, ayb, o);
+            azb += __shfl_xor_sync(FULL, azb, o);
+        }
+        if (slice == 0 && tl < gcnt) {
+            const uint32_t row = a.tgt_perm ? a.tgt_perm[ia] : (uint32_t)ia;
+            float *o = a.out + (size_t)row * a.dim;
+            o[0] = axa;
+            o[1] = aya;
+            if (a.dim == 3) o[2] = aza;
+        }
+        if (slice == 0 && tl + half < gcnt) {
+            const uint32_t row = a.tgt_perm ? a.tgt_perm[ib] : (uint32_t)ib;
+            float *o = a.out + (size_t)row * a.dim;
+            o[0] = axb;
+            o[1] = ayb;
+            if (a.dim == 3) o[2] = azb;
+        }
+        if (COUNT) {
+            c_node += g_node * gcnt;
+            c_part += g_part * gcnt;
+            c_entries += g_node + g_part;
+        }
+    }
+    if (COUNT && lane == 0) {
+        atomicAdd(a.counters + 0, c_node);
+        atomicAdd(a.counters + 1, c_part);
+        atomicAdd(a.counters + 2, c_test);
+        atomicAdd(a.counters + 5, c_entries);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side.
 template <int DIM>
 static int sort_by_key(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n, const Frame *d_frame,
@@ -865,7 +1247,7 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
     unsigned *d_mmax = reinterpret_cast<unsigned *>(t->d_frame.as<Frame>() + 1);
     PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_mmax, 0, sizeof(unsigned), st));
     bbox_partial<DIM><<<nb, 256, 0, st>>>(d_particles, stride, (int)n, t->partial.as<float>(), d_mmax);
-    frame_kernel<DIM><<<1, 32, 0, st>>>(t->partial.as<float>(), nb, (int)n, d_mmax,
+    frame_kernel<DIM><<<1, 256, 0, st>>>(t->partial.as<float>(), nb, (int)n, d_mmax,
                                         t->d_frame.as<Frame>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 2;
@@ -887,7 +1269,9 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
         PCUDA_CUDA_TRY(ctx, t->nodes.ensure(cap_nodes * sizeof(NodeRec)));
         cap_nodes = std::min<size_t>(t->nodes.cap / sizeof(NodeRec), 0xfffffff0ull);
         PCUDA_CUDA_TRY(ctx, t->moments.ensure(cap_nodes * 4 * sizeof(double)));
-        const size_t max_tiles = (cap_nodes + EXPAND_BLOCK - 1) / EXPAND_BLOCK + 1;
+        // tiles of 128 nodes, or of 128 / 2^DIM nodes on levels of <= SMALL_LEVEL nodes
+        const size_t max_tiles = (cap_nodes + EXPAND_BLOCK - 1) / EXPAND_BLOCK + 1 +
+                                 SMALL_LEVEL / (EXPAND_BLOCK / Dims<DIM>::X);
         PCUDA_CUDA_TRY(ctx, t->scan_in.ensure(sizeof(BuildState)));
         PCUDA_CUDA_TRY(ctx, t->scan_out.ensure(max_tiles * sizeof(unsigned long long)));
         BuildState *d_state = t->scan_in.as<BuildState>();
@@ -933,6 +1317,7 @@ static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d
 
 static bool g_count = true;  // instrumentation of the traversal (pcuda_tree_last_counters)
 static int g_seg_max = 256;  // largest cell (in targets) that is cut into groups (tuning hook)
+static int g_tpl = 2;        // targets per lane in the traversal: 1 (groups of 32) or 2 (groups of 64)
 
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
 // tgt_stride: floats per target row (0 = bare positions, i.e. `dim`).
@@ -988,25 +1373,29 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
     PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
     uint32_t *d_work = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 3);
     uint32_t *d_ngroups = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 4);
-    // d_stack layout: L (n bytes, padded) | flag (n u32) | pos (n u32) | group_start (n + 1 u32)
+    // d_stack layout: L (n bytes, padded) | flag (n u32) | pos (n u32) | group_start (n + 1 u32) |
+    // hard-boundary bits (one word per 32 targets, padded to whole blocks)
     const size_t n4 = ((size_t)n + 3) & ~size_t(3);
-    PCUDA_CUDA_TRY(ctx, ctx->d_stack.ensure(n4 + (3 * (size_t)n + 1) * 4));
+    const size_t nhw = ((size_t)n + GROUP_BLOCK - 1) / GROUP_BLOCK * (GROUP_BLOCK / 32);
+    PCUDA_CUDA_TRY(ctx, ctx->d_stack.ensure(n4 + (3 * (size_t)n + 1 + nhw) * 4));
     uint8_t *d_L = ctx->d_stack.as<uint8_t>();
     uint32_t *d_flag = reinterpret_cast<uint32_t *>(d_L + n4);
     uint32_t *d_pos = d_flag + n;
     uint32_t *d_gstart = d_pos + n;
+    uint32_t *d_hard = d_gstart + n + 1;
     const unsigned nb256 = (unsigned)((n + 255) / 256);
     if (dim == 3) boundary_levels<3><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
     else boundary_levels<2><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
-    group_flags<<<(unsigned)((n + GROUP_BLOCK - 1) / GROUP_BLOCK), GROUP_BLOCK, 0, st>>>(
-        d_L, n, t->bits, g_seg_max, d_flag);
+    const unsigned ngb = (unsigned)((n + GROUP_BLOCK - 1) / GROUP_BLOCK);
+    hard_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_L, n, t->bits, g_seg_max, d_hard);
+    group_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_hard, n, g_seg_max, 32 * g_tpl, d_flag);
     size_t tmp = 0;
     PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_flag, d_pos, n, st));
     PCUDA_CUDA_TRY(ctx, ctx->d_cub_tmp.ensure(tmp));
     PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, tmp, d_flag, d_pos, n, st));
     scatter_groups<<<nb256, 256, 0, st>>>(d_flag, d_pos, n, d_gstart, d_ngroups);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 5;
+    ctx->launches += 6;
 
     TravArgs a;
     a.nodes = t->nodes.as<NodeRec>();
@@ -1026,10 +1415,13 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
                                                        (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
-    if (g_count)
-        traverse_kernel<true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
-    else
-        traverse_kernel<false><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+    if (g_tpl == 2) {
+        if (g_count) traverse2_kernel<true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+        else traverse2_kernel<false><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+    } else {
+        if (g_count) traverse_kernel<true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+        else traverse_kernel<false><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+    }
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return PCUDA_OK;
@@ -1133,6 +1525,10 @@ int bh_debug_set(const char *key, int value) {
     const std::string k = key ? key : "";
     if (k == "bh_seg_max" && value >= 32 && value <= bh::SEG_MAX_LIMIT && value % 32 == 0) {
         bh::g_seg_max = value;
+        return PCUDA_OK;
+    }
+    if (k == "bh_tpl" && (value == 1 || value == 2)) {
+        bh::g_tpl = value;
         return PCUDA_OK;
     }
     if (k == "bh_count") {

@@ -70,6 +70,13 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
+// One 32-bit read-only load that the compiler cannot merge with its neighbours into a vector load.
+__device__ __forceinline__ float ldg_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // Packed FP32 pairs (sm_100+: fma.rn.f32x2 etc.).  One issue slot does two lanes of work, which
 // is what lets MUFU / LDS / loop overhead hide under the FMA pipe in the pair kernel.
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }

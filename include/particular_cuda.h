@@ -237,6 +237,59 @@ int pcuda_barneshut_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_
                                   size_t n_total, float theta, float softening, int checked,
                                   float *out_xyz);
 
+/* ---- device-resident stepping (new) --------------------------------------
+ * Every caller of the reference integrates the accelerations right after computing them
+ * (examples/simple/src/main.rs:45-59, examples/particle-toy/src/physics.rs:128-138 + 166-176, the
+ * reference's own circular_orbit! test gravity/newtonian/mod.rs:318-331), and its wgpu operator
+ * uploads and reads back on every call (gpu/resources.rs:37-39, 318-349).  A pcuda_sim keeps
+ * particles {position, mu}, velocities and accelerations in device memory; one step is
+ *     a = algorithm(Between(all particles, affecting particles))
+ *     velocity += a * dt;  position += velocity * dt          (semi-implicit Euler, unfused)
+ * and nothing crosses PCIe until pcuda_sim_read().  Brute-force steps replay from a CUDA graph. */
+typedef struct pcuda_sim pcuda_sim;
+typedef enum pcuda_algorithm { PCUDA_BRUTE_FORCE = 0, PCUDA_BARNES_HUT = 1 } pcuda_algorithm;
+typedef enum pcuda_scalar { PCUDA_F32 = 0, PCUDA_F64 = 1 } pcuda_scalar;
+/* affecting = the particles with mu != 0, in input order; affected = all particles in input order:
+ * the `Reordered` storage (storage.rs:153-163, 219-229; ring-formation/src/nbody.rs:25-28). */
+#define PCUDA_SIM_AFFECTING_MASSIVE_ONLY 1u
+#define PCUDA_SIM_NO_GRAPH 2u /* launch every kernel individually (debugging / profiling) */
+
+typedef struct pcuda_sim_config {
+    uint32_t dim;       /* 2 or 3 */
+    uint32_t scalar;    /* pcuda_scalar; PCUDA_F64 needs dim 3 + PCUDA_BRUTE_FORCE */
+    uint32_t algorithm; /* pcuda_algorithm */
+    uint32_t flags;     /* PCUDA_SIM_* */
+    double theta;       /* Barnes-Hut opening parameter */
+    double softening;   /* 0 = Acceleration, > 0 = AccelerationSoftened */
+    double dt;
+    int32_t checked;    /* brute force: a zero-distance pair contributes nothing */
+    uint32_t reserved;
+} pcuda_sim_config;
+
+typedef struct pcuda_sim_info_t {
+    uint64_t n_particles;
+    uint64_t n_affecting;
+    uint64_t steps_done;
+    void *d_particles;     /* device: n x (dim+1) scalars {position, mu} — e.g. for rendering */
+    void *d_velocities;    /* device: n x dim */
+    void *d_accelerations; /* device: n x dim, accelerations of the last step */
+    uint32_t graph_active; /* brute-force steps are being replayed from a CUDA graph */
+    uint32_t launches_per_step;
+} pcuda_sim_info_t;
+
+/* HOST buffers: particles n x (dim+1), velocities n x dim (NULL = at rest); copied, not retained. */
+int pcuda_sim_create(pcuda_ctx *ctx, const pcuda_sim_config *config, const void *particles,
+                     const void *velocities, size_t n, pcuda_sim **out);
+/* Changes theta / softening / dt / checked / algorithm of a live simulation. */
+int pcuda_sim_configure(pcuda_ctx *ctx, pcuda_sim *sim, const pcuda_sim_config *config);
+/* Enqueues n_steps steps on the context stream; does not wait for them. */
+int pcuda_sim_step(pcuda_ctx *ctx, pcuda_sim *sim, uint32_t n_steps);
+/* Blocking read-back into HOST buffers; any of the three may be NULL. */
+int pcuda_sim_read(pcuda_ctx *ctx, pcuda_sim *sim, void *particles, void *velocities,
+                   void *accelerations);
+int pcuda_sim_info(const pcuda_sim *sim, pcuda_sim_info_t *out);
+void pcuda_sim_destroy(pcuda_ctx *ctx, pcuda_sim *sim);
+
 #ifdef __cplusplus
 }
 #endif

@@ -250,3 +250,26 @@ def morton_keys(positions, origin, inv):
         _ptr(positions), C.c_size_t(len(positions)), C.c_size_t(d), _ptr(origin), C.c_float(inv),
         _ptr(keys))
     return keys
+
+
+# ---- the loop every caller writes around compute() -------------------------------------------------
+def semi_implicit_euler(compute, particles, velocities, dt, steps, massive_only=False):
+    """``steps`` times: a = compute(affected positions, affecting particles);
+    velocity += a * dt; position += velocity * dt — examples/simple/src/main.rs:45-59 and the
+    reference's circular_orbit! test (gravity/newtonian/mod.rs:318-331), each operation rounded
+    separately in the particle scalar type (Rust never fuses a * b + c).
+
+    ``compute(affected, affecting)`` is one of the oracle algorithms above.  massive_only: the
+    `Reordered` storage — all particles affected, those with mu != 0 affecting
+    (storage.rs:153-163, 219-229).  Returns (particles, velocities, last accelerations)."""
+    p = np.array(particles, copy=True)
+    dt_s = p.dtype.type(dt)
+    d = p.shape[1] - 1
+    v = np.zeros((len(p), d), p.dtype) if velocities is None else np.array(velocities, dtype=p.dtype)
+    a = np.zeros((len(p), d), p.dtype)
+    for _ in range(steps):
+        src = np.ascontiguousarray(p[p[:, -1] != 0]) if massive_only else p
+        a = compute(np.ascontiguousarray(p[:, :d]), src)
+        v = v + a * dt_s          # numpy keeps the dtype: two roundings, like the Rust expression
+        p[:, :d] = p[:, :d] + v * dt_s
+    return p, v, a

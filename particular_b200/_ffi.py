@@ -53,6 +53,23 @@ class TreeInfo(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class SimConfig(C.Structure):
+    _fields_ = [("dim", C.c_uint32), ("scalar", C.c_uint32), ("algorithm", C.c_uint32),
+                ("flags", C.c_uint32), ("theta", C.c_double), ("softening", C.c_double),
+                ("dt", C.c_double), ("checked", C.c_int32), ("reserved", C.c_uint32)]
+
+
+class SimInfo(C.Structure):
+    _fields_ = [("n_particles", C.c_uint64), ("n_affecting", C.c_uint64), ("steps_done", C.c_uint64),
+                ("d_particles", C.c_void_p), ("d_velocities", C.c_void_p),
+                ("d_accelerations", C.c_void_p), ("graph_active", C.c_uint32),
+                ("launches_per_step", C.c_uint32)]
+
+
+BRUTE_FORCE, BARNES_HUT = 0, 1
+F32, F64 = 0, 1
+SIM_AFFECTING_MASSIVE_ONLY, SIM_NO_GRAPH = 1, 2
+
 TREE_KEYS, TREE_PERM, TREE_NODE_BEGIN, TREE_NODE_COUNT, TREE_NODE_LEVEL, TREE_NODE_FIRST_CHILD, \
     TREE_NODE_NUM_CHILDREN, TREE_NODE_COM_MASS = range(8)
 
@@ -96,6 +113,12 @@ SIGNATURES = {
     "pcuda_bruteforce_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _i, _vp, _vp]),
     "pcuda_barneshut_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp, _vp]),
     "pcuda_barneshut_f32x3_sharded": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp]),
+    "pcuda_sim_create": (_i, [_vp, C.POINTER(SimConfig), _vp, _vp, _sz, C.POINTER(_vp)]),
+    "pcuda_sim_configure": (_i, [_vp, _vp, C.POINTER(SimConfig)]),
+    "pcuda_sim_step": (_i, [_vp, _vp, C.c_uint32]),
+    "pcuda_sim_read": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "pcuda_sim_info": (_i, [_vp, C.POINTER(SimInfo)]),
+    "pcuda_sim_destroy": (None, [_vp, _vp]),
     # not in the stable header: measurement / tuning hooks
     "pcuda_probe_fp32": (_i, [_vp, _i, _i, _i, C.POINTER(_d), C.POINTER(_f)]),
     "pcuda_debug_set": (_i, [C.c_char_p, _i]),

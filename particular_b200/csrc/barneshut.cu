@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(128) moments_kernel(NodeRec *__restrict__ node
 // chunks of <= 32 consecutive targets.  Without this, 32 consecutive keys that cross e.g. the
 // centre of a Plummer sphere have a bounding box spanning the core and open millions of nodes.
 constexpr int GROUP_BLOCK = 256;
-constexpr int SEG_MAX_LIMIT = 256;
+constexpr int SEG_MAX_LIMIT = 1024;
 
 template <int DIM>
 __global__ void __launch_bounds__(256) boundary_levels(const uint64_t *__restrict__ keys, int n,
@@ -1440,7 +1440,7 @@ static int read_counters(pcuda_ctx *ctx) {
 
 // One-shot Barnes-Hut with device pointers: build over `affecting`, traverse for `affected`.
 static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t na, const float *d_src,
-                       size_t nb, float theta, float eps, float *d_out) {
+                       size_t nb, float theta, float eps, float *d_out, int tgt_stride = 0) {
     if (!d_aff && na != nb)
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
                     "affected == NULL means affected == affecting, but n_affected != n_affecting");
@@ -1449,7 +1449,7 @@ static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t 
     PCUDA_TRY(build_dim(ctx, ctx->call_tree, dim, d_src, nb));
     phase_end(ctx, PH_BUILD);
     phase_begin(ctx, PH_COMPUTE);
-    PCUDA_TRY(traverse(ctx, ctx->call_tree, d_aff, na, theta, eps, d_out));
+    PCUDA_TRY(traverse(ctx, ctx->call_tree, d_aff, na, theta, eps, d_out, tgt_stride));
     phase_end(ctx, PH_COMPUTE);
     return PCUDA_OK;
 }
@@ -1520,6 +1520,12 @@ static int oneshot_host(pcuda_ctx *ctx, uint32_t dim, const float *aff, size_t n
 }
 
 }  // namespace bh
+
+int bh_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, size_t na,
+                   const float *d_src, size_t nb, float theta, float softening, float *d_out) {
+    return bh::oneshot_dev(ctx, (uint32_t)dim, tgt_stride ? d_tgt : nullptr, na, d_src, nb, theta,
+                           softening, d_out, tgt_stride);
+}
 
 int bh_debug_set(const char *key, int value) {
     const std::string k = key ? key : "";

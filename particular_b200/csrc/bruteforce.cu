@@ -510,8 +510,9 @@ static int dev_f32x3(pcuda_ctx *ctx, const float *d_aff, size_t na, const float 
                       checked, d_out);
 }
 
-static int dev_f32x2(pcuda_ctx *ctx, const float *d_aff, size_t na, const float *d_src, size_t nb,
-                     float eps, int checked, float *d_out) {
+// tgt == nullptr: the targets are the sources (stride 3).
+static int run_f32x2(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na,
+                     const float *d_src, size_t nb, float eps, int checked, float *d_out) {
     float4 *packed = nullptr;
     if (nb) {
         PCUDA_CUDA_TRY(ctx, ctx->d_packed_src.ensure(nb * sizeof(float4)));
@@ -520,9 +521,13 @@ static int dev_f32x2(pcuda_ctx *ctx, const float *d_aff, size_t na, const float 
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
     }
-    const float *tgt = d_aff ? d_aff : d_src;
-    const int stride = d_aff ? 2 : 3;
-    return run_f32<2>(ctx, tgt, stride, na, packed, nb, eps, checked, d_out);
+    return run_f32<2>(ctx, d_tgt ? d_tgt : d_src, d_tgt ? tgt_stride : 3, na, packed, nb, eps,
+                      checked, d_out);
+}
+
+static int dev_f32x2(pcuda_ctx *ctx, const float *d_aff, size_t na, const float *d_src, size_t nb,
+                     float eps, int checked, float *d_out) {
+    return run_f32x2(ctx, d_aff, 2, na, d_src, nb, eps, checked, d_out);
 }
 
 static int dev_f64x3(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src, size_t nb,
@@ -624,6 +629,24 @@ static int dev_call(pcuda_ctx *ctx, RunFn run) {
 }
 
 }  // namespace bf
+
+int bf_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, size_t na,
+                   const float *d_src, size_t nb, float softening, int checked, float *d_out) {
+    if (dim == 2) return bf::run_f32x2(ctx, d_tgt, tgt_stride, na, d_src, nb, softening, checked, d_out);
+    if (nb && !bf::aligned(d_src, 16))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "affecting must be 16-byte aligned");
+    return bf::run_f32<3>(ctx, d_tgt, tgt_stride, na, reinterpret_cast<const float4 *>(d_src), nb,
+                          softening, checked, d_out);
+}
+
+int bf_enqueue_f64x3(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t na,
+                     const double *d_src, size_t nb, double softening, int checked, double *d_out) {
+    if (nb && !bf::aligned(d_src, 16))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "affecting must be 16-byte aligned");
+    return bf::run_f64(ctx, d_tgt, tgt_stride, na, reinterpret_cast<const double4 *>(d_src), nb,
+                       softening, checked, d_out);
+}
+
 }  // namespace pcuda
 
 using namespace pcuda;

@@ -71,6 +71,7 @@ struct pcuda_ctx {
     pcuda_tree *call_tree = nullptr;  // tree reused by the one-shot Barnes-Hut entry points
 
     pcuda::Nccl *nccl = nullptr;
+    int live_sims = 0;  // pcuda_sim objects created on this context (sim.cu)
 };
 
 namespace pcuda {
@@ -95,6 +96,17 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// Internal enqueue-only entry points shared with sim.cu (device pointers, context stream, no
+// synchronisation, no timing).  Target rows have `tgt_stride` scalars (positions first); source
+// rows are {position, mu} = dim + 1 scalars.
+int bf_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, size_t na,
+                   const float *d_src, size_t nb, float softening, int checked, float *d_out);
+int bf_enqueue_f64x3(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t na,
+                     const double *d_src, size_t nb, double softening, int checked, double *d_out);
+// tgt_stride == 0: the targets are the sources themselves (the `&[P]` storage).
+int bh_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, size_t na,
+                   const float *d_src, size_t nb, float theta, float softening, float *d_out);
 
 void tree_free(pcuda_ctx *ctx, pcuda_tree *t);
 int bh_debug_set(const char *key, int value);  // barneshut.cu tuning hooks

@@ -33,7 +33,7 @@ from ._ffi import CudaError, check, lib
 
 __all__ = [
     "Between", "Ordered", "Reordered", "Acceleration", "AccelerationSoftened", "CudaContext",
-    "BruteForce", "BarnesHut", "RootedOrthtree", "cuda_brute_force", "cuda_barnes_hut",
+    "BruteForce", "BarnesHut", "RootedOrthtree", "Simulation", "cuda_brute_force", "cuda_barnes_hut",
     "is_affecting", "CudaError",
 ]
 
@@ -421,6 +421,105 @@ class BarnesHut:
         check(lib.pcuda_tree_last_counters(self.ctx.handle, C.byref(c)), self.ctx.handle)
         return {"node_interactions": int(c[0]), "particle_interactions": int(c[1]),
                 "node_tests": int(c[2]), "list_entries": int(c[3]), "groups": int(c[4])}
+
+
+# ---- device-resident stepping -------------------------------------------------
+class Simulation:
+    """Particles, velocities and accelerations resident on the device; ``step(n)`` runs n times
+
+        accelerations = algorithm.compute(storage)           # BruteForce or BarnesHut
+        velocity += acceleration * dt; position += velocity * dt
+
+    i.e. the loop every caller of the reference writes around ``compute`` (examples/simple/src/
+    main.rs:45-59; circular_orbit!, gravity/newtonian/mod.rs:318-331) without the per-call
+    upload / read-back of the wgpu operator (gpu/resources.rs:37-39, 318-349).
+
+    ``algorithm`` is a ``BruteForce`` or ``BarnesHut`` object (it supplies the context, the
+    interaction and theta).  ``affecting="massive"`` is the ``Reordered`` storage: every particle is
+    affected, only those with mu != 0 affect (storage.rs:153-163, 219-229)."""
+
+    def __init__(self, algorithm, particles, velocities=None, *, dt: float, affecting: str = "all",
+                 graph: bool = True):
+        p = _as_particles(particles)
+        _suffix(p)
+        d = p.shape[1] - 1
+        if affecting not in ("all", "massive"):
+            raise ValueError("affecting must be 'all' or 'massive'")
+        if velocities is not None:
+            velocities = np.ascontiguousarray(velocities, dtype=p.dtype)
+            if velocities.shape != (len(p), d):
+                raise TypeError(f"velocities must be {(len(p), d)}, got {velocities.shape}")
+        self.ctx, self.algorithm = algorithm.ctx, algorithm
+        self.n, self.dim, self.dtype = len(p), d, p.dtype
+        self._flags = ((_ffi.SIM_AFFECTING_MASSIVE_ONLY if affecting == "massive" else 0)
+                       | (0 if graph else _ffi.SIM_NO_GRAPH))
+        self.dt = float(dt)
+        h = C.c_void_p()
+        cfg = self._config()
+        check(lib.pcuda_sim_create(self.ctx.handle, C.byref(cfg), _ptr(p), _ptr(velocities), len(p),
+                                   C.byref(h)), self.ctx.handle)
+        self._h = h
+
+    def _config(self) -> "_ffi.SimConfig":
+        alg, it = self.algorithm, self.algorithm.interaction
+        is_bh = isinstance(alg, BarnesHut)
+        return _ffi.SimConfig(self.dim, _ffi.F64 if self.dtype == np.float64 else _ffi.F32,
+                              _ffi.BARNES_HUT if is_bh else _ffi.BRUTE_FORCE, self._flags,
+                              alg.theta if is_bh else 0.0, float(it.softening), self.dt,
+                              int(it.is_checked), 0)
+
+    def configure(self, algorithm=None, dt: Optional[float] = None) -> None:
+        """Swap the algorithm / interaction / dt of a live simulation."""
+        if algorithm is not None:
+            self.algorithm = algorithm
+        if dt is not None:
+            self.dt = float(dt)
+        cfg = self._config()
+        check(lib.pcuda_sim_configure(self.ctx.handle, self._h, C.byref(cfg)), self.ctx.handle)
+
+    def step(self, n_steps: int = 1) -> None:
+        """Enqueue n_steps steps on the context stream (asynchronous; read() waits)."""
+        check(lib.pcuda_sim_step(self.ctx.handle, self._h, int(n_steps)), self.ctx.handle)
+
+    def read(self, particles: bool = True, velocities: bool = True, accelerations: bool = False):
+        """Blocking read-back -> (particles, velocities, accelerations); skipped ones are None."""
+        p = np.empty((self.n, self.dim + 1), self.dtype) if particles else None
+        v = np.empty((self.n, self.dim), self.dtype) if velocities else None
+        a = np.empty((self.n, self.dim), self.dtype) if accelerations else None
+        check(lib.pcuda_sim_read(self.ctx.handle, self._h, _ptr(p), _ptr(v), _ptr(a)),
+              self.ctx.handle)
+        return p, v, a
+
+    def particles(self) -> np.ndarray:
+        return self.read(True, False, False)[0]
+
+    def velocities(self) -> np.ndarray:
+        return self.read(False, True, False)[1]
+
+    def accelerations(self) -> np.ndarray:
+        return self.read(False, False, True)[2]
+
+    def info(self) -> dict:
+        i = _ffi.SimInfo()
+        check(lib.pcuda_sim_info(self._h, C.byref(i)), self.ctx.handle)
+        return {k: getattr(i, k) for k, _ in i._fields_}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self.ctx._h is not None:
+            lib.pcuda_sim_destroy(self.ctx.handle, self._h)
+        self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- extension-trait sugar (GpuCompute, gpu/mod.rs:13-37) -------------------------------------------

@@ -90,6 +90,28 @@ def test_circular_orbit_barnes_hut():
     assert e_d < 1e-1 and e_e < 1e-1
 
 
+def test_semi_implicit_euler_helper_is_the_reference_loop():
+    """oracle.semi_implicit_euler (the checker of the device-resident stepping tests) reproduces
+    the circular_orbit! loop above step for step, bit for bit."""
+    for dtype in (np.float32, np.float64):
+        dt = dtype(1.0 / 60.0)
+        particles = np.array([[0, 0, 0, 1e6], [100, 0, 0, 0]], dtype=dtype)
+        vel = np.array([[0, 0, 0], [0, 100, 0]], dtype=dtype)
+        p_ref, v_ref = particles.copy(), vel.copy()
+        for _ in range(50):
+            acc = oracle.brute_force(p_ref[:, :3], p_ref)
+            v_ref = (v_ref + acc * dt).astype(dtype)
+            p_ref[:, :3] = p_ref[:, :3] + v_ref * dt
+        p, v, a = oracle.semi_implicit_euler(lambda aff, src: oracle.brute_force(aff, src),
+                                             particles, vel, float(dt), 50)
+        assert p.dtype == dtype and np.array_equal(p, p_ref) and np.array_equal(v, v_ref)
+    # massive_only: massless particles are affected but do not affect (Reordered storage)
+    p0 = np.array([[0, 0, 0, 1.0], [1, 0, 0, 0.0], [0, 2, 0, 0.0]], dtype=np.float64)
+    _, _, a = oracle.semi_implicit_euler(lambda aff, src: oracle.brute_force(aff, src), p0, None,
+                                         0.1, 1, massive_only=True)
+    assert np.array_equal(a[0], [0, 0, 0]) and np.allclose(a[1], [-1, 0, 0]) and np.allclose(a[2], [0, -0.25, 0])
+
+
 def test_doctest_fold_identities():
     """lib.rs:247-261: forces[i] is the left fold 0 + f(i,0) + f(i,1) + f(i,2), bit-exactly, in f64.
     Stated for accelerations: out[i] == ((0 + t(i,0)) + t(i,1)) + t(i,2) with t the pair term."""

@@ -3,7 +3,7 @@
  * `particular` N-body crate.
  *
  * This is the drop-in boundary: exactly what a `particular-cuda` Rust crate binds through
- * `extern "C"` (see INTEGRATION.md and rust/particular-cuda/src/ffi.rs) so that its
+ * `extern "C"` (see INTEGRATION.md and rust/particular-cuda/src/ffi.rs (source only: no Rust toolchain here)) so that its
  * `cuda::BruteForce` / `cuda::BarnesHut` types can implement the crate's operator trait
  *     Interaction<Between<&[P1], &[P2]>>           (reference particular/src/lib.rs:364-370)
  * the same way the existing wgpu operator does     (reference particular/src/gpu/mod.rs:179-208).

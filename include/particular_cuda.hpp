@@ -15,6 +15,7 @@
 //   sequential::BarnesHut<S, T>              sequential.rs:439-543 -> cuda::BarnesHut<T>
 //   RootedOrthtree                           storage.rs:11-46    -> cuda::RootedOrthtree
 //   GpuResources + wgpu::Device + Queue      gpu/mod.rs:85-159   -> cuda::CudaContext
+//   the caller's integration loop            examples/simple/src/main.rs:45-59 -> cuda::Simulation
 //
 // A user particle type needs `position()` returning something indexable with operator[] for D
 // components and `mu()` returning the gravitational parameter — what `#[derive(Position, Mass)]`
@@ -337,6 +338,95 @@ private:
     CudaContext *ctx_;
     double theta_;
     T interaction_;
+};
+
+// Device-resident stepping (particular_cuda.h "device-resident stepping"): the loop every caller of
+// the reference writes around compute() — accelerations, then velocity += a * dt and
+// position += velocity * dt (examples/simple/src/main.rs:45-59) — with the particles kept on the
+// device between steps.  `Algorithm` is cuda::BruteForce<T> or cuda::BarnesHut<T>.
+enum class Affecting { All, Massive };  // Massive == the Reordered storage (storage.rs:153-163)
+
+template <class S, std::size_t D>
+class Simulation {
+public:
+    using Vector = std::array<S, D>;
+
+    template <class T, class P>
+    Simulation(CudaContext &ctx, const BruteForce<T> &, T interaction, const std::vector<P> &particles,
+               const std::vector<Vector> &velocities, double dt, Affecting affecting = Affecting::All)
+        : ctx_(&ctx) {
+        create(PCUDA_BRUTE_FORCE, 0.0, interaction.softening(), T::checked, particles, velocities, dt,
+               affecting);
+    }
+    template <class T, class P>
+    Simulation(CudaContext &ctx, const BarnesHut<T> &, double theta, T interaction,
+               const std::vector<P> &particles, const std::vector<Vector> &velocities, double dt,
+               Affecting affecting = Affecting::All)
+        : ctx_(&ctx) {
+        create(PCUDA_BARNES_HUT, theta, interaction.softening(), T::checked, particles, velocities, dt,
+               affecting);
+    }
+    ~Simulation() { pcuda_sim_destroy(ctx_->handle(), sim_); }
+    Simulation(const Simulation &) = delete;
+    Simulation &operator=(const Simulation &) = delete;
+
+    void step(unsigned n_steps = 1) { ctx_->check(pcuda_sim_step(ctx_->handle(), sim_, n_steps)); }
+    std::vector<GravitationalField<S, D>> particles() {
+        std::vector<S> flat(n_ * (D + 1));
+        ctx_->check(pcuda_sim_read(ctx_->handle(), sim_, flat.data(), nullptr, nullptr));
+        std::vector<GravitationalField<S, D>> out(n_);
+        for (std::size_t i = 0; i < n_; ++i) {
+            for (std::size_t k = 0; k < D; ++k) out[i].position_[k] = flat[i * (D + 1) + k];
+            out[i].m = flat[i * (D + 1) + D];
+        }
+        return out;
+    }
+    std::vector<Vector> velocities() {
+        std::vector<S> flat(n_ * D);
+        ctx_->check(pcuda_sim_read(ctx_->handle(), sim_, nullptr, flat.data(), nullptr));
+        return detail::unpack<S, D>(flat, n_);
+    }
+    std::vector<Vector> accelerations() {
+        std::vector<S> flat(n_ * D);
+        ctx_->check(pcuda_sim_read(ctx_->handle(), sim_, nullptr, nullptr, flat.data()));
+        return detail::unpack<S, D>(flat, n_);
+    }
+    pcuda_sim_info_t info() const {
+        pcuda_sim_info_t i{};
+        pcuda_sim_info(sim_, &i);
+        return i;
+    }
+
+private:
+    template <class P>
+    void create(uint32_t algorithm, double theta, double softening, bool checked,
+                const std::vector<P> &particles, const std::vector<Vector> &velocities, double dt,
+                Affecting affecting) {
+        static_assert(std::is_same_v<S, float> || std::is_same_v<S, double>, "f32 or f64");
+        n_ = particles.size();
+        auto flat = detail::pack_affecting<S, D>(particles.data(), n_);
+        std::vector<S> vel;
+        if (!velocities.empty()) {
+            if (velocities.size() != n_) throw Error(PCUDA_ERR_INVALID_ARGUMENT, "one velocity per particle");
+            vel.resize(n_ * D);
+            for (std::size_t i = 0; i < n_; ++i)
+                for (std::size_t k = 0; k < D; ++k) vel[i * D + k] = velocities[i][k];
+        }
+        pcuda_sim_config cfg{};
+        cfg.dim = (uint32_t)D;
+        cfg.scalar = std::is_same_v<S, double> ? PCUDA_F64 : PCUDA_F32;
+        cfg.algorithm = algorithm;
+        cfg.flags = affecting == Affecting::Massive ? PCUDA_SIM_AFFECTING_MASSIVE_ONLY : 0u;
+        cfg.theta = theta;
+        cfg.softening = softening;
+        cfg.dt = dt;
+        cfg.checked = checked ? 1 : 0;
+        ctx_->check(pcuda_sim_create(ctx_->handle(), &cfg, flat.data(), vel.empty() ? nullptr : vel.data(),
+                                     n_, &sim_));
+    }
+    CudaContext *ctx_;
+    pcuda_sim *sim_ = nullptr;
+    std::size_t n_ = 0;
 };
 
 // Extension-trait sugar (GpuCompute, gpu/mod.rs:13-37).

@@ -133,6 +133,27 @@ int main() {
         auto a_tree = cuda::BarnesHut(ctx, 0.5, Acceleration<true>{})
                           .compute(Between<const std::vector<B> &, const cuda::RootedOrthtree &>{ps, tree});
         CHECK(a_tree.size() == 1500 && tree.info().n_particles == 1500, "tree traversal");
+        // circular_orbit! run on the device (cuda::Simulation): 20 orbits of 377 steps, and a
+        // Reordered-style simulation in which the massless particles do not affect anything
+        {
+            std::vector<B> two = {{{0, 0, 0}, 1e6f}, {{100, 0, 0}, 0.f}};
+            std::vector<std::array<float, 3>> vel = {{0, 0, 0}, {0, 100, 0}};
+            cuda::Simulation<float, 3> sim(ctx, bf, Acceleration<true>{}, two, vel, 1.0 / 60.0,
+                                           cuda::Affecting::Massive);
+            sim.step(377 * 20);
+            auto after = sim.particles();
+            double d2 = 0;
+            for (int k = 0; k < 3; ++k) d2 += std::pow((double)after[0].position_[k] - after[1].position_[k], 2);
+            CHECK(std::fabs(1.0 - 100.0 / std::sqrt(d2)) < 1e-2, "device orbit drift %.3e",
+                  std::fabs(1.0 - 100.0 / std::sqrt(d2)));
+            CHECK(after[0].position_[0] == 0.f && after[0].position_[1] == 0.f,
+                  "the massless satellite must not move the primary");
+            CHECK(sim.info().steps_done == 377 * 20 && sim.info().n_affecting == 1, "sim info");
+            cuda::BarnesHut bh(ctx, 0.5, AccelerationSoftened<true>(1.0));
+            cuda::Simulation<float, 3> sim_bh(ctx, bh, 0.5, AccelerationSoftened<true>(1.0), ps, {}, 1e-3);
+            sim_bh.step(2);
+            CHECK(sim_bh.accelerations().size() == 1500 && sim_bh.velocities().size() == 1500, "bh sim sizes");
+        }
         // empty input: CPU-path semantics (the wgpu path panics, gpu/resources.rs:24)
         std::vector<B> none;
         CHECK(bf.compute(none).empty(), "empty slice");

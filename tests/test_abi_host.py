@@ -31,6 +31,33 @@ def test_library_exports_every_declared_symbol():
     assert _ffi.lib.pcuda_abi_version() == 1
 
 
+def test_rust_ffi_declares_every_symbol_with_matching_arity():
+    """rust/particular-cuda/src/ffi.rs cannot be compiled here (no Rust toolchain), so at least keep
+    it in lock-step with the header: same symbol set, same number of arguments, and build.rs lists
+    the translation units build.py compiles."""
+    def arities(text, pat):
+        out = {}
+        for name, args in re.findall(pat, text, flags=re.S):
+            args = args.strip()
+            out[name] = 0 if args in ("", "void") else args.count(",") + 1
+        return out
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    c_ar = arities(hdr, r"\b(pcuda_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;")
+    rs = open(os.path.join(ROOT, "rust", "particular-cuda", "src", "ffi.rs")).read()
+    rs = re.sub(r"//.*", "", rs)
+    rs_ar = arities(rs, r"pub fn (pcuda_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]*)?;")
+    assert set(c_ar) == set(declared_symbols())
+    missing = set(c_ar) - set(rs_ar)
+    assert not missing, f"ffi.rs lacks {sorted(missing)}"
+    assert not set(rs_ar) - set(c_ar), f"ffi.rs declares unknown {sorted(set(rs_ar) - set(c_ar))}"
+    for name, n in c_ar.items():
+        assert rs_ar[name] == n, f"{name}: header has {n} arguments, ffi.rs {rs_ar[name]}"
+    from particular_b200.build import SOURCES
+    build_rs = open(os.path.join(ROOT, "rust", "particular-cuda", "build.rs")).read()
+    for unit in SOURCES:
+        assert f'"{unit}"' in build_rs, f"build.rs does not compile {unit}"
+
+
 def test_header_compiles_as_c():
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
                        capture_output=True, text=True)

@@ -135,6 +135,134 @@ def measured_hbm_peak():
         return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_digest.py --traffic; measured under the
+    profiler at the bench's own workload, so it is reported beside the timing, never derived
+    from it).  None when no capture is committed for this kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[kernel_key]
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), t.get("source")
+    except Exception:
+        return None, None
+
+
+# ---- the other BASELINE.json configs + the stepping path (ride along at 1 GPU) -----------------------
+def other_configs(ctx, stream, flush, steps=3):
+    """configs[2] (10k massive + 16M massless split), configs[4] (f64 N=256k; 2-D Barnes-Hut N=4M)
+    and device-resident stepping at the reference's criterion size: device-resident times with
+    CUDA events on the context stream, L2 flushed between steps."""
+    import torch
+
+    import particular_b200 as pb
+    dev = torch.device("cuda", ctx.device)
+    out = {}
+
+    def timed(fn, k=steps, warm=2):
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        ts = []
+        for _ in range(k):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            ctx.sync()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    rng = np.random.default_rng(SEED)
+    # configs[2]: ring-formation style split, `Reordered`: all particles affected, massive affecting
+    n_massive, n_massless = 10_000, 16_000_000
+    src = uniform_cloud(n_massive)
+    d_src = torch.from_numpy(src).to(dev)
+    tgt = np.empty((n_massive + n_massless, 3), np.float32)
+    tgt[:n_massive] = src[:, :3]
+    tgt[n_massive:] = rng.uniform(-5e3, 5e3, (n_massless, 3))
+    d_tgt = torch.from_numpy(tgt).to(dev)
+    d_out = torch.empty_like(d_tgt)
+    bf = pb.BruteForce(ctx, pb.AccelerationSoftened.checked(1.0))
+    ms = timed(lambda: bf.compute_device(d_tgt.data_ptr(), len(tgt), d_src.data_ptr(), n_massive,
+                                         d_out.data_ptr()))
+    h_tgt = ctx.pinned_empty(tgt.shape, np.float32)
+    h_tgt[:] = tgt
+    h_out = ctx.pinned_empty(tgt.shape, np.float32)
+    e2e = timed(lambda: bf.compute(pb.Between(h_tgt, src), out=h_out), k=2, warm=1)
+    pairs = float(len(tgt)) * n_massive
+    out["split_10k_massive_16M_massless"] = {
+        "config": "BASELINE configs[2]: 10,000 massive + 16,000,000 massless, Between(all, massive) "
+                  "(Reordered storage), AccelerationSoftened::checked(1.0)",
+        "pairs_per_step": pairs, "ms_per_step": ms, "value": pairs / ms / 1e6, "unit": "Gpairs/s",
+        "e2e": {"ms_per_step": e2e, "value": pairs / e2e / 1e6, "unit": "Gpairs/s",
+                "h2d_bytes_per_step": int(tgt.nbytes + src.nbytes), "d2h_bytes_per_step": int(tgt.nbytes)}}
+    del d_tgt, d_out, d_src
+
+    # configs[4a]: f64 precision path
+    n64 = 262_144
+    p64 = uniform_cloud(n64).astype(np.float64)
+    d_p = torch.from_numpy(p64).to(dev)
+    d_o = torch.empty((n64, 3), dtype=torch.float64, device=dev)
+    bf64 = pb.BruteForce(ctx, pb.Acceleration.checked())
+    ms = timed(lambda: bf64.compute_device(None, n64, d_p.data_ptr(), n64, d_o.data_ptr(), "f64x3"))
+    peak64 = ctx.sm_count * 64 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
+    tf = FLOP_PER_PAIR * float(n64) * n64 / (ms * 1e-3) / 1e12
+    out["f64_256k"] = {"config": "BASELINE configs[4]: brute force 3-D f64, N=262144, Acceleration::checked()",
+                       "ms_per_step": ms, "value": float(n64) * n64 / ms / 1e6, "unit": "Gpairs/s",
+                       "fp64_tflops_20flop_per_pair": tf, "fp64_peak_tflops_nominal": peak64,
+                       "frac": tf / peak64}
+    del d_p, d_o
+
+    # configs[4b]: particle-toy style 2-D quadtree
+    n2 = 4_194_304
+    p2 = np.empty((n2, 3), np.float32)
+    p2[:, :2] = rng.uniform(-5e3, 5e3, (n2, 2))
+    p2[:, 2] = rng.uniform(1e3, 1e9, n2)
+    d_p = torch.from_numpy(p2).to(dev)
+    d_o = torch.empty((n2, 2), dtype=torch.float32, device=dev)
+    bh2 = pb.BarnesHut(ctx, 0.5, pb.AccelerationSoftened.checked(100.0))
+    ms = timed(lambda: bh2.compute_device(None, n2, d_p.data_ptr(), n2, d_o.data_ptr(), "f32x2"))
+    t = ctx.timings()
+    out["barnes_hut_2d_4M"] = {"config": "BASELINE configs[4]: Barnes-Hut 2-D f32 quadtree, theta=0.5, N=4194304 "
+                                         "uniform square, AccelerationSoftened::checked(100)",
+                               "ms_per_step": ms, "build_ms": t["build_ms"], "traverse_ms": t["compute_ms"],
+                               "value": n2 / (ms * 1e-3), "unit": "particles/s"}
+    del d_p, d_o
+
+    # device-resident stepping at the reference's criterion size (benches/benchmark.rs: N = 2^k)
+    nb = 1024
+    pb_small = uniform_cloud(nb)
+    inter = pb.Acceleration.checked()
+    res = {}
+    for label, graph in (("graph", True), ("eager", False)):
+        with pb.Simulation(pb.BruteForce(ctx, inter), pb_small, dt=1e-3, graph=graph) as sim:
+            sim.step(64)
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            sim.step(2048)
+            e1.record(stream)
+            ctx.sync()
+            wall = time.perf_counter() - t0
+            res[label] = {"us_per_step_device": 1e3 * e0.elapsed_time(e1) / 2048,
+                          "us_per_step_wall": 1e6 * wall / 2048}
+    one = pb.BruteForce(ctx, inter)
+    one.compute(pb_small)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        one.compute(pb_small)
+    res["one_shot_host_api"] = {"us_per_step_wall": 1e6 * (time.perf_counter() - t0) / 200}
+    out["stepping_1024"] = {"config": "device-resident stepping (pcuda_sim_*), brute force 3-D f32, N=1024 "
+                                      "(criterion bench shape), 2048 steps; one_shot_host_api = upload + "
+                                      "kernel + read-back per step, as the reference's wgpu operator works",
+                            **res}
+    return out
+
+
 # ---- CPU arms ----------------------------------------------------------------------------------------
 def cpu_bruteforce_rate(P, seconds, steps=1):
     """Restated parallel::BruteForceSimd<8> on a bounded target sample x all sources.
@@ -380,6 +508,8 @@ def bench_bruteforce(args, n, rank, world, local_rank):
                 "peak_probe_ffma2": probe_tf, "frac_of_probe": achieved / probe_tf,
                 "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": n_local * n,
                 "kernel_ms": k_ms, "traffic": None}
+    if world == 1:
+        roofline["traffic"], roofline["traffic_source"] = ncu_traffic("pair_kernel_f32_n1M")
 
     line = {"metric": "brute-force pair interactions per second", "value": value,
             "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -402,6 +532,10 @@ def bench_bruteforce(args, n, rank, world, local_rank):
                                                    steps=3, warmup=2, cpu_seconds=args.cpu_seconds)
         except Exception as e:  # keep the headline line even if the ride-along fails
             line["barnes_hut"] = {"error": repr(e)}
+        try:
+            line["other_configs"] = other_configs(ctx, stream, flush)
+        except Exception as e:
+            line["other_configs"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -494,12 +628,12 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
                    "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 12,
                    "bytes_are": "per rank"},
            "gpu_launches": total_launches, "counters_last_step_rank0": counters,
-           "roofline": {"bound": "hbm", "kernel": "pcuda::bh::traverse_kernel", "achieved": achieved_gbs,
+           "roofline": {"bound": "hbm", "kernel": "pcuda::bh::traverse2_kernel", "achieved": achieved_gbs,
                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                         "peak_source": hbm_src, "bytes_per_launch": trav_bytes, "kernel_ms": trav_ms,
-                        "traffic": None,
-                        "note": "the node set is served from L2 (ncu: 96 % hit rate, ~1 GB of DRAM "
-                                "traffic per launch); the kernel is instruction-issue bound, see "
+                        "traffic": ncu_traffic("traverse2_kernel_n10M")[0] if world == 1 and n == 10_000_000 else None,
+                        "note": "the node set is served from L2 (ncu: 93 % hit rate, ~1.1 GB of DRAM "
+                                "traffic per launch); the kernel is FP32-pipe / issue bound, see "
                                 "traversal_fp32 and profiles/"},
            "traversal_fp32": {"achieved": FLOP_PER_PAIR * inter_n / (trav_ms * 1e-3) / 1e12,
                               "unit": "TFLOP/s", "interactions_per_target": inter_n / max(n_local, 1),

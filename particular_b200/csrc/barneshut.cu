@@ -283,7 +283,7 @@ __global__ void init_build(NodeRec *nodes, uint32_t n, BuildState *st, uint32_t 
 }
 
 constexpr int EXPAND_BLOCK = 128;
-constexpr uint32_t SMALL_LEVEL = 8192;  // levels up to this many nodes take the node-x-digit path
+static uint32_t g_small_level = 131072;  // levels up to this many nodes take the node-x-digit path
 
 // One level: every node with more than `nleaf` particles (and above the last level) is split into
 // the distinct next-level digits present in its key range (binary searches); the children of the
@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(EXPAND_BLOCK) expand_level(NodeRec *__restrict
                                                              const uint64_t *__restrict__ keys,
                                                              BuildState *st,
                                                              unsigned long long *tile_state,
-                                                             int level, uint32_t nleaf) {
+                                                             int level, uint32_t nleaf,
+                                                             uint32_t small_level) {
     constexpr int X = Dims<DIM>::X;
     const uint32_t lvl_begin = st->level_begin[level], lvl_end = st->level_begin[level + 1];
     const uint32_t lvl_count = lvl_end - lvl_begin;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(EXPAND_BLOCK) expand_level(NodeRec *__restrict
     // A level with few nodes (the top of the tree: huge key ranges, hardly any parallelism) is
     // latency bound, so there X threads serve one node: thread d finds where digit d starts by an
     // independent binary search, instead of one thread walking from digit to digit.
-    const bool small = lvl_count <= SMALL_LEVEL;
+    const bool small = lvl_count <= small_level;
     const uint32_t tile_nodes = small ? EXPAND_BLOCK / X : EXPAND_BLOCK;
     const uint32_t n_tiles = (lvl_count + tile_nodes - 1) / tile_nodes;
     const uint32_t capacity = st->capacity;
@@ -1270,8 +1271,7 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
         cap_nodes = std::min<size_t>(t->nodes.cap / sizeof(NodeRec), 0xfffffff0ull);
         PCUDA_CUDA_TRY(ctx, t->moments.ensure(cap_nodes * 4 * sizeof(double)));
         // tiles of 128 nodes, or of 128 / 2^DIM nodes on levels of <= SMALL_LEVEL nodes
-        const size_t max_tiles = (cap_nodes + EXPAND_BLOCK - 1) / EXPAND_BLOCK + 1 +
-                                 SMALL_LEVEL / (EXPAND_BLOCK / Dims<DIM>::X);
+        const size_t max_tiles = cap_nodes / (EXPAND_BLOCK / Dims<DIM>::X) + 2;
         PCUDA_CUDA_TRY(ctx, t->scan_in.ensure(sizeof(BuildState)));
         PCUDA_CUDA_TRY(ctx, t->scan_out.ensure(max_tiles * sizeof(unsigned long long)));
         BuildState *d_state = t->scan_in.as<BuildState>();
@@ -1281,7 +1281,7 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
         for (int level = 0; level <= BITS; ++level)
             expand_level<DIM><<<grid, EXPAND_BLOCK, 0, st>>>(
                 t->nodes.as<NodeRec>(), t->d_keys(), d_state,
-                t->scan_out.as<unsigned long long>(), level, t->leaf_size);
+                t->scan_out.as<unsigned long long>(), level, t->leaf_size, g_small_level);
         const unsigned mgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (cap_nodes + 127) / 128);
         for (int level = BITS; level >= 0; --level)
             moments_kernel<DIM><<<mgrid, 128, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(),
@@ -1535,6 +1535,10 @@ int bh_debug_set(const char *key, int value) {
     }
     if (k == "bh_tpl" && (value == 1 || value == 2)) {
         bh::g_tpl = value;
+        return PCUDA_OK;
+    }
+    if (k == "bh_small_level" && value >= 0) {
+        bh::g_small_level = (uint32_t)value;
         return PCUDA_OK;
     }
     if (k == "bh_count") {

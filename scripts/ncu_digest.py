@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-nlines = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+nlines = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 30
 
 
 def ncu(*args):
@@ -31,6 +31,20 @@ want = ["gpu__time_duration.sum", "sm__issue_active.avg.pct_of_peak_sustained_el
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "launch__registers_per_thread",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 units = rows[1]
+if "--traffic" in sys.argv:  # python scripts/ncu_digest.py <rep> --traffic <key>: update profiles/ncu_traffic.json
+    import json
+    import os
+    key = sys.argv[sys.argv.index("--traffic") + 1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    val = lambda k: float(v[h.index(k)]) * scale[units[h.index(k)]]  # noqa: E731
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[key] = {"dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+                 "kernel": v[h.index("Kernel Name")], "gpu_time_ms_under_ncu": float(v[h.index("gpu__time_duration.sum")]),
+                 "source": f"ncu --set full --clock-control none, one launch; report {os.path.basename(rep)}"}
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    print(json.dumps(data[key]))
+    sys.exit(0)
 for k in want:
     if k in h:
         print(f"{k:75s} {v[h.index(k)]} {units[h.index(k)]}")

@@ -227,8 +227,11 @@ int pcuda_bruteforce_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size
 /* One multi-GPU Barnes-Hut step ("replicated build"): rank r owns the contiguous
  * block [r * cap, r * cap + n_local) of the n_total particles, cap = ceil(n_total / world_size)
  * (the call fails if n_local does not match).  The records are all-gathered in place into
- * d_gathered_xyzm (world_size * cap records), every GPU builds the identical tree over all
- * n_total particles and traverses it for its own block: out[i] = acceleration of local particle i.
+ * d_gathered_xyzm (world_size * cap records) and every GPU builds the identical tree over all
+ * n_total particles.  The traversal is sharded by key range (rank r walks the tree for the r-th
+ * block of the Morton-sorted particles: compact target groups, no target sort), the per-range
+ * accelerations are all-gathered (12 B per particle) and every rank keeps the rows of the
+ * particles it owns: out[i] = acceleration of local particle i.
  * _dev: device pointers, enqueued on the context stream, no synchronisation. */
 int pcuda_barneshut_f32x3_sharded_dev(pcuda_ctx *ctx, const float *d_local_xyzm, size_t n_local,
                                       size_t n_total, float theta, float softening, int checked,

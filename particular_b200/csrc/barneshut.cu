@@ -1321,6 +1321,10 @@ static int g_tpl = 2;        // targets per lane in the traversal: 1 (groups of 
 
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
 // tgt_stride: floats per target row (0 = bare positions, i.e. `dim`).
+static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
+                           const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
+                           float eps, float *d_out);
+
 static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na, float theta,
                     float eps, float *d_out, int tgt_stride = 0) {
     const int dim = t->dim;
@@ -1367,6 +1371,16 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         tgt_perm = p;
         tgt_keys = keys[cur].as<uint64_t>();
     }
+    return traverse_sorted(ctx, t, tgt_sorted, tgt_keys, tgt_perm, na, theta, eps, d_out);
+}
+
+// Targets already in key order ({x,y,z,_} records + their keys in the tree's frame); tgt_perm maps
+// traversal order to the output row (nullptr: out row = traversal position).
+static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
+                           const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
+                           float eps, float *d_out) {
+    const int dim = t->dim;
+    cudaStream_t st = ctx->stream;
     // K5a: groups from the target keys
     const int n = (int)na;
     PCUDA_CUDA_TRY(ctx, ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
@@ -1456,8 +1470,28 @@ static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t 
 
 // Multi-GPU step (one process per GPU), "replicated build": every rank owns the contiguous block
 // [rank * cap, rank * cap + n_local) of the n_total particles (cap = ceil(n_total / world)).  The
-// local records are all-gathered in place over NVLink, every GPU builds the identical tree over
-// all n_total particles, and only the local block is traversed.
+// local records are all-gathered in place over NVLink and every GPU builds the identical tree over
+// all n_total particles.  The traversal is sharded by KEY RANGE, not by input block: rank r walks
+// the tree for the sorted particles [r * cap, (r + 1) * cap) — spatially compact, so its target
+// groups are as tight as on one GPU and alias the tree's own sorted records (no target sort) —
+// writes their accelerations in key order, the per-range results are all-gathered in place
+// (12 B per particle), and each rank picks the rows of the particles it owns through the sort
+// permutation.  (Sharding the traversal by input block made every rank walk a sparse random sample
+// of the cloud: 8.7 ms instead of 6.0 ms per rank at N = 10M on 4 GPUs.)
+__global__ void __launch_bounds__(256) pick_owned_rows(const float *__restrict__ acc_sorted,
+                                                       const uint32_t *__restrict__ perm, int n,
+                                                       uint32_t lo, uint32_t hi,
+                                                       float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t orig = perm[i];
+    if (orig < lo || orig >= hi) return;
+    float *o = out + (size_t)(orig - lo) * 3;
+    o[0] = acc_sorted[(size_t)i * 3 + 0];
+    o[1] = acc_sorted[(size_t)i * 3 + 1];
+    o[2] = acc_sorted[(size_t)i * 3 + 2];
+}
+
 static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total,
                        float theta, float eps, float *d_gathered, float *d_out) {
     int world = 1, rank = 0;
@@ -1476,12 +1510,33 @@ static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, siz
     if (world > 1) PCUDA_TRY(pcuda_comm_allgather_dev(ctx, slot, d_gathered, cap * 16));
     phase_end(ctx, PH_COMM);
     if (!ctx->call_tree) ctx->call_tree = new pcuda_tree();
+    pcuda_tree *t = ctx->call_tree;
     phase_begin(ctx, PH_BUILD);
-    PCUDA_TRY(build_dim(ctx, ctx->call_tree, 3, d_gathered, n_total));
+    PCUDA_TRY(build_dim(ctx, t, 3, d_gathered, n_total));
     phase_end(ctx, PH_BUILD);
+    if (world == 1) {
+        phase_begin(ctx, PH_COMPUTE);
+        PCUDA_TRY(traverse(ctx, t, nullptr, n_total, theta, eps, d_out));
+        phase_end(ctx, PH_COMPUTE);
+        return PCUDA_OK;
+    }
+    // accelerations of all particles in key order, world * cap rows; this rank fills rows [lo, hi)
+    PCUDA_CUDA_TRY(ctx, ctx->d_misc.ensure((size_t)world * cap * 3 * sizeof(float)));
+    float *acc_sorted = ctx->d_misc.as<float>();
     phase_begin(ctx, PH_COMPUTE);
-    PCUDA_TRY(traverse(ctx, ctx->call_tree, slot, n_local, theta, eps, d_out, 4));
+    if (n_local)
+        PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>() + lo, t->d_keys() + lo, nullptr, n_local,
+                                  theta, eps, acc_sorted + lo * 3));
     phase_end(ctx, PH_COMPUTE);
+    phase_begin(ctx, PH_COMM2);  // the second exchange of the call; reported inside comm_ms
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, acc_sorted + (size_t)rank * cap * 3, acc_sorted, cap * 12));
+    if (n_local) {
+        pick_owned_rows<<<(unsigned)((n_total + 255) / 256), 256, 0, ctx->stream>>>(
+            acc_sorted, t->d_perm(), (int)n_total, (uint32_t)lo, (uint32_t)hi, d_out);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    phase_end(ctx, PH_COMM2);
     return PCUDA_OK;
 }
 

@@ -42,7 +42,7 @@ struct DevBuf {
 
 struct Nccl;  // comm.cu
 
-enum Phase { PH_UPLOAD = 0, PH_COMM, PH_BUILD, PH_COMPUTE, PH_DOWNLOAD, PH_COUNT };
+enum Phase { PH_UPLOAD = 0, PH_COMM, PH_BUILD, PH_COMPUTE, PH_DOWNLOAD, PH_COMM2, PH_COUNT };  // COMM2: a second exchange (added to comm_ms)
 
 }  // namespace pcuda
 

@@ -40,13 +40,13 @@ void phase_end(pcuda_ctx *ctx, Phase p) {
 int timings_collect(pcuda_ctx *ctx) {
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float *dst[PH_COUNT] = {&ctx->timings.upload_ms, &ctx->timings.comm_ms, &ctx->timings.build_ms,
-                            &ctx->timings.compute_ms, &ctx->timings.download_ms};
+                            &ctx->timings.compute_ms, &ctx->timings.download_ms, nullptr};
+    ctx->timings = pcuda_timings{};
     for (int i = 0; i < PH_COUNT; ++i) {
-        *dst[i] = 0.f;
-        if (ctx->ev_used[i]) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ctx->ev0[i], ctx->ev1[i]) == cudaSuccess) *dst[i] = ms;
-        }
+        if (!ctx->ev_used[i]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0[i], ctx->ev1[i]) != cudaSuccess) continue;
+        *(dst[i] ? dst[i] : &ctx->timings.comm_ms) += ms;
     }
     ctx->timings.kernel_launches = ctx->launches;
     return PCUDA_OK;

@@ -28,7 +28,7 @@ for kv in os.environ.get("PCUDA_DEBUG", "").split(","):  # e.g. PCUDA_DEBUG=bh_t
 P = plummer_cloud(N) if DIST == "plummer" else uniform_cloud(N)
 d_src = torch.from_numpy(P).cuda()
 d_out = torch.zeros((N, 3), dtype=torch.float32, device="cuda")
-with pb.CudaContext(0) as ctx:
+with pb.CudaContext(0, leaf_size=int(os.environ.get("PCUDA_LEAF", "0"))) as ctx:
     bh = pb.BarnesHut(ctx, THETA, pb.Acceleration.checked())
     for it in range(ITERS):
         bh.compute_device(None, N, d_src.data_ptr(), N, d_out.data_ptr())

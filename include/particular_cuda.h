@@ -293,6 +293,33 @@ int pcuda_sim_read(pcuda_ctx *ctx, pcuda_sim *sim, void *particles, void *veloci
 int pcuda_sim_info(const pcuda_sim *sim, pcuda_sim_info_t *out);
 void pcuda_sim_destroy(pcuda_ctx *ctx, pcuda_sim *sim);
 
+/* ---- user-defined interactions (new) -------------------------------------
+ * The reference's GPU operator is generic over the interaction: an InteractionShader supplies WGSL
+ * source defining the types Affected / Affecting / Interaction and `fn compute(p1, p2, out)`, their
+ * byte sizes and optional push constants (gpu/mod.rs:40-82), which the operator pastes into a
+ * brute-force template and compiles at run time (gpu/bruteforce.wgsl, gpu/resources.rs:126-233).
+ * CUDA counterpart: `source` is CUDA C++ that defines
+ *     struct Affected {..}; struct Affecting {..}; struct Interaction {..}; struct Push {..};
+ *     __device__ void compute(const Affected &p1, const Affecting &p2, Interaction &out);
+ * (`push` is a __constant__ Push visible to compute; Interaction() is the start value, as
+ * `var out = Interaction()` in the WGSL template; struct sizes must be multiples of 4 bytes; floating
+ * point contraction is off, so a * b + c rounds twice like the Rust CPU path unless the source calls
+ * fmaf itself).  It is compiled with NVRTC for sm_100a and evaluated as
+ *     interactions[i] = fold over all affecting j, in order, of compute(affected[i], affecting[j], out)
+ * Gravity itself does not go through here (Acceleration / AccelerationSoftened have tuned kernels). */
+typedef struct pcuda_interaction pcuda_interaction;
+/* Compile only (no device needed): status + compiler log; the analogue of shader validation. */
+int pcuda_interaction_check(const char *source, char *log, size_t log_len);
+int pcuda_interaction_create(pcuda_ctx *ctx, const char *source, pcuda_interaction **out);
+/* sizes[0..3] = sizeof(Affected), sizeof(Affecting), sizeof(Interaction), sizeof(Push) on the device
+ * (AFFECTED_SIZE / AFFECTING_SIZE / INTERACTION_SIZE of the reference trait). */
+int pcuda_interaction_sizes(const pcuda_interaction *interaction, uint32_t sizes[4]);
+/* HOST buffers laid out as arrays of the source's structs; blocking. */
+int pcuda_interaction_brute_force(pcuda_ctx *ctx, pcuda_interaction *interaction, const void *affected,
+                                  size_t n_affected, const void *affecting, size_t n_affecting,
+                                  const void *push, size_t push_bytes, void *out);
+void pcuda_interaction_destroy(pcuda_ctx *ctx, pcuda_interaction *interaction);
+
 #ifdef __cplusplus
 }
 #endif

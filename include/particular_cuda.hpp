@@ -30,6 +30,7 @@
 #include <cstddef>
 #include <stdexcept>
 #include <string>
+#include <cstdint>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -427,6 +428,49 @@ private:
     CudaContext *ctx_;
     pcuda_sim *sim_ = nullptr;
     std::size_t n_ = 0;
+};
+
+// A user-defined pair interaction compiled for the device at run time: the counterpart of
+// implementing InteractionShader<P1, P2> for the wgpu operator (gpu/mod.rs:40-82).  `source` is CUDA
+// C++ defining struct Affected / Affecting / Interaction / Push and
+// `__device__ void compute(const Affected &, const Affecting &, Interaction &)`; the host-side
+// template arguments must be trivially copyable types with the same layouts (sizes are checked
+// against the device compiler's sizeof, the reference's AFFECTED_SIZE / AFFECTING_SIZE /
+// INTERACTION_SIZE).
+struct NoPush {};
+template <class Affected, class Affecting, class Interaction, class Push = NoPush>
+class CustomInteraction {
+public:
+    CustomInteraction(CudaContext &ctx, const std::string &source) : ctx_(&ctx) {
+        static_assert(std::is_trivially_copyable_v<Affected> && std::is_trivially_copyable_v<Affecting> &&
+                      std::is_trivially_copyable_v<Interaction> && std::is_trivially_copyable_v<Push>);
+        ctx.check(pcuda_interaction_create(ctx.handle(), source.c_str(), &it_));
+        uint32_t sz[4];
+        pcuda_interaction_sizes(it_, sz);
+        if (sz[0] != sizeof(Affected) || sz[1] != sizeof(Affecting) || sz[2] != sizeof(Interaction) ||
+            (!std::is_same_v<Push, NoPush> && sz[3] < sizeof(Push))) {
+            pcuda_interaction_destroy(ctx.handle(), it_);
+            throw Error(PCUDA_ERR_INVALID_ARGUMENT, "host types do not match the device structs");
+        }
+    }
+    ~CustomInteraction() { pcuda_interaction_destroy(ctx_->handle(), it_); }
+    CustomInteraction(const CustomInteraction &) = delete;
+    CustomInteraction &operator=(const CustomInteraction &) = delete;
+
+    // Interaction<Between<&[P1], &[P2]>> with the brute-force algorithm
+    std::vector<Interaction> brute_force(const std::vector<Affected> &affected,
+                                         const std::vector<Affecting> &affecting, const Push &push = Push{}) {
+        std::vector<Interaction> out(affected.size());
+        const bool has_push = !std::is_same_v<Push, NoPush>;
+        ctx_->check(pcuda_interaction_brute_force(ctx_->handle(), it_, affected.data(), affected.size(),
+                                                  affecting.data(), affecting.size(), has_push ? &push : nullptr,
+                                                  has_push ? sizeof(Push) : 0, out.data()));
+        return out;
+    }
+
+private:
+    CudaContext *ctx_;
+    pcuda_interaction *it_ = nullptr;
 };
 
 // Extension-trait sugar (GpuCompute, gpu/mod.rs:13-37).

@@ -8,7 +8,7 @@ run before the library exists; any use of the API without the built library rais
 (there is no CPU fallback).
 """
 __all__ = ["Acceleration", "AccelerationSoftened", "BarnesHut", "Between", "BruteForce",
-           "CudaContext", "CudaError", "Ordered", "Reordered", "RootedOrthtree", "Simulation",
+           "CudaContext", "CudaError", "CustomInteraction", "check_interaction_source", "Ordered", "Reordered", "RootedOrthtree", "Simulation",
            "cuda_barnes_hut", "cuda_brute_force", "is_affecting", "ShardedBruteForce",
            "ShardedBarnesHut",
            "shard_bounds", "shard_capacity"]

@@ -119,6 +119,11 @@ SIGNATURES = {
     "pcuda_sim_read": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "pcuda_sim_info": (_i, [_vp, C.POINTER(SimInfo)]),
     "pcuda_sim_destroy": (None, [_vp, _vp]),
+    "pcuda_interaction_check": (_i, [C.c_char_p, C.c_char_p, _sz]),
+    "pcuda_interaction_create": (_i, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "pcuda_interaction_sizes": (_i, [_vp, C.POINTER(C.c_uint32 * 4)]),
+    "pcuda_interaction_brute_force": (_i, [_vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "pcuda_interaction_destroy": (None, [_vp, _vp]),
     # not in the stable header: measurement / tuning hooks
     "pcuda_probe_fp32": (_i, [_vp, _i, _i, _i, C.POINTER(_d), C.POINTER(_f)]),
     "pcuda_debug_set": (_i, [C.c_char_p, _i]),

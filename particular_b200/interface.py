@@ -33,7 +33,8 @@ from ._ffi import CudaError, check, lib
 
 __all__ = [
     "Between", "Ordered", "Reordered", "Acceleration", "AccelerationSoftened", "CudaContext",
-    "BruteForce", "BarnesHut", "RootedOrthtree", "Simulation", "cuda_brute_force", "cuda_barnes_hut",
+    "BruteForce", "BarnesHut", "RootedOrthtree", "Simulation", "CustomInteraction",
+    "check_interaction_source", "cuda_brute_force", "cuda_barnes_hut",
     "is_affecting", "CudaError",
 ]
 
@@ -181,6 +182,73 @@ class AccelerationSoftened:
     @staticmethod
     def unchecked(softening):
         return AccelerationSoftened(float(softening), False)
+
+
+def check_interaction_source(source: str) -> str:
+    """Compile an interaction source without a device (the analogue of validating a shader);
+    returns the compiler log, raises CudaError with the log when it does not compile."""
+    log = C.create_string_buffer(1 << 16)
+    check(lib.pcuda_interaction_check(source.encode(), log, len(log)))
+    return log.value.decode()
+
+
+class CustomInteraction:
+    """A user-defined pair interaction compiled for the device at run time — the counterpart of
+    implementing ``InteractionShader<P1, P2>`` (gpu/mod.rs:40-82) for the wgpu operator.
+
+    ``source`` is CUDA C++ defining ``struct Affected``, ``struct Affecting``, ``struct Interaction``,
+    ``struct Push`` (push constants) and
+    ``__device__ void compute(const Affected &p1, const Affecting &p2, Interaction &out)``.
+    ``affected_dtype`` / ``affecting_dtype`` / ``interaction_dtype`` / ``push_dtype`` are numpy
+    (structured) dtypes with exactly those layouts (AFFECTED_SIZE / AFFECTING_SIZE /
+    INTERACTION_SIZE of the reference trait are checked against the device compiler's sizeof).
+    Use it with ``BruteForce(ctx, custom).compute(Between(affected, affecting))``."""
+
+    def __init__(self, ctx: "CudaContext", source: str, affected_dtype, affecting_dtype,
+                 interaction_dtype, push_dtype=None, push=None):
+        self.ctx = ctx
+        self.affected_dtype = np.dtype(affected_dtype)
+        self.affecting_dtype = np.dtype(affecting_dtype)
+        self.interaction_dtype = np.dtype(interaction_dtype)
+        self.push_dtype = None if push_dtype is None else np.dtype(push_dtype)
+        self.push = push
+        h = C.c_void_p()
+        check(lib.pcuda_interaction_create(ctx.handle, source.encode(), C.byref(h)), ctx.handle)
+        self._h = h
+        sizes = (C.c_uint32 * 4)()
+        check(lib.pcuda_interaction_sizes(h, C.byref(sizes)), ctx.handle)
+        self.sizes = tuple(int(x) for x in sizes)
+        want = (self.affected_dtype.itemsize, self.affecting_dtype.itemsize, self.interaction_dtype.itemsize)
+        if want != self.sizes[:3]:
+            self.close()
+            raise TypeError(f"dtype sizes {want} do not match the device structs {self.sizes[:3]}")
+        if self.push_dtype is not None and self.push_dtype.itemsize > self.sizes[3]:
+            self.close()
+            raise TypeError(f"push dtype has {self.push_dtype.itemsize} bytes, struct Push {self.sizes[3]}")
+
+    def brute_force(self, affected, affecting, push=None) -> np.ndarray:
+        a = np.ascontiguousarray(affected, dtype=self.affected_dtype)
+        b = np.ascontiguousarray(affecting, dtype=self.affecting_dtype)
+        out = np.zeros(len(a), dtype=self.interaction_dtype)
+        push = self.push if push is None else push
+        pbytes = None
+        if push is not None:
+            pbytes = np.ascontiguousarray(np.asarray(push, dtype=self.push_dtype).reshape(1))
+        check(lib.pcuda_interaction_brute_force(
+            self.ctx.handle, self._h, _ptr(a), len(a), _ptr(b), len(b),
+            _ptr(pbytes), 0 if pbytes is None else pbytes.nbytes, _ptr(out)), self.ctx.handle)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self.ctx._h is not None:
+            lib.pcuda_interaction_destroy(self.ctx.handle, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- context (the analogue of GpuResources + wgpu::Device + wgpu::Queue, gpu/mod.rs:85-159) -------
@@ -353,6 +421,13 @@ class BruteForce:
         """`out`: optional preallocated (n_affected, D) result array (e.g. from
         ``ctx.pinned_empty``); by default a fresh array is returned, as the reference returns a
         fresh Vec (gpu/mod.rs:184, 205)."""
+        if isinstance(self.interaction, CustomInteraction):
+            if isinstance(storage, Between):
+                return self.interaction.brute_force(storage.affected, storage.affecting)
+            if self.interaction.affected_dtype != self.interaction.affecting_dtype:
+                raise TypeError("a slice storage needs Affected and Affecting to be the same type; "
+                                "use Between(affected, affecting)")
+            return self.interaction.brute_force(storage, storage)  # &[P] => Between(slice, slice)
         aff, src = _resolve(storage)
         sfx = _suffix(src)
         d = src.shape[1] - 1

@@ -5,7 +5,7 @@
 // there is no link-time NCCL dependency.
 use std::{env, path::PathBuf, process::Command};
 
-const UNITS: [&str; 6] = ["context.cu", "bruteforce.cu", "barneshut.cu", "comm.cu", "sim.cu", "probe.cu"];
+const UNITS: [&str; 7] = ["context.cu", "bruteforce.cu", "barneshut.cu", "comm.cu", "sim.cu", "custom.cu", "probe.cu"];
 
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());

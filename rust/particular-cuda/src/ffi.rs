@@ -14,6 +14,10 @@ pub struct pcuda_tree {
 pub struct pcuda_sim {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct pcuda_interaction {
+    _private: [u8; 0],
+}
 
 pub const PCUDA_OK: c_int = 0;
 pub const PCUDA_ERR_NO_DEVICE: c_int = -2;
@@ -173,4 +177,13 @@ extern "C" {
                           velocities: *mut c_void, accelerations: *mut c_void) -> c_int;
     pub fn pcuda_sim_info(sim: *const pcuda_sim, out: *mut pcuda_sim_info_t) -> c_int;
     pub fn pcuda_sim_destroy(ctx: *mut pcuda_ctx, sim: *mut pcuda_sim);
+
+    pub fn pcuda_interaction_check(source: *const c_char, log: *mut c_char, log_len: usize) -> c_int;
+    pub fn pcuda_interaction_create(ctx: *mut pcuda_ctx, source: *const c_char, out: *mut *mut pcuda_interaction) -> c_int;
+    pub fn pcuda_interaction_sizes(interaction: *const pcuda_interaction, sizes: *mut u32) -> c_int;
+    pub fn pcuda_interaction_brute_force(ctx: *mut pcuda_ctx, interaction: *mut pcuda_interaction,
+                                         affected: *const c_void, n_affected: usize, affecting: *const c_void,
+                                         n_affecting: usize, push: *const c_void, push_bytes: usize,
+                                         out: *mut c_void) -> c_int;
+    pub fn pcuda_interaction_destroy(ctx: *mut pcuda_ctx, interaction: *mut pcuda_interaction);
 }

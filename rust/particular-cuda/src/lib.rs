@@ -370,6 +370,48 @@ impl<S, const D: usize> Drop for Simulation<'_, S, D> {
     }
 }
 
+/// A user-defined pair interaction compiled for the device at run time — the counterpart of
+/// implementing `InteractionShader<P1, P2>` (gpu/mod.rs:40-82).  `source` is CUDA C++ defining
+/// `struct Affected / Affecting / Interaction / Push` and
+/// `__device__ void compute(const Affected&, const Affecting&, Interaction&)`.  `A`, `B`, `I`, `P` are
+/// `#[repr(C)]` `Copy` types with the same layouts (checked against the device `sizeof`).
+pub struct CustomInteraction<A, B, I, P = ()> {
+    raw: *mut ffi::pcuda_interaction,
+    _types: PhantomData<(A, B, I, P)>,
+}
+
+impl<A: Copy, B: Copy, I: Copy + Default, P: Copy> CustomInteraction<A, B, I, P> {
+    pub fn new(ctx: &mut CudaContext, source: &str) -> Self {
+        let src = std::ffi::CString::new(source).expect("interaction source contains a NUL byte");
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { ffi::pcuda_interaction_create(ctx.raw, src.as_ptr(), &mut raw) }, ctx.raw);
+        let mut sizes = [0u32; 4];
+        unsafe { ffi::pcuda_interaction_sizes(raw, sizes.as_mut_ptr()) };
+        assert_eq!(
+            [sizes[0] as usize, sizes[1] as usize, sizes[2] as usize],
+            [std::mem::size_of::<A>(), std::mem::size_of::<B>(), std::mem::size_of::<I>()],
+            "host types do not match the device structs"
+        );
+        Self { raw, _types: PhantomData }
+    }
+
+    /// `interactions[i] = fold over affecting of compute(affected[i], affecting[j], out)`.
+    pub fn brute_force(&mut self, ctx: &mut CudaContext, affected: &[A], affecting: &[B], push: &P) -> Vec<I> {
+        let mut out = vec![I::default(); affected.len()];
+        check(unsafe {
+            ffi::pcuda_interaction_brute_force(ctx.raw, self.raw, affected.as_ptr().cast(), affected.len(),
+                affecting.as_ptr().cast(), affecting.len(), (push as *const P).cast(), std::mem::size_of::<P>(),
+                out.as_mut_ptr().cast())
+        }, ctx.raw);
+        out
+    }
+
+    /// Frees the device module; must be called with the context that created it.
+    pub fn destroy(self, ctx: &mut CudaContext) {
+        unsafe { ffi::pcuda_interaction_destroy(ctx.raw, self.raw) }
+    }
+}
+
 #[cfg(test)]
 mod tests {
     //! The reference's own algorithm tests, instantiated for the CUDA operators: `tests_algorithms!`

@@ -154,6 +154,33 @@ int main() {
             sim_bh.step(2);
             CHECK(sim_bh.accelerations().size() == 1500 && sim_bh.velocities().size() == 1500, "bh sim sizes");
         }
+        // a user-defined interaction (InteractionShader counterpart): neighbour count within a radius
+        {
+            struct Pos { float x, y, z; };
+            struct Count { uint32_t n; };
+            struct Cut { float r2; };
+            cuda::CustomInteraction<Pos, Pos, Count, Cut> neighbours(ctx, R"(
+                struct Affected { float x, y, z; };
+                typedef Affected Affecting;
+                struct Interaction { uint32_t n; };
+                struct Push { float r2; };
+                __device__ void compute(const Affected &a, const Affecting &b, Interaction &out) {
+                    const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+                    const float d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 != 0.f && d2 <= push.r2) out.n += 1u;
+                })");
+            std::vector<Pos> pts;
+            for (const B &b : ps) pts.push_back({b.pos[0], b.pos[1], b.pos[2]});
+            auto counts = neighbours.brute_force(pts, pts, Cut{100.f});
+            uint32_t expect0 = 0;
+            for (const Pos &q : pts) {
+                const float dx = q.x - pts[0].x, dy = q.y - pts[0].y, dz = q.z - pts[0].z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 != 0.f && d2 <= 100.f) ++expect0;
+            }
+            CHECK(counts.size() == pts.size() && counts[0].n == expect0, "custom interaction: %u vs %u",
+                  counts.empty() ? 0u : counts[0].n, expect0);
+        }
         // empty input: CPU-path semantics (the wgpu path panics, gpu/resources.rs:24)
         std::vector<B> none;
         CHECK(bf.compute(none).empty(), "empty slice");

@@ -20,6 +20,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 ABI_VERSION = 1
+FLAG_NO_PHASE_TIMINGS = 1
 UNIQUE_ID_BYTES = 128
 
 OK = 0

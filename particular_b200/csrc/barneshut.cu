@@ -443,6 +443,44 @@ __global__ void __launch_bounds__(EXPAND_BLOCK) expand_level(NodeRec *__restrict
 //   internal:  sums of the children's moments in child order
 //   com_k = (float)(Mx_k / M), mass = (float)M;  M == 0 => com = position of the first particle.
 template <int DIM>
+__device__ __forceinline__ void node_moments(NodeRec *__restrict__ nodes, double *__restrict__ mom,
+                                             const float4 *__restrict__ sorted, uint32_t j) {
+    NodeRec nd = nodes[j];
+    const uint32_t nc = nd.nchild_level & 0xffu;
+    double m[4] = {0.0, 0.0, 0.0, 0.0};  // x, y, z, M
+    if (nc == 0) {
+        for (uint32_t i = nd.begin; i < nd.begin + nd.count; ++i) {
+            const float4 p = sorted[i];
+            const double mi = (double)p.w;
+            m[0] = __dadd_rn(m[0], __dmul_rn(mi, (double)p.x));
+            m[1] = __dadd_rn(m[1], __dmul_rn(mi, (double)p.y));
+            if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(mi, (double)p.z));
+            m[3] = __dadd_rn(m[3], mi);
+        }
+    } else {
+        for (uint32_t c = nd.first_child; c < nd.first_child + nc; ++c) {
+            const double4 q = reinterpret_cast<const double4 *>(mom)[c];
+            m[0] = __dadd_rn(m[0], q.x);
+            m[1] = __dadd_rn(m[1], q.y);
+            if (DIM == 3) m[2] = __dadd_rn(m[2], q.z);
+            m[3] = __dadd_rn(m[3], q.w);
+        }
+    }
+    reinterpret_cast<double4 *>(mom)[j] = make_double4(m[0], m[1], m[2], m[3]);
+    float4 cm;
+    if (m[3] == 0.0) {
+        const float4 p = sorted[nd.begin];
+        cm = make_float4(p.x, p.y, DIM == 3 ? p.z : 0.f, 0.f);
+    } else {
+        cm.x = (float)__ddiv_rn(m[0], m[3]);
+        cm.y = (float)__ddiv_rn(m[1], m[3]);
+        cm.z = DIM == 3 ? (float)__ddiv_rn(m[2], m[3]) : 0.f;
+        cm.w = (float)m[3];
+    }
+    nodes[j].cm = cm;
+}
+
+template <int DIM>
 __global__ void __launch_bounds__(128) moments_kernel(NodeRec *__restrict__ nodes,
                                                       double *__restrict__ mom,
                                                       const float4 *__restrict__ sorted,
@@ -450,41 +488,127 @@ __global__ void __launch_bounds__(128) moments_kernel(NodeRec *__restrict__ node
     const uint32_t lvl_begin = st->level_begin[level];
     const uint32_t lvl_count = st->level_begin[level + 1] - lvl_begin;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < lvl_count;
-         t += gridDim.x * blockDim.x) {
-        const uint32_t j = lvl_begin + t;
-        NodeRec nd = nodes[j];
-        const uint32_t nc = nd.nchild_level & 0xffu;
-        double m[4] = {0.0, 0.0, 0.0, 0.0};  // x, y, z, M
-        if (nc == 0) {
-            for (uint32_t i = nd.begin; i < nd.begin + nd.count; ++i) {
-                const float4 p = sorted[i];
-                const double mi = (double)p.w;
-                m[0] = __dadd_rn(m[0], __dmul_rn(mi, (double)p.x));
-                m[1] = __dadd_rn(m[1], __dmul_rn(mi, (double)p.y));
-                if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(mi, (double)p.z));
-                m[3] = __dadd_rn(m[3], mi);
+         t += gridDim.x * blockDim.x)
+        node_moments<DIM>(nodes, mom, sorted, lvl_begin + t);
+}
+
+// K4 for small inputs: the whole tree — every level of the expansion, then every level of the
+// moments — in ONE single-block launch with __syncthreads() between levels.  Below ~32k particles
+// the per-level kernels above are pure launch latency (44 launches ~ 150 us for a tree that takes
+// a few microseconds to build), and the reference's own benchmark lives at those sizes
+// (benches/benchmark.rs: N = 2 .. 65536).  Same numbering (children in node order, breadth-first)
+// and the same arithmetic as the per-level path: the arrays are bit-identical.
+constexpr int SMALL_TREE_BLOCK = 1024;
+constexpr size_t SMALL_TREE_MAX_N = 32768;
+
+template <int DIM>
+__global__ void __launch_bounds__(SMALL_TREE_BLOCK) build_small(NodeRec *__restrict__ nodes,
+                                                                double *__restrict__ mom,
+                                                                const uint64_t *__restrict__ keys,
+                                                                const float4 *__restrict__ sorted,
+                                                                BuildState *st, uint32_t n,
+                                                                uint32_t capacity, uint32_t nleaf) {
+    constexpr int X = Dims<DIM>::X;
+    constexpr int BITS = Dims<DIM>::BITS;
+    typedef cub::BlockScan<uint32_t, SMALL_TREE_BLOCK> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ uint32_t s_begin[36];
+    __shared__ uint32_t s_overflow;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        NodeRec r;
+        r.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.first_child = 0;
+        r.nchild_level = 0;
+        r.begin = 0;
+        r.count = n;
+        nodes[0] = r;
+        for (int i = 0; i < 36; ++i) s_begin[i] = i == 0 ? 0u : 1u;
+        s_overflow = 0;
+    }
+    __syncthreads();
+    int levels = 0;
+    for (int level = 0; level <= BITS; ++level) {
+        const uint32_t lvl_begin = s_begin[level], lvl_end = s_begin[level + 1];
+        const uint32_t lvl_count = lvl_end - lvl_begin;
+        if (lvl_count == 0 || s_overflow) break;
+        levels = level + 1;
+        const int shift = DIM * (BITS - level - 1);
+        uint32_t running = 0;  // children emitted so far on this level (uniform)
+        for (uint32_t base = 0; base < lvl_count; base += SMALL_TREE_BLOCK) {
+            const uint32_t t = base + tid;
+            uint32_t c = 0, cb[X + 1];
+            if (t < lvl_count) {
+                const uint32_t begin = nodes[lvl_begin + t].begin, count = nodes[lvl_begin + t].count;
+                if (count > nleaf && level < BITS) {
+                    uint32_t pos = begin;
+                    const uint32_t end = begin + count;
+#pragma unroll
+                    for (int k = 0; k < X; ++k) {
+                        if (pos < end) {
+                            cb[k] = pos;
+                            pos = next_digit_start<DIM>(keys, pos, end, shift);
+                            ++c;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k <= X; ++k)
+                        if (k == (int)c) cb[k] = end;
+                }
             }
-        } else {
-            for (uint32_t c = nd.first_child; c < nd.first_child + nc; ++c) {
-                const double4 q = reinterpret_cast<const double4 *>(mom)[c];
-                m[0] = __dadd_rn(m[0], q.x);
-                m[1] = __dadd_rn(m[1], q.y);
-                if (DIM == 3) m[2] = __dadd_rn(m[2], q.z);
-                m[3] = __dadd_rn(m[3], q.w);
+            uint32_t off, total;
+            __syncthreads();  // scan_tmp reuse
+            Scan(scan_tmp).ExclusiveSum(c, off, total);
+            const unsigned long long first = (unsigned long long)lvl_end + running + off;
+            if ((unsigned long long)lvl_end + running + total > capacity) {
+                if (tid == 0) s_overflow = 1;
+                c = 0;
             }
+            if (t < lvl_count) {
+                NodeRec &nd = nodes[lvl_begin + t];
+                if (c == 0) {
+                    nd.first_child = 0;
+                    nd.nchild_level = (uint32_t)level << 8;
+                } else {
+                    nd.first_child = (uint32_t)first;
+                    nd.nchild_level = c | (uint32_t)level << 8;
+#pragma unroll
+                    for (int k = 0; k < X; ++k) {
+                        if (k < (int)c) {
+                            NodeRec ch;
+                            ch.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+                            ch.first_child = 0;
+                            ch.nchild_level = (uint32_t)(level + 1) << 8;
+                            ch.begin = cb[k];
+                            ch.count = cb[k + 1] - cb[k];
+                            nodes[first + k] = ch;
+                        }
+                    }
+                }
+            }
+            running += total;
         }
-        reinterpret_cast<double4 *>(mom)[j] = make_double4(m[0], m[1], m[2], m[3]);
-        float4 cm;
-        if (m[3] == 0.0) {
-            const float4 p = sorted[nd.begin];
-            cm = make_float4(p.x, p.y, DIM == 3 ? p.z : 0.f, 0.f);
-        } else {
-            cm.x = (float)__ddiv_rn(m[0], m[3]);
-            cm.y = (float)__ddiv_rn(m[1], m[3]);
-            cm.z = DIM == 3 ? (float)__ddiv_rn(m[2], m[3]) : 0.f;
-            cm.w = (float)m[3];
+        __syncthreads();
+        if (tid == 0 && !s_overflow) s_begin[level + 2] = lvl_end + running;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        // levels past the last one are empty: level_begin stays at the end of the last level
+        for (int l = levels + 1; l < 36; ++l) s_begin[l] = s_begin[levels];
+    }
+    __syncthreads();
+    if (!s_overflow) {
+        for (int level = levels - 1; level >= 0; --level) {
+            const uint32_t lvl_begin = s_begin[level], lvl_count = s_begin[level + 1] - lvl_begin;
+            for (uint32_t t = tid; t < lvl_count; t += SMALL_TREE_BLOCK)
+                node_moments<DIM>(nodes, mom, sorted, lvl_begin + t);
+            __syncthreads();
         }
-        nodes[j].cm = cm;
+    }
+    if (tid < 36) st->level_begin[tid] = s_begin[tid];
+    if (tid == 0) {
+        st->overflow = s_overflow;
+        st->capacity = capacity;
     }
 }
 
@@ -1276,18 +1400,26 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
         PCUDA_CUDA_TRY(ctx, t->scan_out.ensure(max_tiles * sizeof(unsigned long long)));
         BuildState *d_state = t->scan_in.as<BuildState>();
         PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(t->scan_out.p, 0, max_tiles * sizeof(unsigned long long), st));
-        init_build<<<1, 1, 0, st>>>(t->nodes.as<NodeRec>(), (uint32_t)n, d_state, (uint32_t)cap_nodes);
-        const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, max_tiles);
-        for (int level = 0; level <= BITS; ++level)
-            expand_level<DIM><<<grid, EXPAND_BLOCK, 0, st>>>(
-                t->nodes.as<NodeRec>(), t->d_keys(), d_state,
-                t->scan_out.as<unsigned long long>(), level, t->leaf_size, g_small_level);
-        const unsigned mgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (cap_nodes + 127) / 128);
-        for (int level = BITS; level >= 0; --level)
-            moments_kernel<DIM><<<mgrid, 128, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(),
-                                                       t->sorted.as<float4>(), d_state, level);
-        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches += 1 + 2 * (BITS + 1);
+        if (n <= SMALL_TREE_MAX_N) {
+            build_small<DIM><<<1, SMALL_TREE_BLOCK, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(),
+                                                             t->d_keys(), t->sorted.as<float4>(), d_state,
+                                                             (uint32_t)n, (uint32_t)cap_nodes, t->leaf_size);
+            PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        } else {
+            init_build<<<1, 1, 0, st>>>(t->nodes.as<NodeRec>(), (uint32_t)n, d_state, (uint32_t)cap_nodes);
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, max_tiles);
+            for (int level = 0; level <= BITS; ++level)
+                expand_level<DIM><<<grid, EXPAND_BLOCK, 0, st>>>(
+                    t->nodes.as<NodeRec>(), t->d_keys(), d_state,
+                    t->scan_out.as<unsigned long long>(), level, t->leaf_size, g_small_level);
+            const unsigned mgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (cap_nodes + 127) / 128);
+            for (int level = BITS; level >= 0; --level)
+                moments_kernel<DIM><<<mgrid, 128, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(),
+                                                           t->sorted.as<float4>(), d_state, level);
+            PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches += 1 + 2 * (BITS + 1);
+        }
         BuildState h;
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(&t->frame, t->d_frame.p, sizeof(Frame), cudaMemcpyDeviceToHost, st));
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(&h, d_state, sizeof h, cudaMemcpyDeviceToHost, st));

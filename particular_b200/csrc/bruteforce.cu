@@ -49,12 +49,12 @@ constexpr float PAD_POS = 1e18f;   // zero-mass padding records sit here: they c
 //               problems.
 // CLAMP == 0: either eps2 > 0 (d = 0 gives 0 without any test) or the caller asked for the
 // unchecked reference behaviour (coincident pair -> NaN, as in the reference).
-template <int DIM, int TP, int BLOCK, int MINB, int CLAMP>
+template <int DIM, int TP, int BLOCK, int MINB, int CLAMP, bool FUSE>
 __global__ void __launch_bounds__(BLOCK, MINB)
     pair_kernel_f32(const float *__restrict__ tgt, int tgt_stride, int n_tgt,
                     const float4 *__restrict__ src, int n_src, int src_chunk, int tile, float eps2,
                     float *__restrict__ out, float *__restrict__ partial, size_t n_pad,
-                    const unsigned *__restrict__ mass_max_bits) {
+                    const unsigned *__restrict__ mass_max_bits, unsigned *__restrict__ tile_done) {
     __shared__ __align__(128) float4 tiles[STAGES][TILE_MAX];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -169,6 +169,13 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     }
 
     // ---- results ----
+    // One source split: straight to `out`.  Several: every CTA stores its partial sums.  FUSE (small
+    // problems): the CTA that finishes LAST for a target tile (a ticket per tile) adds the partials
+    // of all splits in split order — a fixed order, so the result does not depend on which CTA that
+    // was — and writes `out`; no second kernel, because at the reference's criterion sizes a
+    // dependent launch costs as much as the whole evaluation.  Large problems keep the separate
+    // reduce_partials kernel (same order, same bits): the ticket epilogue costs the hot loop's
+    // register allocation 0.7 % there.
     const bool direct = gridDim.y == 1;
 #pragma unroll
     for (int p = 0; p < TP; ++p) {
@@ -191,6 +198,40 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             }
         }
     }
+    if (direct || !FUSE) return;  // !FUSE: reduce_partials runs as a second kernel
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&tile_done[blockIdx.x], 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int splits = (int)gridDim.y;
+    for (int k = 0; k < 2 * TP; ++k) {
+        const int i = tbase + k * BLOCK;
+        if (i >= n_tgt) break;
+        // eight splits x DIM components of loads in flight at a time (they are L2 round trips);
+        // the additions stay in split order
+        float acc[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) acc[c] = 0.f;
+        for (int y0 = 0; y0 < splits; y0 += 8) {
+            float v[8][DIM];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c)
+                    v[u][c] = y0 + u < splits ? __ldcg(partial + ((size_t)(y0 + u) * DIM + c) * n_pad + i) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c)
+                    if (y0 + u < splits) acc[c] += v[u][c];
+        }
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) out[(size_t)i * DIM + c] = acc[c];
+    }
+    if (tid == 0) tile_done[blockIdx.x] = 0;  // ready for the next launch
 }
 
 // max |mu| over the source records (bit pattern of a non-negative float orders like an unsigned).
@@ -348,6 +389,7 @@ static int g_waves = 48;       // equal-cost CTAs per resident slot (tail < 1 / 
 struct Plan {
     int tp, block, minb;
     int n_tb, splits, chunk, tile;
+    bool small;  // latency-bound problem size (see make_plan)
 };
 
 static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
@@ -360,11 +402,16 @@ static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
     pl.minb = pl.tp == 4 ? 2 : (pl.tp == 2 ? 3 : 4);
     const int tile_t = pl.block * 2 * pl.tp;
     pl.n_tb = (int)((na + tile_t - 1) / tile_t);
-    pl.tile = nb >= 4096 ? TILE_MAX : 64;
+    // Small problems (the reference's criterion sizes) are latency bound: a warp retires one source
+    // per ~70 cycles, so the sources are cut as finely as one 64-record tile per CTA and two waves
+    // of CTAs are enough; large problems want tens of waves of long, equal-cost CTAs.
+    const bool small = (double)na * (double)nb < 2.5e8;
+    pl.small = small;
+    pl.tile = !small && nb >= 4096 ? TILE_MAX : 64;
     const long slots = (long)sm_count * pl.minb;
-    const long want = slots * g_waves;
+    const long want = slots * (small ? 2 : g_waves);
     long splits = (want + pl.n_tb - 1) / pl.n_tb;
-    const long max_splits = std::max<long>(1, (long)(nb / ((size_t)pl.tile * 4)));
+    const long max_splits = std::max<long>(1, (long)(nb / ((size_t)pl.tile * (small ? 1 : 4))));
     splits = std::max<long>(1, std::min(splits, max_splits));
     if (splits > 1 && pl.n_tb >= want) splits = 1;
     long chunk = ((long)nb + splits - 1) / splits;
@@ -376,24 +423,36 @@ static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
 }
 
 
-template <int DIM, int TP, int BLOCK, int MINB>
+template <int DIM, int TP, int BLOCK, int MINB, bool FUSE>
 static cudaError_t launch_f32(const Plan &pl, int clamp, cudaStream_t stream, const float *tgt,
                               int tgt_stride, int na, const float4 *src, int nb, float eps2,
-                              float *out, float *partial, size_t n_pad, const unsigned *mass_max) {
+                              float *out, float *partial, size_t n_pad, const unsigned *mass_max,
+                              unsigned *tile_done) {
     dim3 grid(pl.n_tb, pl.splits);
     if (clamp == 3)
-        pair_kernel_f32<DIM, TP, BLOCK, MINB, 3><<<grid, BLOCK, 0, stream>>>(
-            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 3, FUSE><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max, tile_done);
     else if (clamp == 2)
-        pair_kernel_f32<DIM, TP, BLOCK, MINB, 2><<<grid, BLOCK, 0, stream>>>(
-            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 2, FUSE><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max, tile_done);
     else if (clamp == 1)
-        pair_kernel_f32<DIM, TP, BLOCK, MINB, 1><<<grid, BLOCK, 0, stream>>>(
-            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 1, FUSE><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max, tile_done);
     else
-        pair_kernel_f32<DIM, TP, BLOCK, MINB, 0><<<grid, BLOCK, 0, stream>>>(
-            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max);
+        pair_kernel_f32<DIM, TP, BLOCK, MINB, 0, FUSE><<<grid, BLOCK, 0, stream>>>(
+            tgt, tgt_stride, na, src, nb, pl.chunk, pl.tile, eps2, out, partial, n_pad, mass_max, tile_done);
     return cudaGetLastError();
+}
+
+// Per-target-tile tickets of the "last CTA reduces" epilogue: zero when allocated, and every
+// launch leaves them zero again.
+static int ensure_tile_tickets(pcuda_ctx *ctx, size_t n_tiles) {
+    const size_t bytes = n_tiles * sizeof(unsigned);
+    if (bytes <= ctx->d_tile_done.cap) return PCUDA_OK;
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // a launch in flight may still hold tickets
+    PCUDA_CUDA_TRY(ctx, ctx->d_tile_done.ensure(bytes));
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_tile_done.p, 0, ctx->d_tile_done.cap, ctx->stream));
+    return PCUDA_OK;
 }
 
 // Enqueues the brute-force evaluation on ctx->stream.  All pointers are device pointers.
@@ -425,23 +484,33 @@ static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na
     }
     const size_t n_pad = (na + 63) & ~size_t(63);
     float *partial = nullptr;
+    unsigned *tile_done = nullptr;
+    const bool fuse = pl.small;  // the last CTA of a target tile reduces the split partial sums
     if (pl.splits > 1) {
         PCUDA_CUDA_TRY(ctx, ctx->d_partial.ensure((size_t)pl.splits * DIM * n_pad * sizeof(float)));
         partial = ctx->d_partial.as<float>();
+        if (fuse) {
+            PCUDA_TRY(ensure_tile_tickets(ctx, (size_t)pl.n_tb));
+            tile_done = ctx->d_tile_done.as<unsigned>();
+        }
     }
     cudaError_t e;
     if (pl.tp == 4)
-        e = launch_f32<DIM, 4, 256, 2>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
-                                       (int)nb, eps2, d_out, partial, n_pad, mass_max);
+        e = launch_f32<DIM, 4, 256, 2, false>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                              (int)nb, eps2, d_out, partial, n_pad, mass_max, tile_done);
     else if (pl.tp == 2)
-        e = launch_f32<DIM, 2, 256, 3>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
-                                       (int)nb, eps2, d_out, partial, n_pad, mass_max);
+        e = fuse ? launch_f32<DIM, 2, 256, 3, true>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                                    (int)nb, eps2, d_out, partial, n_pad, mass_max, tile_done)
+                 : launch_f32<DIM, 2, 256, 3, false>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                                     (int)nb, eps2, d_out, partial, n_pad, mass_max, tile_done);
     else
-        e = launch_f32<DIM, 1, 128, 4>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
-                                       (int)nb, eps2, d_out, partial, n_pad, mass_max);
+        e = fuse ? launch_f32<DIM, 1, 128, 4, true>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                                    (int)nb, eps2, d_out, partial, n_pad, mass_max, tile_done)
+                 : launch_f32<DIM, 1, 128, 4, false>(pl, clamp, ctx->stream, d_tgt, tgt_stride, (int)na, d_src4,
+                                                     (int)nb, eps2, d_out, partial, n_pad, mass_max, tile_done);
     PCUDA_CUDA_TRY(ctx, e);
     ctx->launches++;
-    if (pl.splits > 1) {
+    if (pl.splits > 1 && !(fuse && pl.tp != 4)) {
         reduce_partials<float, DIM><<<(unsigned)((na + 255) / 256), 256, 0, ctx->stream>>>(
             partial, pl.splits, n_pad, (int)na, d_out);
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());

@@ -53,6 +53,7 @@ struct pcuda_ctx {
     size_t smem_optin = 0;
     char name[128] = {0};
     uint32_t leaf_size = 16;
+    bool phase_timings = true;  // PCUDA_FLAG_NO_PHASE_TIMINGS clears it
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -63,7 +64,8 @@ struct pcuda_ctx {
     uint32_t launches = 0;
 
     // brute force scratch
-    pcuda::DevBuf d_affected, d_affecting, d_out, d_partial, d_packed_src, d_packed_tgt, d_massmax;
+    pcuda::DevBuf d_affected, d_affecting, d_out, d_partial, d_packed_src, d_packed_tgt, d_massmax,
+        d_tile_done;
     // Barnes-Hut scratch (barneshut.cu owns the layout)
     pcuda::DevBuf d_stack, d_counters, d_tgt_keys, d_tgt_keys_alt, d_tgt_perm, d_tgt_perm_alt,
         d_tgt_sorted, d_cub_tmp, d_misc;

@@ -29,10 +29,11 @@ void timings_reset(pcuda_ctx *ctx) {
 }
 
 void phase_begin(pcuda_ctx *ctx, Phase p) {
-    if (!ctx->ev_used[p]) cudaEventRecord(ctx->ev0[p], ctx->stream);
+    if (ctx->phase_timings && !ctx->ev_used[p]) cudaEventRecord(ctx->ev0[p], ctx->stream);
 }
 
 void phase_end(pcuda_ctx *ctx, Phase p) {
+    if (!ctx->phase_timings) return;
     cudaEventRecord(ctx->ev1[p], ctx->stream);
     ctx->ev_used[p] = true;
 }
@@ -116,6 +117,7 @@ int pcuda_create(const pcuda_config *config, pcuda_ctx **out) {
     ctx->sm_clock_khz = khz;
     strncpy(ctx->name, prop.name, sizeof(ctx->name) - 1);
     if (config && config->leaf_size) ctx->leaf_size = config->leaf_size;
+    ctx->phase_timings = !(config && (config->flags & PCUDA_FLAG_NO_PHASE_TIMINGS));
     if (ctx->leaf_size > 32) ctx->leaf_size = 32;
 
     DeviceGuard guard(dev);
@@ -140,7 +142,7 @@ void pcuda_destroy(pcuda_ctx *ctx) {
     nccl_free(ctx);
     if (ctx->call_tree) tree_free(ctx, ctx->call_tree);
     DevBuf *bufs[] = {&ctx->d_affected, &ctx->d_affecting, &ctx->d_out, &ctx->d_partial,
-                      &ctx->d_packed_src, &ctx->d_packed_tgt, &ctx->d_massmax, &ctx->d_stack, &ctx->d_counters,
+                      &ctx->d_packed_src, &ctx->d_packed_tgt, &ctx->d_massmax, &ctx->d_tile_done, &ctx->d_stack, &ctx->d_counters,
                       &ctx->d_tgt_keys, &ctx->d_tgt_keys_alt, &ctx->d_tgt_perm,
                       &ctx->d_tgt_perm_alt, &ctx->d_tgt_sorted, &ctx->d_cub_tmp, &ctx->d_misc};
     for (DevBuf *b : bufs) b->release();

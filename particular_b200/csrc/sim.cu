@@ -75,7 +75,7 @@ struct pcuda_sim {
     uint64_t steps_done = 0;
     bool warm = false;  // one eager step has sized every scratch buffer
     cudaGraphExec_t graph = nullptr;
-    const void *graph_key[4] = {nullptr, nullptr, nullptr, nullptr};  // scratch pointers baked into the graph
+    const void *graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // scratch pointers baked into the graph
     uint32_t launches_per_step = 0;
     size_t scalar_bytes() const { return cfg.scalar == PCUDA_F64 ? 8 : 4; }
 };
@@ -129,7 +129,8 @@ static int step_once(pcuda_ctx *ctx, pcuda_sim *s) {
     return s->cfg.dim == 3 ? step_once_t<float, 3>(ctx, s) : step_once_t<float, 2>(ctx, s);
 }
 
-static void scratch_key(const pcuda_ctx *ctx, const void *key[4]) {
+static void scratch_key(const pcuda_ctx *ctx, const void *key[5]) {
+    key[4] = ctx->d_tile_done.p;
     key[0] = ctx->d_partial.p;
     key[1] = ctx->d_massmax.p;
     key[2] = ctx->d_packed_src.p;
@@ -280,7 +281,7 @@ int pcuda_sim_step(pcuda_ctx *ctx, pcuda_sim *s, uint32_t n_steps) {
     while (left) {
         // the first step runs eagerly: it sizes every scratch buffer and counts its launches
         if (graphable && s->warm && left >= (uint32_t)sim::GRAPH_STEPS) {
-            const void *key[4];
+            const void *key[5];
             sim::scratch_key(ctx, key);
             if ((!s->graph || memcmp(key, s->graph_key, sizeof key) != 0) && !sim::capture(ctx, s)) {
                 graphable = false;  // not capturable here: stay eager for good

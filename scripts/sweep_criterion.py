@@ -39,7 +39,7 @@ def measure(fn, min_time=0.3, min_samples=15):
     return 1e9 * float(np.mean(times)), 1e9 * float(np.median(times)), len(times)
 
 
-ctx = pb.CudaContext(0)
+ctx = pb.CudaContext(0, phase_timings=False)  # the lean product path: no per-phase events
 rows = []
 for k in range(1, 17):
     n = 2 ** k

@@ -275,6 +275,29 @@ __global__ void pack_sources_2d(const float *__restrict__ in, int n, float4 *__r
 constexpr int TILE64 = 128;
 constexpr double PAD_POS_64 = 1e100;
 
+// x == +0.0 ? 1.0 : x, with integer instructions (a DSETP would take an FP64-pipe slot, and the
+// FP64 pipe is the limiter of this kernel).  x is a sum of squares: never -0.0.
+__device__ __forceinline__ double one_if_zero(double x) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    return __hiloint2double((hi | lo) == 0 ? 0x3ff00000 : hi, lo);
+}
+
+// mu * x^(-3/2) in 7 FP64 operations (CUDA's rsqrt() + three multiplies take 8 plus a range
+// check): y0 = MUFU.RSQ64H(x) carries ~20 bits; with e = 1 - x*y0^2 (|e| < 2^-19),
+//     x^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + e (3/2 + 15/8 e)) + O(e^3),   35/16 e^3 < 2^-56,
+// so the result is good to a few ulp — far inside the 1e-12 parity bound.  x must be a normal
+// positive number: the kernel's r2 is one (coincident pairs are handled before the call); x = 0
+// (unchecked, eps = 0) gives NaN like the reference's 0 * inf.
+__device__ __forceinline__ double mu_rcbrt2(double x, double mu) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double t = y0 * y0;
+    const double e = fma(-x, t, 1.0);
+    const double q = fma(1.875, e, 1.5);
+    const double um = (t * y0) * mu;
+    return fma(um, e * q, um);
+}
+
 template <int T, int BLOCK, bool CLAMP>
 __global__ void __launch_bounds__(BLOCK)
     pair_kernel_f64(const double *__restrict__ tgt, int tgt_stride, int n_tgt,
@@ -347,9 +370,8 @@ __global__ void __launch_bounds__(BLOCK)
                     double r2 = fma(dx, dx, eps2);
                     r2 = fma(dy, dy, r2);
                     r2 = fma(dz, dz, r2);
-                    if (CLAMP) r2 = r2 == 0.0 ? __longlong_as_double(0x7ff0000000000000ll) : r2;
-                    const double ri = rsqrt(r2);
-                    const double sc = (ri * ri) * (ri * s.w);
+                    if (CLAMP) r2 = one_if_zero(r2);  // d == 0 there, so the term is 0 * finite = 0
+                    const double sc = mu_rcbrt2(r2, s.w);
                     ax[k] = fma(dx, sc, ax[k]);
                     ay[k] = fma(dy, sc, ay[k]);
                     az[k] = fma(dz, sc, az[k]);
@@ -531,7 +553,7 @@ static int run_f64(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t n
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     const double eps2 = softening * softening;
     const bool clamp = checked && eps2 == 0.0;
-    constexpr int T = 2, BLOCK = 128;
+    constexpr int T = 4, BLOCK = 128;
     const int tile_t = T * BLOCK;
     const int n_tb = (int)((na + tile_t - 1) / tile_t);
     const int tile = nb >= 2048 ? TILE64 : 32;

@@ -670,6 +670,75 @@ static int sharded_f32x3(pcuda_ctx *ctx, const float *d_local, size_t n_local, s
 }
 
 // Host-pointer wrapper shared by the three precisions: upload, run, download, collect timings.
+//
+// Large target sets (the massive -> massless split of BASELINE configs[2]: 16M targets, 192 MB up
+// and 192 MB down per call) take the chunked path: the targets are cut into chunks whose upload
+// (H2D copy engine, own stream), evaluation (context stream) and download (D2H copy engine, own
+// stream) overlap through events, with two chunk buffers in flight, so that PCIe disappears behind
+// the kernels except for the first upload and the last download.  The reference's wgpu operator
+// does the opposite: one blocking write, one dispatch, one blocking map (gpu/resources.rs:318-349).
+constexpr size_t CHUNK_MIN_TARGETS = 4u << 20;  // below this the copies are too short to matter
+constexpr size_t CHUNK_TARGETS = 1u << 20;
+
+static int ensure_copy_streams(pcuda_ctx *ctx) {
+    if (ctx->stream_h2d) return PCUDA_OK;
+    PCUDA_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking));
+    PCUDA_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk_up[i], cudaEventDisableTiming));
+        PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk_done[i], cudaEventDisableTiming));
+        PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk_free[i], cudaEventDisableTiming));
+    }
+    PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h_end, cudaEventDisableTiming));
+    return PCUDA_OK;
+}
+
+// run(d_tgt, n_tgt, d_src, d_out) enqueues the evaluation of n_tgt targets on ctx->stream.
+template <typename S, typename RunFn>
+static int host_call_chunked(pcuda_ctx *ctx, const S *affected, size_t na, int dim, S *d_src, S *out,
+                             RunFn run) {
+    PCUDA_TRY(ensure_copy_streams(ctx));
+    const size_t row = (size_t)dim * sizeof(S);
+    const size_t chunk = CHUNK_TARGETS;
+    // two chunk slots for targets and results
+    PCUDA_CUDA_TRY(ctx, ctx->d_affected.ensure(2 * chunk * row));
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(2 * chunk * row));
+    S *d_tgt = ctx->d_affected.as<S>(), *d_out = ctx->d_out.as<S>();
+    // the copy streams start after everything already queued on the context stream (the source
+    // upload in particular)
+    PCUDA_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_d2h_end, ctx->stream));
+    PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ctx->ev_d2h_end, 0));
+    PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ctx->ev_d2h_end, 0));
+    phase_begin(ctx, PH_COMPUTE);
+    size_t k = 0;
+    for (size_t off = 0; off < na; off += chunk, ++k) {
+        const size_t n = std::min(chunk, na - off);
+        const int slot = (int)(k & 1);
+        S *t = d_tgt + (size_t)slot * chunk * dim, *o = d_out + (size_t)slot * chunk * dim;
+        // slot reuse: the upload of chunk k waits until chunk k-2 has been evaluated, and the
+        // evaluation of chunk k until the download of chunk k-2 has left its result slot
+        if (k >= 2) PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ctx->ev_chunk_done[slot], 0));
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(t, affected + off * dim, n * row, cudaMemcpyHostToDevice,
+                                            ctx->stream_h2d));
+        PCUDA_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk_up[slot], ctx->stream_h2d));
+        PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk_up[slot], 0));
+        if (k >= 2) PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk_free[slot], 0));
+        PCUDA_TRY(run(t, n, d_src, o));
+        PCUDA_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk_done[slot], ctx->stream));
+        PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ctx->ev_chunk_done[slot], 0));
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out + off * dim, o, n * row, cudaMemcpyDeviceToHost,
+                                            ctx->stream_d2h));
+        PCUDA_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk_free[slot], ctx->stream_d2h));
+    }
+    phase_end(ctx, PH_COMPUTE);
+    // the call ends when the last download has landed
+    phase_begin(ctx, PH_DOWNLOAD);
+    PCUDA_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_d2h_end, ctx->stream_d2h));
+    PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h_end, 0));
+    phase_end(ctx, PH_DOWNLOAD);
+    return timings_collect(ctx);
+}
+
 template <typename S, typename RunFn>
 static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, const S *affecting,
                      size_t nb, S *out, RunFn run) {
@@ -691,6 +760,10 @@ static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, cons
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_src, affecting, src_bytes, cudaMemcpyHostToDevice,
                                             ctx->stream));
     }
+    if (affected && na >= CHUNK_MIN_TARGETS && nb) {
+        phase_end(ctx, PH_UPLOAD);
+        return host_call_chunked<S>(ctx, affected, na, dim, d_src, out, run);
+    }
     if (affected) {
         PCUDA_CUDA_TRY(ctx, ctx->d_affected.ensure(tgt_bytes));
         d_tgt = ctx->d_affected.as<S>();
@@ -700,7 +773,7 @@ static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, cons
     PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(tgt_bytes));
     phase_end(ctx, PH_UPLOAD);
     phase_begin(ctx, PH_COMPUTE);
-    PCUDA_TRY(run(d_tgt, d_src, ctx->d_out.as<S>()));
+    PCUDA_TRY(run(d_tgt, na, d_src, ctx->d_out.as<S>()));
     phase_end(ctx, PH_COMPUTE);
     phase_begin(ctx, PH_DOWNLOAD);
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out.p, tgt_bytes, cudaMemcpyDeviceToHost,
@@ -747,16 +820,16 @@ extern "C" {
 int pcuda_bruteforce_f32x3(pcuda_ctx *ctx, const float *affected, size_t na, const float *affecting,
                            size_t nb, float softening, int checked, float *out) {
     return bf::host_call<float>(ctx, affected, na, 3, affecting, nb, out,
-                                [&](float *dt, float *ds, float *dout) {
-                                    return bf::dev_f32x3(ctx, dt, na, ds, nb, softening, checked, dout);
+                                [&](float *dt, size_t n, float *ds, float *dout) {
+                                    return bf::dev_f32x3(ctx, dt, n, ds, nb, softening, checked, dout);
                                 });
 }
 
 int pcuda_bruteforce_f32x2(pcuda_ctx *ctx, const float *affected, size_t na, const float *affecting,
                            size_t nb, float softening, int checked, float *out) {
     return bf::host_call<float>(ctx, affected, na, 2, affecting, nb, out,
-                                [&](float *dt, float *ds, float *dout) {
-                                    return bf::dev_f32x2(ctx, dt, na, ds, nb, softening, checked, dout);
+                                [&](float *dt, size_t n, float *ds, float *dout) {
+                                    return bf::dev_f32x2(ctx, dt, n, ds, nb, softening, checked, dout);
                                 });
 }
 
@@ -764,8 +837,8 @@ int pcuda_bruteforce_f64x3(pcuda_ctx *ctx, const double *affected, size_t na,
                            const double *affecting, size_t nb, double softening, int checked,
                            double *out) {
     return bf::host_call<double>(ctx, affected, na, 3, affecting, nb, out,
-                                 [&](double *dt, double *ds, double *dout) {
-                                     return bf::dev_f64x3(ctx, dt, na, ds, nb, softening, checked, dout);
+                                 [&](double *dt, size_t n, double *ds, double *dout) {
+                                     return bf::dev_f64x3(ctx, dt, n, ds, nb, softening, checked, dout);
                                  });
 }
 

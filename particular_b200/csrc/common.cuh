@@ -55,6 +55,10 @@ struct pcuda_ctx {
     uint32_t leaf_size = 16;
     bool phase_timings = true;  // PCUDA_FLAG_NO_PHASE_TIMINGS clears it
     cudaStream_t stream = nullptr;
+    // copy engines' streams + events of the chunked host path (created on first use, bruteforce.cu)
+    cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
+    cudaEvent_t ev_chunk_up[2] = {nullptr, nullptr}, ev_chunk_done[2] = {nullptr, nullptr},
+                ev_chunk_free[2] = {nullptr, nullptr}, ev_d2h_end = nullptr;
     std::string err;
 
     // phase timing: start/stop event per phase, recorded lazily

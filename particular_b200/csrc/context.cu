@@ -150,6 +150,14 @@ void pcuda_destroy(pcuda_ctx *ctx) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
         if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_chunk_up[i]) cudaEventDestroy(ctx->ev_chunk_up[i]);
+        if (ctx->ev_chunk_done[i]) cudaEventDestroy(ctx->ev_chunk_done[i]);
+        if (ctx->ev_chunk_free[i]) cudaEventDestroy(ctx->ev_chunk_free[i]);
+    }
+    if (ctx->ev_d2h_end) cudaEventDestroy(ctx->ev_d2h_end);
+    if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
+    if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -592,6 +592,7 @@ __global__ void __launch_bounds__(SMALL_TREE_BLOCK) build_small(NodeRec *__restr
         if (tid == 0 && !s_overflow) s_begin[level + 2] = lvl_end + running;
         __syncthreads();
     }
+    __syncthreads();  // every thread has read the level table of the iteration that left the loop
     if (tid == 0) {
         // levels past the last one are empty: level_begin stays at the end of the last level
         for (int l = levels + 1; l < 36; ++l) s_begin[l] = s_begin[levels];
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(SMALL_TREE_BLOCK) build_small(NodeRec *__restr
         }
     }
     if (tid < 36) st->level_begin[tid] = s_begin[tid];
+    if (tid < 34) st->ticket[tid] = 0;  // unused here; the host reads the whole state back
     if (tid == 0) {
         st->overflow = s_overflow;
         st->capacity = capacity;

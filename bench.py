@@ -264,23 +264,26 @@ def other_configs(ctx, stream, flush, steps=3):
 
 
 # ---- CPU arms ----------------------------------------------------------------------------------------
-def cpu_bruteforce_rate(P, seconds, steps=1):
+def cpu_bruteforce_rate(P, seconds, steps=1, targets=None, softening=0.0):
     """Restated parallel::BruteForceSimd<8> on a bounded target sample x all sources.
+    `targets`: affected positions when they are not the sources themselves.
     Returns (Gpairs/s, sample description, cores, per-step seconds list)."""
     import oracle
     n = len(P)
+    T = P[:, :3] if targets is None else targets
+    nt = len(T)
     oracle.use_all_cores()
     cores = oracle.baseline_threads()
-    probe = min(n, 256 * cores)
+    probe = min(nt, 256 * cores)
     t0 = time.perf_counter()
-    oracle.brute_force_simd8_parallel(P[:probe, :3], P)
+    oracle.brute_force_simd8_parallel(T[:probe], P, softening)
     dt = max(time.perf_counter() - t0, 1e-6)
-    sample = int(min(n, max(probe, probe * seconds / dt)))
+    sample = int(min(nt, max(probe, probe * seconds / dt)))
     sample = max(64, sample - sample % 64)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        oracle.brute_force_simd8_parallel(P[:sample, :3], P)
+        oracle.brute_force_simd8_parallel(T[:sample], P, softening)
         times.append(time.perf_counter() - t0)
     rate = sample * n / (sum(times) / len(times)) / 1e9
     return rate, f"first {sample} targets x all {n} sources, scaled linearly", cores, times
@@ -318,7 +321,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bruteforce", choices=["bruteforce", "barneshut"])
+    ap.add_argument("--workload", default="bruteforce", choices=["bruteforce", "barneshut", "split"])
     ap.add_argument("--n", type=int, default=0, help="particle count (default: BASELINE config)")
     ap.add_argument("--theta", type=float, default=0.5)
     ap.add_argument("--no-extra", action="store_true",
@@ -330,7 +333,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n = args.n or (1_000_000 if args.workload == "bruteforce" else 10_000_000)
+    n = args.n or {"bruteforce": 1_000_000, "barneshut": 10_000_000, "split": 16_000_000}[args.workload]
 
     if args.impl == "reference":
         if rank == 0:
@@ -338,6 +341,8 @@ def main():
         return 0
     if args.workload == "bruteforce":
         return bench_bruteforce(args, n, rank, world, local_rank)
+    if args.workload == "split":
+        return bench_split(args, n, rank, world, local_rank)
     return bench_barneshut(args, n, rank, world, local_rank)
 
 
@@ -355,6 +360,27 @@ def reference_arm(args, n, world):
                 "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": bruteforce_config(n, world, "cpu"),
+                "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": "port",
+                                 "sample": sample + "; restated parallel::BruteForceSimd<8> "
+                                 "(AVX2 rsqrt + OpenMP), oracle/baseline_simd.c"},
+                "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    elif args.workload == "split":
+        tgt, src = split_cloud(10_000, n)
+        per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+        rate, sample, cores, times = cpu_bruteforce_rate(src, per_step, steps=args.steps + args.warmup,
+                                                         targets=tgt, softening=1.0)
+        times = times[args.warmup:] or times
+        sample_n = int(sample.split()[1])
+        value = sample_n * float(len(src)) / (sum(times) / len(times)) / 1e9
+        line = {"impl": "reference", "metric": "brute-force pair interactions per second",
+                "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"brute force 3-D f32 massive/massless split: 10000 massive + {n} "
+                                       f"massless (BASELINE configs[2]); AccelerationSoftened::checked(1.0)",
+                           "parallelism": "host threads over targets"},
                 "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": "port",
                                  "sample": sample + "; restated parallel::BruteForceSimd<8> "
                                  "(AVX2 rsqrt + OpenMP), oracle/baseline_simd.c"},
@@ -536,6 +562,113 @@ def bench_bruteforce(args, n, rank, world, local_rank):
             line["other_configs"] = other_configs(ctx, stream, flush)
         except Exception as e:
             line["other_configs"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def split_cloud(n_massive, n_massless):
+    """BASELINE configs[2]: the massive bodies first, then the massless ones (the order Reordered's
+    affected side has when the input is already partitioned); same draws as other_configs()."""
+    rng = np.random.default_rng(SEED)
+    src = uniform_cloud(n_massive)
+    tgt = np.empty((n_massive + n_massless, 3), np.float32)
+    tgt[:n_massive] = src[:, :3]
+    tgt[n_massive:] = rng.uniform(-5e3, 5e3, (n_massless, 3))
+    return tgt, src
+
+
+def bench_split(args, n_massless, rank, world, local_rank):
+    """BASELINE configs[2] at 1/2/4/8 GPUs: 10,000 massive act on themselves + n_massless massless
+    particles; the affected particles are sharded, the massive records all-gathered each step
+    (pcuda_bruteforce_f32x3_between_sharded).  Strong scaling."""
+    import torch
+
+    import particular_b200 as pb
+    dist = _dist_setup(world, local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = pb.CudaContext(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    n_massive = 10_000
+    sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0))
+    tgt, src = split_cloud(n_massive, n_massless)
+    n_aff = len(tgt)
+    lo, hi = pb.shard_bounds(n_aff, world, rank)
+    slo, shi = pb.shard_bounds(n_massive, world, rank)
+    d_tgt = torch.from_numpy(tgt[lo:hi]).to(dev)
+    d_src = torch.from_numpy(src[slo:shi]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+
+    def timed_steps(step_fn, k):
+        times, launches = [], 0
+        for _ in range(k):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn()
+            e1.record(stream)
+            ctx.sync()
+            times.append(e0.elapsed_time(e1))
+            launches += ctx.timings()["kernel_launches"]
+        return times, launches
+
+    dev_step = lambda: sb.step_device(d_tgt, d_src, n_massive)  # noqa: E731
+    for _ in range(args.warmup):
+        dev_step()
+    _barrier(world, dist)
+    sampler.start()
+    times, launches = timed_steps(dev_step, args.steps)
+    _barrier(world, dist)
+    sampler.stop()
+    ms_per_step = _max_over_ranks(sum(times), world, dist) / args.steps
+    pairs = float(n_aff) * n_massive
+    total_launches = int(_sum_over_ranks(launches, world, dist))
+
+    h_tgt = ctx.pinned_empty((hi - lo, 3), np.float32)
+    h_tgt[:] = tgt[lo:hi]
+    h_src = np.ascontiguousarray(src[slo:shi])
+    h_out = ctx.pinned_empty((hi - lo, 3), np.float32)
+    e2e_step = lambda: sb.compute_local(h_tgt, h_src, n_massive, out=h_out)  # noqa: E731
+    for _ in range(2):
+        e2e_step()
+    _barrier(world, dist)
+    e2e_times, _ = timed_steps(e2e_step, args.steps)
+    _barrier(world, dist)
+    e2e_ms = _max_over_ranks(sum(e2e_times), world, dist) / args.steps
+
+    k_ms = sum(times) / len(times)
+    achieved = FLOP_PER_PAIR * float(hi - lo) * n_massive / (k_ms * 1e-3) / 1e12
+    sm_max_mhz = (sampler.max_mhz or ctx.sm_clock_khz / 1e3)
+    peak_nominal = ctx.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    line = {"metric": "brute-force pair interactions per second", "value": pairs / ms_per_step / 1e6,
+            "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"brute force 3-D f32 massive/massless split: {n_massive} massive + "
+                                   f"{n_massless} massless, Between(all, massive) (Reordered storage; "
+                                   f"BASELINE configs[2]); uniform cube, seed {SEED}; "
+                                   f"AccelerationSoftened::checked(1.0)",
+                       "n_affected": n_aff, "n_affecting": n_massive, "pairs_per_step": pairs,
+                       "parallelism": f"affected sharded over {world} GPU(s), massive records "
+                                      f"all-gathered (NCCL, {16 * n_massive} B)",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); the 160 KB source "
+                             "set is re-read from L2 by design"},
+            "e2e": {"value": pairs / e2e_ms / 1e6, "unit": "Gpairs/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h_tgt.nbytes + h_src.nbytes),
+                    "d2h_bytes_per_step": int(h_out.nbytes), "bytes_are": "per rank"},
+            "gpu_launches": total_launches,
+            "roofline": {"bound": "fp32", "kernel": "pcuda::bf::pair_kernel_f32<3,...>",
+                         "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
+                         "frac": achieved / peak_nominal, "flop_per_pair": FLOP_PER_PAIR,
+                         "kernel_ms": k_ms, "traffic": None,
+                         "note": "whole device-resident step of this rank (fill + all-gather + pair "
+                                 "kernel + split reduction)"},
+            "clocks": sampler.summary(), "device": ctx.name}
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()

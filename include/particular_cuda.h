@@ -195,6 +195,18 @@ int pcuda_tree_traverse_f32(pcuda_ctx *ctx, const pcuda_tree *tree, const float 
 int pcuda_tree_last_counters(pcuda_ctx *ctx, uint64_t counters[5]);
 void pcuda_tree_destroy(pcuda_ctx *ctx, pcuda_tree *tree);
 
+/* Morton keys and the stable sort permutation alone (the first half of the build; SURVEY.md 8b/8c:
+ * the reference has no Morton code, tree/mod.rs:117-126 is a recursive bucket partition, so the
+ * specification is ours — root cube per BoundingBox::square_with, tree/partition.rs:136-153,
+ * 21 bits per axis in 3-D / 31 in 2-D, axis 0 in the lowest bit — and parity is bit-exact against
+ * oracle/oracle_octree.inc).  HOST buffers: particles = n records {x,y[,z],mu};
+ * keys_out[i] = i-th smallest key, perm_out[i] = input index of the particle holding it (equal keys
+ * keep input order).  frame_out (may be NULL) receives origin / extent / inv of the root cube. */
+int pcuda_morton_f32x3(pcuda_ctx *ctx, const float *particles_xyzm, size_t n, uint64_t *keys_out,
+                       uint32_t *perm_out, pcuda_tree_info *frame_out);
+int pcuda_morton_f32x2(pcuda_ctx *ctx, const float *particles_xym, size_t n, uint64_t *keys_out,
+                       uint32_t *perm_out, pcuda_tree_info *frame_out);
+
 /* ---- multi-GPU (one process per GPU; new — the reference is single-device) --------------------
  * Targets are sharded by the caller; sources are replicated with an all-gather over NVLink each
  * step.  NCCL is dlopen()ed on first use.  id is the 128-byte ncclUniqueId made by rank 0 and
@@ -226,6 +238,26 @@ int pcuda_bruteforce_f32x3_sharded_dev(pcuda_ctx *ctx, const float *d_local_xyzm
 int pcuda_bruteforce_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_t n_local,
                                    size_t shard_capacity, float softening, int checked,
                                    float *out_xyz);
+
+/* Multi-GPU `Between(affected, affecting)` step for the massive -> massless split (BASELINE
+ * configs[2]; the storage mapping of Reordered, storage.rs:153-163, 207-229):
+ * the AFFECTED positions are sharded by the caller (this rank passes only its n_affected targets —
+ * no collective ever touches them), the AFFECTING records are sharded too (n_local_src <=
+ * src_capacity per rank, same capacity on all ranks) and all-gathered in place into
+ * d_gathered_src_xyzm (world_size * src_capacity records, zero-mass padding contributes exactly 0).
+ * out[i] = acceleration of this rank's i-th affected particle.  Every rank must call, also with
+ * n_affected == 0.  _dev: device pointers, enqueued on the context stream, no synchronisation.
+ * Host version: blocking; large target shards take the chunked upload / evaluate / download
+ * pipeline of pcuda_bruteforce_f32x3. */
+int pcuda_bruteforce_f32x3_between_sharded_dev(pcuda_ctx *ctx, const float *d_affected_xyz,
+                                               size_t n_affected, const float *d_local_src_xyzm,
+                                               size_t n_local_src, size_t src_capacity,
+                                               float softening, int checked,
+                                               float *d_gathered_src_xyzm, float *d_out_xyz);
+int pcuda_bruteforce_f32x3_between_sharded(pcuda_ctx *ctx, const float *affected_xyz,
+                                           size_t n_affected, const float *local_src_xyzm,
+                                           size_t n_local_src, size_t src_capacity, float softening,
+                                           int checked, float *out_xyz);
 
 /* One multi-GPU Barnes-Hut step ("replicated build"): rank r owns the contiguous
  * block [r * cap, r * cap + n_local) of the n_total particles, cap = ceil(n_total / world_size)

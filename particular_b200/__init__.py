@@ -10,12 +10,13 @@ run before the library exists; any use of the API without the built library rais
 __all__ = ["Acceleration", "AccelerationSoftened", "BarnesHut", "Between", "BruteForce",
            "CudaContext", "CudaError", "CustomInteraction", "check_interaction_source", "Ordered", "Reordered", "RootedOrthtree", "Simulation",
            "cuda_barnes_hut", "cuda_brute_force", "is_affecting", "ShardedBruteForce",
-           "ShardedBarnesHut",
+           "ShardedBarnesHut", "ShardedBetween", "morton_keys",
            "shard_bounds", "shard_capacity"]
 
 
 def __getattr__(name):
-    if name in ("ShardedBruteForce", "ShardedBarnesHut", "shard_bounds", "shard_capacity"):
+    if name in ("ShardedBruteForce", "ShardedBarnesHut", "ShardedBetween", "shard_bounds",
+                "shard_capacity"):
         from . import sharded
         return getattr(sharded, name)
     if name in __all__:

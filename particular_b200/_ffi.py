@@ -112,6 +112,10 @@ SIGNATURES = {
     "pcuda_comm_allgather_dev": (_i, [_vp, _vp, _vp, _sz]),
     "pcuda_bruteforce_f32x3_sharded": (_i, [_vp, _vp, _sz, _sz, _f, _i, _vp]),
     "pcuda_bruteforce_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _i, _vp, _vp]),
+    "pcuda_bruteforce_f32x3_between_sharded": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _f, _i, _vp]),
+    "pcuda_bruteforce_f32x3_between_sharded_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _f, _i, _vp, _vp]),
+    "pcuda_morton_f32x3": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "pcuda_morton_f32x2": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "pcuda_barneshut_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp, _vp]),
     "pcuda_barneshut_f32x3_sharded": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp]),
     "pcuda_sim_create": (_i, [_vp, C.POINTER(SimConfig), _vp, _vp, _sz, C.POINTER(_vp)]),

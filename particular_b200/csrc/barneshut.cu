@@ -1352,7 +1352,8 @@ static int sort_by_key(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n,
 }
 
 template <int DIM>
-static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n) {
+static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n,
+                 bool keys_only = false) {
     constexpr int BITS = Dims<DIM>::BITS;
     const int stride = DIM + 1;
     t->dim = DIM;
@@ -1381,6 +1382,11 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
     // K3: sort + gather
     PCUDA_TRY(sort_by_key<DIM>(ctx, d_particles, stride, n, t->d_frame.as<Frame>(), t->keys, t->perm,
                                &t->cur, t->cub_tmp));
+    if (keys_only) {  // pcuda_morton_*: root cube, keys and sort permutation only
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(&t->frame, t->d_frame.p, sizeof(Frame), cudaMemcpyDeviceToHost, st));
+        PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        return PCUDA_OK;
+    }
     PCUDA_CUDA_TRY(ctx, t->sorted.ensure(n * sizeof(float4)));
     gather_kernel<DIM><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
         d_particles, stride, true, (int)n, t->d_perm(), t->sorted.as<float4>());
@@ -1443,9 +1449,10 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
     return PCUDA_OK;
 }
 
-static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d_particles, size_t n) {
-    if (dim == 3) return build<3>(ctx, t, d_particles, n);
-    if (dim == 2) return build<2>(ctx, t, d_particles, n);
+static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d_particles, size_t n,
+                     bool keys_only = false) {
+    if (dim == 3) return build<3>(ctx, t, d_particles, n, keys_only);
+    if (dim == 2) return build<2>(ctx, t, d_particles, n, keys_only);
     return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
 }
 
@@ -1861,6 +1868,63 @@ int pcuda_tree_build_f32(pcuda_ctx *ctx, uint32_t dim, const float *affecting, s
     }
     *out = t;
     return PCUDA_OK;
+}
+
+// Morton keys + stable sort permutation alone (SURVEY.md 8b `pcuda_morton_*`): the first half of
+// the tree build (root cube per BoundingBox::square_with, tree/partition.rs:136-153; quantisation;
+// stable radix sort), read back to the host.  keys_out[i] = i-th smallest key, perm_out[i] = index
+// of the particle that holds it (ties in input order).
+static int morton_host(pcuda_ctx *ctx, uint32_t dim, const float *particles, size_t n, uint64_t *keys_out,
+                       uint32_t *perm_out, pcuda_tree_info *frame_out) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n && (!particles || !keys_out || !perm_out))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    pcuda_tree t;
+    int s = PCUDA_OK;
+    do {
+        if (n == 0) break;
+        const size_t bytes = n * (dim + 1) * sizeof(float);
+        phase_begin(ctx, PH_UPLOAD);
+        if (ctx->d_affecting.ensure(bytes) != cudaSuccess) {
+            s = fail(ctx, PCUDA_ERR_OUT_OF_MEMORY, "out of device memory");
+            break;
+        }
+        cudaMemcpyAsync(ctx->d_affecting.p, particles, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        phase_end(ctx, PH_UPLOAD);
+        phase_begin(ctx, PH_BUILD);
+        s = bh::build_dim(ctx, &t, dim, ctx->d_affecting.as<float>(), n, true);
+        if (s != PCUDA_OK) break;
+        phase_end(ctx, PH_BUILD);
+        phase_begin(ctx, PH_DOWNLOAD);
+        cudaMemcpyAsync(keys_out, t.d_keys(), n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(perm_out, t.d_perm(), n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        phase_end(ctx, PH_DOWNLOAD);
+        s = timings_collect(ctx);
+        if (s == PCUDA_OK && cudaGetLastError() != cudaSuccess) s = fail(ctx, PCUDA_ERR_CUDA, "copy failed");
+    } while (0);
+    if (s == PCUDA_OK && frame_out) {
+        t.dim = (int)dim;
+        t.bits = dim == 3 ? 21 : 31;
+        t.n = n;
+        pcuda_tree_info_get(&t, frame_out);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (pcuda::DevBuf *b : {&t.keys[0], &t.keys[1], &t.perm[0], &t.perm[1], &t.sorted, &t.nodes, &t.moments,
+                             &t.d_frame, &t.scan_in, &t.scan_out, &t.cub_tmp, &t.partial})
+        b->release();
+    return s;
+}
+
+int pcuda_morton_f32x3(pcuda_ctx *ctx, const float *particles_xyzm, size_t n, uint64_t *keys_out,
+                       uint32_t *perm_out, pcuda_tree_info *frame_out) {
+    return morton_host(ctx, 3, particles_xyzm, n, keys_out, perm_out, frame_out);
+}
+
+int pcuda_morton_f32x2(pcuda_ctx *ctx, const float *particles_xym, size_t n, uint64_t *keys_out,
+                       uint32_t *perm_out, pcuda_tree_info *frame_out) {
+    return morton_host(ctx, 2, particles_xym, n, keys_out, perm_out, frame_out);
 }
 
 int pcuda_tree_info_get(const pcuda_tree *t, pcuda_tree_info *out) {

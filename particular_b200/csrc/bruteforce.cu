@@ -669,6 +669,35 @@ static int sharded_f32x3(pcuda_ctx *ctx, const float *d_local, size_t n_local, s
     return PCUDA_OK;
 }
 
+// Multi-GPU `Between(affected, affecting)` step (BASELINE configs[2]: massive -> massless): the
+// AFFECTING records are sharded (every rank holds n_local_src of them, capacity `cap` per rank)
+// and all-gathered in place into d_gathered; the AFFECTED positions of this rank (its shard of the
+// targets, d_aff == nullptr: none) are evaluated against all world * cap sources.  No collective
+// touches the targets: with 10k sources the exchange is 160 KB per step.
+static int gather_sources_f32x3(pcuda_ctx *ctx, const float *d_local_src, size_t n_local_src,
+                                size_t cap, float *d_gathered, size_t *nb_out) {
+    int world = 1, rank = 0;
+    nccl_world(ctx, &world, &rank);
+    if (cap == 0 || n_local_src > cap)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "n_local (%zu) exceeds shard capacity (%zu)",
+                    n_local_src, cap);
+    if ((n_local_src && !aligned(d_local_src, 16)) || !aligned(d_gathered, 16))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "records must be 16-byte aligned");
+    if ((size_t)world * cap > 0x7fffffffull)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    float4 *all = reinterpret_cast<float4 *>(d_gathered);
+    float4 *slot = all + (size_t)rank * cap;
+    phase_begin(ctx, PH_COMM);
+    fill_slot_f32x3<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const float4 *>(d_local_src), (int)n_local_src, (int)cap, slot);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (world > 1) PCUDA_TRY(pcuda_comm_allgather_dev(ctx, slot, all, cap * sizeof(float4)));
+    phase_end(ctx, PH_COMM);
+    *nb_out = (size_t)world * cap;
+    return PCUDA_OK;
+}
+
 // Host-pointer wrapper shared by the three precisions: upload, run, download, collect timings.
 //
 // Large target sets (the massive -> massless split of BASELINE configs[2]: 16M targets, 192 MB up
@@ -740,6 +769,10 @@ static int host_call_chunked(pcuda_ctx *ctx, const S *affected, size_t na, int d
 }
 
 template <typename S, typename RunFn>
+static int host_targets(pcuda_ctx *ctx, const S *affected, size_t na, int dim, S *d_src, size_t nb,
+                        S *out, RunFn run);
+
+template <typename S, typename RunFn>
 static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, const S *affecting,
                      size_t nb, S *out, RunFn run) {
     if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
@@ -751,15 +784,25 @@ static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, cons
     DeviceGuard guard(ctx->device);
     timings_reset(ctx);
     if (na == 0) return PCUDA_OK;
-    const size_t src_bytes = nb * (dim + 1) * sizeof(S), tgt_bytes = na * dim * sizeof(S);
+    const size_t src_bytes = nb * (dim + 1) * sizeof(S);
     phase_begin(ctx, PH_UPLOAD);
-    S *d_src = nullptr, *d_tgt = nullptr;
+    S *d_src = nullptr;
     if (nb) {
         PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(src_bytes));
         d_src = ctx->d_affecting.as<S>();
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_src, affecting, src_bytes, cudaMemcpyHostToDevice,
                                             ctx->stream));
     }
+    return host_targets<S>(ctx, affected, na, dim, d_src, nb, out, run);
+}
+
+// Second half of a host call: the sources are already on the device (or on their way on the
+// context stream) and the upload phase is open.  Uploads the targets, evaluates, downloads.
+template <typename S, typename RunFn>
+static int host_targets(pcuda_ctx *ctx, const S *affected, size_t na, int dim, S *d_src, size_t nb,
+                        S *out, RunFn run) {
+    const size_t tgt_bytes = na * dim * sizeof(S);
+    S *d_tgt = nullptr;
     if (affected && na >= CHUNK_MIN_TARGETS && nb) {
         phase_end(ctx, PH_UPLOAD);
         return host_call_chunked<S>(ctx, affected, na, dim, d_src, out, run);
@@ -909,6 +952,64 @@ int pcuda_bruteforce_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size
                                             cudaMemcpyDeviceToHost, ctx->stream));
     phase_end(ctx, PH_DOWNLOAD);
     return timings_collect(ctx);
+}
+
+int pcuda_bruteforce_f32x3_between_sharded_dev(pcuda_ctx *ctx, const float *d_affected_xyz,
+                                               size_t n_affected, const float *d_local_src_xyzm,
+                                               size_t n_local_src, size_t src_capacity,
+                                               float softening, int checked,
+                                               float *d_gathered_src_xyzm, float *d_out_xyz) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n_affected && (!d_affected_xyz || !d_out_xyz))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    size_t nb = 0;
+    int s = bf::gather_sources_f32x3(ctx, d_local_src_xyzm, n_local_src, src_capacity,
+                                     d_gathered_src_xyzm, &nb);
+    if (s == PCUDA_OK) {
+        phase_begin(ctx, PH_COMPUTE);
+        s = bf::run_f32<3>(ctx, d_affected_xyz, 3, n_affected,
+                           reinterpret_cast<const float4 *>(d_gathered_src_xyzm), nb, softening,
+                           checked, d_out_xyz);
+        phase_end(ctx, PH_COMPUTE);
+    }
+    ctx->timings.kernel_launches = ctx->launches;
+    return s;
+}
+
+int pcuda_bruteforce_f32x3_between_sharded(pcuda_ctx *ctx, const float *affected_xyz,
+                                           size_t n_affected, const float *local_src_xyzm,
+                                           size_t n_local_src, size_t src_capacity, float softening,
+                                           int checked, float *out_xyz) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if ((n_affected && (!affected_xyz || !out_xyz)) || (n_local_src && !local_src_xyzm))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    int world = 1, rank = 0;
+    nccl_world(ctx, &world, &rank);
+    const size_t cap = src_capacity;
+    if (cap == 0 || n_local_src > cap)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "n_local (%zu) exceeds shard capacity (%zu)",
+                    n_local_src, cap);
+    phase_begin(ctx, PH_UPLOAD);
+    PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(cap * 16));
+    PCUDA_CUDA_TRY(ctx, ctx->d_packed_src.ensure((size_t)world * cap * 16));
+    if (n_local_src)
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_affecting.p, local_src_xyzm, n_local_src * 16,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+    phase_end(ctx, PH_UPLOAD);
+    // every rank must enter the collective, even one that owns no targets
+    size_t nb = 0;
+    PCUDA_TRY(bf::gather_sources_f32x3(ctx, ctx->d_affecting.as<float>(), n_local_src, cap,
+                                       ctx->d_packed_src.as<float>(), &nb));
+    if (n_affected == 0) return timings_collect(ctx);
+    phase_begin(ctx, PH_UPLOAD);
+    return bf::host_targets<float>(ctx, affected_xyz, n_affected, 3, ctx->d_packed_src.as<float>(), nb,
+                                   out_xyz, [&](float *dt, size_t n, float *ds, float *dout) {
+                                       return bf::dev_f32x3(ctx, dt, n, ds, nb, softening, checked, dout);
+                                   });
 }
 
 // Tuning hook: force the targets-per-thread variant (0 = automatic).  Not part of the stable ABI.

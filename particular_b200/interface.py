@@ -35,7 +35,7 @@ __all__ = [
     "Between", "Ordered", "Reordered", "Acceleration", "AccelerationSoftened", "CudaContext",
     "BruteForce", "BarnesHut", "RootedOrthtree", "Simulation", "CustomInteraction",
     "check_interaction_source", "cuda_brute_force", "cuda_barnes_hut",
-    "is_affecting", "CudaError",
+    "is_affecting", "CudaError", "morton_keys",
 ]
 
 
@@ -409,6 +409,22 @@ class RootedOrthtree:
             self.close()
         except Exception:
             pass
+
+
+def morton_keys(ctx: CudaContext, particles):
+    """Sorted Morton keys, stable sort permutation and the root cube of a particle slice
+    (pcuda_morton_f32x3 / _f32x2: the first half of the tree build).  Returns
+    ``(keys uint64[n], perm uint32[n], TreeInfo)``."""
+    p = _as_particles(particles)
+    if p.dtype != np.float32:
+        raise NotImplementedError("device trees are f32")
+    d = p.shape[1] - 1
+    keys = np.zeros(len(p), dtype=np.uint64)
+    perm = np.zeros(len(p), dtype=np.uint32)
+    info = _ffi.TreeInfo()
+    fn = lib.pcuda_morton_f32x3 if d == 3 else lib.pcuda_morton_f32x2
+    check(fn(ctx.handle, _ptr(p), len(p), _ptr(keys), _ptr(perm), C.byref(info)), ctx.handle)
+    return keys, perm, info
 
 
 # ---- algorithms -----------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "shard_capacity", "ShardedBruteForce", "ShardedBarnesHut"]
+__all__ = ["shard_bounds", "shard_capacity", "ShardedBruteForce", "ShardedBarnesHut", "ShardedBetween"]
 
 
 def shard_capacity(n: int, world: int) -> int:
@@ -150,3 +150,68 @@ class ShardedBarnesHut(ShardedBruteForce):
             self.theta, it.softening, int(it.is_checked), out.ctypes.data_as(C.c_void_p)),
             self.ctx.handle)
         return out
+
+
+class ShardedBetween(ShardedBruteForce):
+    """``ShardedBetween(ctx, interaction).compute(storage)``: multi-GPU brute force for the storages
+    whose affecting set is a (small) subset — ``Between(affected, affecting)``, ``Ordered`` and
+    ``Reordered`` (storage.rs:61-95, 153-163, 207-229; BASELINE configs[2]: 10 k massive act on
+    16 M massless).  The AFFECTED particles are sharded in contiguous blocks (input order kept, so
+    the ranks' outputs concatenate to the reference's output order); the AFFECTING records are
+    sharded too and all-gathered over NVLink by the library (16 B each); nothing else is exchanged.
+    f32 3-D."""
+
+    def compute_local(self, affected_local: np.ndarray, src_local: np.ndarray, n_src_total: int,
+                      out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`affected_local`: this rank's (n, 3) positions; `src_local`: this rank's block of the
+        {x,y,z,mu} affecting records (``shard_bounds(n_src_total, world, rank)``)."""
+        import ctypes as C
+
+        from ._ffi import check, lib
+        it = self.interaction
+        if out is None:
+            out = np.zeros((len(affected_local), 3), dtype=np.float32)
+        check(lib.pcuda_bruteforce_f32x3_between_sharded(
+            self.ctx.handle, affected_local.ctypes.data_as(C.c_void_p), len(affected_local),
+            src_local.ctypes.data_as(C.c_void_p), len(src_local),
+            shard_capacity(n_src_total, self.world), it.softening, int(it.is_checked),
+            out.ctypes.data_as(C.c_void_p)), self.ctx.handle)
+        return out
+
+    def step_device(self, affected_local, src_local, n_src_total: int):
+        """Device-resident step: `affected_local` (n, 3) and `src_local` (m, 4) float32 CUDA
+        tensors.  Returns the (n, 3) accelerations (owned by this object).  Not synchronised."""
+        import torch
+        from ._ffi import check, lib
+        cap = shard_capacity(n_src_total, self.world)
+        n = int(affected_local.shape[0])
+        if self._gathered is None or self._gathered.shape[0] < self.world * cap:
+            self._gathered = torch.empty((self.world * cap, 4), dtype=torch.float32,
+                                         device=affected_local.device)
+        if self._out is None or self._out.shape[0] < max(n, 1):
+            self._out = torch.empty((max(n, 1), 3), dtype=torch.float32, device=affected_local.device)
+        it = self.interaction
+        check(lib.pcuda_bruteforce_f32x3_between_sharded_dev(
+            self.ctx.handle, affected_local.data_ptr(), n, src_local.data_ptr(),
+            int(src_local.shape[0]), cap, it.softening, int(it.is_checked),
+            self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
+        return self._out[:n]
+
+    def compute(self, storage, gather: bool = True) -> Optional[np.ndarray]:
+        """Every rank passes the same storage.  Returns all accelerations in the storage's affected
+        order on every rank (gather=True) or only this rank's block."""
+        from .interface import _resolve
+        aff, src = _resolve(storage)
+        if src.dtype != np.float32 or src.shape[1] != 4:
+            raise NotImplementedError("sharded brute force is f32 3-D")
+        if aff is None:
+            aff = np.ascontiguousarray(src[:, :3])
+        lo, hi = shard_bounds(len(aff), self.world, self.rank)
+        slo, shi = shard_bounds(len(src), self.world, self.rank)
+        local = self.compute_local(np.ascontiguousarray(aff[lo:hi]),
+                                   np.ascontiguousarray(src[slo:shi]), len(src))
+        if not gather or self.world == 1:
+            return local
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, local, group=self.group)
+        return np.concatenate(parts, axis=0)

@@ -163,6 +163,19 @@ extern "C" {
     pub fn pcuda_bruteforce_f32x3_sharded(ctx: *mut pcuda_ctx, local_xyzm: *const f32, n_local: usize,
                                           shard_capacity: usize, softening: f32, checked: c_int,
                                           out_xyz: *mut f32) -> c_int;
+    pub fn pcuda_bruteforce_f32x3_between_sharded_dev(ctx: *mut pcuda_ctx, d_affected_xyz: *const f32,
+                                                      n_affected: usize, d_local_src_xyzm: *const f32,
+                                                      n_local_src: usize, src_capacity: usize, softening: f32,
+                                                      checked: c_int, d_gathered_src_xyzm: *mut f32,
+                                                      d_out_xyz: *mut f32) -> c_int;
+    pub fn pcuda_bruteforce_f32x3_between_sharded(ctx: *mut pcuda_ctx, affected_xyz: *const f32,
+                                                  n_affected: usize, local_src_xyzm: *const f32,
+                                                  n_local_src: usize, src_capacity: usize, softening: f32,
+                                                  checked: c_int, out_xyz: *mut f32) -> c_int;
+    pub fn pcuda_morton_f32x3(ctx: *mut pcuda_ctx, particles_xyzm: *const f32, n: usize, keys_out: *mut u64,
+                              perm_out: *mut u32, frame_out: *mut pcuda_tree_info) -> c_int;
+    pub fn pcuda_morton_f32x2(ctx: *mut pcuda_ctx, particles_xym: *const f32, n: usize, keys_out: *mut u64,
+                              perm_out: *mut u32, frame_out: *mut pcuda_tree_info) -> c_int;
     pub fn pcuda_barneshut_f32x3_sharded_dev(ctx: *mut pcuda_ctx, d_local_xyzm: *const f32, n_local: usize,
                                              n_total: usize, theta: f32, softening: f32, checked: c_int,
                                              d_gathered_xyzm: *mut f32, d_out_xyz: *mut f32) -> c_int;

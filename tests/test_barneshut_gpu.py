@@ -229,6 +229,27 @@ def test_full_size_plummer(pb, ctx):
     t.close()
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("n", [1, 2, 1000, 100003])
+def test_morton_entry_bit_exact(pb, ctx, dim, n):
+    """pcuda_morton_f32x3 / _f32x2: keys, stable permutation and root cube equal the CPU
+    specification (oracle/oracle_octree.inc) bit for bit, and the keys the tree build uses."""
+    p = plummer_cloud(n, d=dim, seed=n + dim) if n > 2 else uniform_cloud(n, d=dim, seed=n)
+    if n > 100:
+        p[10:30, :dim] = p[10, :dim]  # equal keys: ties must keep input order
+    keys, perm, info = pb.morton_keys(ctx, p)
+    o = oracle.Octree(p, nleaf=16)
+    assert np.array_equal(keys, o.keys) and np.array_equal(perm, o.perm)
+    assert np.array_equal(np.array(info.origin[:dim], np.float32), o.origin)
+    assert np.float32(info.extent) == np.float32(o.ext) and np.float32(info.inv) == np.float32(o.inv)
+    assert np.array_equal(oracle.morton_keys(p[:, :dim], o.origin, o.inv)[perm], keys)
+    assert (np.diff(keys.astype(np.int64)) >= 0).all()
+    ties = np.flatnonzero(np.diff(keys.astype(np.int64)) == 0)
+    assert (perm[ties] < perm[ties + 1]).all()
+    k0, p0, _ = pb.morton_keys(ctx, np.zeros((0, dim + 1), np.float32))
+    assert k0.shape == (0,) and p0.shape == (0,)
+
+
 def test_sharded_entry_single_rank(pb, ctx):
     """The multi-GPU step degenerates to the plain evaluation without a communicator."""
     p = plummer_cloud(10000, seed=14)

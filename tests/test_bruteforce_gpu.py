@@ -210,6 +210,32 @@ def test_sharded_entry_single_rank(pb, ctx):
     assert t["kernel_launches"] >= 2 and t["compute_ms"] > 0
 
 
+def test_between_sharded_single_rank(pb, ctx):
+    """pcuda_bruteforce_f32x3_between_sharded[_dev] without a communicator: the Reordered storage
+    (all affected, massive affecting) evaluated through the multi-GPU entry equals the oracle and,
+    bit for bit, the plain entry evaluated against the same padded source set."""
+    import torch
+    p = uniform_cloud(6000, seed=31, massive_ratio=0.03)
+    st = pb.Reordered.new(p)
+    aff, src = oracle.between_of_reordered(p)
+    sh = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.5))
+    got = sh.compute(st)
+    assert_bruteforce_parity(got, oracle.brute_force_parallel(aff, src, 1.5), aff, src, 1.5)
+    assert np.array_equal(got, pb.BruteForce(ctx, pb.AccelerationSoftened.checked(1.5)).compute(st))
+    # device-resident step
+    d_aff = torch.from_numpy(np.ascontiguousarray(aff)).cuda()
+    d_src = torch.from_numpy(np.ascontiguousarray(src)).cuda()
+    torch.cuda.synchronize()
+    d_out = sh.step_device(d_aff, d_src, len(src))
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy(), got)
+    # no targets on this rank: still a valid call (the collective must be entered)
+    assert sh.compute_local(np.zeros((0, 3), np.float32), np.ascontiguousarray(src), len(src)).shape == (0, 3)
+    # no sources at all: zeros
+    z = sh.compute_local(np.ascontiguousarray(aff[:10]), np.zeros((0, 4), np.float32), 0)
+    assert z.shape == (10, 3) and not z.any()
+
+
 def test_pinned_buffers(pb, ctx):
     p = ctx.pinned_empty((1500, 4), np.float32)
     p[:] = uniform_cloud(1500, seed=4)

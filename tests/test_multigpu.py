@@ -38,6 +38,13 @@ e_1 = np.linalg.norm(singleb - truth, axis=1) / den
 res["bh_shape"] = list(fullb.shape)
 res["bh_err_sharded"] = [float(np.median(e_sh)), float(np.percentile(e_sh, 99)), float(e_sh.max())]
 res["bh_err_single"] = [float(np.median(e_1)), float(np.percentile(e_1, 99)), float(e_1.max())]
+r = uniform_cloud(20011, seed=6, massive_ratio=0.01)
+sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0), init_comm=False)
+sb.world, sb.rank = sh.world, sh.rank
+fulls = sb.compute(pb.Reordered.new(r))
+singles = pb.BruteForce(ctx, pb.AccelerationSoftened.checked(1.0)).compute(pb.Reordered.new(r))
+res["split_shape"] = list(fulls.shape)
+res["split_max_rel"] = float(np.max(np.linalg.norm(fulls - singles, axis=1) / np.linalg.norm(singles, axis=1)))
 res["comm_ms"] = ctx.timings()["comm_ms"]
 if rank == 0:
     print("RESULT " + json.dumps(res), flush=True)
@@ -67,6 +74,8 @@ def test_two_gpus_match_single_gpu(tmp_path):
     res = json.loads(line[7:])
     assert res["bf_shape"] == [30001, 3]
     assert res["bf_max_rel"] <= 1e-5   # same kernel, other source-split boundaries
+    assert res["split_shape"] == [20011, 3]
+    assert res["split_max_rel"] <= 1e-5
     # identical tree on every GPU; the target groups differ (each rank groups its own block), so
     # the results agree to the theta-approximation error, which must be the same as on one GPU
     assert res["bh_shape"] == [40003, 3]

@@ -90,3 +90,56 @@ def test_world2_gloo_sharded_equals_single(n):
         p.join(60)
     assert sorted(r for r, _ in res) == [0, 1]
     assert all(ok for _, ok in res), res
+
+
+def _worker_between(rank, world, port, n_massive, n_massless, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from particular_b200.interface import Reordered
+        from particular_b200.sharded import ShardedBetween, shard_capacity
+
+        class GlooOracleBetween(ShardedBetween):
+            """Stand-in for pcuda_bruteforce_f32x3_between_sharded: same source-slot layout,
+            exchange over gloo, evaluation by the CPU oracle."""
+
+            def compute_local(self, affected_local, src_local, n_src_total, out=None):
+                cap = shard_capacity(n_src_total, self.world)
+                slot = np.zeros((cap, 4), np.float32)
+                slot[:, :3] = 1e18
+                slot[: len(src_local)] = src_local
+                parts = [torch.empty((cap, 4)) for _ in range(self.world)]
+                self.dist.all_gather(parts, torch.from_numpy(slot))
+                gathered = torch.cat(parts).numpy()
+                if len(affected_local) == 0:
+                    return np.zeros((0, 3), np.float32)
+                return oracle.brute_force(affected_local, gathered)
+
+        p = uniform_cloud(n_massive + n_massless, seed=5)
+        massless = np.random.default_rng(9).permutation(len(p))[:n_massless]
+        p[massless, 3] = 0.0
+        storage = Reordered(p)  # affected: all, input order; affecting: the massive, input order
+        sh = GlooOracleBetween(None, None, init_comm=False)
+        full = sh.compute(storage)
+        massive = p[p[:, 3] != 0]
+        ref = oracle.brute_force(p[:, :3], massive) if len(massive) else np.zeros((len(p), 3), np.float32)
+        q.put((rank, full.shape == ref.shape and bool(np.array_equal(full, ref))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_massive,n_massless", [(1, 5), (7, 130), (33, 0), (2, 1)])
+def test_world2_gloo_between_equals_single(n_massive, n_massless):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_between, args=(r, world, port, n_massive, n_massless, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert sorted(r for r, _ in res) == [0, 1]
+    assert all(ok for _, ok in res), res

@@ -1091,7 +1091,9 @@ __device__ __forceinline__ void eval_entry(const float4 e, float2 npx, float2 np
     az = ptx::fma2(dz, sc, az);
 }
 
-template <bool COUNT>
+// VAR: experiment bits (tuning only).  1 = walk only (no evaluation), 2 = prefetch the next round's
+// node records into L1 before the evaluation.
+template <bool COUNT, int VAR = 0>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs a) {
     __shared__ uint32_t s_stack[TRAV_WARPS][STACK_CAP];
     __shared__ __align__(16) float4 s_list[TRAV_WARPS][LIST_CAP];
@@ -1163,7 +1165,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
             if (fill >= 32) {
                 __syncwarp();
                 const float4 *blk = list4 + head;
-                if (slices == 1) {
+                if (VAR & 1) {
+                } else if (slices == 1) {
 #pragma unroll 16
                     for (int q = 0; q < 32; ++q) eval_entry(blk[q], npx, npy, npz, eps2p, ax2, ay2, az2);
                 } else {
@@ -1236,6 +1239,11 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
                     if (j < c_child) stack[base + j] = nd.first_child + j;
                 sp += total;
             }
+            if (VAR & 2) {  // the next round's nodes are known now: pull them into L1
+                __syncwarp();
+                if (lane < sp)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nodes + stack[sp - 1 - lane]));
+            }
             if (wide) {
                 leaf_incl = c_leaf;
 #pragma unroll
@@ -1282,7 +1290,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
             }
             __syncwarp();
         }
-        if (fill > 0) {
+        if (fill > 0 && !(VAR & 1)) {
             __syncwarp();
             for (int q = slice; q < fill; q += slices)
                 eval_entry(list4[(head + q) & (LIST_CAP - 1)], npx, npy, npz, eps2p, ax2, ay2, az2);
@@ -1456,6 +1464,7 @@ static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d
     return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
 }
 
+static int g_variant = 0;     // experimental traversal variants (tuning hook)
 static bool g_count = true;  // instrumentation of the traversal (pcuda_tree_last_counters)
 static int g_seg_max = 256;  // largest cell (in targets) that is cut into groups (tuning hook)
 static int g_tpl = 2;        // targets per lane in the traversal: 1 (groups of 32) or 2 (groups of 64)
@@ -1570,7 +1579,11 @@ static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tg
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
                                                        (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
-    if (g_tpl == 2) {
+    if (g_tpl == 2 && g_variant) {
+        if (g_variant == 1) traverse2_kernel<false, 1><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+        else if (g_variant == 2) traverse2_kernel<false, 2><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+        else traverse2_kernel<false, 3><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+    } else if (g_tpl == 2) {
         if (g_count) traverse2_kernel<true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else traverse2_kernel<false><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
     } else {
@@ -1689,6 +1702,8 @@ static int oneshot_host(pcuda_ctx *ctx, uint32_t dim, const float *aff, size_t n
     if (!aff && na != nb)
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
                     "affected == NULL means affected == affecting, but n_affected != n_affecting");
+    if (na > 0x7fffffffull || nb > 0x7fffffffull)  // before any buffer is touched
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     DeviceGuard guard(ctx->device);
     timings_reset(ctx);
     if (na == 0) return PCUDA_OK;
@@ -1735,6 +1750,10 @@ int bh_debug_set(const char *key, int value) {
     }
     if (k == "bh_small_level" && value >= 0) {
         bh::g_small_level = (uint32_t)value;
+        return PCUDA_OK;
+    }
+    if (k == "bh_variant" && value >= 0 && value <= 3) {
+        bh::g_variant = value;
         return PCUDA_OK;
     }
     if (k == "bh_count") {
@@ -1843,6 +1862,7 @@ int pcuda_tree_build_f32(pcuda_ctx *ctx, uint32_t dim, const float *affecting, s
     *out = nullptr;
     if (dim != 2 && dim != 3) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
     if (n && !affecting) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     DeviceGuard guard(ctx->device);
     timings_reset(ctx);
     const size_t bytes = n * (dim + 1) * sizeof(float);
@@ -1879,6 +1899,7 @@ static int morton_host(pcuda_ctx *ctx, uint32_t dim, const float *particles, siz
     if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
     if (n && (!particles || !keys_out || !perm_out))
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     DeviceGuard guard(ctx->device);
     timings_reset(ctx);
     pcuda_tree t;

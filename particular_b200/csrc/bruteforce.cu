@@ -781,6 +781,8 @@ static int host_call(pcuda_ctx *ctx, const S *affected, size_t na, int dim, cons
     if (!affected && na != nb)
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
                     "affected == NULL means affected == affecting, but n_affected != n_affecting");
+    if (na > 0x7fffffffull || nb > 0x7fffffffull)  // before any buffer is touched
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     DeviceGuard guard(ctx->device);
     timings_reset(ctx);
     if (na == 0) return PCUDA_OK;

@@ -180,6 +180,12 @@ def test_error_convention(pb, ctx):
                                          1, out.ctypes.data_as(C.c_void_p))
     assert st == _ffi.ERR_INVALID_ARGUMENT
     assert b"n_affected != n_affecting" in _ffi.lib.pcuda_last_error(ctx.handle)
+    # maximum sizes: counts beyond 2^31-1 are rejected before any buffer is read or allocated
+    for fn, extra in ((_ffi.lib.pcuda_bruteforce_f32x3, (0.0, 1)), (_ffi.lib.pcuda_barneshut_f32x3, (0.5, 0.0, 1))):
+        st = fn(ctx.handle, None, 1 << 31, p.ctypes.data_as(C.c_void_p), 1 << 31, *extra,
+                out.ctypes.data_as(C.c_void_p))
+        assert st == _ffi.ERR_INVALID_ARGUMENT
+        assert b"2^31-1" in _ffi.lib.pcuda_last_error(ctx.handle)
     # the context stays usable after an error
     assert pb.BruteForce(ctx, pb.Acceleration.checked()).compute(p).shape == (8, 3)
 

@@ -147,6 +147,10 @@ int pcuda_bruteforce_f32x2(pcuda_ctx *ctx, const float *affected_xy, size_t n_af
 int pcuda_bruteforce_f64x3(pcuda_ctx *ctx, const double *affected_xyz, size_t n_affected,
                            const double *affecting_xyzm, size_t n_affecting, double softening,
                            int checked, double *out_xyz);
+/* DVec2 (the pair term is wired for it at gravity/impls/glam.rs:231-235): {x,y,mu} records. */
+int pcuda_bruteforce_f64x2(pcuda_ctx *ctx, const double *affected_xy, size_t n_affected,
+                           const double *affecting_xym, size_t n_affecting, double softening,
+                           int checked, double *out_xy);
 
 /* DEVICE buffers in/out, enqueued on the context stream, returns without synchronising.
  * The device-resident stepping path and the multi-GPU driver use these. */
@@ -159,6 +163,9 @@ int pcuda_bruteforce_f32x2_dev(pcuda_ctx *ctx, const float *d_affected_xy, size_
 int pcuda_bruteforce_f64x3_dev(pcuda_ctx *ctx, const double *d_affected_xyz, size_t n_affected,
                                const double *d_affecting_xyzm, size_t n_affecting,
                                double softening, int checked, double *d_out_xyz);
+int pcuda_bruteforce_f64x2_dev(pcuda_ctx *ctx, const double *d_affected_xy, size_t n_affected,
+                               const double *d_affecting_xym, size_t n_affecting,
+                               double softening, int checked, double *d_out_xy);
 
 /* ---- Barnes-Hut: new on the GPU (the reference has sequential/parallel CPU versions only:
  * sequential.rs:439-543, parallel.rs:297-367).  One call = build the tree over `affecting`

@@ -207,6 +207,10 @@ template <>
 struct Kernels<double, 3> {
     static constexpr auto brute = pcuda_bruteforce_f64x3;
 };
+template <>
+struct Kernels<double, 2> {
+    static constexpr auto brute = pcuda_bruteforce_f64x2;
+};
 
 }  // namespace detail
 

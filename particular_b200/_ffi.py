@@ -96,6 +96,8 @@ SIGNATURES = {
     "pcuda_bruteforce_f32x3_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _i, _vp]),
     "pcuda_bruteforce_f32x2_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _i, _vp]),
     "pcuda_bruteforce_f64x3_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _d, _i, _vp]),
+    "pcuda_bruteforce_f64x2": (_i, [_vp, _vp, _sz, _vp, _sz, _d, _i, _vp]),
+    "pcuda_bruteforce_f64x2_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _d, _i, _vp]),
     "pcuda_barneshut_f32x3": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _f, _i, _vp]),
     "pcuda_barneshut_f32x2": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _f, _i, _vp]),
     "pcuda_barneshut_f32x3_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _f, _i, _vp]),

@@ -298,7 +298,8 @@ __device__ __forceinline__ double mu_rcbrt2(double x, double mu) {
     return fma(um, e * q, um);
 }
 
-template <int T, int BLOCK, bool CLAMP>
+// DIM 2 (DVec2): sources repacked to {x, y, 0, mu}; the z terms are compiled out.
+template <int DIM, int T, int BLOCK, bool CLAMP>
 __global__ void __launch_bounds__(BLOCK)
     pair_kernel_f64(const double *__restrict__ tgt, int tgt_stride, int n_tgt,
                     const double4 *__restrict__ src, int n_src, int src_chunk, int tile,
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(BLOCK)
         const double *a = tgt + (size_t)i * tgt_stride;
         tx[k] = a[0];
         ty[k] = a[1];
-        tz[k] = a[2];
+        tz[k] = DIM == 3 ? a[2] : 0.0;
         ax[k] = ay[k] = az[k] = 0.0;
     }
 
@@ -366,15 +367,19 @@ __global__ void __launch_bounds__(BLOCK)
                 const double4 s = sp[j + u];
 #pragma unroll
                 for (int k = 0; k < T; ++k) {
-                    const double dx = s.x - tx[k], dy = s.y - ty[k], dz = s.z - tz[k];
+                    const double dx = s.x - tx[k], dy = s.y - ty[k];
                     double r2 = fma(dx, dx, eps2);
                     r2 = fma(dy, dy, r2);
-                    r2 = fma(dz, dz, r2);
+                    double dz = 0.0;
+                    if (DIM == 3) {
+                        dz = s.z - tz[k];
+                        r2 = fma(dz, dz, r2);
+                    }
                     if (CLAMP) r2 = one_if_zero(r2);  // d == 0 there, so the term is 0 * finite = 0
                     const double sc = mu_rcbrt2(r2, s.w);
                     ax[k] = fma(dx, sc, ax[k]);
                     ay[k] = fma(dy, sc, ay[k]);
-                    az[k] = fma(dz, sc, az[k]);
+                    if (DIM == 3) az[k] = fma(dz, sc, az[k]);
                 }
             }
         }
@@ -388,14 +393,14 @@ __global__ void __launch_bounds__(BLOCK)
         const int i = tbase + k * BLOCK;
         if (i >= n_tgt) continue;
         if (direct) {
-            out[(size_t)i * 3 + 0] = ax[k];
-            out[(size_t)i * 3 + 1] = ay[k];
-            out[(size_t)i * 3 + 2] = az[k];
+            out[(size_t)i * DIM + 0] = ax[k];
+            out[(size_t)i * DIM + 1] = ay[k];
+            if (DIM == 3) out[(size_t)i * DIM + 2] = az[k];
         } else {
-            double *pp = partial + (size_t)blockIdx.y * 3 * n_pad + i;
+            double *pp = partial + (size_t)blockIdx.y * DIM * n_pad + i;
             pp[0] = ax[k];
             pp[n_pad] = ay[k];
-            pp[2 * n_pad] = az[k];
+            if (DIM == 3) pp[2 * n_pad] = az[k];
         }
     }
 }
@@ -541,12 +546,13 @@ static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na
     return PCUDA_OK;
 }
 
+template <int DIM = 3>
 static int run_f64(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t na,
                    const double4 *d_src4, size_t nb, double softening, int checked,
                    double *d_out) {
     if (na == 0) return PCUDA_OK;
     if (nb == 0) {
-        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * 3 * sizeof(double), ctx->stream));
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * DIM * sizeof(double), ctx->stream));
         return PCUDA_OK;
     }
     if (na > 0x7fffffffull || nb > 0x7fffffffull)
@@ -567,20 +573,20 @@ static int run_f64(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t n
     const size_t n_pad = (na + 63) & ~size_t(63);
     double *partial = nullptr;
     if (splits > 1) {
-        PCUDA_CUDA_TRY(ctx, ctx->d_partial.ensure((size_t)splits * 3 * n_pad * sizeof(double)));
+        PCUDA_CUDA_TRY(ctx, ctx->d_partial.ensure((size_t)splits * DIM * n_pad * sizeof(double)));
         partial = ctx->d_partial.as<double>();
     }
     dim3 grid(n_tb, (unsigned)splits);
     if (clamp)
-        pair_kernel_f64<T, BLOCK, true><<<grid, BLOCK, 0, ctx->stream>>>(
+        pair_kernel_f64<DIM, T, BLOCK, true><<<grid, BLOCK, 0, ctx->stream>>>(
             d_tgt, tgt_stride, (int)na, d_src4, (int)nb, (int)chunk, tile, eps2, d_out, partial, n_pad);
     else
-        pair_kernel_f64<T, BLOCK, false><<<grid, BLOCK, 0, ctx->stream>>>(
+        pair_kernel_f64<DIM, T, BLOCK, false><<<grid, BLOCK, 0, ctx->stream>>>(
             d_tgt, tgt_stride, (int)na, d_src4, (int)nb, (int)chunk, tile, eps2, d_out, partial, n_pad);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     if (splits > 1) {
-        reduce_partials<double, 3><<<(unsigned)((na + 255) / 256), 256, 0, ctx->stream>>>(
+        reduce_partials<double, DIM><<<(unsigned)((na + 255) / 256), 256, 0, ctx->stream>>>(
             partial, (int)splits, n_pad, (int)na, d_out);
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
@@ -619,6 +625,26 @@ static int run_f32x2(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t 
 static int dev_f32x2(pcuda_ctx *ctx, const float *d_aff, size_t na, const float *d_src, size_t nb,
                      float eps, int checked, float *d_out) {
     return run_f32x2(ctx, d_aff, 2, na, d_src, nb, eps, checked, d_out);
+}
+
+// DVec2: {x,y,mu} (24 B) -> {x, y, 0, mu} records for the f64 kernel.
+__global__ void pack_sources_2d_f64(const double *__restrict__ in, int n, double4 *__restrict__ outp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) outp[i] = make_double4(in[3 * (size_t)i], in[3 * (size_t)i + 1], 0.0, in[3 * (size_t)i + 2]);
+}
+
+static int dev_f64x2(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src, size_t nb,
+                     double eps, int checked, double *d_out) {
+    double4 *packed = nullptr;
+    if (nb) {
+        if (nb > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+        PCUDA_CUDA_TRY(ctx, ctx->d_packed_src.ensure(nb * sizeof(double4)));
+        packed = ctx->d_packed_src.as<double4>();
+        pack_sources_2d_f64<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(d_src, (int)nb, packed);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return run_f64<2>(ctx, d_aff ? d_aff : d_src, d_aff ? 2 : 3, na, packed, nb, eps, checked, d_out);
 }
 
 static int dev_f64x3(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src, size_t nb,
@@ -885,6 +911,23 @@ int pcuda_bruteforce_f64x3(pcuda_ctx *ctx, const double *affected, size_t na,
                                  [&](double *dt, size_t n, double *ds, double *dout) {
                                      return bf::dev_f64x3(ctx, dt, n, ds, nb, softening, checked, dout);
                                  });
+}
+
+int pcuda_bruteforce_f64x2(pcuda_ctx *ctx, const double *affected, size_t na,
+                           const double *affecting, size_t nb, double softening, int checked,
+                           double *out) {
+    return bf::host_call<double>(ctx, affected, na, 2, affecting, nb, out,
+                                 [&](double *dt, size_t n, double *ds, double *dout) {
+                                     return bf::dev_f64x2(ctx, dt, n, ds, nb, softening, checked, dout);
+                                 });
+}
+
+int pcuda_bruteforce_f64x2_dev(pcuda_ctx *ctx, const double *d_affected, size_t na,
+                               const double *d_affecting, size_t nb, double softening, int checked,
+                               double *d_out) {
+    return bf::dev_call(ctx, [&] {
+        return bf::dev_f64x2(ctx, d_affected, na, d_affecting, nb, softening, checked, d_out);
+    });
 }
 
 int pcuda_bruteforce_f32x3_dev(pcuda_ctx *ctx, const float *d_affected, size_t na,

@@ -347,7 +347,8 @@ class CudaContext:
 def _suffix(src: np.ndarray) -> str:
     d = src.shape[1] - 1
     key = (src.dtype.type, d)
-    table = {(np.float32, 3): "f32x3", (np.float32, 2): "f32x2", (np.float64, 3): "f64x3"}
+    table = {(np.float32, 3): "f32x3", (np.float32, 2): "f32x2", (np.float64, 3): "f64x3",
+             (np.float64, 2): "f64x2"}
     if key not in table:
         # the reference does the same for shader dimensions it lacks: unimplemented!()
         # (gravity/impls/mod.rs:362, 374)

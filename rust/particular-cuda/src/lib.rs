@@ -206,6 +206,7 @@ impl_cuda_interaction!(glam::Vec3, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x
 impl_cuda_interaction!(glam::Vec3A, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x3, Some(ffi::pcuda_barneshut_f32x3 as BarnesFn<f32>));
 impl_cuda_interaction!(glam::Vec2, f32, 2, [x, y], ffi::pcuda_bruteforce_f32x2, Some(ffi::pcuda_barneshut_f32x2 as BarnesFn<f32>));
 impl_cuda_interaction!(glam::DVec3, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, None);
+impl_cuda_interaction!(glam::DVec2, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, None);
 
 /// Brute-force algorithm on the GPU; same shape as `gpu::BruteForce<'a, T>` (gpu/mod.rs:149-177).
 pub struct BruteForce<'a, T> {

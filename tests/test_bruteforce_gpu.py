@@ -39,7 +39,7 @@ def _reset_tp():
     force_tp(0)
 
 
-@pytest.mark.parametrize("dim,dtype", [(3, np.float32), (2, np.float32), (3, np.float64)])
+@pytest.mark.parametrize("dim,dtype", [(3, np.float32), (2, np.float32), (3, np.float64), (2, np.float64)])
 def test_reference_fixture(pb, ctx, dim, dtype):
     """acceleration_error! (gravity/newtonian/mod.rs:228-277) through Reordered, as the
     reference's gpu test does (:474-521); its tolerance is 1e-2, ours the parity bound."""
@@ -90,20 +90,31 @@ def test_interaction_variants_f32(pb, ctx, dim, soft, checked):
     assert_bruteforce_parity(got, ref, p[:, :dim], p, soft)
 
 
+@pytest.mark.parametrize("dim", [3, 2])
 @pytest.mark.parametrize("n", [1, 5, 129, 1000, 4099])
-def test_random_cloud_f64(pb, ctx, n):
-    p = uniform_cloud(n, dtype=np.float64, seed=n + 1)
+def test_random_cloud_f64(pb, ctx, n, dim):
+    """DVec3 and DVec2 (gravity/impls/glam.rs:231-235), <= 1e-12."""
+    p = uniform_cloud(n, d=dim, dtype=np.float64, seed=n + 1)
     got = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(p)
-    ref = oracle.brute_force_parallel(p[:, :3], p)
-    assert got.dtype == np.float64
+    ref = oracle.brute_force_parallel(p[:, :dim], p)
+    assert got.dtype == np.float64 and got.shape == (n, dim)
     if n > 1:
-        assert_bruteforce_parity(got, ref, p[:, :3], p)
+        assert_bruteforce_parity(got, ref, p[:, :dim], p)
     got = pb.BruteForce(ctx, pb.AccelerationSoftened.checked(3.0)).compute(p)
-    assert_bruteforce_parity(got, oracle.brute_force_parallel(p[:, :3], p, 3.0), p[:, :3], p, 3.0)
+    assert_bruteforce_parity(got, oracle.brute_force_parallel(p[:, :dim], p, 3.0), p[:, :dim], p, 3.0)
+    if n == 4099:  # large enough for source splits: device entry == host entry, bit for bit
+        import torch
+        d_p = torch.from_numpy(p).cuda()
+        d_o = torch.zeros((n, dim), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        pb.BruteForce(ctx, pb.AccelerationSoftened.checked(3.0)).compute_device(
+            None, n, d_p.data_ptr(), n, d_o.data_ptr(), f"f64x{dim}")
+        ctx.sync()
+        assert np.array_equal(d_o.cpu().numpy(), got)
 
 
 @pytest.mark.parametrize("na,nb", [(1, 1000), (1000, 1), (777, 1234), (5000, 33), (33, 5000)])
-@pytest.mark.parametrize("dim,dtype", [(3, np.float32), (2, np.float32), (3, np.float64)])
+@pytest.mark.parametrize("dim,dtype", [(3, np.float32), (2, np.float32), (3, np.float64), (2, np.float64)])
 def test_rectangular_between(pb, ctx, na, nb, dim, dtype):
     """Between(affected, affecting) with distinct sets (sequential.rs:196-209)."""
     src = uniform_cloud(nb, d=dim, dtype=dtype, seed=3)

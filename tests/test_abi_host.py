@@ -138,8 +138,9 @@ def test_unsupported_shapes_raise():
     import particular_b200.interface as pi
     with pytest.raises(TypeError):
         pi._as_particles(np.zeros((4, 6), np.float32))
+    assert pi._suffix(np.zeros((4, 3), np.float64)) == "f64x2"  # DVec2
     with pytest.raises(NotImplementedError):
-        pi._suffix(np.zeros((4, 3), np.float64))  # f64 2-D: no kernel, like unimplemented!()
+        pi._suffix(np.zeros((4, 3), np.float16))  # no kernel, like unimplemented!()
 
 
 def test_cpp_host_api_builds_and_refuses_without_gpu():

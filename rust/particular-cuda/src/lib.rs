@@ -208,6 +208,26 @@ impl_cuda_interaction!(glam::Vec2, f32, 2, [x, y], ffi::pcuda_bruteforce_f32x2, 
 impl_cuda_interaction!(glam::DVec3, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, None);
 impl_cuda_interaction!(glam::DVec2, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, None);
 
+// The reference's other vector front-ends (particular/Cargo.toml:19-34; their pair terms are wired
+// at gravity/impls/nalgebra.rs and gravity/impls/ultraviolet.rs): same packing, same entry points.
+// `v.x` reaches nalgebra's coordinates through Deref; both crates provide `From<[S; D]>`.
+#[cfg(feature = "nalgebra")]
+mod nalgebra_impls {
+    use super::*;
+    impl_cuda_interaction!(nalgebra::SVector<f32, 3>, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x3, Some(ffi::pcuda_barneshut_f32x3 as BarnesFn<f32>));
+    impl_cuda_interaction!(nalgebra::SVector<f32, 2>, f32, 2, [x, y], ffi::pcuda_bruteforce_f32x2, Some(ffi::pcuda_barneshut_f32x2 as BarnesFn<f32>));
+    impl_cuda_interaction!(nalgebra::SVector<f64, 3>, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, None);
+    impl_cuda_interaction!(nalgebra::SVector<f64, 2>, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, None);
+}
+#[cfg(feature = "ultraviolet")]
+mod ultraviolet_impls {
+    use super::*;
+    impl_cuda_interaction!(ultraviolet::Vec3, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x3, Some(ffi::pcuda_barneshut_f32x3 as BarnesFn<f32>));
+    impl_cuda_interaction!(ultraviolet::Vec2, f32, 2, [x, y], ffi::pcuda_bruteforce_f32x2, Some(ffi::pcuda_barneshut_f32x2 as BarnesFn<f32>));
+    impl_cuda_interaction!(ultraviolet::DVec3, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, None);
+    impl_cuda_interaction!(ultraviolet::DVec2, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, None);
+}
+
 /// Brute-force algorithm on the GPU; same shape as `gpu::BruteForce<'a, T>` (gpu/mod.rs:149-177).
 pub struct BruteForce<'a, T> {
     pub ctx: &'a mut CudaContext,

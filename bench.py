@@ -769,8 +769,12 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
                                 "traffic per launch); the kernel is FP32-pipe / issue bound, see "
                                 "traversal_fp32 and profiles/"},
            "traversal_fp32": {"achieved": FLOP_PER_PAIR * inter_n / (trav_ms * 1e-3) / 1e12,
+                              "peak": ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12,
+                              "frac": FLOP_PER_PAIR * inter_n / (trav_ms * 1e-3) / 1e12
+                              / (ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12),
                               "unit": "TFLOP/s", "interactions_per_target": inter_n / max(n_local, 1),
-                              "note": "20 flop per accepted interaction, this rank's targets"}}
+                              "note": "20 flop per accepted interaction, this rank's targets; the binding "
+                                      "resource (DESIGN.md K5): issue cycles, 2 per packed FP32 instruction"}}
     if not args.no_extra and rank == 0 and world == 1:
         rate, sample, cores, tb, tt = cpu_barneshut_rate(P, theta, cpu_seconds)
         out["cpu_baseline"] = {"value": rate, "unit": "particles/s", "cores": cores, "kind": "port",

@@ -184,6 +184,24 @@ int pcuda_barneshut_f32x2_dev(pcuda_ctx *ctx, const float *d_affected_xy, size_t
                               const float *d_affecting_xym, size_t n_affecting, float theta,
                               float softening, int checked, float *d_out_xy);
 
+/* Double precision (DVec3 / DVec2; the reference's BarnesHut is generic over the scalar,
+ * sequential.rs:439-543, and its own tests run it in f64, gravity/newtonian/mod.rs:407-418).  The
+ * tree STRUCTURE (keys, cells, opening decisions) is the f32 one over the particles rounded to
+ * f32; sources, centres of mass, targets and the pair term are double precision, so theta = 0 is
+ * the f64 brute-force sum.  Same argument meaning as the f32 entry points. */
+int pcuda_barneshut_f64x3(pcuda_ctx *ctx, const double *affected_xyz, size_t n_affected,
+                          const double *affecting_xyzm, size_t n_affecting, double theta,
+                          double softening, int checked, double *out_xyz);
+int pcuda_barneshut_f64x2(pcuda_ctx *ctx, const double *affected_xy, size_t n_affected,
+                          const double *affecting_xym, size_t n_affecting, double theta,
+                          double softening, int checked, double *out_xy);
+int pcuda_barneshut_f64x3_dev(pcuda_ctx *ctx, const double *d_affected_xyz, size_t n_affected,
+                              const double *d_affecting_xyzm, size_t n_affecting, double theta,
+                              double softening, int checked, double *d_out_xyz);
+int pcuda_barneshut_f64x2_dev(pcuda_ctx *ctx, const double *d_affected_xy, size_t n_affected,
+                              const double *d_affecting_xym, size_t n_affecting, double theta,
+                              double softening, int checked, double *d_out_xy);
+
 /* Split phase (replaces RootedOrthtree::new, storage.rs:20-33, and
  * BarnesHut::compute(Between<&[P1], &RootedOrthtree>), sequential.rs:508-524): build once,
  * traverse many times, inspect the arrays for parity tests. HOST buffers. `dim` is 2 or 3. */

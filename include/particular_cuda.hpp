@@ -206,10 +206,12 @@ struct Kernels<float, 2> {
 template <>
 struct Kernels<double, 3> {
     static constexpr auto brute = pcuda_bruteforce_f64x3;
+    static constexpr auto barnes = pcuda_barneshut_f64x3;
 };
 template <>
 struct Kernels<double, 2> {
     static constexpr auto brute = pcuda_bruteforce_f64x2;
+    static constexpr auto barnes = pcuda_barneshut_f64x2;
 };
 
 }  // namespace detail
@@ -330,13 +332,12 @@ private:
     auto run(const P1 *aff, std::size_t na, const P2 *src, std::size_t nb, bool alias) {
         using S = detail::scalar_t<P2>;
         constexpr std::size_t D = detail::dim_of<detail::position_t<P2>>();
-        static_assert(std::is_same_v<S, float>, "Barnes-Hut on the device is f32 (2-D / 3-D)");
         auto s = detail::pack_affecting<S, D>(src, nb);
         std::vector<S> a;
         if (!alias) a = detail::pack_affected<S, D>(aff, na);
         std::vector<S> out(na * D);
         ctx_->check(detail::Kernels<S, D>::barnes(ctx_->handle(), alias ? nullptr : a.data(), na, s.data(),
-                                                  nb, (float)theta_, (float)interaction_.softening(),
+                                                  nb, (S)theta_, (S)interaction_.softening(),
                                                   T::checked ? 1 : 0, out.data()));
         return detail::unpack<S, D>(out, na);
     }

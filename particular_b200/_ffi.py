@@ -102,6 +102,10 @@ SIGNATURES = {
     "pcuda_barneshut_f32x2": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _f, _i, _vp]),
     "pcuda_barneshut_f32x3_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _f, _i, _vp]),
     "pcuda_barneshut_f32x2_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _f, _f, _i, _vp]),
+    "pcuda_barneshut_f64x3": (_i, [_vp, _vp, _sz, _vp, _sz, _d, _d, _i, _vp]),
+    "pcuda_barneshut_f64x2": (_i, [_vp, _vp, _sz, _vp, _sz, _d, _d, _i, _vp]),
+    "pcuda_barneshut_f64x3_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _d, _d, _i, _vp]),
+    "pcuda_barneshut_f64x2_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _d, _d, _i, _vp]),
     "pcuda_tree_build_f32": (_i, [_vp, C.c_uint32, _vp, _sz, C.POINTER(_vp)]),
     "pcuda_tree_info_get": (_i, [_vp, C.POINTER(TreeInfo)]),
     "pcuda_tree_read": (_i, [_vp, _vp, _i, _vp, _sz]),

@@ -70,6 +70,8 @@ struct pcuda_tree {
     pcuda::bh::Frame frame = {};
     pcuda::DevBuf keys[2], perm[2], sorted, nodes, moments, d_frame, scan_in, scan_out, cub_tmp,
         partial;
+    pcuda::DevBuf sorted64;  // f64 trees: the sources in key order as double4 {x, y, z|0, mu};
+                             // `moments` then holds the double-precision {com, mass} per node
     int cur = 0;  // which of keys[]/perm[] holds the sorted data
     uint64_t *d_keys() const { return keys[cur].as<uint64_t>(); }
     uint32_t *d_perm() const { return perm[cur].as<uint32_t>(); }
@@ -1333,6 +1335,281 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5d: double precision (DVec2 / DVec3 particles; the reference's BarnesHut is generic over the
+// scalar, sequential.rs:439-543).  The TREE STRUCTURE — keys, sort, cells, opening decisions — is
+// the f32 one, built over the particles rounded to f32 (an opening decision moved by 2^-24 of the
+// box size is immaterial).  Everything that enters an acceleration is double precision: the
+// sources in key order (double4), the centre of mass of every node (recomputed bottom-up from the
+// f64 positions), the targets, and the pair term (the 16-operation FP64 sequence of the f64
+// brute-force kernel).  theta = 0 opens every cell, so the result is the f64 brute-force sum.
+__global__ void __launch_bounds__(256) narrow_kernel(const double *__restrict__ in, size_t count,
+                                                     float *__restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i];
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) gather64_kernel(const double *__restrict__ p, int stride,
+                                                       bool has_mass, int n,
+                                                       const uint32_t *__restrict__ perm,
+                                                       double4 *__restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *q = p + (size_t)perm[i] * stride;
+    sorted[i] = make_double4(q[0], q[1], DIM == 3 ? q[2] : 0.0, has_mass ? q[DIM] : 0.0);
+}
+
+// Bottom-up sums {sum m x, sum m y, sum m z, sum m} of one level from the f64 records (leaves) or
+// the children's sums (internal nodes), same fixed order as node_moments.
+template <int DIM>
+__global__ void __launch_bounds__(128) moments64_kernel(const NodeRec *__restrict__ nodes,
+                                                        double4 *__restrict__ mom,
+                                                        const double4 *__restrict__ sorted64,
+                                                        const BuildState *__restrict__ st, int level) {
+    const uint32_t lvl_begin = st->level_begin[level];
+    const uint32_t lvl_count = st->level_begin[level + 1] - lvl_begin;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < lvl_count;
+         t += gridDim.x * blockDim.x) {
+        const uint32_t j = lvl_begin + t;
+        const NodeRec nd = nodes[j];
+        const uint32_t nc = nd.nchild_level & 0xffu;
+        double m[4] = {0.0, 0.0, 0.0, 0.0};
+        if (nc == 0) {
+            for (uint32_t i = nd.begin; i < nd.begin + nd.count; ++i) {
+                const double4 q = sorted64[i];
+                m[0] = __dadd_rn(m[0], __dmul_rn(q.w, q.x));
+                m[1] = __dadd_rn(m[1], __dmul_rn(q.w, q.y));
+                if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(q.w, q.z));
+                m[3] = __dadd_rn(m[3], q.w);
+            }
+        } else {
+            for (uint32_t c = nd.first_child; c < nd.first_child + nc; ++c) {
+                const double4 q = mom[c];
+                m[0] = __dadd_rn(m[0], q.x);
+                m[1] = __dadd_rn(m[1], q.y);
+                if (DIM == 3) m[2] = __dadd_rn(m[2], q.z);
+                m[3] = __dadd_rn(m[3], q.w);
+            }
+        }
+        mom[j] = make_double4(m[0], m[1], m[2], m[3]);
+    }
+}
+
+// sums -> {com, mass} in place (a massless cell sits at its first particle, as in the f32 tree).
+__global__ void __launch_bounds__(256) finalize_cm64(const NodeRec *__restrict__ nodes,
+                                                     double4 *__restrict__ mom,
+                                                     const double4 *__restrict__ sorted64,
+                                                     uint32_t n_nodes) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_nodes; j += gridDim.x * blockDim.x) {
+        const double4 q = mom[j];
+        if (q.w == 0.0) {
+            const double4 f = sorted64[nodes[j].begin];
+            mom[j] = make_double4(f.x, f.y, f.z, 0.0);
+        } else {
+            mom[j] = make_double4(__ddiv_rn(q.x, q.w), __ddiv_rn(q.y, q.w), __ddiv_rn(q.z, q.w), q.w);
+        }
+    }
+}
+
+struct Ext64 {
+    const double4 *src64;  // sources in key order
+    const double4 *cm64;   // {com, mass} per node
+    const double4 *tgt64;  // targets in traversal order {x, y, z|0, _}
+    double *out;
+    double eps2;
+};
+
+constexpr int TRAV64_WARPS = 4;
+
+__device__ __forceinline__ void eval_entry64(const double4 e, double px, double py, double pz,
+                                             double eps2, double &ax, double &ay, double &az) {
+    const double dx = e.x - px, dy = e.y - py, dz = e.z - pz;
+    double r2 = fma(dx, dx, eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    r2 = ptx::one_if_zero(r2);  // zero distance: d == 0, so the term is 0 * finite = 0
+    const double sc = ptx::mu_rcbrt2(r2, e.w);
+    ax = fma(dx, sc, ax);
+    ay = fma(dy, sc, ay);
+    az = fma(dz, sc, az);
+}
+
+// The walk of traverse2_kernel (shared stack, group bounding box, ring of list entries), one
+// target per lane, groups of <= 32, entries and arithmetic in double precision.
+__global__ void __launch_bounds__(TRAV64_WARPS * 32) traverse64_kernel(TravArgs a, Ext64 x) {
+    __shared__ uint32_t s_stack[TRAV64_WARPS][STACK_CAP];
+    __shared__ __align__(16) double4 s_list[TRAV64_WARPS][LIST_CAP];
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *stack = s_stack[warp];
+    double4 *list = s_list[warp];
+    const uint32_t n_groups = *a.n_groups;
+    const float ext = a.frame->ext;
+
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(a.work, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= n_groups) break;
+        const int t0 = (int)a.group_start[g];
+        const int gcnt = (int)a.group_start[g + 1] - t0;  // 1..32 targets
+        int gpad = 1;
+        while (gpad < gcnt) gpad <<= 1;
+        const int slices = 32 / gpad;
+        const int tl = lane & (gpad - 1), slice = lane / gpad;
+        const int ti = t0 + min(tl, gcnt - 1);
+        const double4 tp = x.tgt64[ti];
+        const double px = tp.x, py = tp.y, pz = tp.z;
+
+        // group bounding box in f32, rounded outwards
+        float lox = __double2float_rd(px), hix = __double2float_ru(px);
+        float loy = __double2float_rd(py), hiy = __double2float_ru(py);
+        float loz = __double2float_rd(pz), hiz = __double2float_ru(pz);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(FULL, lox, o));
+            hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, o));
+            loy = fminf(loy, __shfl_xor_sync(FULL, loy, o));
+            hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, o));
+            loz = fminf(loz, __shfl_xor_sync(FULL, loz, o));
+            hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, o));
+        }
+        const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+        const float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
+
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        int sp = 1, head = 0, fill = 0;
+        __syncwarp();
+        if (lane == 0) stack[0] = 0;
+        __syncwarp();
+
+        auto flush_full = [&]() {
+            if (fill >= 32) {
+                __syncwarp();
+                const double4 *blk = list + head;
+                for (int q = slice; q < 32; q += slices) eval_entry64(blk[q], px, py, pz, x.eps2, ax, ay, az);
+                fill -= 32;
+                head ^= 32;
+                __syncwarp();
+            }
+        };
+
+        while (sp > 0) {
+            const int room = (STACK_CAP - STACK_RESERVE - sp) / 7;
+            const int k = min(min(32, sp), max(room, 1));
+            const bool has = lane < k;
+            NodeRec nd;
+            nd.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+            nd.first_child = 0;
+            nd.begin = 0;
+            nd.count = 0;
+            nd.nchild_level = 0;
+            uint32_t id = 0;
+            if (has) {
+                id = stack[sp - 1 - lane];
+                const uint4 *q = reinterpret_cast<const uint4 *>(a.nodes + id);
+                const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                nd.cm = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y),
+                                    __uint_as_float(q0.z), __uint_as_float(q0.w));
+                nd.first_child = q1.x;
+                nd.nchild_level = q1.y;
+                nd.begin = q1.z;
+                nd.count = q1.w;
+            }
+            sp -= k;
+            __syncwarp();
+
+            bool open = false;
+            if (has) {
+                const float ddx = fmaxf(fabsf(nd.cm.x - cx) - hx, 0.f);
+                const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
+                const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
+                const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                const int level = (int)(nd.nchild_level >> 8);
+                const float w = ext * __int_as_float((127 - level) << 23);
+                open = a.theta2 * d2 < w * w;
+            }
+            const uint32_t nc = nd.nchild_level & 0xffu;
+            const bool open_internal = has && open && nc > 0;
+            const bool open_leaf = has && open && nc == 0;
+            const bool accept = has && !open;
+
+            const int c_child = open_internal ? (int)nc : 0;
+            const int c_leaf = open_leaf ? (int)nd.count : 0;
+            int child_incl = c_child, leaf_incl = c_leaf;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, child_incl, o);
+                const int u = __shfl_up_sync(FULL, leaf_incl, o);
+                if (lane >= o) {
+                    child_incl += v;
+                    leaf_incl += u;
+                }
+            }
+            {
+                const int total = __shfl_sync(FULL, child_incl, 31);
+                const int base = sp + child_incl - c_child;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < c_child) stack[base + j] = nd.first_child + j;
+                sp += total;
+            }
+
+            {  // accepted nodes -> ring (their double-precision {com, mass})
+                const unsigned m = __ballot_sync(FULL, accept);
+                if (m) {
+                    if (accept)
+                        list[(head + fill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1)] = x.cm64[id];
+                    fill += __popc(m);
+                    flush_full();
+                }
+            }
+
+            {  // particles of opened leaves -> ring, 32 per round
+                const int incl = leaf_incl;
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int excl = incl - c_leaf;
+                for (int base = 0; base < total; base += 32) {
+                    const int f = base + lane;
+                    int owner = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, (owner + step - 1) & 31);
+                        if (v <= f) owner += step;
+                    }
+                    owner = min(owner, 31);
+                    const uint32_t ob = __shfl_sync(FULL, nd.begin, owner);
+                    const int oe = __shfl_sync(FULL, excl, owner);
+                    if (f < total) list[(head + fill + lane) & (LIST_CAP - 1)] = x.src64[ob + (f - oe)];
+                    fill += min(32, total - base);
+                    flush_full();
+                }
+            }
+            __syncwarp();
+        }
+        if (fill > 0) {
+            __syncwarp();
+            for (int q = slice; q < fill; q += slices)
+                eval_entry64(list[(head + q) & (LIST_CAP - 1)], px, py, pz, x.eps2, ax, ay, az);
+        }
+        for (int o = gpad; o < 32; o <<= 1) {  // combine the slices of each target
+            ax += __shfl_xor_sync(FULL, ax, o);
+            ay += __shfl_xor_sync(FULL, ay, o);
+            az += __shfl_xor_sync(FULL, az, o);
+        }
+        if (slice == 0 && tl < gcnt) {
+            const uint32_t row = a.tgt_perm ? a.tgt_perm[ti] : (uint32_t)ti;
+            double *o = x.out + (size_t)row * a.dim;
+            o[0] = ax;
+            o[1] = ay;
+            if (a.dim == 3) o[2] = az;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side.
 template <int DIM>
 static int sort_by_key(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n, const Frame *d_frame,
@@ -1465,24 +1742,72 @@ static int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d
 }
 
 static int g_variant = 0;     // experimental traversal variants (tuning hook)
+// Tree over double-precision particles: the f32 structure over the rounded records, then the f64
+// layer (sources in key order, {com, mass} per node from the f64 positions, bottom-up).
+template <int DIM>
+static int build64(pcuda_ctx *ctx, pcuda_tree *t, const double *d_particles64, size_t n) {
+    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    cudaStream_t st = ctx->stream;
+    const size_t count = n * (DIM + 1);
+    if (n) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_packed_src.ensure(count * sizeof(float)));
+        narrow_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 65535), 256, 0, st>>>(
+            d_particles64, count, ctx->d_packed_src.as<float>());
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    PCUDA_TRY(build<DIM>(ctx, t, ctx->d_packed_src.as<float>(), n));
+    if (n == 0) return PCUDA_OK;
+    PCUDA_CUDA_TRY(ctx, t->sorted64.ensure(n * sizeof(double4)));
+    gather64_kernel<DIM><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        d_particles64, DIM + 1, true, (int)n, t->d_perm(), t->sorted64.as<double4>());
+    const BuildState *d_state = t->scan_in.as<BuildState>();
+    for (int level = t->n_levels - 1; level >= 0; --level) {
+        const uint32_t cnt = t->level_begin[level + 1] - t->level_begin[level];
+        const unsigned grid = std::min<unsigned>((unsigned)ctx->sm_count * 8, (cnt + 127) / 128);
+        moments64_kernel<DIM><<<grid, 128, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double4>(),
+                                                    t->sorted64.as<double4>(), d_state, level);
+    }
+    finalize_cm64<<<std::min<unsigned>((unsigned)ctx->sm_count * 8, (unsigned)((t->n_nodes + 255) / 256)), 256, 0,
+                    st>>>(t->nodes.as<NodeRec>(), t->moments.as<double4>(), t->sorted64.as<double4>(),
+                          (uint32_t)t->n_nodes);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2 + t->n_levels;
+    return PCUDA_OK;
+}
+
 static bool g_count = true;  // instrumentation of the traversal (pcuda_tree_last_counters)
 static int g_seg_max = 256;  // largest cell (in targets) that is cut into groups (tuning hook)
 static int g_tpl = 2;        // targets per lane in the traversal: 1 (groups of 32) or 2 (groups of 64)
 
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
 // tgt_stride: floats per target row (0 = bare positions, i.e. `dim`).
+struct Ext64;
 static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
                            const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
-                           float eps, float *d_out);
+                           float eps, float *d_out, const Ext64 *x64 = nullptr);
 
+// Double precision (tree built by build64): d_tgt64 / d_out64 replace d_tgt / d_out; the f32 copy of
+// separate targets that keys them is made here.
 static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na, float theta,
-                    float eps, float *d_out, int tgt_stride = 0) {
+                    float eps, float *d_out, int tgt_stride = 0, const double *d_tgt64 = nullptr,
+                    double *d_out64 = nullptr, double eps64 = 0.0) {
     const int dim = t->dim;
     const int ts = tgt_stride ? tgt_stride : dim;
+    const bool f64 = d_out64 != nullptr;
     if (na == 0) return PCUDA_OK;
     if (t->n == 0) {
-        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * dim * sizeof(float), ctx->stream));
+        if (f64) PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out64, 0, na * dim * sizeof(double), ctx->stream));
+        else PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * dim * sizeof(float), ctx->stream));
         return PCUDA_OK;
+    }
+    if (f64 && d_tgt64) {  // f32 copy of the targets (bare positions), only to key and group them
+        PCUDA_CUDA_TRY(ctx, ctx->d_misc.ensure(na * dim * sizeof(float)));
+        narrow_kernel<<<(unsigned)std::min<size_t>((na * dim + 255) / 256, 65535), 256, 0, ctx->stream>>>(
+            d_tgt64, na * dim, ctx->d_misc.as<float>());
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+        d_tgt = ctx->d_misc.as<float>();
     }
     if (na > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     if (!d_tgt && na != t->n)
@@ -1507,9 +1832,15 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         ctx->d_tgt_perm = perm[0];
         ctx->d_tgt_perm_alt = perm[1];
         PCUDA_TRY(s);
-        PCUDA_CUDA_TRY(ctx, ctx->d_tgt_sorted.ensure(na * sizeof(float4)));
+        PCUDA_CUDA_TRY(ctx, ctx->d_tgt_sorted.ensure(na * (f64 ? sizeof(double4) : sizeof(float4))));
         const uint32_t *p = perm[cur].as<uint32_t>();
-        if (dim == 3)
+        if (f64 && dim == 3)
+            gather64_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt64, dim, false, (int)na, p,
+                                                                             ctx->d_tgt_sorted.as<double4>());
+        else if (f64)
+            gather64_kernel<2><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt64, dim, false, (int)na, p,
+                                                                             ctx->d_tgt_sorted.as<double4>());
+        else if (dim == 3)
             gather_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, ts, false, (int)na, p,
                                                                            ctx->d_tgt_sorted.as<float4>());
         else
@@ -1521,6 +1852,15 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         tgt_perm = p;
         tgt_keys = keys[cur].as<uint64_t>();
     }
+    if (f64) {
+        Ext64 x;
+        x.src64 = t->sorted64.as<double4>();
+        x.cm64 = t->moments.as<double4>();
+        x.tgt64 = d_tgt64 ? ctx->d_tgt_sorted.as<double4>() : t->sorted64.as<double4>();
+        x.out = d_out64;
+        x.eps2 = eps64 * eps64;
+        return traverse_sorted(ctx, t, nullptr, tgt_keys, tgt_perm, na, theta, eps, nullptr, &x);
+    }
     return traverse_sorted(ctx, t, tgt_sorted, tgt_keys, tgt_perm, na, theta, eps, d_out);
 }
 
@@ -1528,9 +1868,10 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
 // traversal order to the output row (nullptr: out row = traversal position).
 static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
                            const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
-                           float eps, float *d_out) {
+                           float eps, float *d_out, const Ext64 *x64) {
     const int dim = t->dim;
     cudaStream_t st = ctx->stream;
+    const int group_cap = x64 ? 32 : 32 * g_tpl;  // the f64 walk holds one target per lane
     // K5a: groups from the target keys
     const int n = (int)na;
     PCUDA_CUDA_TRY(ctx, ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
@@ -1552,7 +1893,7 @@ static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tg
     else boundary_levels<2><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
     const unsigned ngb = (unsigned)((n + GROUP_BLOCK - 1) / GROUP_BLOCK);
     hard_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_L, n, t->bits, g_seg_max, d_hard);
-    group_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_hard, n, g_seg_max, 32 * g_tpl, d_flag);
+    group_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_hard, n, g_seg_max, group_cap, d_flag);
     size_t tmp = 0;
     PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_flag, d_pos, n, st));
     PCUDA_CUDA_TRY(ctx, ctx->d_cub_tmp.ensure(tmp));
@@ -1579,7 +1920,11 @@ static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tg
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
                                                        (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
-    if (g_tpl == 2 && g_variant) {
+    if (x64) {
+        const unsigned blocks64 = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8,
+                                                            (max_groups + TRAV64_WARPS - 1) / TRAV64_WARPS);
+        traverse64_kernel<<<blocks64, TRAV64_WARPS * 32, 0, st>>>(a, *x64);
+    } else if (g_tpl == 2 && g_variant) {
         if (g_variant == 1) traverse2_kernel<false, 1><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else if (g_variant == 2) traverse2_kernel<false, 2><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else traverse2_kernel<false, 3><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
@@ -1620,6 +1965,57 @@ static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t 
     PCUDA_TRY(traverse(ctx, ctx->call_tree, d_aff, na, theta, eps, d_out, tgt_stride));
     phase_end(ctx, PH_COMPUTE);
     return PCUDA_OK;
+}
+
+static int oneshot_dev64(pcuda_ctx *ctx, uint32_t dim, const double *d_aff, size_t na, const double *d_src,
+                         size_t nb, double theta, double eps, double *d_out) {
+    if (!d_aff && na != nb)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
+                    "affected == NULL means affected == affecting, but n_affected != n_affecting");
+    if (dim != 2 && dim != 3) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+    if (!ctx->call_tree) ctx->call_tree = new pcuda_tree();
+    phase_begin(ctx, PH_BUILD);
+    PCUDA_TRY(dim == 3 ? build64<3>(ctx, ctx->call_tree, d_src, nb) : build64<2>(ctx, ctx->call_tree, d_src, nb));
+    phase_end(ctx, PH_BUILD);
+    phase_begin(ctx, PH_COMPUTE);
+    PCUDA_TRY(traverse(ctx, ctx->call_tree, nullptr, na, (float)theta, 0.f, nullptr, 0, d_aff, d_out, eps));
+    phase_end(ctx, PH_COMPUTE);
+    return PCUDA_OK;
+}
+
+static int oneshot_host64(pcuda_ctx *ctx, uint32_t dim, const double *aff, size_t na, const double *src,
+                          size_t nb, double theta, double eps, double *out) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if ((na && !out) || (nb && !src))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    if (!aff && na != nb)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
+                    "affected == NULL means affected == affecting, but n_affected != n_affecting");
+    if (na > 0x7fffffffull || nb > 0x7fffffffull)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    if (na == 0) return PCUDA_OK;
+    const size_t src_bytes = nb * (dim + 1) * sizeof(double), tgt_bytes = na * dim * sizeof(double);
+    phase_begin(ctx, PH_UPLOAD);
+    double *d_src = nullptr, *d_tgt = nullptr;
+    if (nb) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(src_bytes));
+        d_src = ctx->d_affecting.as<double>();
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (aff) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_affected.ensure(tgt_bytes));
+        d_tgt = ctx->d_affected.as<double>();
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_tgt, aff, tgt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(tgt_bytes));
+    phase_end(ctx, PH_UPLOAD);
+    PCUDA_TRY(oneshot_dev64(ctx, dim, d_tgt, na, d_src, nb, theta, eps, ctx->d_out.as<double>()));
+    phase_begin(ctx, PH_DOWNLOAD);
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out.p, tgt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    phase_end(ctx, PH_DOWNLOAD);
+    return timings_collect(ctx);
 }
 
 // Multi-GPU step (one process per GPU), "replicated build": every rank owns the contiguous block
@@ -1767,7 +2163,8 @@ void tree_free(pcuda_ctx *ctx, pcuda_tree *t) {
     if (!t) return;
     (void)ctx;
     DevBuf *bufs[] = {&t->keys[0], &t->keys[1], &t->perm[0], &t->perm[1], &t->sorted, &t->nodes,
-                      &t->moments, &t->d_frame, &t->scan_in, &t->scan_out, &t->cub_tmp, &t->partial};
+                      &t->moments, &t->d_frame, &t->scan_in, &t->scan_out, &t->cub_tmp, &t->partial,
+                      &t->sorted64};
     for (DevBuf *b : bufs) b->release();
     delete t;
 }
@@ -1788,6 +2185,41 @@ int pcuda_barneshut_f32x2(pcuda_ctx *ctx, const float *aff, size_t na, const flo
                           float theta, float softening, int checked, float *out) {
     (void)checked;
     return bh::oneshot_host(ctx, 2, aff, na, src, nb, theta, softening, out);
+}
+
+int pcuda_barneshut_f64x3(pcuda_ctx *ctx, const double *aff, size_t na, const double *src, size_t nb,
+                          double theta, double softening, int checked, double *out) {
+    (void)checked;  // a pair at zero distance contributes nothing either way (sequential.rs:485-487)
+    return bh::oneshot_host64(ctx, 3, aff, na, src, nb, theta, softening, out);
+}
+
+int pcuda_barneshut_f64x2(pcuda_ctx *ctx, const double *aff, size_t na, const double *src, size_t nb,
+                          double theta, double softening, int checked, double *out) {
+    (void)checked;
+    return bh::oneshot_host64(ctx, 2, aff, na, src, nb, theta, softening, out);
+}
+
+static int bh_dev64(pcuda_ctx *ctx, uint32_t dim, const double *d_aff, size_t na, const double *d_src,
+                    size_t nb, double theta, double softening, double *d_out) {
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    if (na == 0) return PCUDA_OK;
+    int s = bh::oneshot_dev64(ctx, dim, d_aff, na, d_src, nb, theta, softening, d_out);
+    ctx->timings.kernel_launches = ctx->launches;
+    return s;
+}
+
+int pcuda_barneshut_f64x3_dev(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src,
+                              size_t nb, double theta, double softening, int checked, double *d_out) {
+    (void)checked;
+    return bh_dev64(ctx, 3, d_aff, na, d_src, nb, theta, softening, d_out);
+}
+
+int pcuda_barneshut_f64x2_dev(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src,
+                              size_t nb, double theta, double softening, int checked, double *d_out) {
+    (void)checked;
+    return bh_dev64(ctx, 2, d_aff, na, d_src, nb, theta, softening, d_out);
 }
 
 static int bh_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t na, const float *d_src,

@@ -275,28 +275,8 @@ __global__ void pack_sources_2d(const float *__restrict__ in, int n, float4 *__r
 constexpr int TILE64 = 128;
 constexpr double PAD_POS_64 = 1e100;
 
-// x == +0.0 ? 1.0 : x, with integer instructions (a DSETP would take an FP64-pipe slot, and the
-// FP64 pipe is the limiter of this kernel).  x is a sum of squares: never -0.0.
-__device__ __forceinline__ double one_if_zero(double x) {
-    const int hi = __double2hiint(x), lo = __double2loint(x);
-    return __hiloint2double((hi | lo) == 0 ? 0x3ff00000 : hi, lo);
-}
-
-// mu * x^(-3/2) in 7 FP64 operations (CUDA's rsqrt() + three multiplies take 8 plus a range
-// check): y0 = MUFU.RSQ64H(x) carries ~20 bits; with e = 1 - x*y0^2 (|e| < 2^-19),
-//     x^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + e (3/2 + 15/8 e)) + O(e^3),   35/16 e^3 < 2^-56,
-// so the result is good to a few ulp — far inside the 1e-12 parity bound.  x must be a normal
-// positive number: the kernel's r2 is one (coincident pairs are handled before the call); x = 0
-// (unchecked, eps = 0) gives NaN like the reference's 0 * inf.
-__device__ __forceinline__ double mu_rcbrt2(double x, double mu) {
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    const double t = y0 * y0;
-    const double e = fma(-x, t, 1.0);
-    const double q = fma(1.875, e, 1.5);
-    const double um = (t * y0) * mu;
-    return fma(um, e * q, um);
-}
+using ptx::mu_rcbrt2;
+using ptx::one_if_zero;
 
 // DIM 2 (DVec2): sources repacked to {x, y, 0, mu}; the z terms are compiled out.
 template <int DIM, int T, int BLOCK, bool CLAMP>

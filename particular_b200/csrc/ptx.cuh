@@ -84,5 +84,28 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
 
+// x == +0.0 ? 1.0 : x, with integer instructions (a DSETP would take an FP64-pipe slot, and the
+// FP64 pipe is the limiter of the f64 kernels).  x is a sum of squares: never -0.0.
+__device__ __forceinline__ double one_if_zero(double x) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    return __hiloint2double((hi | lo) == 0 ? 0x3ff00000 : hi, lo);
+}
+
+// mu * x^(-3/2) in 7 FP64 operations (CUDA's rsqrt() + three multiplies take 8 plus a range
+// check): y0 = MUFU.RSQ64H(x) carries ~20 bits; with e = 1 - x*y0^2 (|e| < 2^-19),
+//     x^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + e (3/2 + 15/8 e)) + O(e^3),   35/16 e^3 < 2^-56,
+// so the result is good to a few ulp — far inside the 1e-12 parity bound.  x must be a normal
+// positive number: the kernel's r2 is one (coincident pairs are handled before the call); x = 0
+// (unchecked, eps = 0) gives NaN like the reference's 0 * inf.
+__device__ __forceinline__ double mu_rcbrt2(double x, double mu) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double t = y0 * y0;
+    const double e = fma(-x, t, 1.0);
+    const double q = fma(1.875, e, 1.5);
+    const double um = (t * y0) * mu;
+    return fma(um, e * q, um);
+}
+
 }  // namespace ptx
 }  // namespace pcuda

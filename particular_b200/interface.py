@@ -493,11 +493,9 @@ class BarnesHut:
                                               _ptr(out)), self.ctx.handle)
             return out
         sfx = _suffix(src)
-        if sfx == "f64x3":
-            raise NotImplementedError("Barnes-Hut on the device is f32 (2-D / 3-D)")
         d = src.shape[1] - 1
         na = len(src) if aff is None else len(aff)
-        out = _out_array(out, (na, d), np.float32)
+        out = _out_array(out, (na, d), src.dtype)
         fn = getattr(lib, f"pcuda_barneshut_{sfx}")
         check(fn(self.ctx.handle, _ptr(aff), na, _ptr(src), len(src), self.theta, it.softening,
                  int(it.is_checked), _ptr(out)), self.ctx.handle)

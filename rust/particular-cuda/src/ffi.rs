@@ -146,6 +146,18 @@ extern "C" {
     pub fn pcuda_barneshut_f32x2_dev(ctx: *mut pcuda_ctx, d_affected: *const f32, n_affected: usize,
                                      d_affecting: *const f32, n_affecting: usize, theta: f32,
                                      softening: f32, checked: c_int, d_out: *mut f32) -> c_int;
+    pub fn pcuda_barneshut_f64x3(ctx: *mut pcuda_ctx, affected_xyz: *const f64, n_affected: usize,
+                                 affecting_xyzm: *const f64, n_affecting: usize, theta: f64,
+                                 softening: f64, checked: c_int, out_xyz: *mut f64) -> c_int;
+    pub fn pcuda_barneshut_f64x2(ctx: *mut pcuda_ctx, affected_xy: *const f64, n_affected: usize,
+                                 affecting_xym: *const f64, n_affecting: usize, theta: f64,
+                                 softening: f64, checked: c_int, out_xy: *mut f64) -> c_int;
+    pub fn pcuda_barneshut_f64x3_dev(ctx: *mut pcuda_ctx, d_affected: *const f64, n_affected: usize,
+                                     d_affecting: *const f64, n_affecting: usize, theta: f64,
+                                     softening: f64, checked: c_int, d_out: *mut f64) -> c_int;
+    pub fn pcuda_barneshut_f64x2_dev(ctx: *mut pcuda_ctx, d_affected: *const f64, n_affected: usize,
+                                     d_affecting: *const f64, n_affecting: usize, theta: f64,
+                                     softening: f64, checked: c_int, d_out: *mut f64) -> c_int;
 
     pub fn pcuda_tree_build_f32(ctx: *mut pcuda_ctx, dim: u32, affecting: *const f32, n: usize,
                                 out: *mut *mut pcuda_tree) -> c_int;

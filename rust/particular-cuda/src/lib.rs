@@ -153,7 +153,18 @@ macro_rules! impl_cuda_interaction {
 }
 
 type BruteFn<S> = unsafe extern "C" fn(*mut ffi::pcuda_ctx, *const S, usize, *const S, usize, S, i32, *mut S) -> i32;
-type BarnesFn<S> = unsafe extern "C" fn(*mut ffi::pcuda_ctx, *const S, usize, *const S, usize, f32, f32, i32, *mut S) -> i32;
+type BarnesFn<S> = unsafe extern "C" fn(*mut ffi::pcuda_ctx, *const S, usize, *const S, usize, S, S, i32, *mut S) -> i32;
+
+/// The two scalar types of the device kernels.
+pub trait DeviceScalar: Copy + Default + Into<f64> {
+    fn from_f64(v: f64) -> Self;
+}
+impl DeviceScalar for f32 {
+    fn from_f64(v: f64) -> Self { v as f32 }
+}
+impl DeviceScalar for f64 {
+    fn from_f64(v: f64) -> Self { v }
+}
 
 /// Pack, call, unpack.  `affected` and `affecting` being the same slice (the `&[P]` storage,
 /// storage.rs:231-241) is detected by address and passed as `affected == NULL`, which lets the
@@ -166,7 +177,7 @@ fn run<V, S, const D: usize, P1, P2>(
 ) -> Vec<V>
 where
     V: From<[S; D]>,
-    S: Copy + Default + Into<f64>,
+    S: DeviceScalar,
     P2: Mass<Scalar = S>,
 {
     let mut src: Vec<S> = Vec::with_capacity(affecting.len() * (D + 1));
@@ -192,11 +203,10 @@ where
                   out.as_mut_ptr().cast())
         },
         (Some(theta), Some(barnes)) => unsafe {
-            barnes(ctx.raw, tgt_ptr, affected.len(), src.as_ptr(), affecting.len(), theta as f32,
-                   softening.into() as f32, checked as i32, out.as_mut_ptr().cast())
+            barnes(ctx.raw, tgt_ptr, affected.len(), src.as_ptr(), affecting.len(), S::from_f64(theta),
+                   softening, checked as i32, out.as_mut_ptr().cast())
         },
-        // same gap as the reference's shaders outside {Vec2, Vec3} (gravity/impls/mod.rs:362, 374)
-        (Some(_), None) => unimplemented!("Barnes-Hut on the device is f32 (2-D / 3-D)"),
+        (Some(_), None) => unimplemented!("no device Barnes-Hut for this vector type"),
     };
     check(status, ctx.raw);
     out.into_iter().map(V::from).collect()
@@ -205,8 +215,8 @@ where
 impl_cuda_interaction!(glam::Vec3, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x3, Some(ffi::pcuda_barneshut_f32x3 as BarnesFn<f32>));
 impl_cuda_interaction!(glam::Vec3A, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x3, Some(ffi::pcuda_barneshut_f32x3 as BarnesFn<f32>));
 impl_cuda_interaction!(glam::Vec2, f32, 2, [x, y], ffi::pcuda_bruteforce_f32x2, Some(ffi::pcuda_barneshut_f32x2 as BarnesFn<f32>));
-impl_cuda_interaction!(glam::DVec3, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, None);
-impl_cuda_interaction!(glam::DVec2, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, None);
+impl_cuda_interaction!(glam::DVec3, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, Some(ffi::pcuda_barneshut_f64x3 as BarnesFn<f64>));
+impl_cuda_interaction!(glam::DVec2, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, Some(ffi::pcuda_barneshut_f64x2 as BarnesFn<f64>));
 
 // The reference's other vector front-ends (particular/Cargo.toml:19-34; their pair terms are wired
 // at gravity/impls/nalgebra.rs and gravity/impls/ultraviolet.rs): same packing, same entry points.
@@ -216,16 +226,16 @@ mod nalgebra_impls {
     use super::*;
     impl_cuda_interaction!(nalgebra::SVector<f32, 3>, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x3, Some(ffi::pcuda_barneshut_f32x3 as BarnesFn<f32>));
     impl_cuda_interaction!(nalgebra::SVector<f32, 2>, f32, 2, [x, y], ffi::pcuda_bruteforce_f32x2, Some(ffi::pcuda_barneshut_f32x2 as BarnesFn<f32>));
-    impl_cuda_interaction!(nalgebra::SVector<f64, 3>, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, None);
-    impl_cuda_interaction!(nalgebra::SVector<f64, 2>, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, None);
+    impl_cuda_interaction!(nalgebra::SVector<f64, 3>, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, Some(ffi::pcuda_barneshut_f64x3 as BarnesFn<f64>));
+    impl_cuda_interaction!(nalgebra::SVector<f64, 2>, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, Some(ffi::pcuda_barneshut_f64x2 as BarnesFn<f64>));
 }
 #[cfg(feature = "ultraviolet")]
 mod ultraviolet_impls {
     use super::*;
     impl_cuda_interaction!(ultraviolet::Vec3, f32, 3, [x, y, z], ffi::pcuda_bruteforce_f32x3, Some(ffi::pcuda_barneshut_f32x3 as BarnesFn<f32>));
     impl_cuda_interaction!(ultraviolet::Vec2, f32, 2, [x, y], ffi::pcuda_bruteforce_f32x2, Some(ffi::pcuda_barneshut_f32x2 as BarnesFn<f32>));
-    impl_cuda_interaction!(ultraviolet::DVec3, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, None);
-    impl_cuda_interaction!(ultraviolet::DVec2, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, None);
+    impl_cuda_interaction!(ultraviolet::DVec3, f64, 3, [x, y, z], ffi::pcuda_bruteforce_f64x3, Some(ffi::pcuda_barneshut_f64x3 as BarnesFn<f64>));
+    impl_cuda_interaction!(ultraviolet::DVec2, f64, 2, [x, y], ffi::pcuda_bruteforce_f64x2, Some(ffi::pcuda_barneshut_f64x2 as BarnesFn<f64>));
 }
 
 /// Brute-force algorithm on the GPU; same shape as `gpu::BruteForce<'a, T>` (gpu/mod.rs:149-177).

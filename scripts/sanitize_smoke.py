@@ -23,6 +23,14 @@ with pb.CudaContext(0) as ctx:
     for n, d in ((1, 3), (50, 3), (3000, 3), (3000, 2), (40000, 3)):   # build_small and per-level build
         q = plummer_cloud(n, d=d, seed=n)
         pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked()).compute(q)
+    for n, d in ((1, 3), (300, 2), (3000, 3), (40000, 3)):   # f64 layer: gather64, moments64, traverse64
+        q64 = plummer_cloud(n, d=d, seed=n, dtype=np.float64)
+        pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked()).compute(q64)
+        pb.BarnesHut(ctx, 0.5, pb.AccelerationSoftened.checked(0.1)).compute(pb.Between(q64[: n // 2 + 1, :d] * 0.5, q64))
+    pb.BruteForce(ctx, pb.Acceleration.checked()).compute(uniform_cloud(700, d=2, dtype=np.float64, seed=6))
+    pb.morton_keys(ctx, plummer_cloud(5000, seed=4))
+    sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0))   # single rank: no communicator
+    sb.compute(pb.Reordered.new(uniform_cloud(3000, seed=7, massive_ratio=0.05)))
     q = plummer_cloud(40000, seed=3)
     tree = pb.RootedOrthtree(ctx, q)
     pb.BarnesHut(ctx, 0.7, pb.Acceleration.checked()).compute(pb.Between(uniform_cloud(777, seed=1)[:, :3] * 1e-3, tree))

@@ -122,6 +122,65 @@ def test_theta0_is_brute_force(pb, ctx, dim):
     assert c["particle_interactions"] == 6000 * 6000 and c["node_interactions"] == 0
 
 
+@pytest.mark.parametrize("cloud", ["uniform", "plummer"])
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("theta", [0.3, 0.7])
+def test_f64_same_theta_error_as_reference(pb, ctx, cloud, dim, theta):
+    """DVec2 / DVec3 (pcuda_barneshut_f64x*): same error-distribution criterion, against the f64
+    restatement of sequential::BarnesHut."""
+    n = 12000
+    p = (uniform_cloud(n, d=dim, seed=6, dtype=np.float64) if cloud == "uniform"
+         else plummer_cloud(n, d=dim, seed=6, dtype=np.float64))
+    exact = oracle.brute_force_exact(p[:, :dim], p)
+    ref = oracle.barnes_hut(p[:, :dim], p, theta, parallel=True)
+    got = pb.BarnesHut(ctx, theta, pb.Acceleration.checked()).compute(p)
+    assert got.dtype == np.float64 and got.shape == (n, dim) and np.isfinite(got).all()
+    assert_same_theta_error(got, ref, exact)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_f64_theta0_is_f64_brute_force(pb, ctx, dim):
+    """theta = 0 opens every cell: the result must meet the f64 brute-force bound (1e-12), i.e.
+    nothing single precision enters an acceleration; separate targets and softening included."""
+    p = uniform_cloud(5000, d=dim, seed=9, dtype=np.float64)
+    p[100:110, :dim] = p[100, :dim]                      # coincident particles
+    p[200, :dim] = p[201, :dim] * (1.0 + 1e-12)          # distinct in f64, equal in f32
+    got = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).compute(p)
+    ref = oracle.brute_force_parallel(p[:, :dim], p)
+    assert_bruteforce_parity(got, ref, p[:, :dim], p, aggregate=False)
+    aff = uniform_cloud(777, d=dim, seed=10, dtype=np.float64)[:, :dim]
+    got = pb.BarnesHut(ctx, 0.0, pb.AccelerationSoftened.checked(2.0)).compute(pb.Between(aff, p))
+    ref = oracle.brute_force_parallel(aff, p, 2.0)
+    assert_bruteforce_parity(got, ref, aff, p, 2.0, aggregate=False)
+
+
+def test_f64_device_api_reference_fixture_and_empty(pb, ctx):
+    import torch
+    p = plummer_cloud(9000, seed=12, dtype=np.float64)
+    bh = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked())
+    host = bh.compute(p)
+    d_p = torch.from_numpy(p).cuda()
+    d_o = torch.zeros((len(p), 3), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    bh.compute_device(None, len(p), d_p.data_ptr(), len(p), d_o.data_ptr(), "f64x3")
+    ctx.sync()
+    assert np.array_equal(d_o.cpu().numpy(), host)
+    assert np.array_equal(bh.compute(p), host)            # deterministic
+    # the reference's own fixture (gravity/newtonian/mod.rs:228-277, 407-418) in f64
+    for dim, theta, key in ((3, 0.0, "barnes_hut_theta0"), (3, 0.5, "barnes_hut_theta05"), (2, 0.5, "barnes_hut_theta05")):
+        fx = GOLD[f"fixture_{dim}d"]
+        q = np.array(fx["particles"], dtype=np.float64)
+        got = pb.BarnesHut(ctx, theta, pb.Acceleration.checked()).compute(pb.Reordered.new(q))
+        err = np.linalg.norm(1.0 - got / np.array(fx["expected"]), axis=1)
+        assert err.max() <= fx["tolerance"][key]
+    # empty inputs
+    assert bh.compute(np.zeros((0, 4), np.float64)).shape == (0, 3)
+    z = bh.compute(pb.Between(p[:9, :3], np.zeros((0, 4), np.float64)))
+    assert z.shape == (9, 3) and not z.any()
+    one = bh.compute(p[:1])
+    assert one.shape == (1, 3) and not one.any()
+
+
 def test_softened_and_unchecked(pb, ctx):
     p = plummer_cloud(15000, seed=6)
     eps = 0.01

@@ -319,7 +319,7 @@ typedef enum pcuda_scalar { PCUDA_F32 = 0, PCUDA_F64 = 1 } pcuda_scalar;
 
 typedef struct pcuda_sim_config {
     uint32_t dim;       /* 2 or 3 */
-    uint32_t scalar;    /* pcuda_scalar; PCUDA_F64 needs dim 3 + PCUDA_BRUTE_FORCE */
+    uint32_t scalar;    /* pcuda_scalar */
     uint32_t algorithm; /* pcuda_algorithm */
     uint32_t flags;     /* PCUDA_SIM_* */
     double theta;       /* Barnes-Hut opening parameter */

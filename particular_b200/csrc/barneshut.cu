@@ -1801,10 +1801,10 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         else PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * dim * sizeof(float), ctx->stream));
         return PCUDA_OK;
     }
-    if (f64 && d_tgt64) {  // f32 copy of the targets (bare positions), only to key and group them
-        PCUDA_CUDA_TRY(ctx, ctx->d_misc.ensure(na * dim * sizeof(float)));
-        narrow_kernel<<<(unsigned)std::min<size_t>((na * dim + 255) / 256, 65535), 256, 0, ctx->stream>>>(
-            d_tgt64, na * dim, ctx->d_misc.as<float>());
+    if (f64 && d_tgt64) {  // f32 copy of the target rows, only to key and group them
+        PCUDA_CUDA_TRY(ctx, ctx->d_misc.ensure(na * ts * sizeof(float)));
+        narrow_kernel<<<(unsigned)std::min<size_t>((na * ts + 255) / 256, 65535), 256, 0, ctx->stream>>>(
+            d_tgt64, na * ts, ctx->d_misc.as<float>());
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
         d_tgt = ctx->d_misc.as<float>();
@@ -1835,10 +1835,10 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
         PCUDA_CUDA_TRY(ctx, ctx->d_tgt_sorted.ensure(na * (f64 ? sizeof(double4) : sizeof(float4))));
         const uint32_t *p = perm[cur].as<uint32_t>();
         if (f64 && dim == 3)
-            gather64_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt64, dim, false, (int)na, p,
+            gather64_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt64, ts, false, (int)na, p,
                                                                              ctx->d_tgt_sorted.as<double4>());
         else if (f64)
-            gather64_kernel<2><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt64, dim, false, (int)na, p,
+            gather64_kernel<2><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt64, ts, false, (int)na, p,
                                                                              ctx->d_tgt_sorted.as<double4>());
         else if (dim == 3)
             gather_kernel<3><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_tgt, ts, false, (int)na, p,
@@ -1968,7 +1968,7 @@ static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t 
 }
 
 static int oneshot_dev64(pcuda_ctx *ctx, uint32_t dim, const double *d_aff, size_t na, const double *d_src,
-                         size_t nb, double theta, double eps, double *d_out) {
+                         size_t nb, double theta, double eps, double *d_out, int tgt_stride = 0) {
     if (!d_aff && na != nb)
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
                     "affected == NULL means affected == affecting, but n_affected != n_affecting");
@@ -1978,7 +1978,8 @@ static int oneshot_dev64(pcuda_ctx *ctx, uint32_t dim, const double *d_aff, size
     PCUDA_TRY(dim == 3 ? build64<3>(ctx, ctx->call_tree, d_src, nb) : build64<2>(ctx, ctx->call_tree, d_src, nb));
     phase_end(ctx, PH_BUILD);
     phase_begin(ctx, PH_COMPUTE);
-    PCUDA_TRY(traverse(ctx, ctx->call_tree, nullptr, na, (float)theta, 0.f, nullptr, 0, d_aff, d_out, eps));
+    PCUDA_TRY(traverse(ctx, ctx->call_tree, nullptr, na, (float)theta, 0.f, nullptr, tgt_stride, d_aff, d_out,
+                       eps));
     phase_end(ctx, PH_COMPUTE);
     return PCUDA_OK;
 }
@@ -2132,6 +2133,12 @@ int bh_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, 
                    const float *d_src, size_t nb, float theta, float softening, float *d_out) {
     return bh::oneshot_dev(ctx, (uint32_t)dim, tgt_stride ? d_tgt : nullptr, na, d_src, nb, theta,
                            softening, d_out, tgt_stride);
+}
+
+int bh_enqueue_f64(pcuda_ctx *ctx, int dim, const double *d_tgt, int tgt_stride, size_t na,
+                   const double *d_src, size_t nb, double theta, double softening, double *d_out) {
+    return bh::oneshot_dev64(ctx, (uint32_t)dim, tgt_stride ? d_tgt : nullptr, na, d_src, nb, theta,
+                             softening, d_out, tgt_stride);
 }
 
 int bh_debug_set(const char *key, int value) {

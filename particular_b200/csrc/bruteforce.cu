@@ -613,8 +613,9 @@ __global__ void pack_sources_2d_f64(const double *__restrict__ in, int n, double
     if (i < n) outp[i] = make_double4(in[3 * (size_t)i], in[3 * (size_t)i + 1], 0.0, in[3 * (size_t)i + 2]);
 }
 
-static int dev_f64x2(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src, size_t nb,
-                     double eps, int checked, double *d_out) {
+// tgt == nullptr: the targets are the sources (stride 3).
+static int run_f64x2(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t na,
+                     const double *d_src, size_t nb, double eps, int checked, double *d_out) {
     double4 *packed = nullptr;
     if (nb) {
         if (nb > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
@@ -624,7 +625,13 @@ static int dev_f64x2(pcuda_ctx *ctx, const double *d_aff, size_t na, const doubl
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
     }
-    return run_f64<2>(ctx, d_aff ? d_aff : d_src, d_aff ? 2 : 3, na, packed, nb, eps, checked, d_out);
+    return run_f64<2>(ctx, d_tgt ? d_tgt : d_src, d_tgt ? tgt_stride : 3, na, packed, nb, eps, checked,
+                      d_out);
+}
+
+static int dev_f64x2(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src, size_t nb,
+                     double eps, int checked, double *d_out) {
+    return run_f64x2(ctx, d_aff, 2, na, d_src, nb, eps, checked, d_out);
 }
 
 static int dev_f64x3(pcuda_ctx *ctx, const double *d_aff, size_t na, const double *d_src, size_t nb,
@@ -854,8 +861,9 @@ int bf_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, 
                           softening, checked, d_out);
 }
 
-int bf_enqueue_f64x3(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t na,
-                     const double *d_src, size_t nb, double softening, int checked, double *d_out) {
+int bf_enqueue_f64(pcuda_ctx *ctx, int dim, const double *d_tgt, int tgt_stride, size_t na,
+                   const double *d_src, size_t nb, double softening, int checked, double *d_out) {
+    if (dim == 2) return bf::run_f64x2(ctx, d_tgt, tgt_stride, na, d_src, nb, softening, checked, d_out);
     if (nb && !bf::aligned(d_src, 16))
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "affecting must be 16-byte aligned");
     return bf::run_f64(ctx, d_tgt, tgt_stride, na, reinterpret_cast<const double4 *>(d_src), nb,

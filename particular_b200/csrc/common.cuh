@@ -108,11 +108,13 @@ struct DeviceGuard {
 // rows are {position, mu} = dim + 1 scalars.
 int bf_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, size_t na,
                    const float *d_src, size_t nb, float softening, int checked, float *d_out);
-int bf_enqueue_f64x3(pcuda_ctx *ctx, const double *d_tgt, int tgt_stride, size_t na,
-                     const double *d_src, size_t nb, double softening, int checked, double *d_out);
+int bf_enqueue_f64(pcuda_ctx *ctx, int dim, const double *d_tgt, int tgt_stride, size_t na,
+                   const double *d_src, size_t nb, double softening, int checked, double *d_out);
 // tgt_stride == 0: the targets are the sources themselves (the `&[P]` storage).
 int bh_enqueue_f32(pcuda_ctx *ctx, int dim, const float *d_tgt, int tgt_stride, size_t na,
                    const float *d_src, size_t nb, float theta, float softening, float *d_out);
+int bh_enqueue_f64(pcuda_ctx *ctx, int dim, const double *d_tgt, int tgt_stride, size_t na,
+                   const double *d_src, size_t nb, double theta, double softening, double *d_out);
 
 void tree_free(pcuda_ctx *ctx, pcuda_tree *t);
 int bh_debug_set(const char *key, int value);  // barneshut.cu tuning hooks

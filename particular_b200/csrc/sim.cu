@@ -107,8 +107,12 @@ static int step_once_t(pcuda_ctx *ctx, pcuda_sim *s) {
     }
     S *acc = s->acc.as<S>();
     if constexpr (sizeof(S) == 8) {
-        PCUDA_TRY(bf_enqueue_f64x3(ctx, part, DIM + 1, n, src, nb, (double)s->cfg.softening,
-                                   s->cfg.checked, acc));
+        if (s->cfg.algorithm == PCUDA_BARNES_HUT)
+            PCUDA_TRY(bh_enqueue_f64(ctx, DIM, part, s->subset ? DIM + 1 : 0, n, src, nb, s->cfg.theta,
+                                     s->cfg.softening, acc));
+        else
+            PCUDA_TRY(bf_enqueue_f64(ctx, DIM, part, DIM + 1, n, src, nb, (double)s->cfg.softening,
+                                     s->cfg.checked, acc));
     } else if (s->cfg.algorithm == PCUDA_BARNES_HUT) {
         // targets == sources unless the sources are a subset
         PCUDA_TRY(bh_enqueue_f32(ctx, DIM, part, s->subset ? DIM + 1 : 0, n, src, nb,
@@ -125,7 +129,8 @@ static int step_once_t(pcuda_ctx *ctx, pcuda_sim *s) {
 }
 
 static int step_once(pcuda_ctx *ctx, pcuda_sim *s) {
-    if (s->cfg.scalar == PCUDA_F64) return step_once_t<double, 3>(ctx, s);
+    if (s->cfg.scalar == PCUDA_F64)
+        return s->cfg.dim == 3 ? step_once_t<double, 3>(ctx, s) : step_once_t<double, 2>(ctx, s);
     return s->cfg.dim == 3 ? step_once_t<float, 3>(ctx, s) : step_once_t<float, 2>(ctx, s);
 }
 
@@ -173,10 +178,6 @@ static int validate(pcuda_ctx *ctx, const pcuda_sim_config *c) {
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "scalar must be PCUDA_F32 or PCUDA_F64");
     if (c->algorithm != PCUDA_BRUTE_FORCE && c->algorithm != PCUDA_BARNES_HUT)
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "unknown algorithm %u", c->algorithm);
-    // the same gaps as the one-shot entry points (the reference's wgpu operator is likewise f32
-    // only: gravity/impls/mod.rs:362, 374 are unimplemented!())
-    if (c->scalar == PCUDA_F64 && (c->dim != 3 || c->algorithm != PCUDA_BRUTE_FORCE))
-        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "f64 stepping is 3-D brute force only");
     if (c->algorithm == PCUDA_BARNES_HUT && !(c->theta >= 0.0))
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "theta must be >= 0");
     return PCUDA_OK;

@@ -20,7 +20,7 @@ def _velocities(n, d, dtype, seed=3, scale=10.0):
     return (np.random.default_rng(seed).normal(size=(n, d)) * scale).astype(dtype)
 
 
-@pytest.mark.parametrize("dim,dtype", [(3, np.float32), (2, np.float32), (3, np.float64)])
+@pytest.mark.parametrize("dim,dtype", [(3, np.float32), (2, np.float32), (3, np.float64), (2, np.float64)])
 def test_one_step_integrator_is_bit_exact(pb, ctx, dim, dtype):
     """Given the accelerations the device itself produced, velocities and positions are the
     reference's unfused `v += a*dt; p += v*dt`, bit for bit."""
@@ -43,7 +43,7 @@ def test_one_step_integrator_is_bit_exact(pb, ctx, dim, dtype):
 
 
 @pytest.mark.parametrize("dim,dtype,tol", [(3, np.float32, 2e-4), (2, np.float32, 2e-4),
-                                           (3, np.float64, 1e-10)])
+                                           (3, np.float64, 1e-10), (2, np.float64, 1e-10)])
 @pytest.mark.parametrize("graph", [True, False])
 def test_brute_force_trajectory_matches_oracle(pb, ctx, dim, dtype, tol, graph):
     """40 steps (eager step + CUDA-graph blocks + eager tail) against the oracle loop.  Softened
@@ -106,13 +106,14 @@ def test_massive_only_is_the_reordered_storage(pb, ctx):
     assert np.abs(p2[:, :3] - pr[:, :3]).max() <= 1e-3 * np.abs(pr[:, :3] - p0[:, :3]).max() + 1e-2
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("dim", [3, 2])
-def test_barnes_hut_stepping(pb, ctx, dim):
+def test_barnes_hut_stepping(pb, ctx, dim, dtype):
     """Barnes-Hut steps: first-step accelerations are the one-shot operator's; the trajectory
     stays within the theta-approximation of the exact (brute-force) trajectory."""
     n, steps, dt, theta = 4000, 5, 1e-4, 0.5
-    p0 = plummer_cloud(n, d=dim, seed=4)
-    v0 = np.zeros((n, dim), np.float32)
+    p0 = plummer_cloud(n, d=dim, seed=4, dtype=dtype)
+    v0 = np.zeros((n, dim), dtype)
     bh = pb.BarnesHut(ctx, theta, pb.AccelerationSoftened.checked(0.01))
     with pb.Simulation(bh, p0, v0, dt=dt) as sim:
         sim.step(1)
@@ -171,10 +172,15 @@ def test_edge_cases_and_errors(pb, ctx):
                        affecting="massive") as sim:
         sim.step(9)
         assert np.array_equal(sim.accelerations(), np.zeros((2, 3), np.float32))
-    # f64 Barnes-Hut does not exist on the device (as in the one-shot API)
-    with pytest.raises(pb.CudaError):
-        pb.Simulation(pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked()),
-                      np.zeros((4, 4), np.float64), dt=0.1)
+    # f64 Barnes-Hut with the massive-only storage: the tree holds the massive subset
+    q = plummer_cloud(3000, seed=8, dtype=np.float64)
+    q[::3, 3] = 0.0
+    bh64 = pb.BarnesHut(ctx, 0.5, pb.AccelerationSoftened.checked(0.01))
+    with pb.Simulation(bh64, q, dt=1e-4, affecting="massive") as sim:
+        sim.step(1)
+        a = sim.accelerations()
+    assert a.dtype == np.float64
+    assert np.array_equal(a, bh64.compute(pb.Reordered.new(q)))
     # dt can be changed on a live simulation
     p0 = uniform_cloud(64, seed=1)
     with pb.Simulation(bf, p0, dt=1e-3) as sim:

@@ -63,7 +63,10 @@ typedef struct pcuda_config {
     int32_t device;        /* CUDA ordinal */
     uint32_t flags;        /* PCUDA_FLAG_* */
     uint32_t leaf_size;    /* max particles per Barnes-Hut leaf; 0 = default (16) */
-    uint32_t reserved;
+    uint32_t expansion_order; /* Barnes-Hut node expansion: 0 or 1 = centre of mass (the reference's
+                               * nodes, gravity/impls/mod.rs:103-135); 2 = + traceless quadrupole
+                               * (an accuracy / speed knob beyond the reference, SURVEY.md 8f rank 4;
+                               * f32 entry points only) */
 } pcuda_config;
 
 #define PCUDA_FLAG_NONE 0u

@@ -125,8 +125,10 @@ struct Error : std::runtime_error {
 // gpu/mod.rs:150-151).
 class CudaContext {
 public:
-    explicit CudaContext(int device = 0, unsigned leaf_size = 0, bool phase_timings = true) {
-        pcuda_config cfg{device, phase_timings ? PCUDA_FLAG_NONE : PCUDA_FLAG_NO_PHASE_TIMINGS, leaf_size, 0};
+    explicit CudaContext(int device = 0, unsigned leaf_size = 0, bool phase_timings = true,
+                         unsigned expansion_order = 1) {
+        pcuda_config cfg{device, phase_timings ? PCUDA_FLAG_NONE : PCUDA_FLAG_NO_PHASE_TIMINGS, leaf_size,
+                         expansion_order};
         int s = pcuda_create(&cfg, &ctx_);
         if (s != PCUDA_OK) throw Error(s, pcuda_last_error(nullptr));
     }

@@ -35,7 +35,7 @@ ERR_NOT_INITIALISED = -7
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("leaf_size", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("expansion_order", C.c_uint32)]
 
 
 class Timings(C.Structure):

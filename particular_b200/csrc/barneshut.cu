@@ -70,6 +70,9 @@ struct pcuda_tree {
     pcuda::bh::Frame frame = {};
     pcuda::DevBuf keys[2], perm[2], sorted, nodes, moments, d_frame, scan_in, scan_out, cub_tmp,
         partial;
+    pcuda::DevBuf quad64, quad;  // expansion order 2: traceless quadrupole per node, 6 doubles
+                                 // (build) and 2 x float4 {xx, xy, xz, yy}{yz, zz, 0, 0} (traversal)
+    int order = 1;
     pcuda::DevBuf sorted64;  // f64 trees: the sources in key order as double4 {x, y, z|0, mu};
                              // `moments` then holds the double-precision {com, mass} per node
     int cur = 0;  // which of keys[]/perm[] holds the sorted data
@@ -1335,6 +1338,328 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4d / K5q: quadrupole nodes (pcuda_config.expansion_order = 2; beyond the reference, whose nodes
+// carry {centre of mass, mass} only, gravity/impls/mod.rs:103-135).  Every node additionally holds
+// the traceless quadrupole about its centre of mass,
+//     Q = sum_i m_i (3 x_i x_i^T - |x_i|^2 I),   x_i = p_i - com,
+// built bottom-up in double precision (leaves from their particles, internal nodes from their
+// children with the parallel-axis term m_c (3 d d^T - |d|^2 I), d = com_c - com).  An accepted
+// node then contributes, with D = com - target and R = |D|,
+//     a = M D / R^3  -  Q D / R^5  +  5/2 (D.Q.D) D / R^7,
+// evaluated as  ri^2 [ M ri u + 5/2 (u.Qu') u - Qu' ],  u = D ri,  Qu' = (Q u) ri^2, so that no
+// intermediate exceeds the magnitude of the monopole term's own factors.
+template <int DIM>
+__global__ void __launch_bounds__(128) quad_kernel(const NodeRec *__restrict__ nodes,
+                                                   const double4 *__restrict__ mom,
+                                                   const float4 *__restrict__ sorted,
+                                                   double *__restrict__ quad64,
+                                                   float4 *__restrict__ quadf,
+                                                   const BuildState *__restrict__ st, int level) {
+    const uint32_t lvl_begin = st->level_begin[level];
+    const uint32_t lvl_count = st->level_begin[level + 1] - lvl_begin;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < lvl_count;
+         t += gridDim.x * blockDim.x) {
+        const uint32_t j = lvl_begin + t;
+        const NodeRec nd = nodes[j];
+        const uint32_t nc = nd.nchild_level & 0xffu;
+        const double4 sm = mom[j];
+        double q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // xx xy xz yy yz zz
+        if (sm.w != 0.0) {
+            const double cx = sm.x / sm.w, cy = sm.y / sm.w, cz = DIM == 3 ? sm.z / sm.w : 0.0;
+            auto add = [&](double m, double x, double y, double z) {
+                const double r2 = x * x + y * y + z * z;
+                q[0] += m * (3.0 * x * x - r2);
+                q[1] += m * (3.0 * x * y);
+                q[2] += m * (3.0 * x * z);
+                q[3] += m * (3.0 * y * y - r2);
+                q[4] += m * (3.0 * y * z);
+                q[5] += m * (3.0 * z * z - r2);
+            };
+            if (nc == 0) {
+                for (uint32_t i = nd.begin; i < nd.begin + nd.count; ++i) {
+                    const float4 p = sorted[i];
+                    add((double)p.w, (double)p.x - cx, (double)p.y - cy, DIM == 3 ? (double)p.z - cz : 0.0);
+                }
+            } else {
+                for (uint32_t c = nd.first_child; c < nd.first_child + nc; ++c) {
+                    const double4 sc = mom[c];
+                    if (sc.w == 0.0) continue;
+                    add(sc.w, sc.x / sc.w - cx, sc.y / sc.w - cy, DIM == 3 ? sc.z / sc.w - cz : 0.0);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) q[k] += quad64[(size_t)c * 6 + k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) quad64[(size_t)j * 6 + k] = q[k];
+        quadf[2 * (size_t)j] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+        quadf[2 * (size_t)j + 1] = make_float4((float)q[4], (float)q[5], 0.f, 0.f);
+    }
+}
+
+// monopole + quadrupole term of one node for the two targets of a lane (packed FP32)
+__device__ __forceinline__ void eval_node_q(const float4 c, const float4 qa, const float4 qb,
+                                            float2 npx, float2 npy, float2 npz, float2 eps2p,
+                                            float2 &ax, float2 &ay, float2 &az) {
+    const float2 dx = ptx::add2(ptx::splat(c.x), npx);
+    const float2 dy = ptx::add2(ptx::splat(c.y), npy);
+    const float2 dz = ptx::add2(ptx::splat(c.z), npz);
+    float2 r2 = ptx::fma2(dx, dx, eps2p);
+    r2 = ptx::fma2(dy, dy, r2);
+    r2 = ptx::fma2(dz, dz, r2);
+    float2 ri;
+    ri.x = ptx::rsqrt_approx(r2.x);
+    ri.y = ptx::rsqrt_approx(r2.y);
+    const float2 ri2 = ptx::mul2(ri, ri);
+    const float2 ux = ptx::mul2(dx, ri), uy = ptx::mul2(dy, ri), uz = ptx::mul2(dz, ri);
+    // Qu' = (Q u) ri^2
+    float2 qx = ptx::mul2(ptx::splat(qa.x), ux);
+    qx = ptx::fma2(ptx::splat(qa.y), uy, qx);
+    qx = ptx::fma2(ptx::splat(qa.z), uz, qx);
+    float2 qy = ptx::mul2(ptx::splat(qa.y), ux);
+    qy = ptx::fma2(ptx::splat(qa.w), uy, qy);
+    qy = ptx::fma2(ptx::splat(qb.x), uz, qy);
+    float2 qz = ptx::mul2(ptx::splat(qa.z), ux);
+    qz = ptx::fma2(ptx::splat(qb.x), uy, qz);
+    qz = ptx::fma2(ptx::splat(qb.y), uz, qz);
+    qx = ptx::mul2(qx, ri2);
+    qy = ptx::mul2(qy, ri2);
+    qz = ptx::mul2(qz, ri2);
+    float2 uqu = ptx::mul2(ux, qx);
+    uqu = ptx::fma2(uy, qy, uqu);
+    uqu = ptx::fma2(uz, qz, uqu);
+    // s = M ri + 5/2 u.Qu'   (coefficient of u)
+    const float2 s = ptx::fma2(ptx::splat(2.5f), uqu, ptx::mul2(ptx::splat(c.w), ri));
+    const float2 vx = ptx::fma2(s, ux, ptx::mul2(qx, ptx::splat(-1.f)));
+    const float2 vy = ptx::fma2(s, uy, ptx::mul2(qy, ptx::splat(-1.f)));
+    const float2 vz = ptx::fma2(s, uz, ptx::mul2(qz, ptx::splat(-1.f)));
+    ax = ptx::fma2(vx, ri2, ax);
+    ay = ptx::fma2(vy, ri2, ay);
+    az = ptx::fma2(vz, ri2, az);
+}
+
+constexpr int TRAVQ_WARPS = 4;
+
+// traverse2_kernel with quadrupole nodes: accepted nodes go to their own ring ({com, mass} + two
+// quadrupole quads per entry), the particles of opened leaves to the plain ring; either ring is
+// evaluated 32 entries at a time.  A node whose centre of mass touches the group's box is opened
+// whatever theta says (the expansion is singular at zero distance).
+__global__ void __launch_bounds__(TRAVQ_WARPS * 32) traverse2q_kernel(TravArgs a, const float4 *__restrict__ quad) {
+    __shared__ uint32_t s_stack[TRAVQ_WARPS][STACK_CAP];
+    __shared__ __align__(16) float4 s_list[TRAVQ_WARPS][LIST_CAP];
+    __shared__ __align__(16) float4 s_nodes[TRAVQ_WARPS][3 * LIST_CAP];
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *stack = s_stack[warp];
+    float4 *list4 = s_list[warp];
+    float4 *nlist = s_nodes[warp];
+    const uint32_t n_groups = *a.n_groups;
+    const float ext = a.frame->ext;
+    const float cb = cbrtf(fminf(a.frame->mass_bound, 3e38f)) * 2.2e-13f;
+    const float tiny = fmaxf(2.f * cb * cb, 1e-36f);
+    const float2 eps2p = make_float2(a.eps2 + tiny, a.eps2 + tiny);
+
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(a.work, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= n_groups) break;
+        const int t0 = (int)a.group_start[g];
+        const int gcnt = (int)a.group_start[g + 1] - t0;  // 1..64 targets
+        int half = 1;
+        while (2 * half < gcnt) half <<= 1;
+        const int slices = 32 / half;
+        const int tl = lane & (half - 1), slice = lane / half;
+        const int ia = t0 + min(tl, gcnt - 1), ib = t0 + min(tl + half, gcnt - 1);
+        float3 ta, tb;
+        ta.x = ptx::ldg_f32(&a.tgt[ia].x);
+        tb.x = ptx::ldg_f32(&a.tgt[ib].x);
+        ta.y = ptx::ldg_f32(&a.tgt[ia].y);
+        tb.y = ptx::ldg_f32(&a.tgt[ib].y);
+        ta.z = ptx::ldg_f32(&a.tgt[ia].z);
+        tb.z = ptx::ldg_f32(&a.tgt[ib].z);
+
+        float lox = fminf(ta.x, tb.x), hix = fmaxf(ta.x, tb.x);
+        float loy = fminf(ta.y, tb.y), hiy = fmaxf(ta.y, tb.y);
+        float loz = fminf(ta.z, tb.z), hiz = fmaxf(ta.z, tb.z);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(FULL, lox, o));
+            hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, o));
+            loy = fminf(loy, __shfl_xor_sync(FULL, loy, o));
+            hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, o));
+            loz = fminf(loz, __shfl_xor_sync(FULL, loz, o));
+            hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, o));
+        }
+        const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+        const float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
+
+        const float2 npx = make_float2(-ta.x, -tb.x), npy = make_float2(-ta.y, -tb.y),
+                     npz = make_float2(-ta.z, -tb.z);
+        float2 ax2 = make_float2(0.f, 0.f), ay2 = ax2, az2 = ax2;
+        int sp = 1;
+        int head = 0, fill = 0;    // particle ring
+        int nhead = 0, nfill = 0;  // node ring
+        __syncwarp();
+        if (lane == 0) stack[0] = 0;
+        __syncwarp();
+
+        auto flush_particles = [&]() {
+            if (fill >= 32) {
+                __syncwarp();
+                const float4 *blk = list4 + head;
+                for (int q = slice; q < 32; q += slices) eval_entry(blk[q], npx, npy, npz, eps2p, ax2, ay2, az2);
+                fill -= 32;
+                head ^= 32;
+                __syncwarp();
+            }
+        };
+        auto flush_nodes = [&]() {
+            if (nfill >= 32) {
+                __syncwarp();
+                const float4 *blk = nlist + 3 * nhead;
+                for (int q = slice; q < 32; q += slices)
+                    eval_node_q(blk[3 * q], blk[3 * q + 1], blk[3 * q + 2], npx, npy, npz, eps2p, ax2, ay2, az2);
+                nfill -= 32;
+                nhead ^= 32;
+                __syncwarp();
+            }
+        };
+
+        while (sp > 0) {
+            const int room = (STACK_CAP - STACK_RESERVE - sp) / 7;
+            const int k = min(min(32, sp), max(room, 1));
+            const bool has = lane < k;
+            NodeRec nd;
+            nd.cm = make_float4(0.f, 0.f, 0.f, 0.f);
+            nd.first_child = 0;
+            nd.begin = 0;
+            nd.count = 0;
+            nd.nchild_level = 0;
+            uint32_t id = 0;
+            if (has) {
+                id = stack[sp - 1 - lane];
+                const uint4 *q = reinterpret_cast<const uint4 *>(a.nodes + id);
+                const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                nd.cm = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y),
+                                    __uint_as_float(q0.z), __uint_as_float(q0.w));
+                nd.first_child = q1.x;
+                nd.nchild_level = q1.y;
+                nd.begin = q1.z;
+                nd.count = q1.w;
+            }
+            sp -= k;
+            __syncwarp();
+
+            bool open = false;
+            if (has) {
+                const float ddx = fmaxf(fabsf(nd.cm.x - cx) - hx, 0.f);
+                const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
+                const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
+                const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                const int level = (int)(nd.nchild_level >> 8);
+                const float w = ext * __int_as_float((127 - level) << 23);
+                open = a.theta2 * d2 < w * w || d2 == 0.f;
+            }
+            const uint32_t nc = nd.nchild_level & 0xffu;
+            const bool open_internal = has && open && nc > 0;
+            const bool open_leaf = has && open && nc == 0;
+            const bool accept = has && !open && nd.cm.w != 0.f;
+
+            const int c_child = open_internal ? (int)nc : 0;
+            const int c_leaf = open_leaf ? (int)nd.count : 0;
+            int child_incl = c_child, leaf_incl = c_leaf;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, child_incl, o);
+                const int u = __shfl_up_sync(FULL, leaf_incl, o);
+                if (lane >= o) {
+                    child_incl += v;
+                    leaf_incl += u;
+                }
+            }
+            {
+                const int total = __shfl_sync(FULL, child_incl, 31);
+                const int base = sp + child_incl - c_child;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < c_child) stack[base + j] = nd.first_child + j;
+                sp += total;
+            }
+
+            {  // accepted nodes -> node ring
+                const unsigned m = __ballot_sync(FULL, accept);
+                if (m) {
+                    if (accept) {
+                        const int slot = (nhead + nfill + __popc(m & ((1u << lane) - 1))) & (LIST_CAP - 1);
+                        nlist[3 * slot] = nd.cm;
+                        nlist[3 * slot + 1] = __ldg(quad + 2 * (size_t)id);
+                        nlist[3 * slot + 2] = __ldg(quad + 2 * (size_t)id + 1);
+                    }
+                    nfill += __popc(m);
+                    flush_nodes();
+                }
+            }
+
+            {  // particles of opened leaves -> particle ring, 32 per round
+                const int incl = leaf_incl;
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int excl = incl - c_leaf;
+                for (int base = 0; base < total; base += 32) {
+                    const int f = base + lane;
+                    int owner = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, (owner + step - 1) & 31);
+                        if (v <= f) owner += step;
+                    }
+                    owner = min(owner, 31);
+                    const uint32_t ob = __shfl_sync(FULL, nd.begin, owner);
+                    const int oe = __shfl_sync(FULL, excl, owner);
+                    if (f < total)
+                        list4[(head + fill + lane) & (LIST_CAP - 1)] = __ldg(a.src + ob + (f - oe));
+                    fill += min(32, total - base);
+                    flush_particles();
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        for (int q = slice; q < fill; q += slices)
+            eval_entry(list4[(head + q) & (LIST_CAP - 1)], npx, npy, npz, eps2p, ax2, ay2, az2);
+        for (int q = slice; q < nfill; q += slices) {
+            const int slot = (nhead + q) & (LIST_CAP - 1);
+            eval_node_q(nlist[3 * slot], nlist[3 * slot + 1], nlist[3 * slot + 2], npx, npy, npz, eps2p, ax2,
+                        ay2, az2);
+        }
+        float axa = ax2.x, aya = ay2.x, aza = az2.x, axb = ax2.y, ayb = ay2.y, azb = az2.y;
+        for (int o = half; o < 32; o <<= 1) {
+            axa += __shfl_xor_sync(FULL, axa, o);
+            aya += __shfl_xor_sync(FULL, aya, o);
+            aza += __shfl_xor_sync(FULL, aza, o);
+            axb += __shfl_xor_sync(FULL, axb, o);
+            ayb += __shfl_xor_sync(FULL, ayb, o);
+            azb += __shfl_xor_sync(FULL, azb, o);
+        }
+        if (slice == 0 && tl < gcnt) {
+            const uint32_t row = a.tgt_perm ? a.tgt_perm[ia] : (uint32_t)ia;
+            float *o = a.out + (size_t)row * a.dim;
+            o[0] = axa;
+            o[1] = aya;
+            if (a.dim == 3) o[2] = aza;
+        }
+        if (slice == 0 && tl + half < gcnt) {
+            const uint32_t row = a.tgt_perm ? a.tgt_perm[ib] : (uint32_t)ib;
+            float *o = a.out + (size_t)row * a.dim;
+            o[0] = axb;
+            o[1] = ayb;
+            if (a.dim == 3) o[2] = azb;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5d: double precision (DVec2 / DVec3 particles; the reference's BarnesHut is generic over the
 // scalar, sequential.rs:439-543).  The TREE STRUCTURE — keys, sort, cells, opening decisions — is
 // the f32 one, built over the particles rounded to f32 (an opening decision moved by 2^-24 of the
@@ -1731,6 +2056,21 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
         t->n_nodes = h.level_begin[levels];
         break;
     }
+    t->order = (int)ctx->order;
+    if (t->order == 2) {  // quadrupoles, bottom-up (K4d)
+        PCUDA_CUDA_TRY(ctx, t->quad64.ensure(t->n_nodes * 6 * sizeof(double)));
+        PCUDA_CUDA_TRY(ctx, t->quad.ensure(t->n_nodes * 2 * sizeof(float4)));
+        const BuildState *d_state = t->scan_in.as<BuildState>();
+        for (int level = t->n_levels - 1; level >= 0; --level) {
+            const uint32_t cnt = t->level_begin[level + 1] - t->level_begin[level];
+            const unsigned grid = std::min<unsigned>((unsigned)ctx->sm_count * 8, (cnt + 127) / 128);
+            quad_kernel<DIM><<<grid, 128, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double4>(),
+                                                   t->sorted.as<float4>(), t->quad64.as<double>(),
+                                                   t->quad.as<float4>(), d_state, level);
+        }
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += t->n_levels;
+    }
     return PCUDA_OK;
 }
 
@@ -1920,7 +2260,11 @@ static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tg
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
                                                        (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
-    if (x64) {
+    if (!x64 && t->order == 2) {
+        const unsigned blocksq = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 6,
+                                                           (max_groups + TRAVQ_WARPS - 1) / TRAVQ_WARPS);
+        traverse2q_kernel<<<blocksq, TRAVQ_WARPS * 32, 0, st>>>(a, t->quad.as<float4>());
+    } else if (x64) {
         const unsigned blocks64 = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8,
                                                             (max_groups + TRAV64_WARPS - 1) / TRAV64_WARPS);
         traverse64_kernel<<<blocks64, TRAV64_WARPS * 32, 0, st>>>(a, *x64);
@@ -2171,7 +2515,7 @@ void tree_free(pcuda_ctx *ctx, pcuda_tree *t) {
     (void)ctx;
     DevBuf *bufs[] = {&t->keys[0], &t->keys[1], &t->perm[0], &t->perm[1], &t->sorted, &t->nodes,
                       &t->moments, &t->d_frame, &t->scan_in, &t->scan_out, &t->cub_tmp, &t->partial,
-                      &t->sorted64};
+                      &t->sorted64, &t->quad64, &t->quad};
     for (DevBuf *b : bufs) b->release();
     delete t;
 }

@@ -53,6 +53,7 @@ struct pcuda_ctx {
     size_t smem_optin = 0;
     char name[128] = {0};
     uint32_t leaf_size = 16;
+    uint32_t order = 1;         // Barnes-Hut expansion order (pcuda_config.expansion_order)
     bool phase_timings = true;  // PCUDA_FLAG_NO_PHASE_TIMINGS clears it
     cudaStream_t stream = nullptr;
     // copy engines' streams + events of the chunked host path (created on first use, bruteforce.cu)

@@ -117,6 +117,11 @@ int pcuda_create(const pcuda_config *config, pcuda_ctx **out) {
     ctx->sm_clock_khz = khz;
     strncpy(ctx->name, prop.name, sizeof(ctx->name) - 1);
     if (config && config->leaf_size) ctx->leaf_size = config->leaf_size;
+    if (config && config->expansion_order > 2) {
+        delete ctx;
+        return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "expansion_order must be 0, 1 or 2");
+    }
+    if (config && config->expansion_order == 2) ctx->order = 2;
     ctx->phase_timings = !(config && (config->flags & PCUDA_FLAG_NO_PHASE_TIMINGS));
     if (ctx->leaf_size > 32) ctx->leaf_size = 32;
 

@@ -257,10 +257,12 @@ class CudaContext:
     Create once and reuse across calls ("should not be recreated for every iteration",
     gpu/mod.rs:150-151)."""
 
-    def __init__(self, device: int = 0, leaf_size: int = 0, phase_timings: bool = True):
+    def __init__(self, device: int = 0, leaf_size: int = 0, phase_timings: bool = True,
+                 expansion_order: int = 1):
         """phase_timings=False skips the per-phase CUDA events (PCUDA_FLAG_NO_PHASE_TIMINGS):
         about 10 us less per call; timings() then carries only kernel_launches."""
-        cfg = _ffi.Config(device, 0 if phase_timings else _ffi.FLAG_NO_PHASE_TIMINGS, leaf_size, 0)
+        cfg = _ffi.Config(device, 0 if phase_timings else _ffi.FLAG_NO_PHASE_TIMINGS, leaf_size,
+                          expansion_order)
         h = C.c_void_p()
         check(lib.pcuda_create(C.byref(cfg), C.byref(h)))
         self._h = h

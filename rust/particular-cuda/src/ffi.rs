@@ -37,7 +37,7 @@ pub struct pcuda_config {
     pub device: i32,
     pub flags: u32,
     pub leaf_size: u32,
-    pub reserved: u32,
+    pub expansion_order: u32,
 }
 
 #[repr(C)]

@@ -181,6 +181,52 @@ def test_f64_device_api_reference_fixture_and_empty(pb, ctx):
     assert one.shape == (1, 3) and not one.any()
 
 
+@pytest.mark.parametrize("cloud,dim", [("plummer", 3), ("uniform", 3), ("uniform", 2)])
+def test_quadrupole_nodes(pb, ctx, cloud, dim):
+    """pcuda_config.expansion_order = 2 (an accuracy / speed knob beyond the
+    reference's centre-of-mass nodes): at equal theta the error against the exact sum drops by a
+    large factor, so it is a fortiori inside the reference's error distribution; theta = 0 is still
+    brute force; order 2 at theta = 0.8 is at least as accurate as order 1 at theta = 0.5."""
+    import particular_b200.interface as pi
+    n = 20000
+    p = plummer_cloud(n, d=dim, seed=21) if cloud == "plummer" else uniform_cloud(n, d=dim, seed=21)
+    exact = oracle.brute_force_exact(p[:, :dim], p)
+    cq = pi.CudaContext(0, expansion_order=2)
+    try:
+        for theta in (0.5, 0.8):
+            mono = pi.BarnesHut(ctx, theta, pi.Acceleration.checked()).compute(p)
+            quad = pi.BarnesHut(cq, theta, pi.Acceleration.checked()).compute(p)
+            assert np.isfinite(quad).all()
+            s_m, s_q = stats(rel_err(mono, exact)), stats(rel_err(quad, exact))
+            assert s_q[0] <= 0.4 * s_m[0] and s_q[1] <= 0.6 * s_m[1], (theta, s_m, s_q)
+            ref = oracle.barnes_hut(p[:, :dim], p, theta, parallel=True)
+            assert_same_theta_error(quad, ref, exact)
+        q08 = pi.BarnesHut(cq, 0.8, pi.Acceleration.checked()).compute(p)
+        m05 = pi.BarnesHut(ctx, 0.5, pi.Acceleration.checked()).compute(p)
+        assert np.median(rel_err(q08, exact)) <= np.median(rel_err(m05, exact))
+        # theta = 0: no node is ever accepted
+        small = p[:3000]
+        got = pi.BarnesHut(cq, 0.0, pi.Acceleration.checked()).compute(small)
+        assert_bruteforce_parity(got, oracle.brute_force_parallel(small[:, :dim], small), small[:, :dim], small,
+                                 aggregate=False)
+        # separate targets, softening, tiny inputs, a prebuilt tree
+        aff = uniform_cloud(501, d=dim, seed=3)[:, :dim] * 1e-3
+        a_q = pi.BarnesHut(cq, 0.5, pi.AccelerationSoftened.checked(0.01)).compute(pi.Between(aff, p))
+        a_x = oracle.brute_force_exact(aff, p, 0.01)
+        a_m = pi.BarnesHut(ctx, 0.5, pi.AccelerationSoftened.checked(0.01)).compute(pi.Between(aff, p))
+        assert np.median(rel_err(a_q, a_x)) <= np.median(rel_err(a_m, a_x))
+        for k in (1, 2, 17):
+            assert np.isfinite(pi.BarnesHut(cq, 0.5, pi.Acceleration.checked()).compute(p[:k])).all()
+        tree = pi.RootedOrthtree(cq, p)
+        a_t = pi.BarnesHut(cq, 0.5, pi.Acceleration.checked()).compute(pi.Between(p[:, :dim], tree))
+        assert np.array_equal(a_t, pi.BarnesHut(cq, 0.5, pi.Acceleration.checked()).compute(p))
+        tree.close()
+    finally:
+        cq.close()
+    with pytest.raises(pi.CudaError):
+        pi.CudaContext(0, expansion_order=3)
+
+
 def test_softened_and_unchecked(pb, ctx):
     p = plummer_cloud(15000, seed=6)
     eps = 0.01

@@ -1346,7 +1346,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
 // children with the parallel-axis term m_c (3 d d^T - |d|^2 I), d = com_c - com).  An accepted
 // node then contributes, with D = com - target and R = |D|,
 //     a = M D / R^3  -  Q D / R^5  +  5/2 (D.Q.D) D / R^7,
-// evaluated as  ri^2 [ M ri u + 5/2 (u.Qu') u - Qu' ],  u = D ri,  Qu' = (Q u) ri^2, so that no
+// evaluated as  ri^2 [ (M + 5/2 u.Qu') u - Qu' ],  u = D ri,  Qu' = (Q u) ri^2, so that no
 // intermediate exceeds the magnitude of the monopole term's own factors.
 template <int DIM>
 __global__ void __launch_bounds__(128) quad_kernel(const NodeRec *__restrict__ nodes,
@@ -1428,8 +1428,8 @@ __device__ __forceinline__ void eval_node_q(const float4 c, const float4 qa, con
     float2 uqu = ptx::mul2(ux, qx);
     uqu = ptx::fma2(uy, qy, uqu);
     uqu = ptx::fma2(uz, qz, uqu);
-    // s = M ri + 5/2 u.Qu'   (coefficient of u)
-    const float2 s = ptx::fma2(ptx::splat(2.5f), uqu, ptx::mul2(ptx::splat(c.w), ri));
+    // s = M + 5/2 u.Qu'   (coefficient of u; everything is multiplied by ri^2 at the end)
+    const float2 s = ptx::fma2(ptx::splat(2.5f), uqu, ptx::splat(c.w));
     const float2 vx = ptx::fma2(s, ux, ptx::mul2(qx, ptx::splat(-1.f)));
     const float2 vy = ptx::fma2(s, uy, ptx::mul2(qy, ptx::splat(-1.f)));
     const float2 vz = ptx::fma2(s, uz, ptx::mul2(qz, ptx::splat(-1.f)));

@@ -324,6 +324,9 @@ def main():
     ap.add_argument("--workload", default="bruteforce", choices=["bruteforce", "barneshut", "split"])
     ap.add_argument("--n", type=int, default=0, help="particle count (default: BASELINE config)")
     ap.add_argument("--theta", type=float, default=0.5)
+    ap.add_argument("--bh-build", default="replicated", choices=["replicated", "partitioned"],
+                    help="multi-GPU Barnes-Hut: every GPU builds the whole tree, or one tree per GPU "
+                         "over its key range walked as a forest (PCUDA_FLAG_BH_PARTITIONED_BUILD)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the cpu_baseline leg and the ride-along Barnes-Hut number")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -412,13 +415,15 @@ def bruteforce_config(n, world, where):
                   "is re-read from L2 by design" if where == "gpu" else "n/a"}
 
 
-def barneshut_config(n, world, theta, where):
+def barneshut_config(n, world, theta, where, build="replicated"):
+    how = ("tree build replicated" if build == "replicated" else
+           "one tree per GPU over its key range (partitioned build), trees all-gathered, forest walk")
     return {"workload": f"Barnes-Hut 3-D f32 octree, theta={theta}, N={n} Plummer sphere (a=1, "
                         f"r<50a, equal mu=1/N, seed {SEED}); tree rebuilt every step "
                         f"(BASELINE configs[3]); Acceleration::checked()",
             "n_particles": n, "theta": theta,
-            "parallelism": (f"{world} GPU(s): particles all-gathered (NCCL), tree build replicated, "
-                            f"targets sharded" if world > 1 else "1 GPU") if where == "gpu"
+            "parallelism": (f"{world} GPU(s): particles all-gathered (NCCL), {how}, "
+                            f"targets sharded by key range" if world > 1 else "1 GPU") if where == "gpu"
             else "host threads over targets",
             "l2": "inputs + tree exceed L2 at N=10M; 256 MiB buffer written between timed steps"
             if where == "gpu" else "n/a"}
@@ -756,7 +761,7 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
     out = {"metric": "Barnes-Hut particles per second (build + traversal)",
            "value": n / (ms * 1e-3), "unit": "particles/s", "ms_per_step": ms,
            "comm_ms": comm_ms, "build_ms": build_ms, "traverse_ms": trav_ms, "steps": steps,
-           "warmup": warmup, "config": barneshut_config(n, world, theta, "gpu"),
+           "warmup": warmup, "config": barneshut_config(n, world, theta, "gpu", args.bh_build),
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 12,
                    "bytes_are": "per rank"},
@@ -790,7 +795,7 @@ def bench_barneshut(args, n, rank, world, local_rank):
     import particular_b200 as pb
     dist = _dist_setup(world, local_rank)
     dev = torch.device("cuda", local_rank)
-    ctx = pb.CudaContext(local_rank)
+    ctx = pb.CudaContext(local_rank, partitioned_build=args.bh_build == "partitioned")
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local_rank)

@@ -73,6 +73,10 @@ typedef struct pcuda_config {
 /* Do not record the per-phase CUDA events (pcuda_timings then reports only kernel_launches): saves
  * ~10 us per call, which matters at the reference's criterion sizes (N <= 65536). */
 #define PCUDA_FLAG_NO_PHASE_TIMINGS 1u
+/* Multi-GPU Barnes-Hut (pcuda_barneshut_f32x3_sharded*): build the tree partitioned by key range
+ * (every GPU sorts and builds only its share of the particles, the per-GPU trees are exchanged and
+ * walked as a forest) instead of replicating the whole build on every GPU.  SURVEY.md 8e "v3". */
+#define PCUDA_FLAG_BH_PARTITIONED_BUILD 2u
 
 /* Per-phase device times of the LAST call on the context, in milliseconds (CUDA events on the
  * context stream).  Phases that did not run are 0.  Replaces nothing in the reference (it has no
@@ -302,6 +306,23 @@ int pcuda_barneshut_f32x3_sharded_dev(pcuda_ctx *ctx, const float *d_local_xyzm,
 int pcuda_barneshut_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_t n_local,
                                   size_t n_total, float theta, float softening, int checked,
                                   float *out_xyz);
+
+/* Partitioned build (PCUDA_FLAG_BH_PARTITIONED_BUILD): with the flag set the sharded entry points
+ * above cut the key space into world_size ranges of about equal population (quantiles of a regular
+ * sample of the keys, the same on every rank), rank r selects, sorts and builds the tree of the
+ * r-th range only — same root cube, same level and leaf rules — the node records and sort
+ * permutations are all-gathered into equal slots, and every rank walks the resulting FOREST (one
+ * root per rank; a cell straddling a range boundary exists in two trees as two partial cells, each
+ * with the centre of mass of its own particles) for the targets of its own key range.
+ * The two entry points below run the same partition / per-part build / forest walk on ONE GPU,
+ * part after part, for all particles ("virtual ranks"): the test vehicle of the multi-GPU path.
+ * xyzm: n {x,y,z,mu} records; out: n accelerations in input order; 1 <= parts <= 16;
+ * parts == 1 gives the ordinary tree. */
+int pcuda_barneshut_f32x3_partitioned(pcuda_ctx *ctx, const float *xyzm, size_t n, int parts,
+                                      float theta, float softening, int checked, float *out_xyz);
+int pcuda_barneshut_f32x3_partitioned_dev(pcuda_ctx *ctx, const float *d_xyzm, size_t n, int parts,
+                                          float theta, float softening, int checked,
+                                          float *d_out_xyz);
 
 /* ---- device-resident stepping (new) --------------------------------------
  * Every caller of the reference integrates the accelerations right after computing them

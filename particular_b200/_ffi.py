@@ -21,6 +21,7 @@ lib = C.CDLL(LIB_PATH)
 
 ABI_VERSION = 1
 FLAG_NO_PHASE_TIMINGS = 1
+FLAG_BH_PARTITIONED_BUILD = 2
 UNIQUE_ID_BYTES = 128
 
 OK = 0
@@ -124,6 +125,8 @@ SIGNATURES = {
     "pcuda_morton_f32x2": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "pcuda_barneshut_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp, _vp]),
     "pcuda_barneshut_f32x3_sharded": (_i, [_vp, _vp, _sz, _sz, _f, _f, _i, _vp]),
+    "pcuda_barneshut_f32x3_partitioned": (_i, [_vp, _vp, _sz, _i, _f, _f, _i, _vp]),
+    "pcuda_barneshut_f32x3_partitioned_dev": (_i, [_vp, _vp, _sz, _i, _f, _f, _i, _vp]),
     "pcuda_sim_create": (_i, [_vp, C.POINTER(SimConfig), _vp, _vp, _sz, C.POINTER(_vp)]),
     "pcuda_sim_configure": (_i, [_vp, _vp, C.POINTER(SimConfig)]),
     "pcuda_sim_step": (_i, [_vp, _vp, C.c_uint32]),

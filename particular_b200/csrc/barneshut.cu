@@ -24,6 +24,8 @@
 // contributes nothing (sequential.rs:485-487 skips a node at the target's position).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -788,6 +790,7 @@ constexpr int TRAV_WARPS = 8;      // warps per block
 constexpr int STACK_CAP = 1024;    // node indices per warp (shared memory)
 constexpr int STACK_RESERVE = 8 * 32;  // room a depth-first descent may still need (7 per level)
 constexpr int LIST_CAP = 64;       // interaction ring per warp (float4 entries)
+constexpr int MAX_PARTS = 16;      // trees in a forest (= GPUs of a partitioned build)
 
 struct TravArgs {
     const NodeRec *nodes;
@@ -805,6 +808,10 @@ struct TravArgs {
     int dim;
     float theta2;
     float eps2;
+    // Roots the walk starts from.  One tree: {0}.  A forest (key-range-partitioned build, one
+    // tree per GPU over the same root cube, see sharded_forest_dev): one root per non-empty part.
+    uint32_t n_roots;
+    uint32_t roots[MAX_PARTS];
 };
 
 // The interaction list of a warp lives in shared memory as PAIRS of entries laid out
@@ -1159,11 +1166,11 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
                      npz = make_float2(-ta.z, -tb.z);
         float2 ax2 = make_float2(0.f, 0.f), ay2 = ax2, az2 = ax2;
         unsigned long long g_node = 0, g_part = 0;
-        int sp = 1;    // stack size (uniform across the warp)
+        int sp = (int)a.n_roots;  // stack size (uniform across the warp)
         int head = 0;  // ring position of the oldest list entry: 0 or 32 (uniform)
         int fill = 0;  // entries in the ring (uniform), < 32 between steps
         __syncwarp();
-        if (lane == 0) stack[0] = 0;
+        if (lane < sp) stack[lane] = a.roots[lane];
         __syncwarp();
 
         auto flush_full = [&]() {  // evaluate the 32 oldest entries once they are ready
@@ -1961,24 +1968,24 @@ static int sort_by_key(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n,
     return PCUDA_OK;
 }
 
+// Resets the host-side description of `t` for a tree of `n` particles.
 template <int DIM>
-static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n,
-                 bool keys_only = false) {
-    constexpr int BITS = Dims<DIM>::BITS;
-    const int stride = DIM + 1;
+static void tree_reset(pcuda_ctx *ctx, pcuda_tree *t, size_t n) {
     t->dim = DIM;
-    t->bits = BITS;
+    t->bits = Dims<DIM>::BITS;
     t->n = n;
     t->n_nodes = 0;
     t->n_levels = 0;
     t->leaf_size = ctx->leaf_size;
     t->level_begin.clear();
     t->frame = Frame{};
-    if (n == 0) return PCUDA_OK;
-    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
-    cudaStream_t st = ctx->stream;
+}
 
-    // K2: root cube + keys
+// K2: root cube of `n` particle rows -> t->d_frame (device).
+template <int DIM>
+static int build_frame(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n) {
+    const int stride = DIM + 1;
+    cudaStream_t st = ctx->stream;
     const int nb = (int)std::min<size_t>(ctx->sm_count * 8, (n + 255) / 256);
     PCUDA_CUDA_TRY(ctx, t->partial.ensure((size_t)nb * 2 * DIM * sizeof(float)));
     PCUDA_CUDA_TRY(ctx, t->d_frame.ensure(sizeof(Frame) + sizeof(unsigned)));
@@ -1989,6 +1996,23 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
                                         t->d_frame.as<Frame>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 2;
+    return PCUDA_OK;
+}
+
+template <int DIM>
+static int build_levels(pcuda_ctx *ctx, pcuda_tree *t, size_t n);
+
+template <int DIM>
+static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n,
+                 bool keys_only = false) {
+    const int stride = DIM + 1;
+    tree_reset<DIM>(ctx, t, n);
+    if (n == 0) return PCUDA_OK;
+    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    cudaStream_t st = ctx->stream;
+
+    // K2: root cube + keys
+    PCUDA_TRY(build_frame<DIM>(ctx, t, d_particles, n));
     // K3: sort + gather
     PCUDA_TRY(sort_by_key<DIM>(ctx, d_particles, stride, n, t->d_frame.as<Frame>(), t->keys, t->perm,
                                &t->cur, t->cub_tmp));
@@ -2002,11 +2026,17 @@ static int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t
         d_particles, stride, true, (int)n, t->d_perm(), t->sorted.as<float4>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
+    return build_levels<DIM>(ctx, t, n);
+}
 
-    // K4: level-by-level linear orthtree, all levels enqueued without host round trips; one
-    // read-back of the level table at the end.  If the node capacity guess was too small the
-    // build is repeated with the capacity it asked for (grow-only, so this happens at most once
-    // per size class).
+// K4: level-by-level linear orthtree over t->d_keys() / t->sorted (n sorted particles, frame in
+// t->d_frame), all levels enqueued without host round trips; one read-back of the level table at
+// the end.  If the node capacity guess was too small the build is repeated with the capacity it
+// asked for (grow-only, so this happens at most once per size class).
+template <int DIM>
+static int build_levels(pcuda_ctx *ctx, pcuda_tree *t, size_t n) {
+    constexpr int BITS = Dims<DIM>::BITS;
+    cudaStream_t st = ctx->stream;
     for (int attempt = 0;; ++attempt) {
         size_t cap_nodes = std::max<size_t>(4096, (size_t)((double)n * t->nodes_per_particle) + 1024);
         PCUDA_CUDA_TRY(ctx, t->nodes.ensure(cap_nodes * sizeof(NodeRec)));
@@ -2123,9 +2153,18 @@ static int g_tpl = 2;        // targets per lane in the traversal: 1 (groups of 
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
 // tgt_stride: floats per target row (0 = bare positions, i.e. `dim`).
 struct Ext64;
+// A forest of trees over the same root cube stored back to back (partitioned build): node and
+// source arrays that replace the tree's own, and the roots the walk starts from.
+struct ForestView {
+    const NodeRec *nodes;
+    const float4 *src;
+    uint32_t n_roots;
+    uint32_t roots[MAX_PARTS];
+};
 static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
                            const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
-                           float eps, float *d_out, const Ext64 *x64 = nullptr);
+                           float eps, float *d_out, const Ext64 *x64 = nullptr,
+                           const ForestView *fv = nullptr);
 
 // Double precision (tree built by build64): d_tgt64 / d_out64 replace d_tgt / d_out; the f32 copy of
 // separate targets that keys them is made here.
@@ -2208,8 +2247,10 @@ static int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, siz
 // traversal order to the output row (nullptr: out row = traversal position).
 static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
                            const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
-                           float eps, float *d_out, const Ext64 *x64) {
+                           float eps, float *d_out, const Ext64 *x64, const ForestView *fv) {
     const int dim = t->dim;
+    if (fv && (x64 || t->order == 2 || g_tpl != 2 || g_variant))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "a forest is walked by traverse2_kernel only");
     cudaStream_t st = ctx->stream;
     const int group_cap = x64 ? 32 : 32 * g_tpl;  // the f64 walk holds one target per lane
     // K5a: groups from the target keys
@@ -2257,6 +2298,14 @@ static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tg
     a.frame = t->d_frame.as<Frame>();
     a.theta2 = theta * theta;
     a.eps2 = eps * eps;
+    a.n_roots = 1;
+    for (int i = 0; i < MAX_PARTS; ++i) a.roots[i] = 0;
+    if (fv) {
+        a.nodes = fv->nodes;
+        a.src = fv->src;
+        a.n_roots = fv->n_roots;
+        for (uint32_t i = 0; i < fv->n_roots; ++i) a.roots[i] = fv->roots[i];
+    }
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
                                                        (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
@@ -2387,6 +2436,363 @@ __global__ void __launch_bounds__(256) pick_owned_rows(const float *__restrict__
     o[2] = acc_sorted[(size_t)i * 3 + 2];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Key-range-partitioned build ("forest").  The replicated build costs every GPU
+// the whole sort + tree (2.3 ms at N = 10M) however many GPUs share the traversal.  Here the key
+// space is cut into `parts` ranges of about equal population and every part builds the tree of ITS
+// particles only — over the same root cube, with the same level / leaf rules — so a forest of
+// `parts` trees results, stored back to back.  Cells that straddle a range boundary exist in two
+// trees as partial cells, each with the centre of mass of its own particles: a walk that starts
+// from all roots therefore meets every particle exactly once, tests a partial cell with the
+// reference's own rule (sequential.rs:490-494: the cell's width against the distance to its
+// centre of mass) and theta = 0 still opens everything.  Nothing has to be merged or stitched.
+//
+//   1. keys of all particles in the common frame (replicated: 0.1 ms at N = 10M);
+//   2. splitters = quantiles of a regular sample of <= 65536 keys (sorted by every rank alike),
+//      per-part populations counted in one pass;
+//   3. stable selection of the part's (key, index) pairs, sort, gather, level-wise build: all over
+//      n / parts particles;
+//   4. exchange: node records and sort permutations are all-gathered into equal slots
+//      (child / particle indices rebased to the slot), the sources are re-gathered locally from the
+//      raw records that every rank already holds (cheaper than sending them once more);
+//   5. every rank walks the forest for the targets of its own key range.
+struct PartRange {
+    const uint64_t *keys;
+    const uint64_t *split;
+    int part;
+    __device__ __forceinline__ bool operator()(const uint32_t &i) const {
+        const uint64_t k = keys[i];
+        return k >= split[part] && (k < split[part + 1] || split[part + 1] == ~0ull);
+    }
+};
+
+__global__ void __launch_bounds__(256) sample_keys(const uint64_t *__restrict__ keys, size_t stride,
+                                                   int m, uint64_t *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) out[j] = keys[(size_t)j * stride];
+}
+
+// split[0] = 0, split[q] = q-th parts-quantile of the sorted sample, split[parts] = ~0 (inclusive).
+__global__ void pick_splitters(const uint64_t *__restrict__ sorted_sample, int m, int parts,
+                               uint64_t *__restrict__ split, uint32_t *__restrict__ counts) {
+    const int q = threadIdx.x;
+    if (q <= parts) {
+        split[q] = q == 0 ? 0ull : q == parts ? ~0ull : sorted_sample[(size_t)q * m / parts];
+        counts[q] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) count_parts(const uint64_t *__restrict__ keys, int n,
+                                                   const uint64_t *__restrict__ split, int parts,
+                                                   uint32_t *__restrict__ counts) {
+    __shared__ uint32_t s_cnt[MAX_PARTS];
+    __shared__ uint64_t s_split[MAX_PARTS + 1];
+    if (threadIdx.x < MAX_PARTS) s_cnt[threadIdx.x] = 0;
+    if ((int)threadIdx.x <= parts) s_split[threadIdx.x] = split[threadIdx.x];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        int q = 0;
+        while (q + 1 < parts && k >= s_split[q + 1]) ++q;
+        atomicAdd(&s_cnt[q], 1u);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < parts && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) take_keys(const uint64_t *__restrict__ keys,
+                                                 const uint32_t *__restrict__ idx, int n,
+                                                 uint64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = keys[idx[i]];
+}
+
+// Local node records -> their slot of the forest: child links and particle ranges rebased.
+__global__ void __launch_bounds__(256) copy_rebase_nodes(const NodeRec *__restrict__ in, uint32_t n_nodes,
+                                                         uint32_t node_base, uint32_t part_base,
+                                                         NodeRec *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    NodeRec r = in[i];
+    if (r.nchild_level & 0xffu) r.first_child += node_base;
+    r.begin += part_base;
+    out[i] = r;
+}
+
+constexpr uint32_t NO_PARTICLE = 0xffffffffu;  // padding of a permutation slot
+
+__global__ void __launch_bounds__(256) copy_pad_perm(const uint32_t *__restrict__ in, uint32_t n,
+                                                     uint32_t slot, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < slot) out[i] = i < n ? in[i] : NO_PARTICLE;
+}
+
+// Sources of the whole forest in slot order, from the raw {x,y,z,mu} rows and the permutation slots.
+__global__ void __launch_bounds__(256) gather_forest(const float4 *__restrict__ raw,
+                                                     const uint32_t *__restrict__ perm, size_t n_slots,
+                                                     float4 *__restrict__ sorted) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const uint32_t o = perm[i];
+    if (o != NO_PARTICLE) sorted[i] = raw[o];
+}
+
+}  // namespace bh
+}  // namespace pcuda
+
+struct pcuda_forest {
+    pcuda_tree *local = nullptr;       // tree of this rank's (or the current part's) key range
+    pcuda::DevBuf gkeys, gidx;         // keys of ALL particles in input order (+ identity scratch)
+    pcuda::DevBuf sample[2], split, counts, sel_tmp, sel_count;
+    pcuda::DevBuf nodes, sorted, perm, keys, acc;  // the forest: equal slots per part
+};
+
+namespace pcuda {
+
+void forest_free(pcuda_ctx *ctx) {
+    pcuda_forest *f = ctx->forest;
+    if (!f) return;
+    if (f->local) tree_free(ctx, f->local);
+    DevBuf *bufs[] = {&f->gkeys, &f->gidx, &f->sample[0], &f->sample[1], &f->split, &f->counts,
+                      &f->sel_tmp, &f->sel_count, &f->nodes, &f->sorted, &f->perm, &f->keys, &f->acc};
+    for (DevBuf *b : bufs) b->release();
+    delete f;
+    ctx->forest = nullptr;
+}
+
+namespace bh {
+
+static pcuda_forest *forest_of(pcuda_ctx *ctx) {
+    if (!ctx->forest) {
+        ctx->forest = new pcuda_forest();
+        ctx->forest->local = new pcuda_tree();
+    }
+    return ctx->forest;
+}
+
+// Steps 1-2: frame, keys, splitters, populations (host copy in counts_h).  One synchronisation.
+static int forest_partition(pcuda_ctx *ctx, pcuda_forest *f, const float *d_particles, size_t n,
+                            int parts, uint32_t counts_h[MAX_PARTS]) {
+    cudaStream_t st = ctx->stream;
+    pcuda_tree *t = f->local;
+    PCUDA_TRY(build_frame<3>(ctx, t, d_particles, n));
+    PCUDA_CUDA_TRY(ctx, f->gkeys.ensure(n * sizeof(uint64_t)));
+    PCUDA_CUDA_TRY(ctx, f->gidx.ensure(n * sizeof(uint32_t)));
+    encode_kernel<3><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        d_particles, 4, (int)n, t->d_frame.as<Frame>(), f->gkeys.as<uint64_t>(), f->gidx.as<uint32_t>());
+    const int m = (int)std::min<size_t>(n, 65536);
+    const size_t stride = n / (size_t)m;
+    for (int i = 0; i < 2; ++i) PCUDA_CUDA_TRY(ctx, f->sample[i].ensure((size_t)m * sizeof(uint64_t)));
+    PCUDA_CUDA_TRY(ctx, f->split.ensure((MAX_PARTS + 1) * sizeof(uint64_t)));
+    PCUDA_CUDA_TRY(ctx, f->counts.ensure((MAX_PARTS + 1) * sizeof(uint32_t)));
+    sample_keys<<<(m + 255) / 256, 256, 0, st>>>(f->gkeys.as<uint64_t>(), stride, m,
+                                                 f->sample[0].as<uint64_t>());
+    cub::DoubleBuffer<uint64_t> sb(f->sample[0].as<uint64_t>(), f->sample[1].as<uint64_t>());
+    size_t tmp = 0;
+    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, sb, m, 0, 63, st));
+    PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
+    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(f->sel_tmp.p, tmp, sb, m, 0, 63, st));
+    pick_splitters<<<1, 32, 0, st>>>(sb.Current(), m, parts, f->split.as<uint64_t>(),
+                                     f->counts.as<uint32_t>());
+    count_parts<<<(unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (n + 255) / 256), 256, 0, st>>>(
+        f->gkeys.as<uint64_t>(), (int)n, f->split.as<uint64_t>(), parts, f->counts.as<uint32_t>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 5 + 9;
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(counts_h, f->counts.p, parts * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, st));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return PCUDA_OK;
+}
+
+// Step 3 for part q (population `count`): f->local becomes the tree of the part's particles.
+// `slot` >= count: capacity the key / permutation buffers must have.
+static int forest_build_part(pcuda_ctx *ctx, pcuda_forest *f, const float *d_particles, size_t n, int q,
+                             size_t count, size_t slot) {
+    cudaStream_t st = ctx->stream;
+    pcuda_tree *t = f->local;
+    tree_reset<3>(ctx, t, count);
+    if (count == 0) return PCUDA_OK;
+    for (int i = 0; i < 2; ++i) {
+        PCUDA_CUDA_TRY(ctx, t->keys[i].ensure(slot * sizeof(uint64_t)));
+        PCUDA_CUDA_TRY(ctx, t->perm[i].ensure(slot * sizeof(uint32_t)));
+    }
+    PCUDA_CUDA_TRY(ctx, f->sel_count.ensure(sizeof(uint32_t)));
+    PartRange in_part{f->gkeys.as<uint64_t>(), f->split.as<uint64_t>(), q};
+    cub::CountingInputIterator<uint32_t> all(0u);
+    size_t tmp = 0;
+    PCUDA_CUDA_TRY(ctx, cub::DeviceSelect::If(nullptr, tmp, all, t->perm[0].as<uint32_t>(),
+                                              f->sel_count.as<uint32_t>(), (int)n, in_part, st));
+    PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
+    PCUDA_CUDA_TRY(ctx, cub::DeviceSelect::If(f->sel_tmp.p, tmp, all, t->perm[0].as<uint32_t>(),
+                                              f->sel_count.as<uint32_t>(), (int)n, in_part, st));
+    take_keys<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
+        f->gkeys.as<uint64_t>(), t->perm[0].as<uint32_t>(), (int)count, t->keys[0].as<uint64_t>());
+    cub::DoubleBuffer<uint64_t> kb(t->keys[0].as<uint64_t>(), t->keys[1].as<uint64_t>());
+    cub::DoubleBuffer<uint32_t> vb(t->perm[0].as<uint32_t>(), t->perm[1].as<uint32_t>());
+    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)count, 0, 63, st));
+    PCUDA_CUDA_TRY(ctx, t->cub_tmp.ensure(tmp));
+    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(t->cub_tmp.p, tmp, kb, vb, (int)count, 0, 63, st));
+    t->cur = kb.selector;
+    PCUDA_CUDA_TRY(ctx, t->sorted.ensure(count * sizeof(float4)));
+    gather_kernel<3><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_particles, 4, true, (int)count,
+                                                                      t->d_perm(), t->sorted.as<float4>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2 + 1 + 9 + 1;
+    return build_levels<3>(ctx, t, count);
+}
+
+// Diagnostic / test entry (one GPU): the forest of `parts` trees is built part after part and
+// walked for all particles; out rows are in input order.  parts == 1 is the ordinary tree.
+static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, int parts, float theta,
+                           float eps, float *d_out) {
+    if (parts < 1 || parts > MAX_PARTS)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "parts must be in [1, %d]", MAX_PARTS);
+    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    if (ctx->order == 2)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "the partitioned build carries centre-of-mass nodes only");
+    if (n == 0) return PCUDA_OK;
+    cudaStream_t st = ctx->stream;
+    pcuda_forest *f = forest_of(ctx);
+    uint32_t counts[MAX_PARTS] = {0};
+    phase_begin(ctx, PH_BUILD);
+    PCUDA_TRY(forest_partition(ctx, f, d_particles, n, parts, counts));
+    size_t slot = 1, total = 0;
+    for (int q = 0; q < parts; ++q) {
+        slot = std::max<size_t>(slot, counts[q]);
+        total += counts[q];
+    }
+    if (total != n) return fail(ctx, PCUDA_ERR_CUDA, "partition lost particles (%zu of %zu)", total, n);
+    PCUDA_CUDA_TRY(ctx, f->sorted.ensure((size_t)parts * slot * sizeof(float4)));
+    PCUDA_CUDA_TRY(ctx, f->perm.ensure((size_t)parts * slot * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->keys.ensure((size_t)parts * slot * sizeof(uint64_t)));
+    ForestView fv{};
+    size_t node_base = 0;
+    for (int q = 0; q < parts; ++q) {
+        PCUDA_TRY(forest_build_part(ctx, f, d_particles, n, q, counts[q], slot));
+        if (counts[q] == 0) continue;
+        const pcuda_tree *t = f->local;
+        const size_t need = (node_base + t->n_nodes) * sizeof(NodeRec);
+        if (need > f->nodes.cap) {  // grow, keeping the parts already placed
+            DevBuf bigger;
+            PCUDA_CUDA_TRY(ctx, bigger.ensure(std::max(need, (size_t)parts * t->n_nodes * sizeof(NodeRec))));
+            if (node_base)
+                PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(bigger.p, f->nodes.p, node_base * sizeof(NodeRec),
+                                                    cudaMemcpyDeviceToDevice, st));
+            PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            f->nodes.release();
+            f->nodes = bigger;
+        }
+        copy_rebase_nodes<<<(unsigned)((t->n_nodes + 255) / 256), 256, 0, st>>>(
+            t->nodes.as<NodeRec>(), (uint32_t)t->n_nodes, (uint32_t)node_base, (uint32_t)(q * slot),
+            f->nodes.as<NodeRec>() + node_base);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->sorted.as<float4>() + q * slot, t->sorted.p,
+                                            counts[q] * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->perm.as<uint32_t>() + q * slot, t->d_perm(),
+                                            counts[q] * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->keys.as<uint64_t>() + q * slot, t->d_keys(),
+                                            counts[q] * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        fv.roots[fv.n_roots++] = (uint32_t)node_base;
+        node_base += t->n_nodes;
+    }
+    phase_end(ctx, PH_BUILD);
+    fv.nodes = f->nodes.as<NodeRec>();
+    fv.src = f->sorted.as<float4>();
+    phase_begin(ctx, PH_COMPUTE);
+    for (int q = 0; q < parts; ++q) {
+        if (counts[q] == 0) continue;
+        PCUDA_TRY(traverse_sorted(ctx, f->local, f->sorted.as<float4>() + q * slot,
+                                  f->keys.as<uint64_t>() + q * slot, f->perm.as<uint32_t>() + q * slot,
+                                  counts[q], theta, eps, d_out, nullptr, &fv));
+    }
+    phase_end(ctx, PH_COMPUTE);
+    return PCUDA_OK;
+}
+
+static int g_forest = 0;  // multi-GPU Barnes-Hut: 0 = as the context flag says, 1 = partitioned, 2 = replicated
+
+// Multi-GPU step with the partitioned build: d_gathered already holds all n_total records.  Rank r
+// builds the tree of the r-th key range, the trees are exchanged, and rank r walks the forest for
+// the targets of its own range.  Same result routing as the replicated path.
+static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, size_t lo, size_t hi,
+                              float theta, float eps, const float *d_gathered, float *d_out) {
+    cudaStream_t st = ctx->stream;
+    pcuda_forest *f = forest_of(ctx);
+    uint32_t counts[MAX_PARTS] = {0};
+    phase_begin(ctx, PH_BUILD);
+    PCUDA_TRY(forest_partition(ctx, f, d_gathered, n_total, world, counts));
+    size_t slot = 1, total = 0;
+    for (int q = 0; q < world; ++q) {
+        slot = std::max<size_t>(slot, counts[q]);
+        total += counts[q];
+    }
+    if (total != n_total)
+        return fail(ctx, PCUDA_ERR_CUDA, "partition lost particles (%zu of %zu)", total, n_total);
+    const size_t mine = counts[rank];
+    PCUDA_TRY(forest_build_part(ctx, f, d_gathered, n_total, rank, mine, slot));
+    phase_end(ctx, PH_BUILD);
+    const pcuda_tree *t = f->local;
+
+    // exchange: node counts -> common slot size; nodes and permutations into equal slots
+    phase_begin(ctx, PH_COMM3);
+    uint32_t *d_nn = f->counts.as<uint32_t>();  // reused: the populations are on the host now
+    const uint32_t my_nodes = (uint32_t)t->n_nodes;
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_nn + rank, &my_nodes, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_nn + rank, d_nn, sizeof(uint32_t)));
+    uint32_t n_nodes[MAX_PARTS] = {0};
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(n_nodes, d_nn, world * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    size_t node_slot = 1;
+    for (int q = 0; q < world; ++q) node_slot = std::max<size_t>(node_slot, n_nodes[q]);
+    if ((size_t)world * node_slot > 0xfffffff0ull || (size_t)world * slot > 0xfffffff0ull)
+        return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "forest does not fit 32-bit indices");
+    PCUDA_CUDA_TRY(ctx, f->nodes.ensure((size_t)world * node_slot * sizeof(NodeRec)));
+    PCUDA_CUDA_TRY(ctx, f->perm.ensure((size_t)world * slot * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->sorted.ensure((size_t)world * slot * sizeof(float4)));
+    PCUDA_CUDA_TRY(ctx, f->acc.ensure((size_t)world * slot * 3 * sizeof(float)));
+    NodeRec *my_node_slot = f->nodes.as<NodeRec>() + (size_t)rank * node_slot;
+    uint32_t *my_perm_slot = f->perm.as<uint32_t>() + (size_t)rank * slot;
+    if (my_nodes)
+        copy_rebase_nodes<<<(my_nodes + 255) / 256, 256, 0, st>>>(
+            t->nodes.as<NodeRec>(), my_nodes, (uint32_t)(rank * node_slot), (uint32_t)(rank * slot),
+            my_node_slot);
+    copy_pad_perm<<<(unsigned)((slot + 255) / 256), 256, 0, st>>>(
+        mine ? t->d_perm() : nullptr, (uint32_t)mine, (uint32_t)slot, my_perm_slot);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, my_node_slot, f->nodes.p, node_slot * sizeof(NodeRec)));
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, my_perm_slot, f->perm.p, slot * sizeof(uint32_t)));
+    const size_t n_slots = (size_t)world * slot;
+    gather_forest<<<(unsigned)((n_slots + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4 *>(d_gathered), f->perm.as<uint32_t>(), n_slots, f->sorted.as<float4>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    phase_end(ctx, PH_COMM3);
+
+    ForestView fv{};
+    fv.nodes = f->nodes.as<NodeRec>();
+    fv.src = f->sorted.as<float4>();
+    for (int q = 0; q < world; ++q)
+        if (n_nodes[q]) fv.roots[fv.n_roots++] = (uint32_t)(q * node_slot);
+    float *acc = f->acc.as<float>();
+    phase_begin(ctx, PH_COMPUTE);
+    if (mine)
+        PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), nullptr, mine, theta, eps,
+                                  acc + (size_t)rank * slot * 3, nullptr, &fv));
+    phase_end(ctx, PH_COMPUTE);
+    phase_begin(ctx, PH_COMM2);
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, acc + (size_t)rank * slot * 3, acc, slot * 12));
+    if (hi > lo) {
+        pick_owned_rows<<<(unsigned)((n_slots + 255) / 256), 256, 0, st>>>(
+            acc, f->perm.as<uint32_t>(), (int)n_slots, (uint32_t)lo, (uint32_t)hi, d_out);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    phase_end(ctx, PH_COMM2);
+    return PCUDA_OK;
+}
+
 static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total,
                        float theta, float eps, float *d_gathered, float *d_out) {
     int world = 1, rank = 0;
@@ -2404,6 +2810,10 @@ static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, siz
                                             ctx->stream));
     if (world > 1) PCUDA_TRY(pcuda_comm_allgather_dev(ctx, slot, d_gathered, cap * 16));
     phase_end(ctx, PH_COMM);
+    const bool forest = g_forest == 1 || (g_forest == 0 && ctx->bh_partitioned);
+    if (forest && world > 1 && world <= MAX_PARTS && n_total >= (size_t)world && ctx->order == 1 &&
+        g_tpl == 2 && !g_variant)
+        return sharded_forest_dev(ctx, world, rank, n_total, lo, hi, theta, eps, d_gathered, d_out);
     if (!ctx->call_tree) ctx->call_tree = new pcuda_tree();
     pcuda_tree *t = ctx->call_tree;
     phase_begin(ctx, PH_BUILD);
@@ -2505,6 +2915,10 @@ int bh_debug_set(const char *key, int value) {
     }
     if (k == "bh_count") {
         bh::g_count = value != 0;
+        return PCUDA_OK;
+    }
+    if (k == "bh_forest" && value >= 0 && value <= 2) {
+        bh::g_forest = value;
         return PCUDA_OK;
     }
     return PCUDA_ERR_INVALID_ARGUMENT;
@@ -2637,6 +3051,42 @@ int pcuda_barneshut_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_
     phase_end(ctx, PH_DOWNLOAD);
     PCUDA_TRY(timings_collect(ctx));
     return bh::read_counters(ctx);
+}
+
+int pcuda_barneshut_f32x3_partitioned_dev(pcuda_ctx *ctx, const float *d_xyzm, size_t n, int parts,
+                                          float theta, float softening, int checked, float *d_out_xyz) {
+    (void)checked;
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n && (!d_xyzm || !d_out_xyz))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    int s = bh::partitioned_dev(ctx, d_xyzm, n, parts, theta, softening, d_out_xyz);
+    ctx->timings.kernel_launches = ctx->launches;
+    return s;
+}
+
+int pcuda_barneshut_f32x3_partitioned(pcuda_ctx *ctx, const float *xyzm, size_t n, int parts, float theta,
+                                      float softening, int checked, float *out_xyz) {
+    (void)checked;
+    if (!ctx) return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (n && (!xyzm || !out_xyz))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL buffer with non-zero count");
+    if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    DeviceGuard guard(ctx->device);
+    timings_reset(ctx);
+    if (n == 0) return PCUDA_OK;
+    phase_begin(ctx, PH_UPLOAD);
+    PCUDA_CUDA_TRY(ctx, ctx->d_affecting.ensure(n * 16));
+    PCUDA_CUDA_TRY(ctx, ctx->d_out.ensure(n * 12));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_affecting.p, xyzm, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    phase_end(ctx, PH_UPLOAD);
+    PCUDA_TRY(bh::partitioned_dev(ctx, ctx->d_affecting.as<float>(), n, parts, theta, softening,
+                                  ctx->d_out.as<float>()));
+    phase_begin(ctx, PH_DOWNLOAD);
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(out_xyz, ctx->d_out.p, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    phase_end(ctx, PH_DOWNLOAD);
+    return timings_collect(ctx);
 }
 
 int pcuda_tree_build_f32(pcuda_ctx *ctx, uint32_t dim, const float *affecting, size_t n,

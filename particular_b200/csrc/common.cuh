@@ -42,9 +42,11 @@ struct DevBuf {
 
 struct Nccl;  // comm.cu
 
-enum Phase { PH_UPLOAD = 0, PH_COMM, PH_BUILD, PH_COMPUTE, PH_DOWNLOAD, PH_COMM2, PH_COUNT };  // COMM2: a second exchange (added to comm_ms)
+enum Phase { PH_UPLOAD = 0, PH_COMM, PH_BUILD, PH_COMPUTE, PH_DOWNLOAD, PH_COMM2, PH_COMM3, PH_COUNT };  // COMM2, COMM3: further exchanges of the call (added to comm_ms)
 
 }  // namespace pcuda
+
+struct pcuda_forest;  // barneshut.cu: buffers of the key-range-partitioned multi-GPU build
 
 struct pcuda_ctx {
     int device = 0;
@@ -76,6 +78,8 @@ struct pcuda_ctx {
         d_tgt_sorted, d_cub_tmp, d_misc;
     uint64_t last_counters[5] = {0, 0, 0, 0, 0};
     pcuda_tree *call_tree = nullptr;  // tree reused by the one-shot Barnes-Hut entry points
+    pcuda_forest *forest = nullptr;   // partitioned multi-GPU build (PCUDA_FLAG_BH_PARTITIONED_BUILD)
+    bool bh_partitioned = false;
 
     pcuda::Nccl *nccl = nullptr;
     int live_sims = 0;  // pcuda_sim objects created on this context (sim.cu)
@@ -118,6 +122,7 @@ int bh_enqueue_f64(pcuda_ctx *ctx, int dim, const double *d_tgt, int tgt_stride,
                    const double *d_src, size_t nb, double theta, double softening, double *d_out);
 
 void tree_free(pcuda_ctx *ctx, pcuda_tree *t);
+void forest_free(pcuda_ctx *ctx);
 int bh_debug_set(const char *key, int value);  // barneshut.cu tuning hooks
 void nccl_free(pcuda_ctx *ctx);
 // comm.cu: world size / rank of the context's communicator (1 / 0 when none was initialised).

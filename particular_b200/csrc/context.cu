@@ -41,7 +41,7 @@ void phase_end(pcuda_ctx *ctx, Phase p) {
 int timings_collect(pcuda_ctx *ctx) {
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float *dst[PH_COUNT] = {&ctx->timings.upload_ms, &ctx->timings.comm_ms, &ctx->timings.build_ms,
-                            &ctx->timings.compute_ms, &ctx->timings.download_ms, nullptr};
+                            &ctx->timings.compute_ms, &ctx->timings.download_ms, nullptr, nullptr};
     ctx->timings = pcuda_timings{};
     for (int i = 0; i < PH_COUNT; ++i) {
         if (!ctx->ev_used[i]) continue;
@@ -123,6 +123,7 @@ int pcuda_create(const pcuda_config *config, pcuda_ctx **out) {
     }
     if (config && config->expansion_order == 2) ctx->order = 2;
     ctx->phase_timings = !(config && (config->flags & PCUDA_FLAG_NO_PHASE_TIMINGS));
+    ctx->bh_partitioned = config && (config->flags & PCUDA_FLAG_BH_PARTITIONED_BUILD);
     if (ctx->leaf_size > 32) ctx->leaf_size = 32;
 
     DeviceGuard guard(dev);
@@ -146,6 +147,7 @@ void pcuda_destroy(pcuda_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     nccl_free(ctx);
     if (ctx->call_tree) tree_free(ctx, ctx->call_tree);
+    forest_free(ctx);
     DevBuf *bufs[] = {&ctx->d_affected, &ctx->d_affecting, &ctx->d_out, &ctx->d_partial,
                       &ctx->d_packed_src, &ctx->d_packed_tgt, &ctx->d_massmax, &ctx->d_tile_done, &ctx->d_stack, &ctx->d_counters,
                       &ctx->d_tgt_keys, &ctx->d_tgt_keys_alt, &ctx->d_tgt_perm,

@@ -258,11 +258,14 @@ class CudaContext:
     gpu/mod.rs:150-151)."""
 
     def __init__(self, device: int = 0, leaf_size: int = 0, phase_timings: bool = True,
-                 expansion_order: int = 1):
+                 expansion_order: int = 1, partitioned_build: bool = False):
         """phase_timings=False skips the per-phase CUDA events (PCUDA_FLAG_NO_PHASE_TIMINGS):
-        about 10 us less per call; timings() then carries only kernel_launches."""
-        cfg = _ffi.Config(device, 0 if phase_timings else _ffi.FLAG_NO_PHASE_TIMINGS, leaf_size,
-                          expansion_order)
+        about 10 us less per call; timings() then carries only kernel_launches.
+        partitioned_build=True (PCUDA_FLAG_BH_PARTITIONED_BUILD): multi-GPU Barnes-Hut builds one
+        tree per GPU over its key range and walks the forest instead of replicating the build."""
+        flags = (0 if phase_timings else _ffi.FLAG_NO_PHASE_TIMINGS) | \
+            (_ffi.FLAG_BH_PARTITIONED_BUILD if partitioned_build else 0)
+        cfg = _ffi.Config(device, flags, leaf_size, expansion_order)
         h = C.c_void_p()
         check(lib.pcuda_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -501,6 +504,20 @@ class BarnesHut:
         fn = getattr(lib, f"pcuda_barneshut_{sfx}")
         check(fn(self.ctx.handle, _ptr(aff), na, _ptr(src), len(src), self.theta, it.softening,
                  int(it.is_checked), _ptr(out)), self.ctx.handle)
+        return out
+
+    def compute_partitioned(self, particles, parts: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """The key-range-partitioned build of the multi-GPU path run on this one GPU, part after
+        part ("virtual ranks"): a forest of `parts` trees over the same root cube, walked for all
+        particles (pcuda_barneshut_f32x3_partitioned).  f32 3-D, `&[P]` storage."""
+        p = np.ascontiguousarray(particles, dtype=np.float32)
+        if p.ndim != 2 or p.shape[1] != 4:
+            raise NotImplementedError("the partitioned build is f32 3-D: particles must be (n, 4)")
+        it = self.interaction
+        out = _out_array(out, (len(p), 3), np.float32)
+        check(lib.pcuda_barneshut_f32x3_partitioned(self.ctx.handle, _ptr(p), len(p), int(parts),
+                                                    self.theta, it.softening, int(it.is_checked),
+                                                    _ptr(out)), self.ctx.handle)
         return out
 
     def compute_device(self, affected_ptr: Optional[int], n_affected: int, affecting_ptr: int,

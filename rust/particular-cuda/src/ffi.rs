@@ -23,6 +23,7 @@ pub const PCUDA_OK: c_int = 0;
 pub const PCUDA_ERR_NO_DEVICE: c_int = -2;
 pub const PCUDA_UNIQUE_ID_BYTES: usize = 128;
 pub const PCUDA_FLAG_NO_PHASE_TIMINGS: u32 = 1;
+pub const PCUDA_FLAG_BH_PARTITIONED_BUILD: u32 = 2;
 
 pub const PCUDA_BRUTE_FORCE: u32 = 0;
 pub const PCUDA_BARNES_HUT: u32 = 1;
@@ -200,6 +201,12 @@ extern "C" {
     pub fn pcuda_barneshut_f32x3_sharded(ctx: *mut pcuda_ctx, local_xyzm: *const f32, n_local: usize,
                                          n_total: usize, theta: f32, softening: f32, checked: c_int,
                                          out_xyz: *mut f32) -> c_int;
+    pub fn pcuda_barneshut_f32x3_partitioned(ctx: *mut pcuda_ctx, xyzm: *const f32, n: usize, parts: c_int,
+                                             theta: f32, softening: f32, checked: c_int,
+                                             out_xyz: *mut f32) -> c_int;
+    pub fn pcuda_barneshut_f32x3_partitioned_dev(ctx: *mut pcuda_ctx, d_xyzm: *const f32, n: usize, parts: c_int,
+                                                 theta: f32, softening: f32, checked: c_int,
+                                                 d_out_xyz: *mut f32) -> c_int;
 
     pub fn pcuda_sim_create(ctx: *mut pcuda_ctx, config: *const pcuda_sim_config, particles: *const c_void,
                             velocities: *const c_void, n: usize, out: *mut *mut pcuda_sim) -> c_int;

@@ -381,3 +381,66 @@ def test_full_size_2d_quadtree(pb, ctx):
     tree = oracle.Tree(p)
     ref = tree.traverse(p[idx, :2], 0.5, 100.0, parallel=True)
     assert_same_theta_error(got[idx], ref, exact, slack=1.25)
+
+
+# ---- key-range-partitioned build (the multi-GPU "forest" path run as virtual ranks on one GPU) ----
+def test_partitioned_one_part_is_the_ordinary_tree(pb, ctx):
+    p = plummer_cloud(30000, seed=21)
+    bh = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked())
+    assert np.array_equal(bh.compute_partitioned(p, 1), bh.compute(p))
+
+
+@pytest.mark.parametrize("cloud", ["uniform", "plummer"])
+@pytest.mark.parametrize("parts", [2, 3, 8, 16])
+def test_partitioned_same_theta_error_as_reference(pb, ctx, cloud, parts):
+    n = 20000
+    p = uniform_cloud(n, seed=5) if cloud == "uniform" else plummer_cloud(n, seed=5)
+    exact = oracle.brute_force_exact(p[:, :3], p)
+    ref = oracle.barnes_hut(p[:, :3], p, 0.5, parallel=True)
+    got = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked()).compute_partitioned(p, parts)
+    assert got.shape == (n, 3) and np.isfinite(got).all()
+    assert_same_theta_error(got, ref, exact)
+
+
+@pytest.mark.parametrize("parts", [2, 5])
+def test_partitioned_theta0_is_brute_force(pb, ctx, parts):
+    p = uniform_cloud(6000, seed=8)
+    got = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).compute_partitioned(p, parts)
+    ref32 = oracle.brute_force_parallel(p[:, :3], p)
+    assert_bruteforce_parity(got, ref32, p[:, :3], p, aggregate=False)
+
+
+def test_partitioned_degenerate_inputs(pb, ctx):
+    """Fewer particles than parts, coincident particles (every key equal: one part gets them all),
+    softened interaction, and the argument checks."""
+    bh = pb.BarnesHut(ctx, 0.5, pb.AccelerationSoftened.checked(0.5))
+    tiny = uniform_cloud(3, seed=2)
+    assert np.allclose(bh.compute_partitioned(tiny, 8), oracle.brute_force(tiny[:, :3], tiny, 0.5),
+                       rtol=1e-5, atol=0)
+    same = np.tile(np.array([[1.0, 2.0, 3.0, 5.0]], np.float32), (500, 1))
+    assert np.array_equal(bh.compute_partitioned(same, 4), np.zeros((500, 3), np.float32))
+    two = np.concatenate([same, same + np.array([[10.0, 0, 0, 0]], np.float32)])
+    got = bh.compute_partitioned(two, 4)
+    ref = oracle.brute_force(two[:, :3], two, 0.5)
+    assert np.allclose(got, ref, rtol=1e-4, atol=0)
+    assert bh.compute_partitioned(np.zeros((0, 4), np.float32), 2).shape == (0, 3)
+    with pytest.raises(pb.CudaError):
+        bh.compute_partitioned(tiny, 0)
+    with pytest.raises(pb.CudaError):
+        bh.compute_partitioned(tiny, 17)
+
+
+def test_partitioned_full_size_counts(pb, ctx):
+    """N = 2M Plummer, 8 parts: the forest walk costs about the same work as the single tree
+    (partial top cells add a few node interactions) and gives the same error distribution."""
+    n = 2_000_000
+    p = plummer_cloud(n, seed=31)
+    bh = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked())
+    one = bh.compute(p)
+    forest = bh.compute_partitioned(p, 8)
+    idx = np.random.default_rng(3).choice(n, 1024, replace=False)
+    exact = oracle.brute_force_exact(p[idx, :3], p)
+    e1, e8 = rel_err(one[idx], exact), rel_err(forest[idx], exact)
+    assert np.median(e8) <= 1.1 * np.median(e1) + 2e-6, (np.median(e8), np.median(e1))
+    assert np.percentile(e8, 99) <= 1.25 * np.percentile(e1, 99) + 2e-6
+    assert np.isfinite(forest).all()

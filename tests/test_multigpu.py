@@ -38,6 +38,22 @@ e_1 = np.linalg.norm(singleb - truth, axis=1) / den
 res["bh_shape"] = list(fullb.shape)
 res["bh_err_sharded"] = [float(np.median(e_sh)), float(np.percentile(e_sh, 99)), float(e_sh.max())]
 res["bh_err_single"] = [float(np.median(e_1)), float(np.percentile(e_1, 99)), float(e_1.max())]
+# partitioned build: one tree per GPU over its key range, walked as a forest (bh_forest = 1 forces it
+# on this context; PCUDA_FLAG_BH_PARTITIONED_BUILD / CudaContext(partitioned_build=True) is the API)
+from particular_b200 import _ffi
+assert _ffi.lib.pcuda_debug_set(b"bh_forest", 1) == 0
+fullf = bh.compute(q)
+e_f = np.linalg.norm(fullf - truth, axis=1) / den
+res["bh_forest_shape"] = list(fullf.shape)
+res["bh_err_forest"] = [float(np.median(e_f)), float(np.percentile(e_f, 99)), float(e_f.max())]
+res["bh_forest_finite"] = bool(np.isfinite(fullf).all())
+bh0 = pb.ShardedBarnesHut(ctx, 0.0, pb.Acceleration.checked(), init_comm=False)
+bh0.world, bh0.rank = sh.world, sh.rank
+small = uniform_cloud(5001, seed=9)
+f0 = bh0.compute(small)
+t0 = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(small)
+res["bh_forest_theta0_max_rel"] = float(np.max(np.linalg.norm(f0 - t0, axis=1) / np.linalg.norm(t0, axis=1)))
+assert _ffi.lib.pcuda_debug_set(b"bh_forest", 0) == 0
 r = uniform_cloud(20011, seed=6, massive_ratio=0.01)
 sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0), init_comm=False)
 sb.world, sb.rank = sh.world, sh.rank
@@ -81,3 +97,8 @@ def test_two_gpus_match_single_gpu(tmp_path):
     assert res["bh_shape"] == [40003, 3]
     for a, b in zip(res["bh_err_sharded"], res["bh_err_single"]):
         assert a <= 1.25 * b + 1e-6, res
+    # partitioned build: a forest of per-GPU trees; same error distribution, theta = 0 exact
+    assert res["bh_forest_shape"] == [40003, 3] and res["bh_forest_finite"]
+    for a, b in zip(res["bh_err_forest"], res["bh_err_single"]):
+        assert a <= 1.25 * b + 1e-6, res
+    assert res["bh_forest_theta0_max_rel"] <= 2e-5, res

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -791,6 +792,7 @@ constexpr int STACK_CAP = 1024;    // node indices per warp (shared memory)
 constexpr int STACK_RESERVE = 8 * 32;  // room a depth-first descent may still need (7 per level)
 constexpr int LIST_CAP = 64;       // interaction ring per warp (float4 entries)
 constexpr int MAX_PARTS = 16;      // trees in a forest (= GPUs of a partitioned build)
+constexpr int MAX_ROOTS = 736;     // start nodes of a forest walk (STACK_CAP - STACK_RESERVE - 32)
 
 struct TravArgs {
     const NodeRec *nodes;
@@ -808,10 +810,11 @@ struct TravArgs {
     int dim;
     float theta2;
     float eps2;
-    // Roots the walk starts from.  One tree: {0}.  A forest (key-range-partitioned build, one
-    // tree per GPU over the same root cube, see sharded_forest_dev): one root per non-empty part.
+    // Nodes the walk starts from.  nullptr: node 0 (one tree).  Partitioned build (one tree per GPU
+    // over the same root cube, see sharded_forest_dev): the root of the merged top tree followed by
+    // the loose leaves (partial cells that are leaves in their own part), at most MAX_ROOTS.
+    const uint32_t *roots;
     uint32_t n_roots;
-    uint32_t roots[MAX_PARTS];
 };
 
 // The interaction list of a warp lives in shared memory as PAIRS of entries laid out
@@ -1166,11 +1169,16 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
                      npz = make_float2(-ta.z, -tb.z);
         float2 ax2 = make_float2(0.f, 0.f), ay2 = ax2, az2 = ax2;
         unsigned long long g_node = 0, g_part = 0;
-        int sp = (int)a.n_roots;  // stack size (uniform across the warp)
+        int sp = 1;    // stack size (uniform across the warp)
         int head = 0;  // ring position of the oldest list entry: 0 or 32 (uniform)
         int fill = 0;  // entries in the ring (uniform), < 32 between steps
         __syncwarp();
-        if (lane < sp) stack[lane] = a.roots[lane];
+        if (a.roots) {
+            sp = (int)a.n_roots;
+            for (int i = lane; i < sp; i += 32) stack[i] = a.roots[i];
+        } else if (lane == 0) {
+            stack[0] = 0;
+        }
         __syncwarp();
 
         auto flush_full = [&]() {  // evaluate the 32 oldest entries once they are ready
@@ -2158,8 +2166,8 @@ struct Ext64;
 struct ForestView {
     const NodeRec *nodes;
     const float4 *src;
+    const uint32_t *d_roots;  // device array
     uint32_t n_roots;
-    uint32_t roots[MAX_PARTS];
 };
 static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
                            const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
@@ -2299,12 +2307,12 @@ static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tg
     a.theta2 = theta * theta;
     a.eps2 = eps * eps;
     a.n_roots = 1;
-    for (int i = 0; i < MAX_PARTS; ++i) a.roots[i] = 0;
+    a.roots = nullptr;
     if (fv) {
         a.nodes = fv->nodes;
         a.src = fv->src;
         a.n_roots = fv->n_roots;
-        for (uint32_t i = 0; i < fv->n_roots; ++i) a.roots[i] = fv->roots[i];
+        a.roots = fv->d_roots;
     }
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
@@ -2437,15 +2445,11 @@ __global__ void __launch_bounds__(256) pick_owned_rows(const float *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// Key-range-partitioned build ("forest").  The replicated build costs every GPU
-// the whole sort + tree (2.3 ms at N = 10M) however many GPUs share the traversal.  Here the key
-// space is cut into `parts` ranges of about equal population and every part builds the tree of ITS
-// particles only — over the same root cube, with the same level / leaf rules — so a forest of
-// `parts` trees results, stored back to back.  Cells that straddle a range boundary exist in two
-// trees as partial cells, each with the centre of mass of its own particles: a walk that starts
-// from all roots therefore meets every particle exactly once, tests a partial cell with the
-// reference's own rule (sequential.rs:490-494: the cell's width against the distance to its
-// centre of mass) and theta = 0 still opens everything.  Nothing has to be merged or stitched.
+// Key-range-partitioned build.  The replicated build costs every GPU the whole
+// sort + tree (2.3 ms at N = 10M) however many GPUs share the traversal.  Here the key space is cut
+// into `parts` ranges of about equal population and every part builds the tree of ITS particles
+// only — over the same root cube, with the same level / leaf rules.  The per-part trees are stored
+// back to back and joined by a small TOP TREE:
 //
 //   1. keys of all particles in the common frame (replicated: 0.1 ms at N = 10M);
 //   2. splitters = quantiles of a regular sample of <= 65536 keys (sorted by every rank alike),
@@ -2455,7 +2459,22 @@ __global__ void __launch_bounds__(256) pick_owned_rows(const float *__restrict__
 //   4. exchange: node records and sort permutations are all-gathered into equal slots
 //      (child / particle indices rebased to the slot), the sources are re-gathered locally from the
 //      raw records that every rank already holds (cheaper than sending them once more);
-//   5. every rank walks the forest for the targets of its own key range.
+//   5. cells that straddle a range boundary exist in several parts as PARTIAL cells (each with the
+//      moments of its own particles).  On every level of a part only the first and the last node
+//      can be partial (nodes of a level are in key order), so at most 2 x 22 x parts cells are
+//      involved: their records, key prefixes, double-precision moments and children are brought to
+//      the host, partial cells with the same (level, prefix) are merged — moments added in part
+//      order, children = the complete children of every part plus the merged children — and the
+//      merged cells are appended to the node array as the top tree.  Where a part's share of a
+//      merged cell is a LEAF (<= leaf_size of the part's particles) that leaf becomes one more child
+//      of the merged cell, with the cell's own level (its particles may lie anywhere in the cell);
+//      a merged cell with more than 8 children keeps 7 and links the others behind a continuation
+//      node of its own level.  A walk from the top root meets every particle exactly once and sees
+//      the same cells, with the same centres of mass (up to the order of the f64 additions), as a
+//      walk of the single tree.  (Walking the per-part trees as a plain forest, partial cells and all, is
+//      also exact at theta = 0 but less accurate at theta > 0 — a half-empty cell has a large
+//      quadrupole: median error 6.8e-4 instead of 2.6e-4 at N = 2M, 8 parts.)
+//   6. every rank walks the joined tree for the targets of its own key range.
 struct PartRange {
     const uint64_t *keys;
     const uint64_t *split;
@@ -2507,7 +2526,7 @@ __global__ void __launch_bounds__(256) take_keys(const uint64_t *__restrict__ ke
     if (i < n) out[i] = keys[idx[i]];
 }
 
-// Local node records -> their slot of the forest: child links and particle ranges rebased.
+// Local node records -> their slot of the joined array: child links and particle ranges rebased.
 __global__ void __launch_bounds__(256) copy_rebase_nodes(const NodeRec *__restrict__ in, uint32_t n_nodes,
                                                          uint32_t node_base, uint32_t part_base,
                                                          NodeRec *__restrict__ out) {
@@ -2527,7 +2546,7 @@ __global__ void __launch_bounds__(256) copy_pad_perm(const uint32_t *__restrict_
     if (i < slot) out[i] = i < n ? in[i] : NO_PARTICLE;
 }
 
-// Sources of the whole forest in slot order, from the raw {x,y,z,mu} rows and the permutation slots.
+// Sources of all parts in slot order, from the raw {x,y,z,mu} rows and the permutation slots.
 __global__ void __launch_bounds__(256) gather_forest(const float4 *__restrict__ raw,
                                                      const uint32_t *__restrict__ perm, size_t n_slots,
                                                      float4 *__restrict__ sorted) {
@@ -2537,6 +2556,65 @@ __global__ void __launch_bounds__(256) gather_forest(const float4 *__restrict__ 
     if (o != NO_PARTICLE) sorted[i] = raw[o];
 }
 
+// What a part tells the others about its tree besides the node records: the level table and, for
+// the first and the last node of every level (the only possibly partial cells), the key prefix of
+// the cell and its double-precision moments {sum m x, sum m y, sum m z, sum m}.
+constexpr int TOP_LEVELS = Dims<3>::BITS + 1;  // 22
+struct PartPack {
+    uint32_t n_nodes, n_levels;
+    uint32_t level_begin[TOP_LEVELS + 2];
+    uint64_t prefix[TOP_LEVELS][2];
+    double mom[TOP_LEVELS][2][4];
+};
+
+__global__ void fill_pack(const NodeRec *__restrict__ nodes, const double *__restrict__ mom,
+                          const uint64_t *__restrict__ keys, const BuildState *__restrict__ st,
+                          uint32_t n_nodes, uint32_t n_levels, PartPack *__restrict__ out) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        out->n_nodes = n_nodes;
+        out->n_levels = n_levels;
+    }
+    if (t < TOP_LEVELS + 2) out->level_begin[t] = n_nodes ? st->level_begin[t] : 0u;
+    if (t < 2 * TOP_LEVELS) {
+        const int l = t >> 1, side = t & 1;
+        uint64_t pre = 0;
+        double m[4] = {0.0, 0.0, 0.0, 0.0};
+        if (n_nodes && l < (int)n_levels) {
+            const uint32_t idx = side ? st->level_begin[l + 1] - 1 : st->level_begin[l];
+            pre = keys[nodes[idx].begin] >> (3 * (Dims<3>::BITS - l));
+            for (int c = 0; c < 4; ++c) m[c] = mom[(size_t)idx * 4 + c];
+        }
+        out->prefix[l][side] = pre;
+        for (int c = 0; c < 4; ++c) out->mom[l][side][c] = m[c];
+    }
+}
+
+// Boundary nodes of every part and their children, from the joined (rebased) node array.
+struct BoundaryRec {
+    NodeRec node;
+    NodeRec child[8];
+};
+struct PartBases {
+    uint32_t node_base[MAX_PARTS];
+};
+
+__global__ void __launch_bounds__(2 * TOP_LEVELS * 9) collect_boundary(const NodeRec *__restrict__ nodes,
+                                                                       const PartPack *__restrict__ packs,
+                                                                       PartBases bases,
+                                                                       BoundaryRec *__restrict__ out) {
+    const int q = blockIdx.x;
+    const int t = threadIdx.x / 9, j = threadIdx.x % 9;  // t = (level, side), j = 0: node, 1..8: child
+    const int l = t >> 1, side = t & 1;
+    const PartPack &pk = packs[q];
+    if (pk.n_nodes == 0 || l >= (int)pk.n_levels) return;
+    const uint32_t local = side ? pk.level_begin[l + 1] - 1 : pk.level_begin[l];
+    const NodeRec nd = nodes[bases.node_base[q] + local];
+    BoundaryRec *o = out + ((size_t)q * TOP_LEVELS + l) * 2 + side;
+    if (j == 0) o->node = nd;
+    else if (j - 1 < (int)(nd.nchild_level & 0xffu)) o->child[j - 1] = nodes[nd.first_child + j - 1];
+}
+
 }  // namespace bh
 }  // namespace pcuda
 
@@ -2544,7 +2622,11 @@ struct pcuda_forest {
     pcuda_tree *local = nullptr;       // tree of this rank's (or the current part's) key range
     pcuda::DevBuf gkeys, gidx;         // keys of ALL particles in input order (+ identity scratch)
     pcuda::DevBuf sample[2], split, counts, sel_tmp, sel_count;
-    pcuda::DevBuf nodes, sorted, perm, keys, acc;  // the forest: equal slots per part
+    pcuda::DevBuf nodes, sorted, perm, keys, acc;  // the joined tree: equal slots per part (+ top tree)
+    pcuda::DevBuf packs, stage, roots;
+    pcuda::bh::PartPack *h_packs = nullptr;        // pinned
+    pcuda::bh::BoundaryRec *h_stage = nullptr;     // pinned
+    cudaEvent_t ev_stage = nullptr;
 };
 
 namespace pcuda {
@@ -2554,20 +2636,37 @@ void forest_free(pcuda_ctx *ctx) {
     if (!f) return;
     if (f->local) tree_free(ctx, f->local);
     DevBuf *bufs[] = {&f->gkeys, &f->gidx, &f->sample[0], &f->sample[1], &f->split, &f->counts,
-                      &f->sel_tmp, &f->sel_count, &f->nodes, &f->sorted, &f->perm, &f->keys, &f->acc};
+                      &f->sel_tmp, &f->sel_count, &f->nodes, &f->sorted, &f->perm, &f->keys, &f->acc,
+                      &f->packs, &f->stage, &f->roots};
     for (DevBuf *b : bufs) b->release();
+    if (f->h_packs) cudaFreeHost(f->h_packs);
+    if (f->h_stage) cudaFreeHost(f->h_stage);
+    if (f->ev_stage) cudaEventDestroy(f->ev_stage);
     delete f;
     ctx->forest = nullptr;
 }
 
 namespace bh {
 
-static pcuda_forest *forest_of(pcuda_ctx *ctx) {
+constexpr size_t TOP_CAP = 4096;  // top-tree nodes: <= 1 + 8 * 22 * MAX_PARTS
+
+static int forest_of(pcuda_ctx *ctx, pcuda_forest **out) {
     if (!ctx->forest) {
-        ctx->forest = new pcuda_forest();
-        ctx->forest->local = new pcuda_tree();
+        pcuda_forest *f = new pcuda_forest();
+        f->local = new pcuda_tree();
+        ctx->forest = f;
     }
-    return ctx->forest;
+    pcuda_forest *f = ctx->forest;
+    if (!f->h_packs) PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&f->h_packs, MAX_PARTS * sizeof(PartPack), cudaHostAllocDefault));
+    if (!f->h_stage)
+        PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&f->h_stage, MAX_PARTS * TOP_LEVELS * 2 * sizeof(BoundaryRec),
+                                          cudaHostAllocDefault));
+    if (!f->ev_stage) PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->ev_stage, cudaEventDisableTiming));
+    PCUDA_CUDA_TRY(ctx, f->packs.ensure(MAX_PARTS * sizeof(PartPack)));
+    PCUDA_CUDA_TRY(ctx, f->stage.ensure(MAX_PARTS * TOP_LEVELS * 2 * sizeof(BoundaryRec)));
+    PCUDA_CUDA_TRY(ctx, f->roots.ensure(MAX_ROOTS * sizeof(uint32_t)));
+    *out = f;
+    return PCUDA_OK;
 }
 
 // Steps 1-2: frame, keys, splitters, populations (host copy in counts_h).  One synchronisation.
@@ -2604,45 +2703,256 @@ static int forest_partition(pcuda_ctx *ctx, pcuda_forest *f, const float *d_part
     return PCUDA_OK;
 }
 
-// Step 3 for part q (population `count`): f->local becomes the tree of the part's particles.
-// `slot` >= count: capacity the key / permutation buffers must have.
+// Step 3 for part q (population `count`): f->local becomes the tree of the part's particles and
+// the part's pack is written to d_pack.  `slot` >= count: capacity of the key / permutation buffers.
 static int forest_build_part(pcuda_ctx *ctx, pcuda_forest *f, const float *d_particles, size_t n, int q,
-                             size_t count, size_t slot) {
+                             size_t count, size_t slot, PartPack *d_pack) {
     cudaStream_t st = ctx->stream;
     pcuda_tree *t = f->local;
     tree_reset<3>(ctx, t, count);
-    if (count == 0) return PCUDA_OK;
-    for (int i = 0; i < 2; ++i) {
-        PCUDA_CUDA_TRY(ctx, t->keys[i].ensure(slot * sizeof(uint64_t)));
-        PCUDA_CUDA_TRY(ctx, t->perm[i].ensure(slot * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, t->scan_in.ensure(sizeof(BuildState)));
+    if (count) {
+        for (int i = 0; i < 2; ++i) {
+            PCUDA_CUDA_TRY(ctx, t->keys[i].ensure(slot * sizeof(uint64_t)));
+            PCUDA_CUDA_TRY(ctx, t->perm[i].ensure(slot * sizeof(uint32_t)));
+        }
+        PCUDA_CUDA_TRY(ctx, f->sel_count.ensure(sizeof(uint32_t)));
+        PartRange in_part{f->gkeys.as<uint64_t>(), f->split.as<uint64_t>(), q};
+        cub::CountingInputIterator<uint32_t> all(0u);
+        size_t tmp = 0;
+        PCUDA_CUDA_TRY(ctx, cub::DeviceSelect::If(nullptr, tmp, all, t->perm[0].as<uint32_t>(),
+                                                  f->sel_count.as<uint32_t>(), (int)n, in_part, st));
+        PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
+        PCUDA_CUDA_TRY(ctx, cub::DeviceSelect::If(f->sel_tmp.p, tmp, all, t->perm[0].as<uint32_t>(),
+                                                  f->sel_count.as<uint32_t>(), (int)n, in_part, st));
+        take_keys<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
+            f->gkeys.as<uint64_t>(), t->perm[0].as<uint32_t>(), (int)count, t->keys[0].as<uint64_t>());
+        cub::DoubleBuffer<uint64_t> kb(t->keys[0].as<uint64_t>(), t->keys[1].as<uint64_t>());
+        cub::DoubleBuffer<uint32_t> vb(t->perm[0].as<uint32_t>(), t->perm[1].as<uint32_t>());
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)count, 0, 63, st));
+        PCUDA_CUDA_TRY(ctx, t->cub_tmp.ensure(tmp));
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(t->cub_tmp.p, tmp, kb, vb, (int)count, 0, 63, st));
+        t->cur = kb.selector;
+        PCUDA_CUDA_TRY(ctx, t->sorted.ensure(count * sizeof(float4)));
+        gather_kernel<3><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_particles, 4, true, (int)count,
+                                                                          t->d_perm(), t->sorted.as<float4>());
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 2 + 1 + 9 + 1;
+        PCUDA_TRY(build_levels<3>(ctx, t, count));
     }
-    PCUDA_CUDA_TRY(ctx, f->sel_count.ensure(sizeof(uint32_t)));
-    PartRange in_part{f->gkeys.as<uint64_t>(), f->split.as<uint64_t>(), q};
-    cub::CountingInputIterator<uint32_t> all(0u);
-    size_t tmp = 0;
-    PCUDA_CUDA_TRY(ctx, cub::DeviceSelect::If(nullptr, tmp, all, t->perm[0].as<uint32_t>(),
-                                              f->sel_count.as<uint32_t>(), (int)n, in_part, st));
-    PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
-    PCUDA_CUDA_TRY(ctx, cub::DeviceSelect::If(f->sel_tmp.p, tmp, all, t->perm[0].as<uint32_t>(),
-                                              f->sel_count.as<uint32_t>(), (int)n, in_part, st));
-    take_keys<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
-        f->gkeys.as<uint64_t>(), t->perm[0].as<uint32_t>(), (int)count, t->keys[0].as<uint64_t>());
-    cub::DoubleBuffer<uint64_t> kb(t->keys[0].as<uint64_t>(), t->keys[1].as<uint64_t>());
-    cub::DoubleBuffer<uint32_t> vb(t->perm[0].as<uint32_t>(), t->perm[1].as<uint32_t>());
-    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)count, 0, 63, st));
-    PCUDA_CUDA_TRY(ctx, t->cub_tmp.ensure(tmp));
-    PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(t->cub_tmp.p, tmp, kb, vb, (int)count, 0, 63, st));
-    t->cur = kb.selector;
-    PCUDA_CUDA_TRY(ctx, t->sorted.ensure(count * sizeof(float4)));
-    gather_kernel<3><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_particles, 4, true, (int)count,
-                                                                      t->d_perm(), t->sorted.as<float4>());
+    fill_pack<<<1, 64, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(), count ? t->d_keys() : nullptr,
+                                t->scan_in.as<BuildState>(), (uint32_t)t->n_nodes, (uint32_t)t->n_levels, d_pack);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 2 + 1 + 9 + 1;
-    return build_levels<3>(ctx, t, count);
+    ctx->launches++;
+    return PCUDA_OK;
 }
 
-// Diagnostic / test entry (one GPU): the forest of `parts` trees is built part after part and
-// walked for all particles; out rows are in input order.  parts == 1 is the ordinary tree.
+// Step 5 on the host.  packs / stage: every part's pack and boundary records (stage indexed
+// [part][level][side]); node_base: first node of every part in the joined array; top_base: where
+// the top tree goes.  Out: the top-tree nodes and the start nodes of the walk.
+static int merge_top_tree(pcuda_ctx *ctx, int parts, const PartPack *packs, const BoundaryRec *stage,
+                          const uint32_t *node_base, uint32_t top_base, std::vector<NodeRec> &top,
+                          std::vector<uint32_t> &roots) {
+    struct Inst {
+        int q, l, side;
+        uint32_t gi;
+        const BoundaryRec *b;
+    };
+    struct Cell {  // a (level, prefix) that occurs as a boundary node
+        int l;
+        uint64_t prefix;
+        std::vector<int> inst;  // indices into `insts`, in part order
+    };
+    std::vector<Inst> insts;
+    std::vector<Cell> cells;
+    top.clear();
+    roots.clear();
+    std::map<std::pair<int, uint64_t>, int> cell_index;  // (level, prefix) -> cells[]
+    std::map<uint32_t, int> inst_index;                  // joined node index -> insts[]
+    auto find_cell = [&](int l, uint64_t prefix) -> int {
+        auto it = cell_index.find({l, prefix});
+        return it == cell_index.end() ? -1 : it->second;
+    };
+    int nonempty = 0, last_nonempty = -1;
+    for (int q = 0; q < parts; ++q) {
+        const PartPack &pk = packs[q];
+        if (pk.n_nodes == 0) continue;
+        ++nonempty;
+        last_nonempty = q;
+        if (pk.n_levels > (uint32_t)TOP_LEVELS) return fail(ctx, PCUDA_ERR_CUDA, "part %d reports %u levels", q, pk.n_levels);
+        for (int l = 0; l < (int)pk.n_levels; ++l) {
+            const uint32_t lb = pk.level_begin[l], le = pk.level_begin[l + 1];
+            for (int side = 0; side < 2; ++side) {
+                if (side == 1 && le - lb == 1) continue;  // one node on the level: first == last
+                Inst in;
+                in.q = q;
+                in.l = l;
+                in.side = side;
+                in.gi = node_base[q] + (side ? le - 1 : lb);
+                in.b = stage + ((size_t)q * TOP_LEVELS + l) * 2 + side;
+                int c = find_cell(l, pk.prefix[l][side]);
+                if (c < 0) {
+                    Cell nc;
+                    nc.l = l;
+                    nc.prefix = pk.prefix[l][side];
+                    cells.push_back(nc);
+                    c = (int)cells.size() - 1;
+                    cell_index[{l, nc.prefix}] = c;
+                }
+                cells[c].inst.push_back((int)insts.size());
+                inst_index[in.gi] = (int)insts.size();
+                insts.push_back(in);
+            }
+        }
+    }
+    if (nonempty == 0) return PCUDA_OK;
+    if (nonempty == 1) {
+        roots.push_back(node_base[last_nonempty]);
+        return PCUDA_OK;
+    }
+    auto merged = [&](int c) { return cells[c].inst.size() >= 2; };
+    // boundary node -> its cell (to recognise children that are themselves merged)
+    auto cell_of_node = [&](uint32_t gi, int l) -> int {
+        auto it = inst_index.find(gi);
+        if (it == inst_index.end()) return -1;
+        const Inst &in = insts[it->second];
+        return find_cell(l, packs[in.q].prefix[in.l][in.side]);
+    };
+    const int root_cell = find_cell(0, 0);
+    if (root_cell < 0 || !merged(root_cell)) return fail(ctx, PCUDA_ERR_CUDA, "top tree: the root cell is not shared");
+    auto record_of = [&](int c) {  // merged cell: moments added in part order
+        double m[4] = {0.0, 0.0, 0.0, 0.0};
+        uint32_t count = 0;
+        for (int ii : cells[c].inst) {
+            const Inst &in = insts[ii];
+            for (int k = 0; k < 4; ++k) m[k] += packs[in.q].mom[in.l][in.side][k];
+            count += in.b->node.count;
+        }
+        const NodeRec &first = insts[cells[c].inst[0]].b->node;
+        NodeRec r;
+        if (m[3] == 0.0) r.cm = make_float4(first.cm.x, first.cm.y, first.cm.z, 0.f);
+        else r.cm = make_float4((float)(m[0] / m[3]), (float)(m[1] / m[3]), (float)(m[2] / m[3]), (float)m[3]);
+        r.first_child = 0;
+        r.nchild_level = (uint32_t)cells[c].l << 8;
+        r.begin = first.begin;
+        r.count = count;
+        return r;
+    };
+    // A node of the top tree that still needs its children written: a merged cell (cell >= 0) or a
+    // continuation node (a merged cell with more than 8 children keeps 7 and links the rest).
+    struct Kid {
+        NodeRec rec;
+        int cell;  // >= 0: merged cell to expand
+    };
+    struct Pending {
+        uint32_t me;
+        int level;
+        std::vector<Kid> kids;
+    };
+    auto kids_of_cell = [&](int c) {
+        std::vector<Kid> kids;
+        std::vector<int> listed;
+        for (int ii : cells[c].inst) {
+            const Inst &in = insts[ii];
+            const uint32_t nc = in.b->node.nchild_level & 0xffu;
+            if (nc == 0) {  // this part's share of the cell is a leaf: a child leaf of the cell's own level
+                kids.push_back({in.b->node, -1});
+                continue;
+            }
+            for (uint32_t j = 0; j < nc; ++j) {
+                const int cc = cell_of_node(in.b->node.first_child + j, in.l + 1);
+                if (cc >= 0 && merged(cc)) {
+                    bool seen = false;
+                    for (int k : listed) seen |= k == cc;
+                    if (seen) continue;
+                    listed.push_back(cc);
+                    kids.push_back({record_of(cc), cc});
+                } else {
+                    kids.push_back({in.b->child[j], -1});  // complete cell: its subtree stays in its part
+                }
+            }
+        }
+        return kids;
+    };
+    std::vector<Pending> queue;
+    top.push_back(record_of(root_cell));
+    queue.push_back({0u, 0, kids_of_cell(root_cell)});
+    for (size_t h = 0; h < queue.size(); ++h) {
+        Pending cur = queue[h];  // copy: the queue grows below
+        std::vector<Kid> rest;
+        if (cur.kids.size() > 8) {  // keep 7, chain the rest behind a continuation node of the same level
+            rest.assign(cur.kids.begin() + 7, cur.kids.end());
+            cur.kids.resize(7);
+            double m[4] = {0.0, 0.0, 0.0, 0.0};
+            uint32_t count = 0;
+            for (const Kid &k : rest) {
+                const double w = (double)k.rec.cm.w;
+                m[0] += w * (double)k.rec.cm.x;
+                m[1] += w * (double)k.rec.cm.y;
+                m[2] += w * (double)k.rec.cm.z;
+                m[3] += w;
+                count += k.rec.count;
+            }
+            NodeRec r;
+            if (m[3] == 0.0) r.cm = make_float4(rest[0].rec.cm.x, rest[0].rec.cm.y, rest[0].rec.cm.z, 0.f);
+            else r.cm = make_float4((float)(m[0] / m[3]), (float)(m[1] / m[3]), (float)(m[2] / m[3]), (float)m[3]);
+            r.first_child = 0;
+            r.nchild_level = (uint32_t)cur.level << 8;
+            r.begin = rest[0].rec.begin;
+            r.count = count;
+            cur.kids.push_back({r, -2});
+        }
+        if (cur.kids.empty()) return fail(ctx, PCUDA_ERR_CUDA, "top tree: cell without children");
+        const uint32_t first_child = (uint32_t)top.size();
+        for (const Kid &k : cur.kids) {
+            const uint32_t idx = (uint32_t)top.size();
+            top.push_back(k.rec);
+            if (k.cell >= 0) queue.push_back({idx, cells[k.cell].l, kids_of_cell(k.cell)});
+            else if (k.cell == -2) queue.push_back({idx, cur.level, rest});
+        }
+        top[cur.me].first_child = top_base + first_child;
+        top[cur.me].nchild_level = (uint32_t)cur.level << 8 | (uint32_t)cur.kids.size();
+        if (top.size() > TOP_CAP) return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "top tree has %zu nodes", top.size());
+    }
+    roots.push_back(top_base);
+    return PCUDA_OK;
+}
+
+// Steps 5-6 glue: boundary records -> host, merge, top tree + start nodes -> device.  `between`
+// is enqueued after the boundary copy and overlaps the host merge.
+template <class Between>
+static int join_parts(pcuda_ctx *ctx, pcuda_forest *f, int parts, const uint32_t *node_base,
+                      uint32_t top_base, Between between, ForestView *fv) {
+    cudaStream_t st = ctx->stream;
+    PartBases bases{};
+    for (int q = 0; q < parts; ++q) bases.node_base[q] = node_base[q];
+    collect_boundary<<<parts, 2 * TOP_LEVELS * 9, 0, st>>>(f->nodes.as<NodeRec>(), f->packs.as<PartPack>(),
+                                                            bases, f->stage.as<BoundaryRec>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_stage, f->stage.p, (size_t)parts * TOP_LEVELS * 2 * sizeof(BoundaryRec),
+                                        cudaMemcpyDeviceToHost, st));
+    PCUDA_CUDA_TRY(ctx, cudaEventRecord(f->ev_stage, st));
+    PCUDA_TRY(between());
+    PCUDA_CUDA_TRY(ctx, cudaEventSynchronize(f->ev_stage));
+    std::vector<NodeRec> top;
+    std::vector<uint32_t> roots;
+    PCUDA_TRY(merge_top_tree(ctx, parts, f->h_packs, f->h_stage, node_base, top_base, top, roots));
+    if (!top.empty())
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->nodes.as<NodeRec>() + top_base, top.data(), top.size() * sizeof(NodeRec),
+                                            cudaMemcpyHostToDevice, st));
+    if (!roots.empty())
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->roots.p, roots.data(), roots.size() * sizeof(uint32_t),
+                                            cudaMemcpyHostToDevice, st));
+    fv->nodes = f->nodes.as<NodeRec>();
+    fv->src = f->sorted.as<float4>();
+    fv->d_roots = f->roots.as<uint32_t>();
+    fv->n_roots = (uint32_t)roots.size();
+    return PCUDA_OK;
+}
+
+// Diagnostic / test entry (one GPU): the parts are built one after the other ("virtual ranks"),
+// joined and walked for all particles; out rows are in input order.  parts == 1 is the ordinary tree.
 static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, int parts, float theta,
                            float eps, float *d_out) {
     if (parts < 1 || parts > MAX_PARTS)
@@ -2650,9 +2960,12 @@ static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, i
     if (n > 0x7fffffffull) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
     if (ctx->order == 2)
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "the partitioned build carries centre-of-mass nodes only");
+    if (g_tpl != 2 || g_variant)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "the partitioned build is walked by traverse2_kernel only");
     if (n == 0) return PCUDA_OK;
     cudaStream_t st = ctx->stream;
-    pcuda_forest *f = forest_of(ctx);
+    pcuda_forest *f = nullptr;
+    PCUDA_TRY(forest_of(ctx, &f));
     uint32_t counts[MAX_PARTS] = {0};
     phase_begin(ctx, PH_BUILD);
     PCUDA_TRY(forest_partition(ctx, f, d_particles, n, parts, counts));
@@ -2665,26 +2978,27 @@ static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, i
     PCUDA_CUDA_TRY(ctx, f->sorted.ensure((size_t)parts * slot * sizeof(float4)));
     PCUDA_CUDA_TRY(ctx, f->perm.ensure((size_t)parts * slot * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, f->keys.ensure((size_t)parts * slot * sizeof(uint64_t)));
-    ForestView fv{};
-    size_t node_base = 0;
+    uint32_t node_base[MAX_PARTS] = {0};
+    size_t next = 0;
     for (int q = 0; q < parts; ++q) {
-        PCUDA_TRY(forest_build_part(ctx, f, d_particles, n, q, counts[q], slot));
+        PCUDA_TRY(forest_build_part(ctx, f, d_particles, n, q, counts[q], slot, f->packs.as<PartPack>() + q));
+        node_base[q] = (uint32_t)next;
         if (counts[q] == 0) continue;
         const pcuda_tree *t = f->local;
-        const size_t need = (node_base + t->n_nodes) * sizeof(NodeRec);
+        const size_t need = (next + t->n_nodes + TOP_CAP) * sizeof(NodeRec);
         if (need > f->nodes.cap) {  // grow, keeping the parts already placed
             DevBuf bigger;
-            PCUDA_CUDA_TRY(ctx, bigger.ensure(std::max(need, (size_t)parts * t->n_nodes * sizeof(NodeRec))));
-            if (node_base)
-                PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(bigger.p, f->nodes.p, node_base * sizeof(NodeRec),
+            PCUDA_CUDA_TRY(ctx, bigger.ensure(std::max(need, ((size_t)parts * t->n_nodes + TOP_CAP) * sizeof(NodeRec))));
+            if (next)
+                PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(bigger.p, f->nodes.p, next * sizeof(NodeRec),
                                                     cudaMemcpyDeviceToDevice, st));
             PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
             f->nodes.release();
             f->nodes = bigger;
         }
         copy_rebase_nodes<<<(unsigned)((t->n_nodes + 255) / 256), 256, 0, st>>>(
-            t->nodes.as<NodeRec>(), (uint32_t)t->n_nodes, (uint32_t)node_base, (uint32_t)(q * slot),
-            f->nodes.as<NodeRec>() + node_base);
+            t->nodes.as<NodeRec>(), (uint32_t)t->n_nodes, (uint32_t)next, (uint32_t)(q * slot),
+            f->nodes.as<NodeRec>() + next);
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->sorted.as<float4>() + q * slot, t->sorted.p,
@@ -2693,12 +3007,12 @@ static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, i
                                             counts[q] * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->keys.as<uint64_t>() + q * slot, t->d_keys(),
                                             counts[q] * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-        fv.roots[fv.n_roots++] = (uint32_t)node_base;
-        node_base += t->n_nodes;
+        next += t->n_nodes;
     }
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_packs, f->packs.p, parts * sizeof(PartPack), cudaMemcpyDeviceToHost, st));
+    ForestView fv{};
+    PCUDA_TRY(join_parts(ctx, f, parts, node_base, (uint32_t)next, [] { return (int)PCUDA_OK; }, &fv));
     phase_end(ctx, PH_BUILD);
-    fv.nodes = f->nodes.as<NodeRec>();
-    fv.src = f->sorted.as<float4>();
     phase_begin(ctx, PH_COMPUTE);
     for (int q = 0; q < parts; ++q) {
         if (counts[q] == 0) continue;
@@ -2713,12 +3027,13 @@ static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, i
 static int g_forest = 0;  // multi-GPU Barnes-Hut: 0 = as the context flag says, 1 = partitioned, 2 = replicated
 
 // Multi-GPU step with the partitioned build: d_gathered already holds all n_total records.  Rank r
-// builds the tree of the r-th key range, the trees are exchanged, and rank r walks the forest for
-// the targets of its own range.  Same result routing as the replicated path.
+// builds the tree of the r-th key range, the trees are exchanged and joined, and rank r walks the
+// result for the targets of its own range.  Same result routing as the replicated path.
 static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, size_t lo, size_t hi,
                               float theta, float eps, const float *d_gathered, float *d_out) {
     cudaStream_t st = ctx->stream;
-    pcuda_forest *f = forest_of(ctx);
+    pcuda_forest *f = nullptr;
+    PCUDA_TRY(forest_of(ctx, &f));
     uint32_t counts[MAX_PARTS] = {0};
     phase_begin(ctx, PH_BUILD);
     PCUDA_TRY(forest_partition(ctx, f, d_gathered, n_total, world, counts));
@@ -2730,24 +3045,24 @@ static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_tota
     if (total != n_total)
         return fail(ctx, PCUDA_ERR_CUDA, "partition lost particles (%zu of %zu)", total, n_total);
     const size_t mine = counts[rank];
-    PCUDA_TRY(forest_build_part(ctx, f, d_gathered, n_total, rank, mine, slot));
+    PartPack *d_packs = f->packs.as<PartPack>();
+    PCUDA_TRY(forest_build_part(ctx, f, d_gathered, n_total, rank, mine, slot, d_packs + rank));
     phase_end(ctx, PH_BUILD);
     const pcuda_tree *t = f->local;
 
-    // exchange: node counts -> common slot size; nodes and permutations into equal slots
+    // exchange: packs (node counts, level tables, boundary moments) -> common slot size; node
+    // records and permutations into equal slots
     phase_begin(ctx, PH_COMM3);
-    uint32_t *d_nn = f->counts.as<uint32_t>();  // reused: the populations are on the host now
-    const uint32_t my_nodes = (uint32_t)t->n_nodes;
-    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(d_nn + rank, &my_nodes, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_nn + rank, d_nn, sizeof(uint32_t)));
-    uint32_t n_nodes[MAX_PARTS] = {0};
-    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(n_nodes, d_nn, world * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_packs + rank, d_packs, sizeof(PartPack)));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_packs, d_packs, world * sizeof(PartPack), cudaMemcpyDeviceToHost, st));
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     size_t node_slot = 1;
-    for (int q = 0; q < world; ++q) node_slot = std::max<size_t>(node_slot, n_nodes[q]);
-    if ((size_t)world * node_slot > 0xfffffff0ull || (size_t)world * slot > 0xfffffff0ull)
-        return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "forest does not fit 32-bit indices");
-    PCUDA_CUDA_TRY(ctx, f->nodes.ensure((size_t)world * node_slot * sizeof(NodeRec)));
+    for (int q = 0; q < world; ++q) node_slot = std::max<size_t>(node_slot, f->h_packs[q].n_nodes);
+    if ((size_t)world * node_slot + TOP_CAP > 0xfffffff0ull || (size_t)world * slot > 0xfffffff0ull)
+        return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "joined tree does not fit 32-bit indices");
+    const uint32_t my_nodes = (uint32_t)t->n_nodes;
+    if (f->h_packs[rank].n_nodes != my_nodes) return fail(ctx, PCUDA_ERR_CUDA, "pack exchange is inconsistent");
+    PCUDA_CUDA_TRY(ctx, f->nodes.ensure(((size_t)world * node_slot + TOP_CAP) * sizeof(NodeRec)));
     PCUDA_CUDA_TRY(ctx, f->perm.ensure((size_t)world * slot * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, f->sorted.ensure((size_t)world * slot * sizeof(float4)));
     PCUDA_CUDA_TRY(ctx, f->acc.ensure((size_t)world * slot * 3 * sizeof(float)));
@@ -2764,17 +3079,22 @@ static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_tota
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, my_node_slot, f->nodes.p, node_slot * sizeof(NodeRec)));
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, my_perm_slot, f->perm.p, slot * sizeof(uint32_t)));
     const size_t n_slots = (size_t)world * slot;
-    gather_forest<<<(unsigned)((n_slots + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const float4 *>(d_gathered), f->perm.as<uint32_t>(), n_slots, f->sorted.as<float4>());
-    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches++;
+    uint32_t node_base[MAX_PARTS] = {0};
+    for (int q = 0; q < world; ++q) node_base[q] = (uint32_t)(q * node_slot);
+    ForestView fv{};
+    PCUDA_TRY(join_parts(
+        ctx, f, world, node_base, (uint32_t)(world * node_slot),
+        [&]() -> int {  // overlaps the host merge
+            gather_forest<<<(unsigned)((n_slots + 255) / 256), 256, 0, st>>>(
+                reinterpret_cast<const float4 *>(d_gathered), f->perm.as<uint32_t>(), n_slots,
+                f->sorted.as<float4>());
+            PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+            return PCUDA_OK;
+        },
+        &fv));
     phase_end(ctx, PH_COMM3);
 
-    ForestView fv{};
-    fv.nodes = f->nodes.as<NodeRec>();
-    fv.src = f->sorted.as<float4>();
-    for (int q = 0; q < world; ++q)
-        if (n_nodes[q]) fv.roots[fv.n_roots++] = (uint32_t)(q * node_slot);
     float *acc = f->acc.as<float>();
     phase_begin(ctx, PH_COMPUTE);
     if (mine)

@@ -322,7 +322,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bruteforce", choices=["bruteforce", "barneshut", "split"])
-    ap.add_argument("--n", type=int, default=0, help="particle count (default: BASELINE config)")
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=0,
+                    help="particle count (default: BASELINE config); use --particles under torchrun, "
+                         "whose own parser rejects the abbreviation --n")
     ap.add_argument("--theta", type=float, default=0.5)
     ap.add_argument("--bh-build", default="replicated", choices=["replicated", "partitioned"],
                     help="multi-GPU Barnes-Hut: every GPU builds the whole tree, or one tree per GPU "

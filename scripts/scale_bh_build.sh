@@ -9,7 +9,7 @@ for n in $2; do
     port=$((port+1))
     log=gpurun_out/${tag}_${b}_${n}_x${w}.log
     timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 \
-      --master-port $port bench.py --gpus $w --workload barneshut --n $n --bh-build $b --no-extra \
+      --master-port $port bench.py --gpus $w --workload barneshut --particles $n --bh-build $b --no-extra \
       --steps 5 --warmup 3 > $log 2>&1
     echo "== $b N=$n x$w rc=$?"
     grep -h '^{' $log | python -c "

@@ -326,9 +326,10 @@ def main():
                     help="particle count (default: BASELINE config); use --particles under torchrun, "
                          "whose own parser rejects the abbreviation --n")
     ap.add_argument("--theta", type=float, default=0.5)
-    ap.add_argument("--bh-build", default="replicated", choices=["replicated", "partitioned"],
+    ap.add_argument("--bh-build", default="auto", choices=["auto", "replicated", "partitioned"],
                     help="multi-GPU Barnes-Hut: every GPU builds the whole tree, or one tree per GPU "
-                         "over its key range walked as a forest (PCUDA_FLAG_BH_PARTITIONED_BUILD)")
+                         "over its key range joined by a top tree (PCUDA_FLAG_BH_PARTITIONED_BUILD); "
+                         "auto = the library's default: partitioned from 4 GPUs on")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the cpu_baseline leg and the ride-along Barnes-Hut number")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -417,9 +418,12 @@ def bruteforce_config(n, world, where):
                   "is re-read from L2 by design" if where == "gpu" else "n/a"}
 
 
-def barneshut_config(n, world, theta, where, build="replicated"):
+def barneshut_config(n, world, theta, where, build="auto"):
+    if build == "auto":
+        build = "partitioned" if world >= 4 else "replicated"
     how = ("tree build replicated" if build == "replicated" else
-           "one tree per GPU over its key range (partitioned build), trees all-gathered, forest walk")
+           "one tree per GPU over its key range (partitioned build), trees all-gathered and joined "
+           "by a top tree")
     return {"workload": f"Barnes-Hut 3-D f32 octree, theta={theta}, N={n} Plummer sphere (a=1, "
                         f"r<50a, equal mu=1/N, seed {SEED}); tree rebuilt every step "
                         f"(BASELINE configs[3]); Acceleration::checked()",
@@ -569,6 +573,14 @@ def bench_bruteforce(args, n, rank, world, local_rank):
             line["other_configs"] = other_configs(ctx, stream, flush)
         except Exception as e:
             line["other_configs"] = {"error": repr(e)}
+    if world > 1 and not args.no_extra:
+        # BASELINE configs[3] at this world size rides along (collective: every rank takes part)
+        try:
+            bh = barneshut_numbers(args, ctx, stream, flush, 10_000_000, args.theta, steps=3, warmup=2,
+                                   cpu_seconds=0.0, rank=rank, world=world, dist=dist, init_comm=False)
+            line["barnes_hut"] = bh
+        except Exception as e:
+            line["barnes_hut"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -685,7 +697,7 @@ def bench_split(args, n_massless, rank, world, local_rank):
 
 
 def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_seconds, rank=0,
-                      world=1, dist=None):
+                      world=1, dist=None, init_comm=True):
     """Barnes-Hut: device-resident particles/s (tree rebuilt + traversal every step), e2e through
     the host API, work counters, CPU restatement beside it.  world > 1: every rank owns a block of
     the particles, all-gathers the records, builds the identical tree and traverses its block."""
@@ -703,7 +715,8 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
         d_out = torch.empty((n, 3), dtype=torch.float32, device=dev)
         dev_step = lambda: bh.compute_device(None, n, d_src.data_ptr(), n, d_out.data_ptr())  # noqa: E731
     else:
-        bh = pb.ShardedBarnesHut(ctx, theta, inter)
+        bh = pb.ShardedBarnesHut(ctx, theta, inter, init_comm=init_comm)  # False: the context's
+        bh.world, bh.rank = world, rank                                   # communicator exists already
         d_src = torch.from_numpy(P[lo:hi]).to(dev)
         dev_step = lambda: bh.step_device(d_src, n)  # noqa: E731
 
@@ -797,7 +810,8 @@ def bench_barneshut(args, n, rank, world, local_rank):
     import particular_b200 as pb
     dist = _dist_setup(world, local_rank)
     dev = torch.device("cuda", local_rank)
-    ctx = pb.CudaContext(local_rank, partitioned_build=args.bh_build == "partitioned")
+    ctx = pb.CudaContext(local_rank, partitioned_build={"auto": None, "partitioned": True,
+                                                        "replicated": False}[args.bh_build])
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local_rank)

@@ -73,10 +73,13 @@ typedef struct pcuda_config {
 /* Do not record the per-phase CUDA events (pcuda_timings then reports only kernel_launches): saves
  * ~10 us per call, which matters at the reference's criterion sizes (N <= 65536). */
 #define PCUDA_FLAG_NO_PHASE_TIMINGS 1u
-/* Multi-GPU Barnes-Hut (pcuda_barneshut_f32x3_sharded*): build the tree partitioned by key range
- * (every GPU sorts and builds only its share of the particles, the per-GPU trees are exchanged and
- * walked as a forest) instead of replicating the whole build on every GPU.  SURVEY.md 8e "v3". */
+/* Multi-GPU Barnes-Hut (pcuda_barneshut_f32x3_sharded*): how the tree is built.
+ * PARTITIONED: every GPU sorts and builds only the tree of its own key range, the per-GPU trees
+ * are exchanged and joined by a small top tree (SURVEY.md 8e "v3").  REPLICATED: every GPU builds
+ * the whole tree (8e "v1").  Neither flag: partitioned from 4 GPUs on (measured on 8 B200s,
+ * N = 10M: 5.8 ms against 6.4 ms per step; N = 80M: 39.7 against 44.6 ms; equal at 2 GPUs). */
 #define PCUDA_FLAG_BH_PARTITIONED_BUILD 2u
+#define PCUDA_FLAG_BH_REPLICATED_BUILD 4u
 
 /* Per-phase device times of the LAST call on the context, in milliseconds (CUDA events on the
  * context stream).  Phases that did not run are 0.  Replaces nothing in the reference (it has no
@@ -307,13 +310,14 @@ int pcuda_barneshut_f32x3_sharded(pcuda_ctx *ctx, const float *local_xyzm, size_
                                   size_t n_total, float theta, float softening, int checked,
                                   float *out_xyz);
 
-/* Partitioned build (PCUDA_FLAG_BH_PARTITIONED_BUILD): with the flag set the sharded entry points
- * above cut the key space into world_size ranges of about equal population (quantiles of a regular
- * sample of the keys, the same on every rank), rank r selects, sorts and builds the tree of the
- * r-th range only — same root cube, same level and leaf rules — the node records and sort
- * permutations are all-gathered into equal slots, and every rank walks the resulting FOREST (one
- * root per rank; a cell straddling a range boundary exists in two trees as two partial cells, each
- * with the centre of mass of its own particles) for the targets of its own key range.
+/* Partitioned build (PCUDA_FLAG_BH_PARTITIONED_BUILD): the sharded entry points above cut the key
+ * space into world_size ranges of about equal population (quantiles of a regular sample of the
+ * keys, the same on every rank), rank r selects, sorts and builds the tree of the r-th range only —
+ * same root cube, same level and leaf rules — the node records and sort permutations are
+ * all-gathered into equal slots, the cells that straddle a range boundary (at most the first and
+ * the last node of every level of every part) are merged into a small top tree (moments added in
+ * double precision), and every rank walks the joined tree for the targets of its own key range:
+ * the same cells and centres of mass as the single tree, up to the order of the f64 additions.
  * The two entry points below run the same partition / per-part build / forest walk on ONE GPU,
  * part after part, for all particles ("virtual ranks"): the test vehicle of the multi-GPU path.
  * xyzm: n {x,y,z,mu} records; out: n accelerations in input order; 1 <= parts <= 16;

@@ -22,6 +22,7 @@ lib = C.CDLL(LIB_PATH)
 ABI_VERSION = 1
 FLAG_NO_PHASE_TIMINGS = 1
 FLAG_BH_PARTITIONED_BUILD = 2
+FLAG_BH_REPLICATED_BUILD = 4
 UNIQUE_ID_BYTES = 128
 
 OK = 0

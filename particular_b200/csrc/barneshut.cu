@@ -3024,7 +3024,7 @@ static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, i
     return PCUDA_OK;
 }
 
-static int g_forest = 0;  // multi-GPU Barnes-Hut: 0 = as the context flag says, 1 = partitioned, 2 = replicated
+static int g_forest = 0;  // multi-GPU Barnes-Hut build: 0 = as the context says, 1 = partitioned, 2 = replicated
 
 // Multi-GPU step with the partitioned build: d_gathered already holds all n_total records.  Rank r
 // builds the tree of the r-th key range, the trees are exchanged and joined, and rank r walks the
@@ -3130,7 +3130,8 @@ static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, siz
                                             ctx->stream));
     if (world > 1) PCUDA_TRY(pcuda_comm_allgather_dev(ctx, slot, d_gathered, cap * 16));
     phase_end(ctx, PH_COMM);
-    const bool forest = g_forest == 1 || (g_forest == 0 && ctx->bh_partitioned);
+    const int how = g_forest ? g_forest : ctx->bh_build;  // 0 = automatic: partitioned from 4 GPUs on
+    const bool forest = how == 1 || (how == 0 && world >= 4);
     if (forest && world > 1 && world <= MAX_PARTS && n_total >= (size_t)world && ctx->order == 1 &&
         g_tpl == 2 && !g_variant)
         return sharded_forest_dev(ctx, world, rank, n_total, lo, hi, theta, eps, d_gathered, d_out);

@@ -123,7 +123,10 @@ int pcuda_create(const pcuda_config *config, pcuda_ctx **out) {
     }
     if (config && config->expansion_order == 2) ctx->order = 2;
     ctx->phase_timings = !(config && (config->flags & PCUDA_FLAG_NO_PHASE_TIMINGS));
-    ctx->bh_partitioned = config && (config->flags & PCUDA_FLAG_BH_PARTITIONED_BUILD);
+    ctx->bh_build = !config ? 0
+                    : (config->flags & PCUDA_FLAG_BH_PARTITIONED_BUILD) ? 1
+                    : (config->flags & PCUDA_FLAG_BH_REPLICATED_BUILD)  ? 2
+                                                                        : 0;
     if (ctx->leaf_size > 32) ctx->leaf_size = 32;
 
     DeviceGuard guard(dev);

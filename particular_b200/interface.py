@@ -258,13 +258,16 @@ class CudaContext:
     gpu/mod.rs:150-151)."""
 
     def __init__(self, device: int = 0, leaf_size: int = 0, phase_timings: bool = True,
-                 expansion_order: int = 1, partitioned_build: bool = False):
+                 expansion_order: int = 1, partitioned_build: Optional[bool] = None):
         """phase_timings=False skips the per-phase CUDA events (PCUDA_FLAG_NO_PHASE_TIMINGS):
         about 10 us less per call; timings() then carries only kernel_launches.
-        partitioned_build=True (PCUDA_FLAG_BH_PARTITIONED_BUILD): multi-GPU Barnes-Hut builds one
-        tree per GPU over its key range and walks the forest instead of replicating the build."""
+        partitioned_build: multi-GPU Barnes-Hut tree build.  True (PCUDA_FLAG_BH_PARTITIONED_BUILD):
+        one tree per GPU over its key range, joined by a top tree; False
+        (PCUDA_FLAG_BH_REPLICATED_BUILD): every GPU builds the whole tree; None: partitioned from
+        4 GPUs on."""
         flags = (0 if phase_timings else _ffi.FLAG_NO_PHASE_TIMINGS) | \
-            (_ffi.FLAG_BH_PARTITIONED_BUILD if partitioned_build else 0)
+            (0 if partitioned_build is None else
+             _ffi.FLAG_BH_PARTITIONED_BUILD if partitioned_build else _ffi.FLAG_BH_REPLICATED_BUILD)
         cfg = _ffi.Config(device, flags, leaf_size, expansion_order)
         h = C.c_void_p()
         check(lib.pcuda_create(C.byref(cfg), C.byref(h)))

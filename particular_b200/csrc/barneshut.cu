@@ -2444,6 +2444,70 @@ __global__ void __launch_bounds__(256) pick_owned_rows(const float *__restrict__
     o[2] = acc_sorted[(size_t)i * 3 + 2];
 }
 
+// Routing of the per-range accelerations to the ranks that own the particles.  The all-gather
+// above moves 12 B x N to every rank although a rank needs only the rows of its own block; with
+// ncclSend / ncclRecv available each row (acceleration + original index, 16 B) is sent to its owner
+// only.  Before the traversal: owners counted per row, counts all-gathered (one synchronisation),
+// every row given a slot in an owner-bucketed send buffer; the traversal then writes straight into
+// that buffer (its row map is `pos`), and one variable all-to-all plus a scatter finish the step.
+struct OwnerOffsets {
+    uint32_t off[MAX_PARTS];
+};
+
+__global__ void __launch_bounds__(256) owner_hist(const uint32_t *__restrict__ idx, int n, uint32_t cap,
+                                                  uint32_t *__restrict__ cnt) {
+    __shared__ uint32_t s_cnt[MAX_PARTS];
+    if (threadIdx.x < MAX_PARTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&s_cnt[idx[i] / cap], 1u);
+    __syncthreads();
+    if (threadIdx.x < MAX_PARTS && s_cnt[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) owner_positions(const uint32_t *__restrict__ idx, int n, uint32_t cap,
+                                                       OwnerOffsets send_off, uint32_t *__restrict__ cursor,
+                                                       uint32_t *__restrict__ pos,
+                                                       uint32_t *__restrict__ idx_send) {
+    __shared__ uint32_t s_cnt[MAX_PARTS], s_base[MAX_PARTS];
+    if (threadIdx.x < MAX_PARTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t o = 0, mine = 0, orig = 0;
+    if (i < n) {
+        orig = idx[i];
+        o = orig / cap;
+        mine = atomicAdd(&s_cnt[o], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < MAX_PARTS && s_cnt[threadIdx.x])
+        s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (i < n) {
+        const uint32_t p = send_off.off[o] + s_base[o] + mine;
+        pos[i] = p;
+        idx_send[p] = orig;
+    }
+}
+
+__global__ void __launch_bounds__(256) scatter_rows(const float *__restrict__ acc,
+                                                    const uint32_t *__restrict__ idx, int n, uint32_t lo,
+                                                    float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float *o = out + (size_t)(idx[i] - lo) * 3;
+    o[0] = acc[(size_t)i * 3 + 0];
+    o[1] = acc[(size_t)i * 3 + 1];
+    o[2] = acc[(size_t)i * 3 + 2];
+}
+
+struct RoutePlan {
+    size_t send_off[MAX_PARTS], send_cnt[MAX_PARTS], recv_off[MAX_PARTS], recv_cnt[MAX_PARTS];
+    size_t n_rows = 0, n_recv = 0;
+    uint32_t *d_pos = nullptr;
+    float *d_acc_send = nullptr;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Key-range-partitioned build.  The replicated build costs every GPU the whole
 // sort + tree (2.3 ms at N = 10M) however many GPUs share the traversal.  Here the key space is cut
@@ -2624,6 +2688,8 @@ struct pcuda_forest {
     pcuda::DevBuf sample[2], split, counts, sel_tmp, sel_count;
     pcuda::DevBuf nodes, sorted, perm, keys, acc;  // the joined tree: equal slots per part (+ top tree)
     pcuda::DevBuf packs, stage, roots;
+    pcuda::DevBuf route_cnt, route_pos, route_idx_send, route_acc_send, route_idx_recv, route_acc_recv;
+    uint32_t *h_route = nullptr;                   // pinned: world x MAX_PARTS owner counts
     pcuda::bh::PartPack *h_packs = nullptr;        // pinned
     pcuda::bh::BoundaryRec *h_stage = nullptr;     // pinned
     cudaEvent_t ev_stage = nullptr;
@@ -2637,8 +2703,10 @@ void forest_free(pcuda_ctx *ctx) {
     if (f->local) tree_free(ctx, f->local);
     DevBuf *bufs[] = {&f->gkeys, &f->gidx, &f->sample[0], &f->sample[1], &f->split, &f->counts,
                       &f->sel_tmp, &f->sel_count, &f->nodes, &f->sorted, &f->perm, &f->keys, &f->acc,
-                      &f->packs, &f->stage, &f->roots};
+                      &f->packs, &f->stage, &f->roots, &f->route_cnt, &f->route_pos, &f->route_idx_send,
+                      &f->route_acc_send, &f->route_idx_recv, &f->route_acc_recv};
     for (DevBuf *b : bufs) b->release();
+    if (f->h_route) cudaFreeHost(f->h_route);
     if (f->h_packs) cudaFreeHost(f->h_packs);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->ev_stage) cudaEventDestroy(f->ev_stage);
@@ -2662,6 +2730,10 @@ static int forest_of(pcuda_ctx *ctx, pcuda_forest **out) {
         PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&f->h_stage, MAX_PARTS * TOP_LEVELS * 2 * sizeof(BoundaryRec),
                                           cudaHostAllocDefault));
     if (!f->ev_stage) PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->ev_stage, cudaEventDisableTiming));
+    if (!f->h_route)
+        PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&f->h_route, MAX_PARTS * MAX_PARTS * sizeof(uint32_t),
+                                          cudaHostAllocDefault));
+    PCUDA_CUDA_TRY(ctx, f->route_cnt.ensure((MAX_PARTS * MAX_PARTS + MAX_PARTS) * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, f->packs.ensure(MAX_PARTS * sizeof(PartPack)));
     PCUDA_CUDA_TRY(ctx, f->stage.ensure(MAX_PARTS * TOP_LEVELS * 2 * sizeof(BoundaryRec)));
     PCUDA_CUDA_TRY(ctx, f->roots.ensure(MAX_ROOTS * sizeof(uint32_t)));
@@ -2951,6 +3023,79 @@ static int join_parts(pcuda_ctx *ctx, pcuda_forest *f, int parts, const uint32_t
     return PCUDA_OK;
 }
 
+static int g_route = 0;  // accelerations to their owners: 0 = all-to-all when available, 1 = all-gather
+
+// d_idx: original index of each of this rank's n_rows traversal rows; cap: particles per owner block.
+static int route_plan(pcuda_ctx *ctx, pcuda_forest *f, const uint32_t *d_idx, size_t n_rows, int world,
+                      int rank, size_t cap, size_t n_own, RoutePlan *plan) {
+    cudaStream_t st = ctx->stream;
+    uint32_t *d_mat = f->route_cnt.as<uint32_t>();           // world rows of MAX_PARTS counts
+    uint32_t *d_cursor = d_mat + MAX_PARTS * MAX_PARTS;      // MAX_PARTS
+    uint32_t *d_row = d_mat + (size_t)rank * MAX_PARTS;
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_row, 0, MAX_PARTS * sizeof(uint32_t), st));
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, MAX_PARTS * sizeof(uint32_t), st));
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 8, (n_rows + 255) / 256));
+    if (n_rows) owner_hist<<<grid, 256, 0, st>>>(d_idx, (int)n_rows, (uint32_t)cap, d_row);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_row, d_mat, MAX_PARTS * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_route, d_mat, (size_t)world * MAX_PARTS * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, st));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    OwnerOffsets so{};
+    size_t s_off = 0, r_off = 0;
+    for (int o = 0; o < world; ++o) {
+        plan->send_off[o] = s_off;
+        plan->send_cnt[o] = f->h_route[(size_t)rank * MAX_PARTS + o];
+        so.off[o] = (uint32_t)s_off;
+        s_off += plan->send_cnt[o];
+        plan->recv_off[o] = r_off;
+        plan->recv_cnt[o] = f->h_route[(size_t)o * MAX_PARTS + rank];
+        r_off += plan->recv_cnt[o];
+    }
+    if (s_off != n_rows || r_off != n_own)
+        return fail(ctx, PCUDA_ERR_NCCL, "routing plan is inconsistent (%zu of %zu rows out, %zu of %zu in)", s_off,
+                    n_rows, r_off, n_own);
+    plan->n_rows = n_rows;
+    plan->n_recv = r_off;
+    const size_t rows = std::max<size_t>(n_rows, 1), own = std::max<size_t>(n_own, 1);
+    PCUDA_CUDA_TRY(ctx, f->route_pos.ensure(rows * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->route_idx_send.ensure(rows * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->route_acc_send.ensure(rows * 3 * sizeof(float)));
+    PCUDA_CUDA_TRY(ctx, f->route_idx_recv.ensure(own * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->route_acc_recv.ensure(own * 3 * sizeof(float)));
+    plan->d_pos = f->route_pos.as<uint32_t>();
+    plan->d_acc_send = f->route_acc_send.as<float>();
+    if (n_rows)
+        owner_positions<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(d_idx, (int)n_rows, (uint32_t)cap, so, d_cursor,
+                                                                         plan->d_pos, f->route_idx_send.as<uint32_t>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return PCUDA_OK;
+}
+
+static int route_exchange(pcuda_ctx *ctx, pcuda_forest *f, const RoutePlan &plan, int world, size_t lo,
+                          float *d_out) {
+    size_t so[MAX_PARTS], sb[MAX_PARTS], ro[MAX_PARTS], rb[MAX_PARTS];
+    for (int pass = 0; pass < 2; ++pass) {  // accelerations (12 B rows), then original indices (4 B)
+        const size_t w = pass == 0 ? 12 : 4;
+        for (int o = 0; o < world; ++o) {
+            so[o] = plan.send_off[o] * w;
+            sb[o] = plan.send_cnt[o] * w;
+            ro[o] = plan.recv_off[o] * w;
+            rb[o] = plan.recv_cnt[o] * w;
+        }
+        PCUDA_TRY(nccl_alltoallv(ctx, pass == 0 ? (const void *)f->route_acc_send.p : (const void *)f->route_idx_send.p, so,
+                                 sb, pass == 0 ? f->route_acc_recv.p : f->route_idx_recv.p, ro, rb));
+    }
+    if (plan.n_recv) {
+        scatter_rows<<<(unsigned)((plan.n_recv + 255) / 256), 256, 0, ctx->stream>>>(
+            f->route_acc_recv.as<float>(), f->route_idx_recv.as<uint32_t>(), (int)plan.n_recv, (uint32_t)lo, d_out);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return PCUDA_OK;
+}
+
 // Diagnostic / test entry (one GPU): the parts are built one after the other ("virtual ranks"),
 // joined and walked for all particles; out rows are in input order.  parts == 1 is the ordinary tree.
 static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, int parts, float theta,
@@ -3093,8 +3238,23 @@ static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_tota
             return PCUDA_OK;
         },
         &fv));
-    phase_end(ctx, PH_COMM3);
 
+    const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
+    if (g_route == 0 && nccl_has_p2p(ctx)) {  // every row goes to its owner only
+        RoutePlan plan;
+        PCUDA_TRY(route_plan(ctx, f, mine ? t->d_perm() : nullptr, mine, world, rank, cap, hi - lo, &plan));
+        phase_end(ctx, PH_COMM3);
+        phase_begin(ctx, PH_COMPUTE);
+        if (mine)
+            PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), plan.d_pos, mine, theta, eps,
+                                      plan.d_acc_send, nullptr, &fv));
+        phase_end(ctx, PH_COMPUTE);
+        phase_begin(ctx, PH_COMM2);
+        PCUDA_TRY(route_exchange(ctx, f, plan, world, lo, d_out));
+        phase_end(ctx, PH_COMM2);
+        return PCUDA_OK;
+    }
+    phase_end(ctx, PH_COMM3);
     float *acc = f->acc.as<float>();
     phase_begin(ctx, PH_COMPUTE);
     if (mine)
@@ -3144,6 +3304,23 @@ static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, siz
         phase_begin(ctx, PH_COMPUTE);
         PCUDA_TRY(traverse(ctx, t, nullptr, n_total, theta, eps, d_out));
         phase_end(ctx, PH_COMPUTE);
+        return PCUDA_OK;
+    }
+    if (g_route == 0 && nccl_has_p2p(ctx)) {  // every row goes to its owner only
+        pcuda_forest *f = nullptr;
+        PCUDA_TRY(forest_of(ctx, &f));
+        RoutePlan plan;
+        phase_begin(ctx, PH_COMM3);
+        PCUDA_TRY(route_plan(ctx, f, t->d_perm() + lo, n_local, world, rank, cap, n_local, &plan));
+        phase_end(ctx, PH_COMM3);
+        phase_begin(ctx, PH_COMPUTE);
+        if (n_local)
+            PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>() + lo, t->d_keys() + lo, plan.d_pos, n_local,
+                                      theta, eps, plan.d_acc_send));
+        phase_end(ctx, PH_COMPUTE);
+        phase_begin(ctx, PH_COMM2);
+        PCUDA_TRY(route_exchange(ctx, f, plan, world, lo, d_out));
+        phase_end(ctx, PH_COMM2);
         return PCUDA_OK;
     }
     // accelerations of all particles in key order, world * cap rows; this rank fills rows [lo, hi)
@@ -3240,6 +3417,10 @@ int bh_debug_set(const char *key, int value) {
     }
     if (k == "bh_forest" && value >= 0 && value <= 2) {
         bh::g_forest = value;
+        return PCUDA_OK;
+    }
+    if (k == "bh_route" && (value == 0 || value == 1)) {
+        bh::g_route = value;
         return PCUDA_OK;
     }
     return PCUDA_ERR_INVALID_ARGUMENT;

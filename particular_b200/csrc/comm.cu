@@ -26,6 +26,10 @@ struct Nccl {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -45,6 +49,10 @@ static int nccl_load(pcuda_ctx *ctx) {
     n->CommDestroy = (decltype(n->CommDestroy))dlsym(h, "ncclCommDestroy");
     n->AllGather = (decltype(n->AllGather))dlsym(h, "ncclAllGather");
     n->GetErrorString = (decltype(n->GetErrorString))dlsym(h, "ncclGetErrorString");
+    n->Send = (decltype(n->Send))dlsym(h, "ncclSend");  // optional: only the all-to-all needs them
+    n->Recv = (decltype(n->Recv))dlsym(h, "ncclRecv");
+    n->GroupStart = (decltype(n->GroupStart))dlsym(h, "ncclGroupStart");
+    n->GroupEnd = (decltype(n->GroupEnd))dlsym(h, "ncclGroupEnd");
     if (!n->GetUniqueId || !n->CommInitRank || !n->CommDestroy || !n->AllGather) {
         delete n;
         return fail(ctx, PCUDA_ERR_NCCL, "libnccl.so.2 lacks required symbols");
@@ -69,6 +77,48 @@ void nccl_world(const pcuda_ctx *ctx, int *world, int *rank) {
 static int nccl_fail(pcuda_ctx *ctx, const char *what, ncclResult_t r) {
     return fail(ctx, PCUDA_ERR_NCCL, "%s failed: %s (%d)", what,
                 ctx->nccl && ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "?", r);
+}
+
+bool nccl_has_p2p(const pcuda_ctx *ctx) {
+    const Nccl *n = ctx->nccl;
+    return n && n->comm && n->Send && n->Recv && n->GroupStart && n->GroupEnd;
+}
+
+// Variable all-to-all on the context stream: rank o gets send_bytes[o] bytes from d_send +
+// send_off[o] and delivers recv_bytes[o] bytes to d_recv + recv_off[o]; one grouped batch of
+// ncclSend / ncclRecv.  The own share is a device-to-device copy.  Zero-byte pairs are skipped
+// (both sides know the whole matrix, so they skip the same pairs).
+int nccl_alltoallv(pcuda_ctx *ctx, const void *d_send, const size_t *send_off, const size_t *send_bytes,
+                   void *d_recv, const size_t *recv_off, const size_t *recv_bytes) {
+    if (!nccl_has_p2p(ctx)) return fail(ctx, PCUDA_ERR_NCCL, "ncclSend / ncclRecv are not available");
+    Nccl *n = ctx->nccl;
+    const char *s = static_cast<const char *>(d_send);
+    char *r = static_cast<char *>(d_recv);
+    const int me = n->rank;
+    if (send_bytes[me] != recv_bytes[me]) return fail(ctx, PCUDA_ERR_NCCL, "all-to-all: own share mismatch");
+    if (send_bytes[me]) {
+        cudaError_t e = cudaMemcpyAsync(r + recv_off[me], s + send_off[me], send_bytes[me],
+                                        cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, PCUDA_ERR_CUDA, "all-to-all: own copy: %s", cudaGetErrorString(e));
+    }
+    ncclResult_t rc = n->GroupStart();
+    if (rc) return nccl_fail(ctx, "ncclGroupStart", rc);
+    ncclResult_t first = 0;
+    for (int o = 0; o < n->world; ++o) {
+        if (o == me) continue;
+        if (send_bytes[o]) {
+            rc = n->Send(s + send_off[o], send_bytes[o], ncclInt8, o, n->comm, ctx->stream);
+            if (rc && !first) first = rc;
+        }
+        if (recv_bytes[o]) {
+            rc = n->Recv(r + recv_off[o], recv_bytes[o], ncclInt8, o, n->comm, ctx->stream);
+            if (rc && !first) first = rc;
+        }
+    }
+    rc = n->GroupEnd();
+    if (first) return nccl_fail(ctx, "ncclSend/ncclRecv", first);
+    if (rc) return nccl_fail(ctx, "ncclGroupEnd", rc);
+    return PCUDA_OK;
 }
 
 }  // namespace pcuda

@@ -53,7 +53,15 @@ small = uniform_cloud(5001, seed=9)
 f0 = bh0.compute(small)
 t0 = pb.BruteForce(ctx, pb.Acceleration.checked()).compute(small)
 res["bh_forest_theta0_max_rel"] = float(np.max(np.linalg.norm(f0 - t0, axis=1) / np.linalg.norm(t0, axis=1)))
+# result routing: rows sent to their owners only (ncclSend / ncclRecv) against the all-gather path
+assert _ffi.lib.pcuda_debug_set(b"bh_route", 1) == 0
+fullf_ag = bh.compute(q)
+assert _ffi.lib.pcuda_debug_set(b"bh_forest", 2) == 0
+fullb_ag = bh.compute(q)
+assert _ffi.lib.pcuda_debug_set(b"bh_route", 0) == 0
 assert _ffi.lib.pcuda_debug_set(b"bh_forest", 0) == 0
+res["route_same_forest"] = bool(np.array_equal(fullf, fullf_ag))
+res["route_same_replicated"] = bool(np.array_equal(fullb, fullb_ag))
 r = uniform_cloud(20011, seed=6, massive_ratio=0.01)
 sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0), init_comm=False)
 sb.world, sb.rank = sh.world, sh.rank
@@ -102,3 +110,4 @@ def test_two_gpus_match_single_gpu(tmp_path):
     for a, b in zip(res["bh_err_forest"], res["bh_err_single"]):
         assert a <= 1.25 * b + 1e-6, res
     assert res["bh_forest_theta0_max_rel"] <= 2e-5, res
+    assert res["route_same_forest"] and res["route_same_replicated"], res

@@ -42,6 +42,7 @@ res["bh_err_single"] = [float(np.median(e_1)), float(np.percentile(e_1, 99)), fl
 # on this context; PCUDA_FLAG_BH_PARTITIONED_BUILD / CudaContext(partitioned_build=True) is the API)
 from particular_b200 import _ffi
 assert _ffi.lib.pcuda_debug_set(b"bh_forest", 1) == 0
+assert _ffi.lib.pcuda_debug_set(b"bh_route", 2) == 0   # all-to-all routing (automatic from 4 GPUs on)
 fullf = bh.compute(q)
 e_f = np.linalg.norm(fullf - truth, axis=1) / den
 res["bh_forest_shape"] = list(fullf.shape)
@@ -58,10 +59,12 @@ assert _ffi.lib.pcuda_debug_set(b"bh_route", 1) == 0
 fullf_ag = bh.compute(q)
 assert _ffi.lib.pcuda_debug_set(b"bh_forest", 2) == 0
 fullb_ag = bh.compute(q)
+assert _ffi.lib.pcuda_debug_set(b"bh_route", 2) == 0
+fullb_a2a = bh.compute(q)
 assert _ffi.lib.pcuda_debug_set(b"bh_route", 0) == 0
 assert _ffi.lib.pcuda_debug_set(b"bh_forest", 0) == 0
 res["route_same_forest"] = bool(np.array_equal(fullf, fullf_ag))
-res["route_same_replicated"] = bool(np.array_equal(fullb, fullb_ag))
+res["route_same_replicated"] = bool(np.array_equal(fullb_a2a, fullb_ag) and np.array_equal(fullb, fullb_ag))
 r = uniform_cloud(20011, seed=6, massive_ratio=0.01)
 sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0), init_comm=False)
 sb.world, sb.rank = sh.world, sh.rank

@@ -330,6 +330,9 @@ def main():
                     help="multi-GPU Barnes-Hut: every GPU builds the whole tree, or one tree per GPU "
                          "over its key range joined by a top tree (PCUDA_FLAG_BH_PARTITIONED_BUILD); "
                          "auto = the library's default: partitioned from 4 GPUs on")
+    ap.add_argument("--bh-route", default="auto", choices=["auto", "allgather", "alltoall"],
+                    help="multi-GPU Barnes-Hut: how the accelerations reach the ranks that own the "
+                         "particles (auto: all-to-all from 4 GPUs on)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the cpu_baseline leg and the ride-along Barnes-Hut number")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -812,6 +815,8 @@ def bench_barneshut(args, n, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     ctx = pb.CudaContext(local_rank, partitioned_build={"auto": None, "partitioned": True,
                                                         "replicated": False}[args.bh_build])
+    from particular_b200._ffi import lib as _lib
+    assert _lib.pcuda_debug_set(b"bh_route", {"auto": 0, "allgather": 1, "alltoall": 2}[args.bh_route]) == 0
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local_rank)

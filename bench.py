@@ -332,7 +332,7 @@ def main():
                          "auto = the library's default: partitioned from 4 GPUs on")
     ap.add_argument("--bh-route", default="auto", choices=["auto", "allgather", "alltoall"],
                     help="multi-GPU Barnes-Hut: how the accelerations reach the ranks that own the "
-                         "particles (auto: all-to-all from 4 GPUs on)")
+                         "particles (auto: all-to-all from 4 GPUs and 32M particles on)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the cpu_baseline leg and the ride-along Barnes-Hut number")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

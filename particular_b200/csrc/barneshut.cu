@@ -3023,11 +3023,12 @@ static int join_parts(pcuda_ctx *ctx, pcuda_forest *f, int parts, const uint32_t
     return PCUDA_OK;
 }
 
-static int g_route = 0;  // accelerations to their owners: 0 = all-to-all from 4 GPUs on (it costs a
-                         // synchronisation and three small launches: 0.2 ms slower than the all-gather at 2
-                         // GPUs), 1 = all-gather, 2 = all-to-all
-static bool route_a2a(const pcuda_ctx *ctx, int world) {
-    return nccl_has_p2p(ctx) && (g_route == 2 || (g_route == 0 && world >= 4));
+static int g_route = 0;  // accelerations to their owners: 0 = automatic, 1 = all-gather, 2 = all-to-all
+// The all-to-all moves 16 B x N / world per rank instead of 12 B x N, but costs a synchronisation and
+// three small launches more.  Measured on 8 B200s: N = 10M 6.01 ms against 5.85 ms per step with the
+// all-gather, N = 80M 38.3 against 39.7 ms (2 GPUs, N = 10M: 0.2 ms slower) - hence only for large N.
+static bool route_a2a(const pcuda_ctx *ctx, int world, size_t n_total) {
+    return nccl_has_p2p(ctx) && (g_route == 2 || (g_route == 0 && world >= 4 && n_total >= (size_t)32 << 20));
 }
 
 // d_idx: original index of each of this rank's n_rows traversal rows; cap: particles per owner block.
@@ -3245,7 +3246,7 @@ static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_tota
         &fv));
 
     const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
-    if (route_a2a(ctx, world)) {  // every row goes to its owner only
+    if (route_a2a(ctx, world, n_total)) {  // every row goes to its owner only
         RoutePlan plan;
         PCUDA_TRY(route_plan(ctx, f, mine ? t->d_perm() : nullptr, mine, world, rank, cap, hi - lo, &plan));
         phase_end(ctx, PH_COMM3);
@@ -3311,7 +3312,7 @@ static int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, siz
         phase_end(ctx, PH_COMPUTE);
         return PCUDA_OK;
     }
-    if (route_a2a(ctx, world)) {  // every row goes to its owner only
+    if (route_a2a(ctx, world, n_total)) {  // every row goes to its owner only
         pcuda_forest *f = nullptr;
         PCUDA_TRY(forest_of(ctx, &f));
         RoutePlan plan;

@@ -1108,7 +1108,8 @@ __device__ __forceinline__ void eval_entry(const float4 e, float2 npx, float2 np
 
 // VAR: experiment bits (tuning only).  1 = walk only (no evaluation), 2 = prefetch the next round's
 // node records into L1 before the evaluation.
-template <bool COUNT, int VAR = 0>
+// FOREST: the walk starts from a.roots[0 .. a.n_roots) (partitioned multi-GPU build) instead of node 0.
+template <bool COUNT, int VAR = 0, bool FOREST = false>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs a) {
     __shared__ uint32_t s_stack[TRAV_WARPS][STACK_CAP];
     __shared__ __align__(16) float4 s_list[TRAV_WARPS][LIST_CAP];
@@ -1173,7 +1174,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
         int head = 0;  // ring position of the oldest list entry: 0 or 32 (uniform)
         int fill = 0;  // entries in the ring (uniform), < 32 between steps
         __syncwarp();
-        if (a.roots) {
+        if (FOREST) {
             sp = (int)a.n_roots;
             for (int i = lane; i < sp; i += 32) stack[i] = a.roots[i];
         } else if (lane == 0) {
@@ -2329,6 +2330,9 @@ static int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tg
         if (g_variant == 1) traverse2_kernel<false, 1><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else if (g_variant == 2) traverse2_kernel<false, 2><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else traverse2_kernel<false, 3><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+    } else if (g_tpl == 2 && fv) {
+        if (g_count) traverse2_kernel<true, 0, true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+        else traverse2_kernel<false, 0, true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
     } else if (g_tpl == 2) {
         if (g_count) traverse2_kernel<true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else traverse2_kernel<false><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);

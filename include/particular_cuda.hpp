@@ -125,10 +125,12 @@ struct Error : std::runtime_error {
 // gpu/mod.rs:150-151).
 class CudaContext {
 public:
+    // extra_flags: PCUDA_FLAG_BH_PARTITIONED_BUILD / PCUDA_FLAG_BH_REPLICATED_BUILD force the
+    // multi-GPU Barnes-Hut tree build (default: partitioned from 4 GPUs on).
     explicit CudaContext(int device = 0, unsigned leaf_size = 0, bool phase_timings = true,
-                         unsigned expansion_order = 1) {
-        pcuda_config cfg{device, phase_timings ? PCUDA_FLAG_NONE : PCUDA_FLAG_NO_PHASE_TIMINGS, leaf_size,
-                         expansion_order};
+                         unsigned expansion_order = 1, unsigned extra_flags = 0) {
+        pcuda_config cfg{device, (phase_timings ? PCUDA_FLAG_NONE : PCUDA_FLAG_NO_PHASE_TIMINGS) | extra_flags,
+                         leaf_size, expansion_order};
         int s = pcuda_create(&cfg, &ctx_);
         if (s != PCUDA_OK) throw Error(s, pcuda_last_error(nullptr));
     }

@@ -1,5 +1,5 @@
 """Multi-GPU brute force and Barnes-Hut: one process per GPU, targets sharded, sources all-gathered
-over NVLink (Barnes-Hut: every GPU then builds the identical tree — "replicated build").
+over NVLink (Barnes-Hut: the tree is built replicated or partitioned by key range, see ShardedBarnesHut).
 
 New functionality (the reference is single-device).  Each rank owns a
 contiguous block of the particle slice (input order is preserved, so concatenating the ranks'
@@ -114,8 +114,12 @@ class ShardedBruteForce:
 class ShardedBarnesHut(ShardedBruteForce):
     """``ShardedBarnesHut(ctx, theta, interaction).compute(particles)``: the multi-GPU counterpart
     of ``BarnesHut(ctx, theta, interaction).compute(particles)`` for the ``&[P]`` storage.  Every
-    rank all-gathers the particle records, builds the identical tree over all of them (replicated
-    build) and traverses it for its own contiguous block of targets.  f32 3-D."""
+    rank all-gathers the particle records; the tree is either built whole on every rank
+    (replicated build) or, from 4 GPUs on, partitioned by key range — each rank builds the tree of
+    its own range, the trees are all-gathered and joined by a small top tree
+    (``CudaContext(partitioned_build=...)``).  Each rank walks the tree for the
+    targets of its key range and the accelerations are routed back to the ranks that own the
+    particles.  f32 3-D."""
 
     def __init__(self, ctx, theta: float, interaction, group=None, init_comm: bool = True):
         super().__init__(ctx, interaction, group, init_comm)

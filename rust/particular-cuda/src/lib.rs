@@ -64,7 +64,18 @@ impl CudaContext {
     /// `leaf_size`: largest Barnes-Hut leaf (0 = default 16).  Per-phase device timings are off
     /// (`PCUDA_FLAG_NO_PHASE_TIMINGS`): the product path records no events.
     pub fn with_leaf_size(device: i32, leaf_size: u32) -> Self {
-        let cfg = ffi::pcuda_config { device, flags: ffi::PCUDA_FLAG_NO_PHASE_TIMINGS, leaf_size, expansion_order: 1 };
+        Self::with_flags(device, leaf_size, 0)
+    }
+
+    /// `flags`: `ffi::PCUDA_FLAG_BH_PARTITIONED_BUILD` / `ffi::PCUDA_FLAG_BH_REPLICATED_BUILD` force how
+    /// multi-GPU Barnes-Hut builds its tree (default: partitioned by key range from 4 GPUs on).
+    pub fn with_flags(device: i32, leaf_size: u32, flags: u32) -> Self {
+        let cfg = ffi::pcuda_config {
+            device,
+            flags: ffi::PCUDA_FLAG_NO_PHASE_TIMINGS | flags,
+            leaf_size,
+            expansion_order: 1,
+        };
         let mut raw = std::ptr::null_mut();
         check(unsafe { ffi::pcuda_create(&cfg, &mut raw) }, std::ptr::null());
         Self { raw }

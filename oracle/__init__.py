@@ -205,13 +205,22 @@ NLEAF_DEFAULT = 16
 class Octree:
     """CPU statement of the library's own tree specification (parity unpinned by the reference)."""
 
-    def __init__(self, affecting, nleaf=NLEAF_DEFAULT):
+    def __init__(self, affecting, nleaf=NLEAF_DEFAULT, frame=None):
+        """frame = (origin[D], ext, inv): build over `affecting` in the quantisation frame of a
+        larger cloud (one part of the key-range-partitioned multi-GPU build)."""
         affecting = np.ascontiguousarray(affecting, dtype=np.float32)
         self.d = affecting.shape[1] - 1
         self.sfx = _SFX[(np.dtype(np.float32), self.d)]
-        fn = getattr(lib(), f"oracle_octree_build_{self.sfx}")
-        fn.restype = C.c_void_p
-        self.h = C.c_void_p(fn(_ptr(affecting), C.c_size_t(len(affecting)), C.c_uint32(nleaf)))
+        if frame is None:
+            fn = getattr(lib(), f"oracle_octree_build_{self.sfx}")
+            fn.restype = C.c_void_p
+            self.h = C.c_void_p(fn(_ptr(affecting), C.c_size_t(len(affecting)), C.c_uint32(nleaf)))
+        else:
+            fr = np.ascontiguousarray(np.concatenate([np.asarray(frame[0], np.float32).ravel(),
+                                                      np.array([frame[1], frame[2]], np.float32)]))
+            fn = getattr(lib(), f"oracle_octree_build_in_frame_{self.sfx}")
+            fn.restype = C.c_void_p
+            self.h = C.c_void_p(fn(_ptr(affecting), C.c_size_t(len(affecting)), C.c_uint32(nleaf), _ptr(fr)))
         info = np.zeros(3, dtype=np.int64)
         frame = np.zeros(self.d + 2, dtype=np.float32)
         getattr(lib(), f"oracle_octree_info_{self.sfx}")(self.h, _ptr(info), _ptr(frame))
@@ -231,6 +240,12 @@ class Octree:
         getattr(lib(), f"oracle_octree_read_{self.sfx}")(
             self.h, _ptr(self.keys), _ptr(self.perm), _ptr(self.begin), _ptr(self.count),
             _ptr(self.level), _ptr(self.first_child), _ptr(self.n_child), _ptr(self.commass))
+
+    def moments(self):
+        """Double-precision {sum m x_k, sum m} per node."""
+        mom = np.zeros((self.n_nodes, self.d + 1), dtype=np.float64)
+        getattr(lib(), f"oracle_octree_read_moments_{self.sfx}")(self.h, _ptr(mom))
+        return mom
 
     def __del__(self):
         try:

@@ -142,6 +142,7 @@ SIGNATURES = {
     # not in the stable header: measurement / tuning hooks
     "pcuda_probe_fp32": (_i, [_vp, _i, _i, _i, C.POINTER(_d), C.POINTER(_f)]),
     "pcuda_debug_set": (_i, [C.c_char_p, _i]),
+    "pcuda_debug_merge_top_tree": (_i, [_i, _vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -3601,6 +3601,27 @@ int pcuda_barneshut_f32x3_partitioned(pcuda_ctx *ctx, const float *xyzm, size_t 
     return timings_collect(ctx);
 }
 
+// Test hook (not in the stable header): the host-side merge of the partitioned build on caller-made
+// inputs, no device involved.  packs: parts x pcuda::bh::PartPack; stage: parts x 22 x 2 x BoundaryRec;
+// top_out: room for top_cap 32-byte node records; roots_out: room for roots_cap indices.
+int pcuda_debug_merge_top_tree(int parts, const void *packs, const void *stage, const uint32_t *node_base,
+                               uint32_t top_base, void *top_out, uint32_t top_cap, uint32_t *n_top,
+                               uint32_t *roots_out, uint32_t roots_cap, uint32_t *n_roots) {
+    if (parts < 1 || parts > bh::MAX_PARTS || !packs || !stage || !node_base || !n_top || !n_roots)
+        return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "bad arguments");
+    std::vector<bh::NodeRec> top;
+    std::vector<uint32_t> roots;
+    PCUDA_TRY(bh::merge_top_tree(nullptr, parts, static_cast<const bh::PartPack *>(packs),
+                                 static_cast<const bh::BoundaryRec *>(stage), node_base, top_base, top, roots));
+    if (top.size() > top_cap || roots.size() > roots_cap)
+        return fail(nullptr, PCUDA_ERR_INVALID_ARGUMENT, "output buffers too small");
+    if (!top.empty()) memcpy(top_out, top.data(), top.size() * sizeof(bh::NodeRec));
+    if (!roots.empty()) memcpy(roots_out, roots.data(), roots.size() * sizeof(uint32_t));
+    *n_top = (uint32_t)top.size();
+    *n_roots = (uint32_t)roots.size();
+    return PCUDA_OK;
+}
+
 int pcuda_tree_build_f32(pcuda_ctx *ctx, uint32_t dim, const float *affecting, size_t n,
                          pcuda_tree **out) {
     if (!ctx || !out) return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "NULL argument");

@@ -1,0 +1,172 @@
+"""CPU coverage of the multi-GPU Barnes-Hut path's host logic (no GPU needed): the merge of the
+per-part trees of the key-range-partitioned build into one joined tree (particular_b200/csrc/
+barneshut.cu: merge_top_tree, reached through the test hook pcuda_debug_merge_top_tree).
+
+The per-part trees are made by the CPU statement of the tree specification (oracle.Octree built in
+the frame of the whole cloud), packed exactly as the device kernels fill_pack / collect_boundary
+pack them, merged by the library, and the joined tree is then checked structurally: every particle
+is reached exactly once from the top root, every internal node carries the mass and centre of mass
+of its children, and every merged cell equals the cell of the single tree over all particles."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.conftest import plummer_cloud, uniform_cloud
+
+BITS, LEVELS = 21, 22
+NODE = np.dtype([("cm", np.float32, 4), ("first_child", np.uint32), ("nchild_level", np.uint32),
+                 ("begin", np.uint32), ("count", np.uint32)])
+PACK = np.dtype([("n_nodes", np.uint32), ("n_levels", np.uint32), ("level_begin", np.uint32, LEVELS + 2),
+                 ("prefix", np.uint64, (LEVELS, 2)), ("mom", np.float64, (LEVELS, 2, 4))])
+BOUND = np.dtype([("node", NODE), ("child", NODE, 8)])
+
+
+def test_layouts_match_the_device_structs():
+    assert NODE.itemsize == 32 and PACK.itemsize == 1864 and BOUND.itemsize == 9 * 32
+
+
+def join(p, parts, nleaf=16):
+    """Per-part trees in the common frame, joined arrays, packs and boundary records."""
+    full = oracle.Octree(p, nleaf)
+    frame = (full.origin, full.ext, full.inv)
+    keys_in = oracle.morton_keys(p[:, :3], full.origin, full.inv)
+    ks = np.sort(keys_in)
+    split = [0] + [int(ks[q * len(p) // parts]) for q in range(1, parts)] + [1 << 64]
+    nodes, keys, node_base, part_base = [], [], [], []
+    packs = np.zeros(parts, PACK)
+    per_part = []
+    for q in range(parts):
+        idx = np.flatnonzero((keys_in >= np.uint64(split[q])) & (keys_in.astype(object) < split[q + 1]))
+        node_base.append(sum(len(x) for x in nodes))
+        part_base.append(sum(len(x) for x in keys))
+        if len(idx) == 0:
+            per_part.append(None)
+            continue
+        t = oracle.Octree(p[idx], nleaf, frame=frame)
+        assert np.array_equal(t.keys, np.sort(keys_in[idx]))
+        rec = np.zeros(t.n_nodes, NODE)
+        rec["cm"] = t.commass
+        internal = t.n_child > 0
+        rec["first_child"] = np.where(internal, t.first_child + node_base[q], 0)
+        rec["nchild_level"] = t.n_child | (t.level << 8)
+        rec["begin"] = t.begin + part_base[q]
+        rec["count"] = t.count
+        nodes.append(rec)
+        keys.append(t.keys)
+        lb = np.searchsorted(t.level, np.arange(LEVELS + 2)).astype(np.uint32)
+        mom = t.moments()
+        packs[q]["n_nodes"], packs[q]["n_levels"] = t.n_nodes, t.n_levels
+        packs[q]["level_begin"] = lb
+        for l in range(t.n_levels):
+            for side, j in enumerate((lb[l], lb[l + 1] - 1)):
+                packs[q]["prefix"][l][side] = int(t.keys[t.begin[j]]) >> (3 * (BITS - l))
+                packs[q]["mom"][l][side] = mom[j]
+        per_part.append((t, lb))
+    nodes = np.concatenate(nodes) if nodes else np.zeros(0, NODE)
+    keys = np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+    stage = np.zeros((parts, LEVELS, 2), BOUND)
+    for q, pp in enumerate(per_part):
+        if pp is None:
+            continue
+        t, lb = pp
+        for l in range(t.n_levels):
+            for side, j in enumerate((lb[l], lb[l + 1] - 1)):
+                nd = nodes[node_base[q] + j]
+                stage[q, l, side]["node"] = nd
+                nc = int(nd["nchild_level"]) & 0xff
+                stage[q, l, side]["child"][:nc] = nodes[nd["first_child"]: nd["first_child"] + nc]
+    return full, nodes, keys, np.array(node_base, np.uint32), packs, stage
+
+
+def merge(parts, packs, stage, node_base, top_base):
+    from particular_b200 import _ffi
+    top = np.zeros(4096, NODE)
+    roots = np.zeros(1024, np.uint32)
+    n_top, n_roots = C.c_uint32(), C.c_uint32()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    _ffi.check(_ffi.lib.pcuda_debug_merge_top_tree(parts, vp(packs), vp(stage), vp(node_base), top_base, vp(top),
+                                                   len(top), C.byref(n_top), vp(roots), len(roots),
+                                                   C.byref(n_roots)))
+    return top[: n_top.value], roots[: n_roots.value]
+
+
+def check_joined(p, parts, nleaf=16):
+    full, nodes, keys, node_base, packs, stage = join(p, parts, nleaf)
+    n = len(p)
+    top, roots = merge(parts, packs, stage, node_base, len(nodes))
+    assert len(roots) == 1
+    joined = np.concatenate([nodes, top])
+    ext = max(full.ext, 1e-30)
+    single = {}
+    for j in range(full.n_nodes):
+        l = int(full.level[j])
+        single[(l, int(full.keys[full.begin[j]]) >> (3 * (BITS - l)))] = j
+    covered = np.zeros(n, np.int32)
+    stack, visited, compared = [int(roots[0])], 0, 0
+    while stack:
+        i = stack.pop()
+        nd = joined[i]
+        visited += 1
+        nc, lvl = int(nd["nchild_level"]) & 0xff, int(nd["nchild_level"]) >> 8
+        assert nc <= 8
+        if nc == 0:
+            covered[nd["begin"]: nd["begin"] + nd["count"]] += 1
+            continue
+        ch = joined[nd["first_child"]: nd["first_child"] + nc]
+        clv = ch["nchild_level"] >> 8
+        assert ((clv == lvl) | (clv == lvl + 1)).all()
+        m = ch["cm"][:, 3].astype(np.float64)
+        assert np.isclose(m.sum(), nd["cm"][3], rtol=2e-6, atol=0), (i, m.sum(), nd["cm"][3])
+        if m.sum() != 0:
+            com = (ch["cm"][:, :3].astype(np.float64) * m[:, None]).sum(0) / m.sum()
+            assert np.abs(com - nd["cm"][:3]).max() <= 2e-6 * ext + 1e-6 * np.abs(com).max(), (i, com, nd["cm"])
+        assert int(ch["count"].sum()) == int(nd["count"])
+        if i >= len(nodes):  # a node of the top tree: the same cell of the single tree, when it is one
+            j = single.get((lvl, int(keys[nd["begin"]]) >> (3 * (BITS - lvl))))
+            if j is not None and int(full.count[j]) == int(nd["count"]):
+                compared += 1
+                assert np.isclose(nd["cm"][3], full.commass[j, 3], rtol=1e-6, atol=0)
+                assert np.abs(nd["cm"][:3] - full.commass[j, :3]).max() <= 1e-6 * ext + 1e-6 * np.abs(full.commass[j, :3]).max()
+        stack.extend(range(int(nd["first_child"]), int(nd["first_child"]) + nc))
+    assert (covered == 1).all(), (int((covered == 0).sum()), int((covered > 1).sum()))
+    nonempty = int((packs["n_nodes"] > 0).sum())
+    if nonempty > 1:
+        assert len(top) >= 1 and compared >= 1 and int(top[0]["count"]) == n
+    else:
+        assert len(top) == 0
+    return len(top), visited
+
+
+@pytest.mark.parametrize("cloud", ["uniform", "plummer"])
+@pytest.mark.parametrize("parts", [1, 2, 3, 8, 16])
+def test_joined_tree_is_a_partition_with_consistent_moments(cloud, parts):
+    p = uniform_cloud(6000, seed=11) if cloud == "uniform" else plummer_cloud(6000, seed=11)
+    n_top, visited = check_joined(p, parts)
+    assert n_top <= 1 + 8 * LEVELS * parts
+
+
+@pytest.mark.parametrize("n,parts,nleaf", [(3, 8, 16), (40, 8, 16), (200, 16, 1), (2500, 5, 4), (1000, 2, 32)])
+def test_small_and_ragged_parts(n, parts, nleaf):
+    check_joined(plummer_cloud(n, seed=n), parts, nleaf)
+
+
+def test_coincident_and_clustered_particles():
+    """All keys equal (one part gets everything), and two tight clumps with deep single-child chains."""
+    same = np.tile(np.array([[1.0, 2.0, 3.0, 5.0]], np.float32), (300, 1))
+    check_joined(same, 4)
+    rng = np.random.default_rng(5)
+    two = np.concatenate([same[:150] + np.concatenate([rng.normal(0, 1e-4, (150, 3)), np.zeros((150, 1))], 1),
+                          same[:150] + np.array([[10.0, 0, 0, 0]]) +
+                          np.concatenate([rng.normal(0, 1e-4, (150, 3)), np.zeros((150, 1))], 1)]).astype(np.float32)
+    check_joined(two, 3)
+    check_joined(two, 8, nleaf=2)
+
+
+def test_zero_mass_particles():
+    p = uniform_cloud(3000, seed=3)
+    p[::2, 3] = 0.0
+    check_joined(p, 4)
+    p[:, 3] = 0.0
+    check_joined(p, 4)

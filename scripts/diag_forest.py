@@ -1,6 +1,8 @@
+"""Accuracy of the key-range-partitioned Barnes-Hut build (virtual ranks on one GPU) against the single tree and the
+exact sum at small N, where the cells next to the cuts are a large share of the tree.  Usage: python scripts/diag_forest.py"""
 import os, sys
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import particular_b200 as pb
 from tests.conftest import uniform_cloud, plummer_cloud
 def st(e): return f"med {np.median(e):.3e} p90 {np.percentile(e,90):.3e} p99 {np.percentile(e,99):.3e} max {e.max():.3e}"

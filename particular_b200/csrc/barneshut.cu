@@ -3144,10 +3144,12 @@ static int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, i
         if (need > f->nodes.cap) {  // grow, keeping the parts already placed
             DevBuf bigger;
             PCUDA_CUDA_TRY(ctx, bigger.ensure(std::max(need, ((size_t)parts * t->n_nodes + TOP_CAP) * sizeof(NodeRec))));
-            if (next)
-                PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(bigger.p, f->nodes.p, next * sizeof(NodeRec),
-                                                    cudaMemcpyDeviceToDevice, st));
-            PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            cudaError_t e = next ? cudaMemcpyAsync(bigger.p, f->nodes.p, next * sizeof(NodeRec),
+                                                   cudaMemcpyDeviceToDevice, st)
+                                 : cudaSuccess;
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) bigger.release();
+            PCUDA_CUDA_TRY(ctx, e);
             f->nodes.release();
             f->nodes = bigger;
         }

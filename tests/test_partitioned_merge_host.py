@@ -170,3 +170,19 @@ def test_zero_mass_particles():
     check_joined(p, 4)
     p[:, 3] = 0.0
     check_joined(p, 4)
+
+
+def test_random_clouds_parts_and_leaf_sizes():
+    """Property test: any cloud, any number of parts, any leaf size gives an exact partition."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(1, 1500), parts=st.integers(1, 16), nleaf=st.sampled_from([1, 2, 8, 16, 32]),
+           seed=st.integers(0, 10_000), clumpy=st.booleans())
+    def run(n, parts, nleaf, seed, clumpy):
+        p = plummer_cloud(n, seed=seed) if clumpy else uniform_cloud(n, seed=seed)
+        if clumpy and n > 10:
+            p[: n // 3, :3] = p[0, :3]  # a block of coincident particles: equal keys never straddle a cut
+        check_joined(p, parts, nleaf)
+
+    run()

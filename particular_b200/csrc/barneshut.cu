@@ -3032,7 +3032,8 @@ static int g_route = 0;  // accelerations to their owners: 0 = automatic, 1 = al
 // three small launches more.  Measured on 8 B200s: N = 10M 6.01 ms against 5.85 ms per step with the
 // all-gather, N = 80M 38.3 against 39.7 ms (2 GPUs, N = 10M: 0.2 ms slower) - hence only for large N.
 static bool route_a2a(const pcuda_ctx *ctx, int world, size_t n_total) {
-    return nccl_has_p2p(ctx) && (g_route == 2 || (g_route == 0 && world >= 4 && n_total >= (size_t)32 << 20));
+    return nccl_has_p2p(ctx) && world <= MAX_PARTS &&
+           (g_route == 2 || (g_route == 0 && world >= 4 && n_total >= (size_t)32 << 20));
 }
 
 // d_idx: original index of each of this rank's n_rows traversal rows; cap: particles per owner block.

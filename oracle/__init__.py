@@ -26,7 +26,11 @@ _SFX = {(np.dtype(np.float32), 3): "f32x3", (np.dtype(np.float32), 2): "f32x2",
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with oracle/Makefile (gcc)."""
-    if force or not os.path.exists(_LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in ("particular_oracle.c", "oracle_impl.inc", "oracle_octree.inc",
+                                              "baseline_simd.c", "Makefile")]
+    stale = not os.path.exists(_LIB_PATH) or any(
+        os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
+    if force or stale:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.DEVNULL)
     return _LIB_PATH

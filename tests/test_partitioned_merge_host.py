@@ -186,3 +186,105 @@ def test_random_clouds_parts_and_leaf_sizes():
         check_joined(p, parts, nleaf)
 
     run()
+
+
+# ---- world_size-2 (and 3) gloo run of the partitioned build's exchange + merge on CPU -----------------
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, n, q):
+    """What sharded_forest_dev does after the raw all-gather, with the oracle standing in for the device
+    build and gloo for NCCL: own part tree in the common frame -> pack + node slot -> all-gather into
+    EQUAL slots (node / particle indices rebased to rank * slot) -> boundary records -> merge."""
+    import hashlib
+    import os
+
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = plummer_cloud(n, seed=77)
+        full = oracle.Octree(p)
+        keys_in = oracle.morton_keys(p[:, :3], full.origin, full.inv)
+        ks = np.sort(keys_in)
+        split = [0] + [int(ks[r * n // world]) for r in range(1, world)] + [1 << 64]
+        counts = [int(((keys_in >= np.uint64(split[r])) & (keys_in.astype(object) < split[r + 1])).sum())
+                  for r in range(world)]
+        slot = max(max(counts), 1)
+        idx = np.flatnonzero((keys_in >= np.uint64(split[rank])) & (keys_in.astype(object) < split[rank + 1]))
+        t = oracle.Octree(p[idx], frame=(full.origin, full.ext, full.inv))
+        lb = np.searchsorted(t.level, np.arange(LEVELS + 2)).astype(np.uint32)
+        pack = np.zeros(1, PACK)
+        pack["n_nodes"], pack["n_levels"], pack["level_begin"] = t.n_nodes, t.n_levels, lb
+        mom = t.moments()
+        for l in range(t.n_levels):
+            for side, j in enumerate((lb[l], lb[l + 1] - 1)):
+                pack["prefix"][0][l][side] = int(t.keys[t.begin[j]]) >> (3 * (BITS - l))
+                pack["mom"][0][l][side] = mom[j]
+        packs_t = [torch.empty(PACK.itemsize, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(packs_t, torch.from_numpy(pack.view(np.uint8).copy()))
+        packs = np.concatenate([x.numpy().view(PACK) for x in packs_t])
+        node_slot = int(packs["n_nodes"].max())
+        rec = np.zeros(node_slot, NODE)  # own slot, indices rebased to the slot (copy_rebase_nodes)
+        rec["cm"][: t.n_nodes] = t.commass
+        rec["first_child"][: t.n_nodes] = np.where(t.n_child > 0, t.first_child + rank * node_slot, 0)
+        rec["nchild_level"][: t.n_nodes] = t.n_child | (t.level << 8)
+        rec["begin"][: t.n_nodes] = t.begin + rank * slot
+        rec["count"][: t.n_nodes] = t.count
+        nodes_t = [torch.empty(node_slot * NODE.itemsize, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(nodes_t, torch.from_numpy(rec.view(np.uint8).copy()))
+        nodes = np.concatenate([x.numpy().view(NODE) for x in nodes_t])
+        node_base = (np.arange(world) * node_slot).astype(np.uint32)
+        stage = np.zeros((world, LEVELS, 2), BOUND)  # collect_boundary
+        for r in range(world):
+            for l in range(int(packs[r]["n_levels"])):
+                b = packs[r]["level_begin"]
+                for side, j in enumerate((b[l], b[l + 1] - 1)):
+                    nd = nodes[node_base[r] + j]
+                    stage[r, l, side]["node"] = nd
+                    nc = int(nd["nchild_level"]) & 0xff
+                    stage[r, l, side]["child"][:nc] = nodes[nd["first_child"]: nd["first_child"] + nc]
+        top_base = world * node_slot
+        top, roots = merge(world, packs, stage, node_base, top_base)
+        joined = np.concatenate([nodes, top])
+        covered = np.zeros(world * slot, np.int32)
+        stack = [int(roots[0])]
+        while stack:
+            nd = joined[stack.pop()]
+            nc = int(nd["nchild_level"]) & 0xff
+            if nc == 0:
+                covered[nd["begin"]: nd["begin"] + nd["count"]] += 1
+            else:
+                stack.extend(range(int(nd["first_child"]), int(nd["first_child"]) + nc))
+        want = np.zeros(world * slot, np.int32)
+        for r in range(world):
+            want[r * slot: r * slot + counts[r]] = 1  # the rest of a slot is padding
+        ok = bool(np.array_equal(covered, want)) and len(roots) == 1 and int(top[0]["count"]) == n
+        ok = ok and np.isclose(top[0]["cm"][3], full.commass[0, 3], rtol=1e-6)
+        q.put((rank, ok, hashlib.sha1(top.tobytes() + roots.tobytes()).hexdigest()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 5000), (3, 1200)])
+def test_gloo_ranks_build_the_same_joined_tree(world, n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert len({h for _, _, h in res}) == 1, res  # every rank merged the identical top tree

@@ -62,8 +62,20 @@ def evaluate(rule):
             if rule[0] == "box":        # shrink the box by rule[1] (1 = the rule in use)
                 d = np.maximum(np.abs(cm[ids] - c) - rule[1] * h, 0.0)
                 d2 = (d * d).sum(1)
-            else:                        # sphere of rule[1] x the group's radius around its centre
+            elif rule[0] == "sphere":    # sphere of rule[1] x the group's radius around its centre
                 d2 = np.maximum(np.sqrt(((cm[ids] - c) ** 2).sum(1)) - rule[1] * r, 0.0) ** 2
+            elif rule[0] == "halves":    # boxes of the first and the second half of the group, the nearer one counts
+                m = (b - a + 1) // 2
+                d2 = None
+                for part in (tg[:m], tg[m:] if b - a > m else tg[:m]):
+                    lo2, hi2 = part.min(0), part.max(0)
+                    dd = np.maximum(np.abs(cm[ids] - 0.5 * (lo2 + hi2)) - 0.5 * (hi2 - lo2), 0.0)
+                    dd = (dd * dd).sum(1)
+                    d2 = dd if d2 is None else np.minimum(d2, dd)
+            else:                        # "both": the larger of the two lower bounds (still conservative)
+                d = np.maximum(np.abs(cm[ids] - c) - h, 0.0)
+                d2 = np.maximum((d * d).sum(1),
+                                np.maximum(np.sqrt(((cm[ids] - c) ** 2).sum(1)) - r, 0.0) ** 2)
             opened = THETA * THETA * d2 < w * w
             for i in ids[opened & (nchild[ids] > 0)]:
                 stack.extend(range(first[i], first[i] + nchild[i]))
@@ -98,7 +110,7 @@ def stats(a):
 rs = stats(ref)
 print(f"{CLOUD} N = {N}, theta = {THETA}, {len(sample)} groups / {len(tg_idx)} targets")
 print(f"reference algorithm (per-particle rule, oracle): median {rs[0]:.2e}  p99 {rs[1]:.2e}  max {rs[2]:.2e}")
-RULES = [("box", float(x)) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else \
+RULES = [(x, 1.0) if x in ("both", "halves") else ("box", float(x)) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else \
     [("box", 1.0), ("box", 0.75), ("box", 0.5), ("box", 0.25), ("box", 0.0), ("sphere", 1.0), ("sphere", 0.5)]
 for rule in RULES:
     a, inter = evaluate(rule)

@@ -116,7 +116,8 @@ def model(seg, cap, policy, sample_frac=0.012, seed=3):
 print(f"N = {N} Plummer, theta = {THETA}; modelled issue cycles per target (lower is better)")
 base = None
 for seg, cap, policy in ((256, 64, "fixed"), (128, 64, "fixed"), (512, 64, "fixed"), (256, 32, "fixed"),
-                         (256, 64, "balanced"), (256, 64, "pow2"), (256, 64, "cells"), (512, 64, "cells")):
+                         (256, 64, "balanced"), (256, 64, "pow2"), (256, 64, "cells"), (512, 64, "cells"),
+                         (256, 128, "fixed"), (512, 128, "fixed"), (1024, 128, "fixed")):  # 4 targets per lane
     c, it, gs = model(seg, cap, policy)
     base = base or c
     print(f"segments <= {seg:3d}, groups <= {cap:2d}, {policy:8s}: {c:8.0f} cycles/target ({100 * c / base:5.1f} %), "

@@ -35,53 +35,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
-namespace pcuda {
-namespace bh {
-
-// One tree node: 32 bytes = one DRAM sector.
-struct __align__(32) NodeRec {
-    float4 cm;             // centre of mass {x, y, z (0 in 2-D)}, w = total mu
-    uint32_t first_child;  // index of the first child (children are contiguous); 0 for leaves
-    uint32_t nchild_level; // n_children | level << 8
-    uint32_t begin;        // first sorted particle of the cell
-    uint32_t count;        // particles in the cell
-};
-
-struct Frame {  // quantisation frame == the reference's root cube
-    float origin[3];
-    float ext;
-    float inv;
-    float mass_bound;  // n * max|mu|: bounds the |mass| of every node (not part of the tree spec)
-};
-
-template <int DIM>
-struct Dims {
-    static constexpr int BITS = DIM == 3 ? 21 : 31;
-    static constexpr int X = 1 << DIM;
-};
-
-}  // namespace bh
-}  // namespace pcuda
-
-struct pcuda_tree {
-    int dim = 3, bits = 21;
-    size_t n = 0, n_nodes = 0;
-    int n_levels = 0;
-    uint32_t leaf_size = 16;
-    double nodes_per_particle = 0.5;    // capacity guess; doubled when a build overflows
-    std::vector<uint32_t> level_begin;  // n_levels + 1 entries
-    pcuda::bh::Frame frame = {};
-    pcuda::DevBuf keys[2], perm[2], sorted, nodes, moments, d_frame, scan_in, scan_out, cub_tmp,
-        partial;
-    pcuda::DevBuf quad64, quad;  // expansion order 2: traceless quadrupole per node, 6 doubles
-                                 // (build) and 2 x float4 {xx, xy, xz, yy}{yz, zz, 0, 0} (traversal)
-    int order = 1;
-    pcuda::DevBuf sorted64;  // f64 trees: the sources in key order as double4 {x, y, z|0, mu};
-                             // `moments` then holds the double-precision {com, mass} per node
-    int cur = 0;  // which of keys[]/perm[] holds the sorted data
-    uint64_t *d_keys() const { return keys[cur].as<uint64_t>(); }
-    uint32_t *d_perm() const { return perm[cur].as<uint32_t>(); }
-};
+#include "bh.cuh"
 
 namespace pcuda {
 namespace bh {
@@ -255,12 +209,6 @@ __global__ void __launch_bounds__(256) gather_kernel(const float *__restrict__ p
 // K4: level-by-level linear orthtree WITHOUT host round trips.  The level bounds live in device
 // memory (BuildState); one kernel per level is enqueued for all BITS levels up front and a kernel
 // whose level turns out empty returns at once.
-struct BuildState {
-    uint32_t level_begin[36];  // level l = nodes [level_begin[l], level_begin[l+1])
-    uint32_t ticket[34];       // tile dispenser of each level's kernel
-    uint32_t overflow;         // a level did not fit into `capacity` nodes
-    uint32_t capacity;
-};
 
 template <int DIM>
 __device__ __forceinline__ uint32_t next_digit_start(const uint64_t *__restrict__ keys, uint32_t pos,
@@ -291,6 +239,8 @@ __global__ void init_build(NodeRec *nodes, uint32_t n, BuildState *st, uint32_t 
 }
 
 constexpr int EXPAND_BLOCK = 128;
+static int g_level_build = 0;  // tuning / test hook: 1 = level-wise build instead of the one-pass build,
+                               // 2 = one-pass build at every size (also where build_small would run)
 static uint32_t g_small_level = 131072;  // levels up to this many nodes take the node-x-digit path
 
 // One level: every node with more than `nleaf` particles (and above the last level) is split into
@@ -2056,14 +2006,16 @@ static int build_levels(pcuda_ctx *ctx, pcuda_tree *t, size_t n) {
         PCUDA_CUDA_TRY(ctx, t->scan_in.ensure(sizeof(BuildState)));
         PCUDA_CUDA_TRY(ctx, t->scan_out.ensure(max_tiles * sizeof(unsigned long long)));
         BuildState *d_state = t->scan_in.as<BuildState>();
-        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(t->scan_out.p, 0, max_tiles * sizeof(unsigned long long), st));
-        if (n <= SMALL_TREE_MAX_N) {
+        if (n <= SMALL_TREE_MAX_N && g_level_build != 2) {
             build_small<DIM><<<1, SMALL_TREE_BLOCK, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(),
                                                              t->d_keys(), t->sorted.as<float4>(), d_state,
                                                              (uint32_t)n, (uint32_t)cap_nodes, t->leaf_size);
             PCUDA_CUDA_TRY(ctx, cudaGetLastError());
             ctx->launches += 1;
-        } else {
+        } else if (g_level_build != 1 && t->leaf_size <= (uint32_t)RB_MAX_LEAF) {
+            PCUDA_TRY(radix_build_enqueue<DIM>(ctx, t, n, cap_nodes, d_state));
+        } else {  // level-wise build (tuning hook bh_level_build; leaf sizes beyond the one-pass window)
+            PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(t->scan_out.p, 0, max_tiles * sizeof(unsigned long long), st));
             init_build<<<1, 1, 0, st>>>(t->nodes.as<NodeRec>(), (uint32_t)n, d_state, (uint32_t)cap_nodes);
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, max_tiles);
             for (int level = 0; level <= BITS; ++level)
@@ -3420,6 +3372,10 @@ int bh_debug_set(const char *key, int value) {
         bh::g_small_level = (uint32_t)value;
         return PCUDA_OK;
     }
+    if (k == "bh_level_build" && value >= 0 && value <= 2) {
+        bh::g_level_build = value;
+        return PCUDA_OK;
+    }
     if (k == "bh_variant" && value >= 0 && value <= 3) {
         bh::g_variant = value;
         return PCUDA_OK;
@@ -3444,7 +3400,7 @@ void tree_free(pcuda_ctx *ctx, pcuda_tree *t) {
     (void)ctx;
     DevBuf *bufs[] = {&t->keys[0], &t->keys[1], &t->perm[0], &t->perm[1], &t->sorted, &t->nodes,
                       &t->moments, &t->d_frame, &t->scan_in, &t->scan_out, &t->cub_tmp, &t->partial,
-                      &t->sorted64, &t->quad64, &t->quad};
+                      &t->sorted64, &t->quad64, &t->quad, &t->rb};
     for (DevBuf *b : bufs) b->release();
     delete t;
 }

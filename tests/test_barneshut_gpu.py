@@ -72,6 +72,35 @@ def test_tree_bit_exact_uniform(pb, ctx, dim, n, nleaf):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("nleaf", [1, 16, 32])
+def test_tree_bit_exact_one_pass_build(pb, ctx, dim, nleaf):
+    """The one-pass (radix) build of bh_radix_build.cu against the CPU statement of the tree
+    specification: clustered cloud above the single-block size, long runs of coincident particles
+    (leaves of unbounded size on the last level), massless particles, keys that differ in the last
+    digit only; then the same build forced at sizes where build_small normally runs (tile and
+    window edges: n around the leaf size, around one warp, around one 2048-particle tile), and the
+    level-wise build it replaces as a cross-check."""
+    from particular_b200._ffi import lib
+    p = plummer_cloud(120_000, d=dim, seed=31 + nleaf)
+    p[500:3700, :dim] = p[500, :dim]              # 3200 coincident particles
+    p[9000:9033, :dim] = p[9000, :dim]            # 33: one more than the widest leaf
+    p[20000:20100, dim] = 0.0                     # massless
+    p[30000:30040, :dim] = p[30000, :dim] * (1 + np.arange(40)[:, None] * 2e-7)  # last-digit neighbours
+    check_tree(pb, ctx, p, nleaf)
+    try:
+        assert lib.pcuda_debug_set(b"bh_level_build", 2) == 0
+        for n in (1, 2, nleaf, nleaf + 1, 31, 32, 33, 2047, 2048, 2049, 4100, 30000):
+            check_tree(pb, ctx, uniform_cloud(n, d=dim, seed=n + 7), nleaf)
+        q = uniform_cloud(5000, d=dim, seed=3)
+        q[:, :dim] = q[0, :dim]                   # every particle at one point: a single deep chain
+        check_tree(pb, ctx, q, nleaf)
+        assert lib.pcuda_debug_set(b"bh_level_build", 1) == 0
+        check_tree(pb, ctx, p, nleaf)
+    finally:
+        assert lib.pcuda_debug_set(b"bh_level_build", 0) == 0
+
+
+@pytest.mark.parametrize("dim", [2, 3])
 def test_tree_bit_exact_clustered_and_degenerate(pb, ctx, dim):
     p = plummer_cloud(30000, d=dim, seed=3)
     p[100:140, :dim] = p[100, :dim]           # 40 coincident particles: a leaf at the last level

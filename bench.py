@@ -148,6 +148,68 @@ def ncu_traffic(kernel_key):
         return None, None
 
 
+
+# ---- parity of the measured result buffers (checker only: the oracle is never on the timed path) ---
+PARITY_ROWS = 1024
+
+
+def _rel(a, ref):
+    den = np.linalg.norm(ref, axis=1)
+    return np.linalg.norm(np.asarray(a, np.float64) - ref, axis=1) / np.where(den > 0, den, 1.0)
+
+
+def _sample_rows(n_rows, m=PARITY_ROWS):
+    return np.unique(np.linspace(0, n_rows - 1, min(m, n_rows)).astype(np.int64))
+
+
+def _oracle_threads(world):
+    import oracle
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    oracle.lib().oracle_set_threads(max(1, cores // max(world, 1)))
+
+
+def parity_bruteforce(targets, rows, got, sources, softening, world=1):
+    """`rows` of the measured buffer `got` against the extended-precision sum over all `sources`
+    (oracle.brute_force_exact) and, beside it, the error of the restated sequential::BruteForce f32
+    left fold itself (err_gpu <= max(1e-5, err_ref) at N = 1M)."""
+    import oracle
+    _oracle_threads(world)
+    t = np.ascontiguousarray(targets[rows])
+    exact = oracle.brute_force_exact(t, sources, softening)
+    ref = oracle.brute_force_parallel(t, sources, softening)
+    e_gpu, e_ref = _rel(got[rows], exact), _rel(ref, exact)
+    return e_gpu, e_ref
+
+
+def parity_summary(e_gpu, e_ref, kind):
+    e_gpu, e_ref = np.asarray(e_gpu), np.asarray(e_ref)
+    out = {"n": int(len(e_gpu)), "max_rel": float(e_gpu.max()), "p99": float(np.percentile(e_gpu, 99)),
+           "median": float(np.median(e_gpu)), "ref_max_rel": float(e_ref.max()),
+           "ref_p99": float(np.percentile(e_ref, 99)), "ref_median": float(np.median(e_ref))}
+    if kind == "bruteforce":
+        out["against"] = ("extended-precision sum (oracle.brute_force_exact); ref_* = the restated "
+                          "sequential::BruteForce f32 fold on the same rows")
+        out["ok"] = bool(e_gpu.max() <= max(1e-5, e_ref.max()))
+    else:
+        out["against"] = ("extended-precision sum; ref_* = the restated sequential::BarnesHut at the "
+                          "same theta on the same rows; bound 1.1 x ref + 2e-6 on median / p99 / max")
+        out["ok"] = bool(out["median"] <= 1.1 * out["ref_median"] + 2e-6 and
+                         out["p99"] <= 1.1 * out["ref_p99"] + 2e-6 and
+                         out["max_rel"] <= 1.1 * out["ref_max_rel"] + 2e-6)
+    return out
+
+
+def gather_errors(e, world, dist):
+    """Every rank's sampled errors on rank 0 (equal-length arrays)."""
+    import torch
+    if world == 1:
+        return e
+    t = torch.from_numpy(np.ascontiguousarray(e, np.float64)).cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return torch.cat(parts).cpu().numpy()
+
+
 # ---- the other BASELINE.json configs + the stepping path (ride along at 1 GPU) -----------------------
 def other_configs(ctx, stream, flush, steps=3):
     """configs[2] (10k massive + 16M massless split), configs[4] (f64 N=256k; 2-D Barnes-Hut N=4M)
@@ -176,31 +238,6 @@ def other_configs(ctx, stream, flush, steps=3):
         return sum(ts) / len(ts)
 
     rng = np.random.default_rng(SEED)
-    # configs[2]: ring-formation style split, `Reordered`: all particles affected, massive affecting
-    n_massive, n_massless = 10_000, 16_000_000
-    src = uniform_cloud(n_massive)
-    d_src = torch.from_numpy(src).to(dev)
-    tgt = np.empty((n_massive + n_massless, 3), np.float32)
-    tgt[:n_massive] = src[:, :3]
-    tgt[n_massive:] = rng.uniform(-5e3, 5e3, (n_massless, 3))
-    d_tgt = torch.from_numpy(tgt).to(dev)
-    d_out = torch.empty_like(d_tgt)
-    bf = pb.BruteForce(ctx, pb.AccelerationSoftened.checked(1.0))
-    ms = timed(lambda: bf.compute_device(d_tgt.data_ptr(), len(tgt), d_src.data_ptr(), n_massive,
-                                         d_out.data_ptr()))
-    h_tgt = ctx.pinned_empty(tgt.shape, np.float32)
-    h_tgt[:] = tgt
-    h_out = ctx.pinned_empty(tgt.shape, np.float32)
-    e2e = timed(lambda: bf.compute(pb.Between(h_tgt, src), out=h_out), k=2, warm=1)
-    pairs = float(len(tgt)) * n_massive
-    out["split_10k_massive_16M_massless"] = {
-        "config": "BASELINE configs[2]: 10,000 massive + 16,000,000 massless, Between(all, massive) "
-                  "(Reordered storage), AccelerationSoftened::checked(1.0)",
-        "pairs_per_step": pairs, "ms_per_step": ms, "value": pairs / ms / 1e6, "unit": "Gpairs/s",
-        "e2e": {"ms_per_step": e2e, "value": pairs / e2e / 1e6, "unit": "Gpairs/s",
-                "h2d_bytes_per_step": int(tgt.nbytes + src.nbytes), "d2h_bytes_per_step": int(tgt.nbytes)}}
-    del d_tgt, d_out, d_src
-
     # configs[4a]: f64 precision path
     n64 = 262_144
     p64 = uniform_cloud(n64).astype(np.float64)
@@ -210,10 +247,19 @@ def other_configs(ctx, stream, flush, steps=3):
     ms = timed(lambda: bf64.compute_device(None, n64, d_p.data_ptr(), n64, d_o.data_ptr(), "f64x3"))
     peak64 = ctx.sm_count * 64 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
     tf = FLOP_PER_PAIR * float(n64) * n64 / (ms * 1e-3) / 1e12
+    rows = _sample_rows(n64)
+    got64 = d_o.cpu().numpy()
+    import oracle
+    _oracle_threads(1)
+    ref64 = oracle.brute_force_parallel(np.ascontiguousarray(p64[rows, :3]), p64)
+    e64 = _rel(got64[rows], ref64)
     out["f64_256k"] = {"config": "BASELINE configs[4]: brute force 3-D f64, N=262144, Acceleration::checked()",
                        "ms_per_step": ms, "value": float(n64) * n64 / ms / 1e6, "unit": "Gpairs/s",
                        "fp64_tflops_20flop_per_pair": tf, "fp64_peak_tflops_nominal": peak64,
-                       "frac": tf / peak64}
+                       "frac": tf / peak64,
+                       "parity": {"n": int(len(rows)), "max_rel": float(e64.max()), "bound": 1e-12,
+                                  "ok": bool(e64.max() <= 1e-12),
+                                  "against": "restated sequential::BruteForce f64 fold, same rows"}}
     del d_p, d_o
 
     # configs[4b]: particle-toy style 2-D quadtree
@@ -226,10 +272,17 @@ def other_configs(ctx, stream, flush, steps=3):
     bh2 = pb.BarnesHut(ctx, 0.5, pb.AccelerationSoftened.checked(100.0))
     ms = timed(lambda: bh2.compute_device(None, n2, d_p.data_ptr(), n2, d_o.data_ptr(), "f32x2"))
     t = ctx.timings()
+    rows = _sample_rows(n2, 512)
+    got2 = d_o.cpu().numpy()
+    ex2 = oracle.brute_force_exact(np.ascontiguousarray(p2[rows, :2]), p2, 100.0)
+    e2 = _rel(got2[rows], ex2)
     out["barnes_hut_2d_4M"] = {"config": "BASELINE configs[4]: Barnes-Hut 2-D f32 quadtree, theta=0.5, N=4194304 "
                                          "uniform square, AccelerationSoftened::checked(100)",
                                "ms_per_step": ms, "build_ms": t["build_ms"], "traverse_ms": t["compute_ms"],
-                               "value": n2 / (ms * 1e-3), "unit": "particles/s"}
+                               "value": n2 / (ms * 1e-3), "unit": "particles/s",
+                               "theta_error_vs_exact": {"n": int(len(rows)), "median": float(np.median(e2)),
+                                                        "p99": float(np.percentile(e2, 99)),
+                                                        "max_rel": float(e2.max())}}
     del d_p, d_o
 
     # device-resident stepping at the reference's criterion size (benches/benchmark.rs: N = 2^k)
@@ -256,14 +309,35 @@ def other_configs(ctx, stream, flush, steps=3):
     for _ in range(200):
         one.compute(pb_small)
     res["one_shot_host_api"] = {"us_per_step_wall": 1e6 * (time.perf_counter() - t0) / 200}
-    out["stepping_1024"] = {"config": "device-resident stepping (pcuda_sim_*), brute force 3-D f32, N=1024 "
-                                      "(criterion bench shape), 2048 steps; one_shot_host_api = upload + "
-                                      "kernel + read-back per step, as the reference's wgpu operator works",
+    res["cpu_scalar"] = cpu_scalar_1024()
+    got = one.compute(pb_small)
+    res["parity"] = {"n": nb, "max_rel": float(_rel(got, oracle.brute_force(pb_small[:, :3], pb_small)
+                                                   .astype(np.float64)).max()),
+                     "bound": 1e-5, "against": "restated sequential::BruteForce (bit-faithful f32 fold)"}
+    res["parity"]["ok"] = bool(res["parity"]["max_rel"] <= 1e-5)
+    out["stepping_1024"] = {"config": "BASELINE configs[0] shape (benches/benchmark.rs:97-131, N=1024): "
+                                      "device-resident stepping (pcuda_sim_*), brute force 3-D f32, 2048 steps; "
+                                      "one_shot_host_api = upload + kernel + read-back per step, as the "
+                                      "reference's wgpu operator works; cpu_scalar = the restated "
+                                      "sequential::BruteForce on one host core",
                             **res}
     return out
 
 
 # ---- CPU arms ----------------------------------------------------------------------------------------
+def cpu_scalar_1024(n=1024, reps=20):
+    """BASELINE configs[0]: sequential::BruteForce (scalar, one core) at the criterion bench shape."""
+    import oracle
+    P = uniform_cloud(n)
+    oracle.brute_force(P[:, :3], P)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.brute_force(P[:, :3], P)
+    dt = (time.perf_counter() - t0) / reps
+    return {"ms_per_step": 1e3 * dt, "value": n * n / dt / 1e9, "unit": "Gpairs/s", "cores": 1, "n": n,
+            "kind": "port", "what": "restated sequential::BruteForce, oracle/oracle_impl.inc"}
+
+
 def cpu_bruteforce_rate(P, seconds, steps=1, targets=None, softening=0.0):
     """Restated parallel::BruteForceSimd<8> on a bounded target sample x all sources.
     `targets`: affected positions when they are not the sources themselves.
@@ -289,16 +363,18 @@ def cpu_bruteforce_rate(P, seconds, steps=1, targets=None, softening=0.0):
     return rate, f"first {sample} targets x all {n} sources, scaled linearly", cores, times
 
 
-def cpu_barneshut_rate(P, theta, seconds):
+def cpu_barneshut_rate(P, theta, seconds, tree=None, t_build=None):
     """Restated parallel::BarnesHut: single-thread build of the full tree + OpenMP traversal of a
-    bounded target sample; the per-evaluation time is build + traversal scaled to all targets."""
+    bounded target sample; the per-evaluation time is build + traversal scaled to all targets.
+    `tree` / `t_build`: a tree over P built (and timed) by the caller already."""
     import oracle
     n = len(P)
     oracle.use_all_cores()
     cores = oracle.baseline_threads()
-    t0 = time.perf_counter()
-    tree = oracle.Tree(P)
-    t_build = time.perf_counter() - t0
+    if tree is None:
+        t0 = time.perf_counter()
+        tree = oracle.Tree(P)
+        t_build = time.perf_counter() - t0
     probe = min(n, 512 * cores)
     idx = np.linspace(0, n - 1, probe).astype(np.int64)
     t0 = time.perf_counter()
@@ -334,7 +410,8 @@ def main():
                     help="multi-GPU Barnes-Hut: how the accelerations reach the ranks that own the "
                          "particles (auto: all-to-all from 4 GPUs and 32M particles on)")
     ap.add_argument("--no-extra", action="store_true",
-                    help="skip the cpu_baseline leg and the ride-along Barnes-Hut number")
+                    help="skip the cpu_baseline leg and the ride-along Barnes-Hut / split numbers")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the result buffers")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -355,87 +432,96 @@ def main():
     return bench_barneshut(args, n, rank, world, local_rank)
 
 
+SIMD_NOTE = "; restated parallel::BruteForceSimd<8> (AVX2 rsqrt + OpenMP), oracle/baseline_simd.c"
+
+
 def reference_arm(args, n, world):
-    """The reference's CPU implementation of the path (restated; kind "port") on all host cores."""
-    if args.workload == "bruteforce":
-        P = uniform_cloud(n)
+    """The reference's CPU implementation of the path (restated; kind "port") on all host cores.
+    The brute-force line also carries the other reference numbers a ratio can be formed from:
+    `scalar_1024` (BASELINE configs[0], sequential::BruteForce at N = 1024, one core) and
+    `barnes_hut` (restated parallel::BarnesHut, configs[3]) — bounded samples, stated."""
+    common = {"impl": "reference", "n_gpus": world, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gpu_launches": 0}
+    if args.workload in ("bruteforce", "split"):
+        if args.workload == "bruteforce":
+            P, tgt, soft = uniform_cloud(n), None, 0.0
+            n_src, config = n, bruteforce_config(n, world)
+        else:
+            tgt, P = split_cloud(10_000, n)
+            soft, n_src, config = 1.0, len(P), split_config(10_000, n, world)
         per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-        rate, sample, cores, times = cpu_bruteforce_rate(P, per_step, steps=args.steps + args.warmup)
+        rate, sample, cores, times = cpu_bruteforce_rate(P, per_step, steps=args.steps + args.warmup,
+                                                         targets=tgt, softening=soft)
         times = times[args.warmup:] or times
         sample_n = int(sample.split()[1])
-        value = sample_n * n / (sum(times) / len(times)) / 1e9
-        line = {"impl": "reference", "metric": "brute-force pair interactions per second",
-                "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": bruteforce_config(n, world, "cpu"),
+        value = sample_n * float(n_src) / (sum(times) / len(times)) / 1e9
+        line = {**common, "metric": "brute-force pair interactions per second", "value": value,
+                "unit": "Gpairs/s", "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * sum(times) / len(times), "config": config,
+                "ms_per_step_is": "the time of the stated target sample, not of a whole step",
                 "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": "port",
-                                 "sample": sample + "; restated parallel::BruteForceSimd<8> "
-                                 "(AVX2 rsqrt + OpenMP), oracle/baseline_simd.c"},
-                "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    elif args.workload == "split":
-        tgt, src = split_cloud(10_000, n)
-        per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-        rate, sample, cores, times = cpu_bruteforce_rate(src, per_step, steps=args.steps + args.warmup,
-                                                         targets=tgt, softening=1.0)
-        times = times[args.warmup:] or times
-        sample_n = int(sample.split()[1])
-        value = sample_n * float(len(src)) / (sum(times) / len(times)) / 1e9
-        line = {"impl": "reference", "metric": "brute-force pair interactions per second",
-                "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": f"brute force 3-D f32 massive/massless split: 10000 massive + {n} "
-                                       f"massless (BASELINE configs[2]); AccelerationSoftened::checked(1.0)",
-                           "parallelism": "host threads over targets"},
-                "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": "port",
-                                 "sample": sample + "; restated parallel::BruteForceSimd<8> "
-                                 "(AVX2 rsqrt + OpenMP), oracle/baseline_simd.c"},
-                "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                                 "sample": sample + SIMD_NOTE},
+                "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if args.workload == "bruteforce" and not args.no_extra:
+            line["scalar_1024"] = cpu_scalar_1024()
+            try:
+                v, smp, c, tb, tt = cpu_barneshut_rate(plummer_cloud(10_000_000), args.theta, 8.0)
+                line["barnes_hut"] = {"value": v, "unit": "particles/s", "cores": c, "kind": "port",
+                                      "build_s": tb, "traverse_s": tt, "sample": smp}
+            except Exception as e:
+                line["barnes_hut"] = {"error": repr(e)}
     else:
         P = plummer_cloud(n)
         value, sample, cores, tb, tt = cpu_barneshut_rate(P, args.theta, 20.0)
-        line = {"impl": "reference", "metric": "Barnes-Hut particles per second (build + traversal)",
-                "value": value, "unit": "particles/s", "n_gpus": world, "steps": 1, "warmup": 0,
-                "ms_per_step": 1e3 * (tb + tt), "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": barneshut_config(n, world, args.theta, "cpu"),
-                "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores,
-                                 "kind": "port", "sample": sample},
+        line = {**common, "metric": "Barnes-Hut particles per second (build + traversal)", "value": value,
+                "unit": "particles/s", "steps": 1, "warmup": 0, "ms_per_step": 1e3 * (tb + tt),
+                "config": barneshut_config(n, args.theta, world, args.bh_build),
+                "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": "port",
+                                 "sample": sample},
                 "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                        "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def bruteforce_config(n, world, where):
+# `config` is the same object in both arms (the driver compares them): it names the workload and says,
+# for either arm, how it is spread and what happens to the L2 between timed steps.
+def bruteforce_config(n, world):
     return {"workload": f"brute force 3-D f32, N={n} massive particles, all pairs "
                         f"(BASELINE configs[1]); uniform cube, mu U[1e3,1e9), seed {SEED}; "
                         f"Acceleration::checked(), softening 0",
             "n_particles": n, "pairs_per_step": n * n,
-            "parallelism": f"targets sharded over {world} GPU(s), sources all-gathered (NCCL)"
-            if where == "gpu" else "host threads over targets",
-            "l2": "256 MiB buffer written between timed steps (L2 flush); the 16 MB source set "
-                  "is re-read from L2 by design" if where == "gpu" else "n/a"}
+            "parallelism": f"GPU arm: targets sharded over {world} GPU(s), sources all-gathered (NCCL); "
+                           f"reference arm: host threads over targets",
+            "l2": "GPU arm: 256 MiB buffer written between timed steps (L2 flush), the 16 MB source set is "
+                  "re-read from L2 by design; reference arm: n/a"}
 
 
-def barneshut_config(n, world, theta, where, build="auto"):
+def split_config(n_massive, n_massless, world):
+    return {"workload": f"brute force 3-D f32 massive/massless split: {n_massive} massive + {n_massless} "
+                        f"massless, Between(all, massive) (Reordered storage; BASELINE configs[2]); "
+                        f"uniform cube, seed {SEED}; AccelerationSoftened::checked(1.0)",
+            "n_affected": n_massive + n_massless, "n_affecting": n_massive,
+            "pairs_per_step": float(n_massive + n_massless) * n_massive,
+            "parallelism": f"GPU arm: affected sharded over {world} GPU(s), massive records all-gathered "
+                           f"(NCCL, {16 * n_massive} B); reference arm: host threads over targets",
+            "l2": "GPU arm: 256 MiB buffer written between timed steps (L2 flush), the 160 KB source set is "
+                  "re-read from L2 by design; reference arm: n/a"}
+
+
+def barneshut_config(n, theta, world, build="auto"):
     if build == "auto":
         build = "partitioned" if world >= 4 else "replicated"
     how = ("tree build replicated" if build == "replicated" else
-           "one tree per GPU over its key range (partitioned build), trees all-gathered and joined "
-           "by a top tree")
+           "one tree per GPU over its key range (partitioned build), joined by a top tree")
     return {"workload": f"Barnes-Hut 3-D f32 octree, theta={theta}, N={n} Plummer sphere (a=1, "
                         f"r<50a, equal mu=1/N, seed {SEED}); tree rebuilt every step "
                         f"(BASELINE configs[3]); Acceleration::checked()",
             "n_particles": n, "theta": theta,
-            "parallelism": (f"{world} GPU(s): particles all-gathered (NCCL), {how}, "
-                            f"targets sharded by key range" if world > 1 else "1 GPU") if where == "gpu"
-            else "host threads over targets",
-            "l2": "inputs + tree exceed L2 at N=10M; 256 MiB buffer written between timed steps"
-            if where == "gpu" else "n/a"}
+            "parallelism": (f"GPU arm: {world} GPU(s), {how}, targets sharded by key range" if world > 1
+                            else "GPU arm: 1 GPU") + "; reference arm: single-thread build, host threads "
+                                                     "over targets",
+            "l2": "GPU arm: inputs + tree exceed L2 at N=10M, 256 MiB buffer written between timed steps; "
+                  "reference arm: n/a"}
 
 
 def _dist_setup(world, local_rank):
@@ -449,7 +535,7 @@ def _dist_setup(world, local_rank):
 
 def _max_over_ranks(x, world, dist):
     import torch
-    if world == 1:
+    if world == 1 or dist is None:
         return x
     t = torch.tensor([x], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -458,7 +544,7 @@ def _max_over_ranks(x, world, dist):
 
 def _sum_over_ranks(x, world, dist):
     import torch
-    if world == 1:
+    if world == 1 or dist is None:
         return x
     t = torch.tensor([x], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -468,9 +554,32 @@ def _sum_over_ranks(x, world, dist):
 def _barrier(world, dist):
     import torch
     torch.cuda.synchronize()
-    if world > 1:
+    if world > 1 and dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+
+
+def _timed_steps(ctx, stream, flush, step_fn, k):
+    """k steps, each bracketed by CUDA events on the context stream; L2 flushed between steps."""
+    import torch
+    times, tm, launches = [], [], 0
+    for _ in range(k):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_fn()
+        e1.record(stream)
+        ctx.sync()
+        times.append(e0.elapsed_time(e1))
+        t = ctx.timings()
+        tm.append(t)
+        launches += t["kernel_launches"]
+    return times, tm, launches
+
+
+def _compact(d, keys):
+    return {k: (round(d[k], 4) if isinstance(d[k], float) else d[k]) for k in keys if k in d}
 
 
 def bench_bruteforce(args, n, rank, world, local_rank):
@@ -490,32 +599,16 @@ def bench_bruteforce(args, n, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local_rank)
 
-    def timed_steps(step_fn, k):
-        """Each step bracketed by events on the context stream; L2 flushed between steps."""
-        times, kernel_ms, launches = [], [], 0
-        for _ in range(k):
-            with torch.cuda.stream(stream):
-                flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step_fn()
-            e1.record(stream)
-            ctx.sync()
-            times.append(e0.elapsed_time(e1))
-            t = ctx.timings()
-            kernel_ms.append(t["compute_ms"])
-            launches += t["kernel_launches"]
-        return times, kernel_ms, launches
-
     # ---- device-resident value ----
     dev_step = lambda: sh.step_device(d_local, n)  # noqa: E731
     for _ in range(args.warmup):
         dev_step()
     _barrier(world, dist)
     sampler.start()
-    times, kernel_ms, launches = timed_steps(dev_step, args.steps)
+    times, tm, launches = _timed_steps(ctx, stream, flush, dev_step, args.steps)
     _barrier(world, dist)
     sampler.stop()
+    kernel_ms = [t["compute_ms"] for t in tm]
     total_ms = _max_over_ranks(sum(times), world, dist)
     ms_per_step = total_ms / args.steps
     value = n * float(n) / (ms_per_step * 1e-3) / 1e9
@@ -529,10 +622,19 @@ def bench_bruteforce(args, n, rank, world, local_rank):
     for _ in range(2):
         e2e_step()
     _barrier(world, dist)
-    e2e_times, _, _ = timed_steps(e2e_step, args.steps)
+    e2e_times, _, _ = _timed_steps(ctx, stream, flush, e2e_step, args.steps)
     _barrier(world, dist)
     e2e_ms = _max_over_ranks(sum(e2e_times), world, dist) / args.steps
     e2e_value = n * float(n) / (e2e_ms * 1e-3) / 1e9
+
+    # ---- parity of the result buffer the e2e steps wrote (every rank: rows of its own block) ----
+    parity = None
+    if not args.no_parity:
+        rows = _sample_rows(n_local, max(128, PARITY_ROWS // world))
+        e_gpu, e_ref = parity_bruteforce(P[lo:hi, :3], rows, np.asarray(h_out), P, 0.0, world)
+        parity = parity_summary(gather_errors(e_gpu, world, dist), gather_errors(e_ref, world, dist),
+                                "bruteforce")
+        parity["rows"] = f"{len(rows)} evenly spaced rows of every rank's block, e2e result buffer"
 
     # ---- roofline of the pair kernel (this rank's launch) ----
     k_ms = sum(kernel_ms) / len(kernel_ms)
@@ -555,7 +657,7 @@ def bench_bruteforce(args, n, rank, world, local_rank):
             "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bruteforce_config(n, world, "gpu"),
+            "config": bruteforce_config(n, world),
             "e2e": {"value": e2e_value, "unit": "Gpairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(n_local * 12),
                     "bytes_are": "per rank"},
@@ -565,25 +667,43 @@ def bench_bruteforce(args, n, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_extra:
         rate, sample, cores, _ = cpu_bruteforce_rate(P, args.cpu_seconds)
         line["cpu_baseline"] = {"value": rate, "unit": "Gpairs/s", "cores": cores, "kind": "port",
-                                "sample": sample + "; restated parallel::BruteForceSimd<8> (AVX2 "
-                                "rsqrt + OpenMP), oracle/baseline_simd.c"}
-        try:
-            line["barnes_hut"] = barneshut_numbers(args, ctx, stream, flush, 10_000_000, args.theta,
-                                                   steps=3, warmup=2, cpu_seconds=args.cpu_seconds)
-        except Exception as e:  # keep the headline line even if the ride-along fails
-            line["barnes_hut"] = {"error": repr(e)}
-        try:
-            line["other_configs"] = other_configs(ctx, stream, flush)
-        except Exception as e:
-            line["other_configs"] = {"error": repr(e)}
-    if world > 1 and not args.no_extra:
-        # BASELINE configs[3] at this world size rides along (collective: every rank takes part)
+                                "sample": sample + SIMD_NOTE}
+    del d_local
+    bh = split = None
+    if not args.no_extra:
+        # BASELINE configs[3] and configs[2] ride along at every world size (collective: every rank takes part)
         try:
             bh = barneshut_numbers(args, ctx, stream, flush, 10_000_000, args.theta, steps=3, warmup=2,
-                                   cpu_seconds=0.0, rank=rank, world=world, dist=dist, init_comm=False)
-            line["barnes_hut"] = bh
+                                   cpu_seconds=args.cpu_seconds, rank=rank, world=world, dist=dist,
+                                   init_comm=False)
+        except Exception as e:  # keep the headline line even if a ride-along fails
+            bh = {"error": repr(e)}
+        try:
+            split = split_numbers(args, ctx, stream, flush, 10_000, 16_000_000, steps=3, warmup=2,
+                                  rank=rank, world=world, dist=dist, init_comm=False)
         except Exception as e:
-            line["barnes_hut"] = {"error": repr(e)}
+            split = {"error": repr(e)}
+        line["barnes_hut"], line["split_10k_massive_16M_massless"] = bh, split
+        if rank == 0 and world == 1:
+            try:
+                line["other_configs"] = other_configs(ctx, stream, flush)
+            except Exception as e:
+                line["other_configs"] = {"error": repr(e)}
+    # compact copies: last in the line (the driver keeps the tail of stdout) and inside `roofline`
+    # (a key the driver's parser keeps whole)
+    ride = {}
+    if parity is not None:
+        ride["parity"] = _compact(parity, ["n", "max_rel", "p99", "ref_max_rel", "ok"])
+    if bh is not None:
+        ride["bh"] = bh.get("compact", bh)
+    if split is not None:
+        ride["split"] = split.get("compact", split)
+    roofline["ride_along"] = ride
+    if parity is not None:
+        line["parity"] = parity
+    for k, v in ride.items():
+        if k != "parity":
+            line[k] = v
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -594,7 +714,7 @@ def bench_bruteforce(args, n, rank, world, local_rank):
 
 def split_cloud(n_massive, n_massless):
     """BASELINE configs[2]: the massive bodies first, then the massless ones (the order Reordered's
-    affected side has when the input is already partitioned); same draws as other_configs()."""
+    affected side has when the input is already partitioned)."""
     rng = np.random.default_rng(SEED)
     src = uniform_cloud(n_massive)
     tgt = np.empty((n_massive + n_massless, 3), np.float32)
@@ -603,51 +723,30 @@ def split_cloud(n_massive, n_massless):
     return tgt, src
 
 
-def bench_split(args, n_massless, rank, world, local_rank):
-    """BASELINE configs[2] at 1/2/4/8 GPUs: 10,000 massive act on themselves + n_massless massless
-    particles; the affected particles are sharded, the massive records all-gathered each step
-    (pcuda_bruteforce_f32x3_between_sharded).  Strong scaling."""
+def split_numbers(args, ctx, stream, flush, n_massive, n_massless, steps, warmup, rank=0, world=1,
+                  dist=None, init_comm=True):
+    """BASELINE configs[2] at 1/2/4/8 GPUs: n_massive massive bodies act on themselves + n_massless
+    massless particles; the affected particles are sharded, the massive records all-gathered each
+    step (pcuda_bruteforce_f32x3_between_sharded).  Strong scaling."""
     import torch
 
     import particular_b200 as pb
-    dist = _dist_setup(world, local_rank)
-    dev = torch.device("cuda", local_rank)
-    ctx = pb.CudaContext(local_rank)
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
-    n_massive = 10_000
-    sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0))
+    dev = torch.device("cuda", ctx.device)
+    sb = pb.ShardedBetween(ctx, pb.AccelerationSoftened.checked(1.0), init_comm=init_comm and world > 1)
+    sb.world, sb.rank = world, rank
     tgt, src = split_cloud(n_massive, n_massless)
     n_aff = len(tgt)
     lo, hi = pb.shard_bounds(n_aff, world, rank)
     slo, shi = pb.shard_bounds(n_massive, world, rank)
     d_tgt = torch.from_numpy(tgt[lo:hi]).to(dev)
     d_src = torch.from_numpy(src[slo:shi]).to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sampler = ClockSampler(local_rank)
-
-    def timed_steps(step_fn, k):
-        times, launches = [], 0
-        for _ in range(k):
-            with torch.cuda.stream(stream):
-                flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step_fn()
-            e1.record(stream)
-            ctx.sync()
-            times.append(e0.elapsed_time(e1))
-            launches += ctx.timings()["kernel_launches"]
-        return times, launches
-
     dev_step = lambda: sb.step_device(d_tgt, d_src, n_massive)  # noqa: E731
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         dev_step()
     _barrier(world, dist)
-    sampler.start()
-    times, launches = timed_steps(dev_step, args.steps)
+    times, tm, launches = _timed_steps(ctx, stream, flush, dev_step, steps)
     _barrier(world, dist)
-    sampler.stop()
-    ms_per_step = _max_over_ranks(sum(times), world, dist) / args.steps
+    ms_per_step = _max_over_ranks(sum(times), world, dist) / steps
     pairs = float(n_aff) * n_massive
     total_launches = int(_sum_over_ranks(launches, world, dist))
 
@@ -659,38 +758,62 @@ def bench_split(args, n_massless, rank, world, local_rank):
     for _ in range(2):
         e2e_step()
     _barrier(world, dist)
-    e2e_times, _ = timed_steps(e2e_step, args.steps)
+    e2e_times, _, _ = _timed_steps(ctx, stream, flush, e2e_step, steps)
     _barrier(world, dist)
-    e2e_ms = _max_over_ranks(sum(e2e_times), world, dist) / args.steps
+    e2e_ms = _max_over_ranks(sum(e2e_times), world, dist) / steps
 
-    k_ms = sum(times) / len(times)
+    parity = None
+    if not args.no_parity:
+        rows = _sample_rows(hi - lo, max(128, PARITY_ROWS // world))
+        e_gpu, e_ref = parity_bruteforce(tgt[lo:hi], rows, np.asarray(h_out), src, 1.0, world)
+        parity = parity_summary(gather_errors(e_gpu, world, dist), gather_errors(e_ref, world, dist),
+                                "bruteforce")
+    k_ms = sum(t["compute_ms"] for t in tm) / len(tm)
     achieved = FLOP_PER_PAIR * float(hi - lo) * n_massive / (k_ms * 1e-3) / 1e12
-    sm_max_mhz = (sampler.max_mhz or ctx.sm_clock_khz / 1e3)
-    peak_nominal = ctx.sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-    line = {"metric": "brute-force pair interactions per second", "value": pairs / ms_per_step / 1e6,
-            "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"brute force 3-D f32 massive/massless split: {n_massive} massive + "
-                                   f"{n_massless} massless, Between(all, massive) (Reordered storage; "
-                                   f"BASELINE configs[2]); uniform cube, seed {SEED}; "
-                                   f"AccelerationSoftened::checked(1.0)",
-                       "n_affected": n_aff, "n_affecting": n_massive, "pairs_per_step": pairs,
-                       "parallelism": f"affected sharded over {world} GPU(s), massive records "
-                                      f"all-gathered (NCCL, {16 * n_massive} B)",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); the 160 KB source "
-                             "set is re-read from L2 by design"},
-            "e2e": {"value": pairs / e2e_ms / 1e6, "unit": "Gpairs/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(h_tgt.nbytes + h_src.nbytes),
-                    "d2h_bytes_per_step": int(h_out.nbytes), "bytes_are": "per rank"},
-            "gpu_launches": total_launches,
-            "roofline": {"bound": "fp32", "kernel": "pcuda::bf::pair_kernel_f32<3,...>",
-                         "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
-                         "frac": achieved / peak_nominal, "flop_per_pair": FLOP_PER_PAIR,
-                         "kernel_ms": k_ms, "traffic": None,
-                         "note": "whole device-resident step of this rank (fill + all-gather + pair "
-                                 "kernel + split reduction)"},
-            "clocks": sampler.summary(), "device": ctx.name}
+    peak_nominal = ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
+    out = {"metric": "brute-force pair interactions per second", "value": pairs / ms_per_step / 1e6,
+           "unit": "Gpairs/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+           "config": split_config(n_massive, n_massless, world),
+           "e2e": {"value": pairs / e2e_ms / 1e6, "unit": "Gpairs/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(h_tgt.nbytes + h_src.nbytes),
+                   "d2h_bytes_per_step": int(h_out.nbytes), "bytes_are": "per rank"},
+           "gpu_launches": total_launches,
+           "roofline": {"bound": "fp32", "kernel": "pcuda::bf::pair_kernel_f32<3,...>",
+                        "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
+                        "frac": achieved / peak_nominal, "flop_per_pair": FLOP_PER_PAIR,
+                        "kernel_ms": k_ms, "traffic": None}}
+    if parity is not None:
+        out["parity"] = parity
+    out["compact"] = {"value": round(out["value"], 1), "unit": "Gpairs/s", "ms": round(ms_per_step, 3),
+                      "e2e": round(out["e2e"]["value"], 1), "e2e_ms": round(e2e_ms, 3),
+                      "frac": round(achieved / peak_nominal, 4)}
+    if parity is not None:
+        out["compact"]["parity"] = _compact(parity, ["n", "max_rel", "ref_max_rel", "ok"])
+    del d_tgt, d_src
+    return out
+
+
+def bench_split(args, n_massless, rank, world, local_rank):
+    import torch
+
+    import particular_b200 as pb
+    dist = _dist_setup(world, local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = pb.CudaContext(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    res = split_numbers(args, ctx, stream, flush, 10_000, n_massless, args.steps, args.warmup, rank, world, dist)
+    sampler.stop()
+    line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": res["config"], "e2e": res["e2e"],
+            "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "clocks": sampler.summary(),
+            "device": ctx.name}
+    if "parity" in res:
+        line["parity"] = res["parity"]
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -702,8 +825,8 @@ def bench_split(args, n_massless, rank, world, local_rank):
 def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_seconds, rank=0,
                       world=1, dist=None, init_comm=True):
     """Barnes-Hut: device-resident particles/s (tree rebuilt + traversal every step), e2e through
-    the host API, work counters, CPU restatement beside it.  world > 1: every rank owns a block of
-    the particles, all-gathers the records, builds the identical tree and traverses its block."""
+    the host API, work counters, parity of the e2e result buffer, CPU restatement beside it.
+    world > 1: every rank owns a block of the particles (pcuda_barneshut_f32x3_sharded)."""
     import torch
 
     import particular_b200 as pb
@@ -723,31 +846,13 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
         d_src = torch.from_numpy(P[lo:hi]).to(dev)
         dev_step = lambda: bh.step_device(d_src, n)  # noqa: E731
 
-    def run(step_fn, k):
-        times, tm, launches = [], [], 0
-        for _ in range(k):
-            with torch.cuda.stream(stream):
-                flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step_fn()
-            e1.record(stream)
-            ctx.sync()
-            times.append(e0.elapsed_time(e1))
-            t = ctx.timings()
-            tm.append(t)
-            launches += t["kernel_launches"]
-        return times, tm, launches
-
     for _ in range(warmup):
         dev_step()
     ctx.sync()
-    if dist is not None:
-        _barrier(world, dist)
-    times, tm, launches = run(dev_step, steps)
-    if dist is not None:
-        _barrier(world, dist)
-    ms = _max_over_ranks(sum(times), world, dist) / steps if dist is not None else sum(times) / steps
+    _barrier(world, dist)
+    times, tm, launches = _timed_steps(ctx, stream, flush, dev_step, steps)
+    _barrier(world, dist)
+    ms = _max_over_ranks(sum(times), world, dist) / steps
     build_ms = sum(t["build_ms"] for t in tm) / len(tm)
     trav_ms = sum(t["compute_ms"] for t in tm) / len(tm)
     comm_ms = sum(t["comm_ms"] for t in tm) / len(tm)
@@ -761,12 +866,10 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
     else:
         e2e_step = lambda: bh.compute_local(h_in, n, out=h_out)  # noqa: E731
     e2e_step()
-    if dist is not None:
-        _barrier(world, dist)
-    e2e_times, _, _ = run(e2e_step, steps)
-    if dist is not None:
-        _barrier(world, dist)
-    e2e_ms = (_max_over_ranks(sum(e2e_times), world, dist) if dist is not None else sum(e2e_times)) / steps
+    _barrier(world, dist)
+    e2e_times, _, _ = _timed_steps(ctx, stream, flush, e2e_step, steps)
+    _barrier(world, dist)
+    e2e_ms = _max_over_ranks(sum(e2e_times), world, dist) / steps
     inter_n = counters["node_interactions"] + counters["particle_interactions"]
     # algorithmic bytes of the traversal: one 32-byte record per node test, one
     # 16-byte record per particle entry appended to a group's list, 16 B read + 12 B written per target
@@ -775,34 +878,75 @@ def barneshut_numbers(args, ctx, stream, flush, n, theta, steps, warmup, cpu_sec
     trav_bytes = 32.0 * counters["node_tests"] + 16.0 * part_entries + 28.0 * n_local
     hbm_peak, hbm_src = measured_hbm_peak()
     achieved_gbs = trav_bytes / (trav_ms * 1e-3) / 1e9
-    total_launches = int(_sum_over_ranks(launches, world, dist)) if dist is not None else launches
+    total_launches = int(_sum_over_ranks(launches, world, dist))
+    fp32_peak = ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
+    fp32_ach = FLOP_PER_PAIR * inter_n / (trav_ms * 1e-3) / 1e12
+
+    # ---- parity of the e2e result buffer: every rank against the extended-precision sum; rank 0 also
+    # runs the restated reference algorithm (sequential::BarnesHut, same theta) on its rows ----
+    parity, cpu_base = None, None
+    want_cpu = not args.no_extra and rank == 0 and world == 1 and cpu_seconds > 0
+    if not args.no_parity:
+        import oracle
+        _oracle_threads(world)
+        rows = _sample_rows(n_local, max(128, PARITY_ROWS // world))
+        t_rows = np.ascontiguousarray(P[lo:hi][rows, :3])
+        exact = oracle.brute_force_exact(t_rows, P)
+        e_gpu = gather_errors(_rel(np.asarray(h_out)[rows], exact), world, dist)
+        if rank == 0:
+            oracle.use_all_cores()
+            t0 = time.perf_counter()
+            tree = oracle.Tree(P)
+            t_build = time.perf_counter() - t0
+            e_ref = _rel(tree.traverse(t_rows, theta, parallel=True), exact)
+            parity = parity_summary(e_gpu, e_ref, "barneshut")
+            parity["rows"] = (f"{len(rows)} evenly spaced rows of every rank's block (e2e result buffer); "
+                              f"reference algorithm on rank 0's {len(rows)} rows")
+            if want_cpu:
+                cpu_base = cpu_barneshut_rate(P, theta, cpu_seconds, tree=tree, t_build=t_build)
+            del tree
+        _barrier(world, dist)
+    elif want_cpu:
+        cpu_base = cpu_barneshut_rate(P, theta, cpu_seconds)
+
     out = {"metric": "Barnes-Hut particles per second (build + traversal)",
            "value": n / (ms * 1e-3), "unit": "particles/s", "ms_per_step": ms,
            "comm_ms": comm_ms, "build_ms": build_ms, "traverse_ms": trav_ms, "steps": steps,
-           "warmup": warmup, "config": barneshut_config(n, world, theta, "gpu", args.bh_build),
+           "warmup": warmup, "config": barneshut_config(n, theta, world, args.bh_build),
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 12,
                    "bytes_are": "per rank"},
            "gpu_launches": total_launches, "counters_last_step_rank0": counters,
-           "roofline": {"bound": "hbm", "kernel": "pcuda::bh::traverse2_kernel", "achieved": achieved_gbs,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                        "peak_source": hbm_src, "bytes_per_launch": trav_bytes, "kernel_ms": trav_ms,
+           "roofline": {"bound": "fp32/issue", "kernel": "pcuda::bh::traverse2_kernel",
+                        "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
+                        "peak_source": f"{ctx.sm_count} SMs x 128 FP32 lanes x 2 flop x "
+                                       f"{ctx.sm_clock_khz / 1e3:.0f} MHz (nominal)",
+                        "flop_per_interaction": FLOP_PER_PAIR,
+                        "interactions_per_target": inter_n / max(n_local, 1), "kernel_ms": trav_ms,
                         "traffic": ncu_traffic("traverse2_kernel_n10M")[0] if world == 1 and n == 10_000_000 else None,
-                        "note": "the node set is served from L2 (ncu: 93 % hit rate, ~1.1 GB of DRAM "
-                                "traffic per launch); the kernel is FP32-pipe / issue bound, see "
-                                "traversal_fp32 and profiles/"},
-           "traversal_fp32": {"achieved": FLOP_PER_PAIR * inter_n / (trav_ms * 1e-3) / 1e12,
-                              "peak": ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12,
-                              "frac": FLOP_PER_PAIR * inter_n / (trav_ms * 1e-3) / 1e12
-                              / (ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12),
-                              "unit": "TFLOP/s", "interactions_per_target": inter_n / max(n_local, 1),
-                              "note": "20 flop per accepted interaction, this rank's targets; the binding "
-                                      "resource (DESIGN.md K5): issue cycles, 2 per packed FP32 instruction"}}
-    if not args.no_extra and rank == 0 and world == 1:
-        rate, sample, cores, tb, tt = cpu_barneshut_rate(P, theta, cpu_seconds)
+                        "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
+                                "bytes_per_launch": trav_bytes,
+                                "note": "algorithmic node / particle record bytes; the node set is served from "
+                                        "L2 (ncu: ~93 % hit rate, ~1.1 GB of DRAM traffic per launch), so HBM is "
+                                        "not the binding roof"},
+                        "note": "20 flop per accepted interaction, this rank's targets; the binding resource "
+                                "(DESIGN.md K5) is issue cycles: 2 per packed FP32 instruction"}}
+    if parity is not None:
+        out["parity"] = parity
+    if cpu_base is not None:
+        rate, sample, cores, tb, tt = cpu_base
         out["cpu_baseline"] = {"value": rate, "unit": "particles/s", "cores": cores, "kind": "port",
                                "sample": sample + "; restated parallel::BarnesHut",
                                "build_s": tb, "traverse_s": tt}
+    out["compact"] = {"value": round(out["value"]), "unit": "particles/s", "ms": round(ms, 3),
+                      "comm": round(comm_ms, 3), "build": round(build_ms, 3), "trav": round(trav_ms, 3),
+                      "e2e": round(out["e2e"]["value"]), "e2e_ms": round(e2e_ms, 3)}
+    if parity is not None:
+        out["compact"]["parity"] = _compact(parity, ["n", "median", "p99", "max_rel", "ref_median", "ref_p99",
+                                                     "ref_max_rel", "ok"])
+    if cpu_base is not None:
+        out["compact"]["cpu"] = round(cpu_base[0])
     del d_src
     return out
 
@@ -830,10 +974,10 @@ def bench_barneshut(args, n, rank, world, local_rank):
             "data": "synthetic", "config": res["config"], "e2e": res["e2e"],
             "gpu_launches": res["gpu_launches"], "clocks": sampler.summary(), "device": ctx.name,
             "comm_ms": res["comm_ms"], "build_ms": res["build_ms"], "traverse_ms": res["traverse_ms"],
-            "counters_last_step_rank0": res["counters_last_step_rank0"],
-            "roofline": res["roofline"], "traversal_fp32": res["traversal_fp32"]}
-    if "cpu_baseline" in res:
-        line["cpu_baseline"] = res["cpu_baseline"]
+            "counters_last_step_rank0": res["counters_last_step_rank0"], "roofline": res["roofline"]}
+    for k in ("cpu_baseline", "parity"):
+        if k in res:
+            line[k] = res[k]
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()

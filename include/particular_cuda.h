@@ -80,6 +80,20 @@ typedef struct pcuda_config {
  * N = 10M: 5.8 ms against 6.4 ms per step; N = 80M: 39.7 against 44.6 ms; equal at 2 GPUs). */
 #define PCUDA_FLAG_BH_PARTITIONED_BUILD 2u
 #define PCUDA_FLAG_BH_REPLICATED_BUILD 4u
+/* `checked` with zero softening (Acceleration::checked, impls/mod.rs:160-161: a pair at zero distance
+ * contributes nothing).  Small f32 brute-force problems (fewer than 2.5e8 pairs) and every f64 path
+ * test r^2 == 0 exactly, as the reference does.  Large f32 brute-force problems instead add a floor
+ *     t = 2 (max|mu| * 1e-38)^(2/3)      (max over the affecting set of the call; 9.3e-20 for mu = 1e9)
+ * to every r^2, through the addend of the FMA chain that already adds softening^2 (no extra
+ * instruction per pair): a coincident pair gives d * finite = 0 exactly, and r^2 + t == r^2 bit for bit
+ * whenever r^2 >= 2^24 t.  That path therefore equals AccelerationSoftened::checked(sqrt(t)) — a
+ * softening length of 3e-10 (max|mu| / 1e9)^(1/3) — and differs from Acceleration::checked() only for
+ * pairs closer than 2^12 sqrt(t) = 1.2e-6 (max|mu| / 1e9)^(1/3), by a relative 1.5 t / r^2 of that pair's
+ * term (above the 1e-5 parity bound only below 1.2e-7 (max|mu| / 1e9)^(1/3)).  The Barnes-Hut traversals
+ * use the same floor with max|mu| replaced by n * max|mu| (a bound on every node mass).
+ * EXACT_CHECKED: test r^2 == 0 exactly at every size in the f32 brute-force kernels (two more ALU
+ * instructions per pair, about 5 % slower at N = 1M). */
+#define PCUDA_FLAG_EXACT_CHECKED 8u
 
 /* Per-phase device times of the LAST call on the context, in milliseconds (CUDA events on the
  * context stream).  Phases that did not run are 0.  Replaces nothing in the reference (it has no
@@ -180,7 +194,18 @@ int pcuda_bruteforce_f64x2_dev(pcuda_ctx *ctx, const double *d_affected_xy, size
 /* ---- Barnes-Hut: new on the GPU (the reference has sequential/parallel CPU versions only:
  * sequential.rs:439-543, parallel.rs:297-367).  One call = build the tree over `affecting`
  * (rebuilt every call like the reference, sequential.rs:539-541), then theta-traverse for every
- * affected particle. */
+ * affected particle.
+ * `checked` is accepted for symmetry with the brute-force entry points and IGNORED: every Barnes-Hut
+ * traversal is checked (a pair at zero distance contributes nothing; f32: through the r^2 floor
+ * described at PCUDA_FLAG_EXACT_CHECKED, f64: exact test), because an unchecked tree walk has no
+ * defined reference behaviour worth reproducing (NaN for every target that is also a source).
+ * Deliberate deviation from sequential.rs:485-487: the reference SKIPS a node, internal or not, whose
+ * centre of mass coincides with the target; here such a node is opened (theta^2 * 0 < w^2), which sums
+ * its content exactly instead of dropping it.
+ * Depth: cells are resolved down to extent / 2^21 (3-D) or extent / 2^31 (2-D), the resolution of the
+ * Morton key; the reference subdivides until positions differ (tree/mod.rs:112-134).  Particles
+ * closer than that share one leaf of unbounded size that is summed directly when opened: results
+ * stay correct, but a cluster of k such particles costs O(k^2). */
 int pcuda_barneshut_f32x3(pcuda_ctx *ctx, const float *affected_xyz, size_t n_affected,
                           const float *affecting_xyzm, size_t n_affecting, float theta,
                           float softening, int checked, float *out_xyz);

@@ -126,7 +126,8 @@ struct Error : std::runtime_error {
 class CudaContext {
 public:
     // extra_flags: PCUDA_FLAG_BH_PARTITIONED_BUILD / PCUDA_FLAG_BH_REPLICATED_BUILD force the
-    // multi-GPU Barnes-Hut tree build (default: partitioned from 4 GPUs on).
+    // multi-GPU Barnes-Hut tree build (default: partitioned from 4 GPUs on); PCUDA_FLAG_EXACT_CHECKED
+    // makes the f32 brute-force kernels test r^2 == 0 exactly at every problem size.
     explicit CudaContext(int device = 0, unsigned leaf_size = 0, bool phase_timings = true,
                          unsigned expansion_order = 1, unsigned extra_flags = 0) {
         pcuda_config cfg{device, (phase_timings ? PCUDA_FLAG_NONE : PCUDA_FLAG_NO_PHASE_TIMINGS) | extra_flags,

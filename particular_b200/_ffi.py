@@ -23,6 +23,7 @@ ABI_VERSION = 1
 FLAG_NO_PHASE_TIMINGS = 1
 FLAG_BH_PARTITIONED_BUILD = 2
 FLAG_BH_REPLICATED_BUILD = 4
+FLAG_EXACT_CHECKED = 8
 UNIQUE_ID_BYTES = 128
 
 OK = 0

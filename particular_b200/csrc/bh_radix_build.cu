@@ -1,7 +1,7 @@
 // bh_radix_build.cu — K4 in one pass: the linear orthtree over the sorted Morton keys, built from the
 // boundary levels between neighbouring keys instead of level by level (Karras-style: every node is
 // found from the key array alone, and the centres of mass climb bottom-up behind atomic arrival
-// counters).  Five launches whatever the depth of the tree; the level-wise build it replaces
+// counters).  Six launches whatever the depth of the tree; the level-wise build it replaces
 // (expand_level / moments_kernel in barneshut.cu, kept for leaf sizes above RB_MAX_LEAF) needed
 // 2 x (BITS + 1) dependent launches, each a round of dependent binary searches.
 //
@@ -241,13 +241,41 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_assign(const uint8_t *__restrict_
     }
 }
 
+// Links of every node to its parent, so that the climb does not have to search: a first child knows
+// its parent from rb_assign; the other children find the first one among their left siblings
+// (consecutive indices, at most 2^DIM - 1 steps).  A child is the LAST one when its right neighbour
+// is a first child (the first node of a level is one) or does not exist; it then knows how many
+// children the parent has, writes that into the parent's record and pre-loads the parent's arrival
+// counter with it (bits 8 and up), so that the climb only counts arrivals (bits 0..7) until both agree.
+__global__ void __launch_bounds__(256) rb_links(NodeRec *__restrict__ nodes,
+                                                const uint32_t *__restrict__ parent,
+                                                uint32_t *__restrict__ plink,
+                                                uint32_t *__restrict__ arrive,
+                                                const BuildState *__restrict__ st) {
+    if (st->overflow) return;
+    const uint32_t n_nodes = st->level_begin[35];
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    uint32_t p = parent[x], s = 0;
+    while (p == RB_NONE) {
+        ++s;
+        p = parent[x - s];
+    }
+    plink[x] = p;
+    if (p == RB_ROOT) return;
+    if (x + 1 == n_nodes || parent[x + 1] != RB_NONE) {
+        const uint32_t nc = s + 1, level = nodes[x].nchild_level >> 8;
+        nodes[p].nchild_level = nc | (level - 1) << 8;
+        arrive[p] = nc << 8;
+    }
+}
+
 // Moments and centres of mass, bottom-up (see the header comment).  Arithmetic and order of
 // node_moments() in barneshut.cu == the CPU statement of the specification.
 template <int DIM>
 __global__ void __launch_bounds__(128) rb_moments(NodeRec *__restrict__ nodes, double *__restrict__ mom,
                                                   const float4 *__restrict__ sorted,
-                                                  const uint8_t *__restrict__ L,
-                                                  const uint32_t *__restrict__ parent,
+                                                  const uint32_t *__restrict__ plink,
                                                   uint32_t *__restrict__ arrive,
                                                   const BuildState *__restrict__ st) {
     if (st->overflow) return;
@@ -255,23 +283,32 @@ __global__ void __launch_bounds__(128) rb_moments(NodeRec *__restrict__ nodes, d
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_nodes; j += gridDim.x * blockDim.x) {
         const uint4 rec = reinterpret_cast<const uint4 *>(nodes + j)[1];
         if (rec.x != 0) continue;  // internal: computed by the child that arrives last
-        uint32_t x = j, beg = rec.z, cnt = rec.w;
-        int lvl = (int)(rec.y >> 8);
+        uint32_t x = j, beg = rec.z;
+        const uint32_t end = rec.z + rec.w;
         double m[4] = {0.0, 0.0, 0.0, 0.0};
-        for (uint32_t i = beg; i < beg + cnt; ++i) {
-            const float4 p = sorted[i];
-            const double mi = (double)p.w;
-            m[0] = __dadd_rn(m[0], __dmul_rn(mi, (double)p.x));
-            m[1] = __dadd_rn(m[1], __dmul_rn(mi, (double)p.y));
-            if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(mi, (double)p.z));
-            m[3] = __dadd_rn(m[3], mi);
+        for (uint32_t i = beg; i < end; i += 4) {  // four loads in flight, additions in key order
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u < end) q[u] = sorted[i + u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + u < end) {
+                    const double mi = (double)q[u].w;
+                    m[0] = __dadd_rn(m[0], __dmul_rn(mi, (double)q[u].x));
+                    m[1] = __dadd_rn(m[1], __dmul_rn(mi, (double)q[u].y));
+                    if (DIM == 3) m[2] = __dadd_rn(m[2], __dmul_rn(mi, (double)q[u].z));
+                    m[3] = __dadd_rn(m[3], mi);
+                }
+            }
         }
         for (;;) {
+            const uint32_t p = plink[x];
             reinterpret_cast<double4 *>(mom)[x] = make_double4(m[0], m[1], m[2], m[3]);
             float4 cm;
             if (m[3] == 0.0) {
-                const float4 p = sorted[beg];
-                cm = make_float4(p.x, p.y, DIM == 3 ? p.z : 0.f, 0.f);
+                const float4 q = sorted[beg];
+                cm = make_float4(q.x, q.y, DIM == 3 ? q.z : 0.f, 0.f);
             } else {
                 cm.x = (float)__ddiv_rn(m[0], m[3]);
                 cm.y = (float)__ddiv_rn(m[1], m[3]);
@@ -279,21 +316,21 @@ __global__ void __launch_bounds__(128) rb_moments(NodeRec *__restrict__ nodes, d
                 cm.w = (float)m[3];
             }
             nodes[x].cm = cm;
-            uint32_t p = parent[x], s = 0;
             if (p == RB_ROOT) break;
-            while (p == RB_NONE) {  // left siblings have consecutive indices; the first one knows
-                ++s;
-                p = parent[x - s];
-            }
-            const bool last = (int)L[beg + cnt] <= lvl - 1;
-            const uint32_t delta = 1u + (last ? (s + 1u) << 8 : 0u);
-            __threadfence();
-            const uint32_t now = atomicAdd(&arrive[p], delta) + delta;
-            if ((now >> 8) == 0 || (now & 0xffu) != (now >> 8)) break;  // siblings still on their way
-            __threadfence();
-            const uint32_t nc = now >> 8, fc = x - s;
+            // release: this node's moments / record are visible before the arrival is counted; the
+            // child that completes the count acquires (one fence for one child in nc) and reads its
+            // siblings' results from L2 (ld.cg).  A __threadfence() pair here costs every node two
+            // MEMBAR.SC + an L1 invalidation, which the particle loop of the next leaf then pays for.
+            uint32_t now;
+            asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(now) : "l"(arrive + p) : "memory");
+            now += 1u;
+            if ((now & 0xffu) != (now >> 8)) break;  // siblings still on their way
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            const uint32_t nc = now >> 8;
+            const uint4 prec = reinterpret_cast<const uint4 *>(nodes + p)[1];  // written by earlier kernels
+            const uint32_t fc = prec.x;
             m[0] = m[1] = m[2] = m[3] = 0.0;
-            uint32_t total = 0, first_begin = 0;
+            uint32_t total = 0;
             for (uint32_t c = 0; c < nc; ++c) {
                 const double2 a = __ldcg(reinterpret_cast<const double2 *>(mom) + 2 * (size_t)(fc + c));
                 const double2 b = __ldcg(reinterpret_cast<const double2 *>(mom) + 2 * (size_t)(fc + c) + 1);
@@ -301,15 +338,11 @@ __global__ void __launch_bounds__(128) rb_moments(NodeRec *__restrict__ nodes, d
                 m[1] = __dadd_rn(m[1], a.y);
                 if (DIM == 3) m[2] = __dadd_rn(m[2], b.x);
                 m[3] = __dadd_rn(m[3], b.y);
-                const uint4 cr = __ldcg(reinterpret_cast<const uint4 *>(nodes + fc + c) + 1);
-                if (c == 0) first_begin = cr.z;
-                total += cr.w;
+                total += __ldcg(&nodes[fc + c].count);
             }
             x = p;
-            lvl -= 1;
-            beg = first_begin;
-            cnt = total;
-            reinterpret_cast<uint4 *>(nodes + x)[1] = make_uint4(fc, nc | (uint32_t)lvl << 8, beg, cnt);
+            beg = prec.z;
+            nodes[x].count = total;
         }
     }
 }
@@ -322,24 +355,28 @@ int radix_build_enqueue(pcuda_ctx *ctx, pcuda_tree *t, size_t n, size_t cap_node
     auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
     const size_t off_L = 0, off_D = up(n + 1 + 4), off_cnt = off_D + up(n),
                  off_parent = off_cnt + up((size_t)RB_LV * tiles_pad * 4),
-                 off_arrive = off_parent + up(cap_nodes * 4), total = off_arrive + up(cap_nodes * 4);
+                 off_plink = off_parent + up(cap_nodes * 4), off_arrive = off_plink + up(cap_nodes * 4),
+                 total = off_arrive + up(cap_nodes * 4);
     PCUDA_CUDA_TRY(ctx, t->rb.ensure(total));
     uint8_t *base = t->rb.as<uint8_t>();
     uint8_t *L = base + off_L, *Dlv = base + off_D;
     uint32_t *tile_cnt = reinterpret_cast<uint32_t *>(base + off_cnt);
     uint32_t *parent = reinterpret_cast<uint32_t *>(base + off_parent);
+    uint32_t *plink = reinterpret_cast<uint32_t *>(base + off_plink);
     uint32_t *arrive = reinterpret_cast<uint32_t *>(base + off_arrive);
     const int nleaf = (int)t->leaf_size;
+    NodeRec *nodes = t->nodes.as<NodeRec>();
     rb_boundaries<DIM><<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(t->d_keys(), (uint32_t)n, L);
     rb_count<DIM><<<n_tiles, RB_BLOCK, 0, st>>>(L, (uint32_t)n, nleaf, Dlv, tile_cnt, tiles_pad);
     rb_scan<<<1, 1024, 0, st>>>(tile_cnt, n_tiles, tiles_pad, d_state, (uint32_t)cap_nodes);
-    rb_assign<DIM><<<n_tiles, RB_BLOCK, 0, st>>>(L, Dlv, (uint32_t)n, tile_cnt, tiles_pad, d_state,
-                                                 t->nodes.as<NodeRec>(), parent, arrive);
+    rb_assign<DIM><<<n_tiles, RB_BLOCK, 0, st>>>(L, Dlv, (uint32_t)n, tile_cnt, tiles_pad, d_state, nodes,
+                                                 parent, arrive);
+    rb_links<<<(unsigned)((cap_nodes + 255) / 256), 256, 0, st>>>(nodes, parent, plink, arrive, d_state);
     const unsigned mgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 16, (cap_nodes + 127) / 128);
-    rb_moments<DIM><<<mgrid, 128, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(),
-                                           t->sorted.as<float4>(), L, parent, arrive, d_state);
+    rb_moments<DIM><<<mgrid, 128, 0, st>>>(nodes, t->moments.as<double>(), t->sorted.as<float4>(), plink,
+                                           arrive, d_state);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 5;
+    ctx->launches += 6;
     return PCUDA_OK;
 }
 

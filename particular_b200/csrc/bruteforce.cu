@@ -477,7 +477,8 @@ static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na
     const float eps2 = softening * softening;
     int clamp = 0;
     if (checked && eps2 == 0.0f)
-        clamp = g_clamp_mode ? g_clamp_mode : ((double)na * (double)nb >= 2.5e8 ? 3 : 1);
+        clamp = g_clamp_mode ? g_clamp_mode
+                             : ((double)na * (double)nb >= 2.5e8 && !ctx->exact_checked ? 3 : 1);
     const Plan pl = make_plan(ctx->sm_count, na, nb, g_force_tp);
     unsigned *mass_max = nullptr;
     if (clamp >= 2) {

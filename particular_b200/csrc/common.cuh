@@ -57,6 +57,7 @@ struct pcuda_ctx {
     uint32_t leaf_size = 16;
     uint32_t order = 1;         // Barnes-Hut expansion order (pcuda_config.expansion_order)
     bool phase_timings = true;  // PCUDA_FLAG_NO_PHASE_TIMINGS clears it
+    bool exact_checked = false;  // PCUDA_FLAG_EXACT_CHECKED
     cudaStream_t stream = nullptr;
     // copy engines' streams + events of the chunked host path (created on first use, bruteforce.cu)
     cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;

@@ -123,6 +123,7 @@ int pcuda_create(const pcuda_config *config, pcuda_ctx **out) {
     }
     if (config && config->expansion_order == 2) ctx->order = 2;
     ctx->phase_timings = !(config && (config->flags & PCUDA_FLAG_NO_PHASE_TIMINGS));
+    ctx->exact_checked = config && (config->flags & PCUDA_FLAG_EXACT_CHECKED);
     ctx->bh_build = !config ? 0
                     : (config->flags & PCUDA_FLAG_BH_PARTITIONED_BUILD) ? 1
                     : (config->flags & PCUDA_FLAG_BH_REPLICATED_BUILD)  ? 2

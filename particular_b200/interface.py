@@ -258,14 +258,19 @@ class CudaContext:
     gpu/mod.rs:150-151)."""
 
     def __init__(self, device: int = 0, leaf_size: int = 0, phase_timings: bool = True,
-                 expansion_order: int = 1, partitioned_build: Optional[bool] = None):
+                 expansion_order: int = 1, partitioned_build: Optional[bool] = None,
+                 exact_checked: bool = False):
         """phase_timings=False skips the per-phase CUDA events (PCUDA_FLAG_NO_PHASE_TIMINGS):
         about 10 us less per call; timings() then carries only kernel_launches.
         partitioned_build: multi-GPU Barnes-Hut tree build.  True (PCUDA_FLAG_BH_PARTITIONED_BUILD):
         one tree per GPU over its key range, joined by a top tree; False
         (PCUDA_FLAG_BH_REPLICATED_BUILD): every GPU builds the whole tree; None: partitioned from
-        4 GPUs on."""
+        4 GPUs on.
+        exact_checked (PCUDA_FLAG_EXACT_CHECKED): the f32 brute-force kernels test r^2 == 0 exactly at
+        every problem size instead of adding the floor t ~ 1e-19 to r^2 on large problems (see
+        include/particular_cuda.h)."""
         flags = (0 if phase_timings else _ffi.FLAG_NO_PHASE_TIMINGS) | \
+            (_ffi.FLAG_EXACT_CHECKED if exact_checked else 0) | \
             (0 if partitioned_build is None else
              _ffi.FLAG_BH_PARTITIONED_BUILD if partitioned_build else _ffi.FLAG_BH_REPLICATED_BUILD)
         cfg = _ffi.Config(device, flags, leaf_size, expansion_order)

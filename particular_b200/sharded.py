@@ -34,6 +34,48 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n, lo + cap)
 
 
+def _check_tensor(t, cols: int, name: str, device: int):
+    """The C ABI reads `t.data_ptr()` as packed float32 rows: anything else would be silently wrong
+    (or out of bounds), so it is refused here."""
+    import torch
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor")
+    if t.device.index != device:
+        raise ValueError(f"{name}: tensor lives on cuda:{t.device.index}, the context on cuda:{device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if t.dim() != 2 or t.shape[1] != cols:
+        raise ValueError(f"{name}: expected shape (n, {cols}), got {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous (packed rows)")
+    if cols == 4 and t.shape[0] and t.data_ptr() % 16:  # {x,y,z,mu} records are read as float4
+        raise ValueError(f"{name}: records must start at a 16-byte aligned address")
+
+
+class _StreamOrder:
+    """The library works on its own non-blocking stream.  Entering makes that stream wait for the
+    work already queued on torch's current stream (which produced the inputs and allocated the
+    outputs); leaving makes torch's current stream wait for the library's work, so that a consumer
+    of the returned tensor on torch's stream is ordered after the kernels."""
+
+    def __init__(self, ctx):
+        import torch
+        self.torch = torch
+        self.ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", ctx.device))
+
+    def __enter__(self):
+        cur = self.torch.cuda.current_stream(self.ext.device)
+        if cur.cuda_stream != self.ext.cuda_stream:
+            self.ext.wait_stream(cur)
+        return self
+
+    def __exit__(self, *exc):
+        cur = self.torch.cuda.current_stream(self.ext.device)
+        if cur.cuda_stream != self.ext.cuda_stream:
+            cur.wait_stream(self.ext)
+        return False
+
+
 class ShardedBruteForce:
     """``ShardedBruteForce(ctx, interaction).compute(particles)``: the multi-GPU counterpart of
     ``BruteForce(ctx, interaction).compute(particles)`` for the ``&[P]`` storage (all particles
@@ -62,9 +104,12 @@ class ShardedBruteForce:
     def step_device(self, local, n_total: int):
         """`local`: this rank's (n_local, 4) float32 CUDA tensor of {x,y,z,mu}; `n_total`: particle
         count over all ranks.  Returns the (n_local, 3) CUDA tensor of accelerations (owned by this
-        object, overwritten by the next call).  Enqueued on the context stream; not synchronised."""
+        object, overwritten by the next call).  Enqueued on the context stream, ordered after the work
+        already queued on torch's current stream; torch's current stream is made to wait for it, so
+        the result can be consumed there without a host synchronisation."""
         import torch
         from ._ffi import check, lib
+        _check_tensor(local, 4, "local", self.ctx.device)
         cap = shard_capacity(n_total, self.world)
         n_local = int(local.shape[0])
         if self._gathered is None or self._gathered.shape[0] < self.world * cap:
@@ -73,9 +118,10 @@ class ShardedBruteForce:
         if self._out is None or self._out.shape[0] < max(n_local, 1):
             self._out = torch.empty((max(n_local, 1), 3), dtype=torch.float32, device=local.device)
         it = self.interaction
-        check(lib.pcuda_bruteforce_f32x3_sharded_dev(
-            self.ctx.handle, local.data_ptr(), n_local, cap, it.softening, int(it.is_checked),
-            self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
+        with _StreamOrder(self.ctx):
+            check(lib.pcuda_bruteforce_f32x3_sharded_dev(
+                self.ctx.handle, local.data_ptr(), n_local, cap, it.softening, int(it.is_checked),
+                self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
         return self._out[:n_local]
 
     # -- host API --------------------------------------------------------------------------------
@@ -128,6 +174,7 @@ class ShardedBarnesHut(ShardedBruteForce):
     def step_device(self, local, n_total: int):
         import torch
         from ._ffi import check, lib
+        _check_tensor(local, 4, "local", self.ctx.device)
         cap = shard_capacity(n_total, self.world)
         n_local = int(local.shape[0])
         if self._gathered is None or self._gathered.shape[0] < self.world * cap:
@@ -136,9 +183,10 @@ class ShardedBarnesHut(ShardedBruteForce):
         if self._out is None or self._out.shape[0] < max(n_local, 1):
             self._out = torch.empty((max(n_local, 1), 3), dtype=torch.float32, device=local.device)
         it = self.interaction
-        check(lib.pcuda_barneshut_f32x3_sharded_dev(
-            self.ctx.handle, local.data_ptr(), n_local, n_total, self.theta, it.softening,
-            int(it.is_checked), self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
+        with _StreamOrder(self.ctx):
+            check(lib.pcuda_barneshut_f32x3_sharded_dev(
+                self.ctx.handle, local.data_ptr(), n_local, n_total, self.theta, it.softening,
+                int(it.is_checked), self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
         return self._out[:n_local]
 
     def compute_local(self, local_records: np.ndarray, n_total: int,
@@ -187,6 +235,8 @@ class ShardedBetween(ShardedBruteForce):
         tensors.  Returns the (n, 3) accelerations (owned by this object).  Not synchronised."""
         import torch
         from ._ffi import check, lib
+        _check_tensor(affected_local, 3, "affected_local", self.ctx.device)
+        _check_tensor(src_local, 4, "src_local", self.ctx.device)
         cap = shard_capacity(n_src_total, self.world)
         n = int(affected_local.shape[0])
         if self._gathered is None or self._gathered.shape[0] < self.world * cap:
@@ -195,10 +245,11 @@ class ShardedBetween(ShardedBruteForce):
         if self._out is None or self._out.shape[0] < max(n, 1):
             self._out = torch.empty((max(n, 1), 3), dtype=torch.float32, device=affected_local.device)
         it = self.interaction
-        check(lib.pcuda_bruteforce_f32x3_between_sharded_dev(
-            self.ctx.handle, affected_local.data_ptr(), n, src_local.data_ptr(),
-            int(src_local.shape[0]), cap, it.softening, int(it.is_checked),
-            self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
+        with _StreamOrder(self.ctx):
+            check(lib.pcuda_bruteforce_f32x3_between_sharded_dev(
+                self.ctx.handle, affected_local.data_ptr(), n, src_local.data_ptr(),
+                int(src_local.shape[0]), cap, it.softening, int(it.is_checked),
+                self._gathered.data_ptr(), self._out.data_ptr()), self.ctx.handle)
         return self._out[:n]
 
     def compute(self, storage, gather: bool = True) -> Optional[np.ndarray]:

@@ -25,6 +25,7 @@ pub const PCUDA_UNIQUE_ID_BYTES: usize = 128;
 pub const PCUDA_FLAG_NO_PHASE_TIMINGS: u32 = 1;
 pub const PCUDA_FLAG_BH_PARTITIONED_BUILD: u32 = 2;
 pub const PCUDA_FLAG_BH_REPLICATED_BUILD: u32 = 4;
+pub const PCUDA_FLAG_EXACT_CHECKED: u32 = 8;
 
 pub const PCUDA_BRUTE_FORCE: u32 = 0;
 pub const PCUDA_BARNES_HUT: u32 = 1;

@@ -68,7 +68,8 @@ impl CudaContext {
     }
 
     /// `flags`: `ffi::PCUDA_FLAG_BH_PARTITIONED_BUILD` / `ffi::PCUDA_FLAG_BH_REPLICATED_BUILD` force how
-    /// multi-GPU Barnes-Hut builds its tree (default: partitioned by key range from 4 GPUs on).
+    /// multi-GPU Barnes-Hut builds its tree (default: partitioned by key range from 4 GPUs on);
+    /// `ffi::PCUDA_FLAG_EXACT_CHECKED` makes the f32 brute-force kernels test `r^2 == 0` exactly at every size.
     pub fn with_flags(device: i32, leaf_size: u32, flags: u32) -> Self {
         let cfg = ffi::pcuda_config {
             device,

@@ -341,14 +341,14 @@ def test_full_size_plummer(pb, ctx):
     c = bh.last_counters()
     per_target = (c["node_interactions"] + c["particle_interactions"]) / n
     assert 500 < per_target < 50000, per_target
-    idx = np.sort(np.random.default_rng(1).choice(n, 96, replace=False))
+    idx = np.sort(np.random.default_rng(1).choice(n, 1024, replace=False))  # >= 1024 at N = 10M
     exact = oracle.brute_force_exact(p[idx, :3], p)
     e_gpu = rel_err(got[idx], exact)
     tree = oracle.Tree(p)                       # the reference's recursive build, single thread
     ref = tree.traverse(p[idx, :3], 0.5, parallel=True)
     e_ref = rel_err(ref, exact)
-    assert np.median(e_gpu) <= 1.1 * np.median(e_ref) + 2e-6, (np.median(e_gpu), np.median(e_ref))
-    assert e_gpu.max() <= max(1.1 * e_ref.max(), 5e-1)
+    print(f"N=10M theta=0.5, 1024 targets: median / p99 / max  gpu {stats(e_gpu)}  reference {stats(e_ref)}")
+    assert (stats(e_gpu) <= 1.1 * stats(e_ref) + 2e-6).all(), (stats(e_gpu), stats(e_ref))
     # sortedness + permutation (checksum of the index set) at full size
     t = pb.RootedOrthtree(ctx, p)
     keys = t.read(_ffi.TREE_KEYS)

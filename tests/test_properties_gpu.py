@@ -9,7 +9,7 @@ from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
 import oracle
-from tests.conftest import assert_bruteforce_parity, rel_err
+from tests.conftest import assert_bruteforce_parity, rel_err, uniform_cloud
 
 pytestmark = pytest.mark.gpu
 
@@ -157,3 +157,31 @@ def test_outputs_follow_affected_order(pb, ctx):
     b1 = bh.compute(pb.Between(np.ascontiguousarray(aff[perm]), src))
     assert np.array_equal(b1, b0[perm])  # the target groups come from the sorted keys: same groups
     assert np.array_equal(bh.compute(pb.Between(aff, src)), b0)  # deterministic
+
+
+def test_sharded_device_step_validates_and_orders_streams(ctx):
+    """step_device refuses tensors the C ABI would misread (dtype, shape, contiguity,
+    device, alignment of the records) and orders the library's stream against torch's current
+    stream in both directions: a producer and a consumer on torch's stream need no host sync."""
+    import torch
+    import particular_b200 as pb
+    from particular_b200.sharded import _check_tensor
+    good = torch.from_numpy(uniform_cloud(4096, seed=2)).cuda()
+    for bad, exc in ((good.double(), TypeError), (good[:, :3], ValueError), (good.t().contiguous().t(), ValueError),
+                     (good.reshape(-1)[1:-3].reshape(-1, 4), ValueError)):
+        with pytest.raises(exc):
+            _check_tensor(bad, 4, "local", ctx.device)
+    sh = pb.ShardedBruteForce(ctx, pb.AccelerationSoftened.checked(1.0), init_comm=False)
+    with pytest.raises(TypeError):
+        sh.step_device(good.double(), 4096)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        src = torch.zeros_like(good)
+        for _ in range(50):                      # a long producer chain on torch's stream
+            src = src * 0.5 + good * 0.5
+        src = src * 0 + good
+        out = sh.step_device(src, 4096)
+        total = out.abs().sum()                  # consumer on torch's stream, no host synchronisation
+    side.synchronize()
+    ref = pb.BruteForce(ctx, pb.AccelerationSoftened.checked(1.0)).compute(good.cpu().numpy())
+    assert np.isclose(float(total), np.abs(ref).sum(), rtol=1e-4)

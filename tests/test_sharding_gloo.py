@@ -143,3 +143,16 @@ def test_world2_gloo_between_equals_single(n_massive, n_massless):
         p.join(60)
     assert sorted(r for r, _ in res) == [0, 1]
     assert all(ok for _, ok in res), res
+
+
+def test_device_step_refuses_tensors_the_c_abi_would_misread():
+    """ShardedBruteForce / ShardedBarnesHut / ShardedBetween.step_device hand `data_ptr()` to the C ABI,
+    which reads packed float32 rows: host tensors are refused before any pointer is taken (the dtype /
+    shape / contiguity / device checks need a GPU: tests/test_properties_gpu.py)."""
+    import pytest
+    import torch
+    from particular_b200.sharded import _check_tensor
+    with pytest.raises(TypeError):
+        _check_tensor(torch.zeros(8, 4), 4, "local", 0)
+    with pytest.raises(TypeError):
+        _check_tensor([[0.0] * 4], 4, "local", 0)

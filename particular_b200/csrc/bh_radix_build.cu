@@ -5,8 +5,8 @@
 // (expand_level / moments_kernel in barneshut.cu, kept for leaf sizes above RB_MAX_LEAF) needed
 // 2 x (BITS + 1) dependent launches, each a round of dependent binary searches.
 //
-// The arrays are the ones of the tree specification (CPU statement:
-// oracle/oracle_octree.inc) bit for bit: nodes breadth-first, children of a node contiguous and in
+// The arrays are the ones of the tree specification (whose CPU statement the
+// parity tests compare them with) bit for bit: nodes breadth-first, children of a node contiguous and in
 // key order, moments in double precision added in key order (leaves) / child order (internal).
 // The reference's own tree is the recursive bucket partition of particular/src/tree/mod.rs:91-138
 // with the node data of gravity/impls/mod.rs:120-134.

@@ -5,7 +5,9 @@
 // there is no link-time NCCL dependency.
 use std::{env, path::PathBuf, process::Command};
 
-const UNITS: [&str; 7] = ["context.cu", "bruteforce.cu", "barneshut.cu", "comm.cu", "sim.cu", "custom.cu", "probe.cu"];
+const UNITS: [&str; 8] = [
+    "context.cu", "bruteforce.cu", "barneshut.cu", "bh_radix_build.cu", "comm.cu", "sim.cu", "custom.cu", "probe.cu",
+];
 
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
@@ -28,7 +30,7 @@ fn main() {
         println!("cargo:rerun-if-changed={}", csrc.join(unit).display());
         objs.push(obj);
     }
-    for header in ["common.cuh", "ptx.cuh"] {
+    for header in ["common.cuh", "ptx.cuh", "bh.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(header).display());
     }
     let lib = out.join("libparticular_cuda.so");

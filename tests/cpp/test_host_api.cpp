@@ -4,12 +4,45 @@
 //   circular_orbit!      particular/src/gravity/newtonian/mod.rs:281-347
 // Exit code 0 = all passed, 77 = no usable GPU (pcuda_create failed), 1 = a check failed.
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <vector>
 
 #include "particular_cuda.hpp"
 
 using namespace particular;
+
+// Layout of every struct that crosses the C ABI by value or by pointer: the numbers a binding in
+// another language (rust/particular-cuda/src/ffi.rs, particular_b200/_ffi.py) relies on.
+static_assert(sizeof(pcuda_config) == 16 && offsetof(pcuda_config, device) == 0 &&
+                  offsetof(pcuda_config, flags) == 4 && offsetof(pcuda_config, leaf_size) == 8 &&
+                  offsetof(pcuda_config, expansion_order) == 12,
+              "pcuda_config layout");
+static_assert(sizeof(pcuda_timings) == 28 && offsetof(pcuda_timings, upload_ms) == 0 &&
+                  offsetof(pcuda_timings, comm_ms) == 4 && offsetof(pcuda_timings, build_ms) == 8 &&
+                  offsetof(pcuda_timings, compute_ms) == 12 && offsetof(pcuda_timings, download_ms) == 16 &&
+                  offsetof(pcuda_timings, kernel_launches) == 20 && offsetof(pcuda_timings, reserved) == 24,
+              "pcuda_timings layout");
+static_assert(sizeof(pcuda_tree_info) == 56 && offsetof(pcuda_tree_info, n_particles) == 0 &&
+                  offsetof(pcuda_tree_info, n_nodes) == 8 && offsetof(pcuda_tree_info, n_levels) == 16 &&
+                  offsetof(pcuda_tree_info, leaf_size) == 20 && offsetof(pcuda_tree_info, dim) == 24 &&
+                  offsetof(pcuda_tree_info, bits) == 28 && offsetof(pcuda_tree_info, origin) == 32 &&
+                  offsetof(pcuda_tree_info, extent) == 44 && offsetof(pcuda_tree_info, inv) == 48 &&
+                  offsetof(pcuda_tree_info, reserved) == 52,
+              "pcuda_tree_info layout");
+static_assert(sizeof(pcuda_sim_config) == 48 && offsetof(pcuda_sim_config, dim) == 0 &&
+                  offsetof(pcuda_sim_config, scalar) == 4 && offsetof(pcuda_sim_config, algorithm) == 8 &&
+                  offsetof(pcuda_sim_config, flags) == 12 && offsetof(pcuda_sim_config, theta) == 16 &&
+                  offsetof(pcuda_sim_config, softening) == 24 && offsetof(pcuda_sim_config, dt) == 32 &&
+                  offsetof(pcuda_sim_config, checked) == 40 && offsetof(pcuda_sim_config, reserved) == 44,
+              "pcuda_sim_config layout");
+static_assert(sizeof(pcuda_sim_info_t) == 56 && offsetof(pcuda_sim_info_t, n_particles) == 0 &&
+                  offsetof(pcuda_sim_info_t, n_affecting) == 8 && offsetof(pcuda_sim_info_t, steps_done) == 16 &&
+                  offsetof(pcuda_sim_info_t, d_particles) == 24 && offsetof(pcuda_sim_info_t, d_velocities) == 32 &&
+                  offsetof(pcuda_sim_info_t, d_accelerations) == 40 && offsetof(pcuda_sim_info_t, graph_active) == 48 &&
+                  offsetof(pcuda_sim_info_t, launches_per_step) == 52,
+              "pcuda_sim_info_t layout");
+static_assert(PCUDA_UNIQUE_ID_BYTES == 128, "ncclUniqueId size");
 
 // What `#[derive(Position, Mass)] struct Body { position: Vec3, mu: f32 }` gives a Rust user.
 template <class S, std::size_t D>

@@ -6,6 +6,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -56,6 +57,83 @@ def test_rust_ffi_declares_every_symbol_with_matching_arity():
     build_rs = open(os.path.join(ROOT, "rust", "particular-cuda", "build.rs")).read()
     for unit in SOURCES:
         assert f'"{unit}"' in build_rs, f"build.rs does not compile {unit}"
+
+
+def _c_structs(hdr):
+    """{name: [(field, type, array_len)]} of the plain structs in the header."""
+    out = {}
+    for body, name in re.findall(r"typedef struct \w+ \{(.*?)\}\s*(\w+);", hdr, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(.*?)\s*(\*?)\s*(\w+)\s*(?:\[(\d+)\])?$", decl, flags=re.S)
+            ctype = (m.group(1).strip() + m.group(2)).replace(" *", "*")
+            fields.append((m.group(3), ctype, int(m.group(4)) if m.group(4) else 0))
+        out[name] = fields
+    return out
+
+
+def _rs_structs(rs):
+    out = {}
+    for name, body in re.findall(r"#\[repr\(C\)\](?:\s*#\[derive\([^)]*\)\])?\s*pub struct (\w+)\s*\{(.*?)\}", rs, flags=re.S):
+        fields = []
+        for decl in body.split(","):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(?:pub\s+)?(\w+)\s*:\s*(.+)$", decl, flags=re.S)
+            fields.append((m.group(1), m.group(2).strip()))
+        out[name] = fields
+    return out
+
+
+def test_rust_repr_c_structs_match_the_header_layouts():
+    """Every `#[repr(C)]` struct with fields in ffi.rs has the same field names, in the same order, with
+    the Rust type of the same size and signedness as the C field (`[T; N]` for arrays, `*mut c_void`
+    for `void *`) — the lock-step check that symbol names and argument counts alone do not give."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    rs = re.sub(r"//.*", "", open(os.path.join(ROOT, "rust", "particular-cuda", "src", "ffi.rs")).read())
+    cmap = {"int32_t": "i32", "uint32_t": "u32", "uint64_t": "u64", "float": "f32", "double": "f64",
+            "void*": "*mut c_void", "int": "c_int", "size_t": "usize"}
+    c_structs, rs_structs = _c_structs(hdr), _rs_structs(rs)
+    checked = 0
+    for name, fields in rs_structs.items():
+        if [f for f in fields if f[0] == "_private"]:
+            continue  # opaque handles
+        assert name in c_structs, f"ffi.rs declares {name}, the header does not"
+        want = [(f, f"[{cmap[t]}; {n}]" if n else cmap[t]) for f, t, n in c_structs[name]]
+        assert fields == want, f"{name}: ffi.rs {fields} != header {want}"
+        checked += 1
+    for name in ("pcuda_config", "pcuda_timings", "pcuda_tree_info", "pcuda_sim_config", "pcuda_sim_info_t"):
+        assert name in rs_structs, f"ffi.rs lacks {name}"
+    assert checked >= 5
+    # the flag / enum constants the Rust side mirrors
+    for cname, value in re.findall(r"#define (PCUDA_FLAG_\w+) (\d+)u", hdr):
+        if cname == "PCUDA_FLAG_NONE":
+            continue
+        assert re.search(rf"pub const {cname}: u32 = {value};", rs), f"ffi.rs lacks {cname} = {value}"
+
+
+def test_ctypes_structs_match_the_header_layouts():
+    """The Python binding's ctypes structures: header field names in header order, and the sizes that
+    tests/cpp/test_host_api.cpp pins with static_assert."""
+    from particular_b200 import _ffi
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    c_structs = _c_structs(hdr)
+    for py, cname, size in ((_ffi.Config, "pcuda_config", 16), (_ffi.Timings, "pcuda_timings", 28),
+                            (_ffi.TreeInfo, "pcuda_tree_info", 56), (_ffi.SimConfig, "pcuda_sim_config", 48),
+                            (_ffi.SimInfo, "pcuda_sim_info_t", 56)):
+        assert [f for f, _ in py._fields_] == [f for f, _, _ in c_structs[cname]], cname
+        assert C.sizeof(py) == size, (cname, C.sizeof(py))
+
+
+def test_integration_md_lists_the_real_files():
+    """INTEGRATION.md sections 1 and 2 are rust/particular-cuda/build.rs and src/ffi.rs verbatim
+    (scripts/gen_integration.py regenerates them)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_integration.py"), "--check"])
+    assert r.returncode == 0, "INTEGRATION.md is out of date: run python scripts/gen_integration.py"
 
 
 def test_header_compiles_as_c():

@@ -579,7 +579,7 @@ def _timed_steps(ctx, stream, flush, step_fn, k):
 
 
 def _compact(d, keys):
-    return {k: (round(d[k], 4) if isinstance(d[k], float) else d[k]) for k in keys if k in d}
+    return {k: (float(f"{d[k]:.3g}") if isinstance(d[k], float) else d[k]) for k in keys if k in d}
 
 
 def bench_bruteforce(args, n, rank, world, local_rank):

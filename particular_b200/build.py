@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libparticular_cuda.so")
 
-SOURCES = ["context.cu", "bruteforce.cu", "barneshut.cu", "bh_radix_build.cu", "comm.cu", "sim.cu", "custom.cu", "probe.cu"]
+SOURCES = ["context.cu", "bruteforce.cu", "barneshut.cu", "bh_build.cu", "bh_radix_build.cu", "bh_traverse.cu", "bh_multigpu.cu", "comm.cu", "sim.cu", "custom.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -64,6 +64,82 @@ struct BuildState {
     uint32_t capacity;
 };
 
+constexpr int MAX_PARTS = 16;       // trees in a forest (= GPUs of a partitioned build)
+constexpr int MAX_ROOTS = 736;      // start nodes of a forest walk (stack capacity of the walk - reserve - 32)
+constexpr int SEG_MAX_LIMIT = 1024; // largest segment size the grouping kernels support
+
+// Tuning / test hooks (pcuda_debug_set); defined in barneshut.cu.
+extern int g_level_build;
+extern uint32_t g_small_level;
+extern int g_variant;
+extern bool g_count;
+extern int g_seg_max;
+extern int g_tpl;
+extern int g_route;
+extern int g_forest;
+
+// Double-precision layer of a traversal (tree built by build64).
+struct Ext64 {
+    const double4 *src64;  // sources in key order
+    const double4 *cm64;   // {com, mass} per node
+    const double4 *tgt64;  // targets in traversal order {x, y, z|0, _}
+    double *out;
+    double eps2;
+};
+
+// A forest of trees over the same root cube stored back to back (partitioned build): node and
+// source arrays that replace the tree's own, and the roots the walk starts from.
+struct ForestView {
+    const NodeRec *nodes;
+    const float4 *src;
+    const uint32_t *d_roots;  // device array
+    uint32_t n_roots;
+};
+
+// ---- bh_build.cu ----
+template <int DIM>
+int sort_by_key(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n, const Frame *d_frame,
+                DevBuf keys[2], DevBuf perm[2], int *cur, DevBuf &cub_tmp);
+template <int DIM>
+void tree_reset(pcuda_ctx *ctx, pcuda_tree *t, size_t n);
+template <int DIM>
+int build_frame(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n);
+template <int DIM>
+int build_levels(pcuda_ctx *ctx, pcuda_tree *t, size_t n);
+template <int DIM>
+int build(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n, bool keys_only = false);
+int build_dim(pcuda_ctx *ctx, pcuda_tree *t, uint32_t dim, const float *d_particles, size_t n,
+              bool keys_only = false);
+template <int DIM>
+int build64(pcuda_ctx *ctx, pcuda_tree *t, const double *d_particles64, size_t n);
+template <int DIM>
+void launch_encode(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n, const Frame *d_frame,
+                   uint64_t *keys, uint32_t *idx);
+template <int DIM>
+void launch_gather(pcuda_ctx *ctx, const float *d_pos, int stride, bool has_mass, size_t n,
+                   const uint32_t *perm, float4 *sorted);
+template <int DIM>
+void launch_gather64(pcuda_ctx *ctx, const double *d_pos, int stride, bool has_mass, size_t n,
+                     const uint32_t *perm, double4 *sorted);
+void launch_narrow(pcuda_ctx *ctx, const double *in, size_t count, float *out);
+
+// ---- bh_traverse.cu ----
+// d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).
+// tgt_stride: floats per target row (0 = bare positions, i.e. `dim`).
+int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na, float theta, float eps,
+             float *d_out, int tgt_stride = 0, const double *d_tgt64 = nullptr, double *d_out64 = nullptr,
+             double eps64 = 0.0);
+int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted, const uint64_t *tgt_keys,
+                    const uint32_t *tgt_perm, size_t na, float theta, float eps, float *d_out,
+                    const Ext64 *x64 = nullptr, const ForestView *fv = nullptr);
+int read_counters(pcuda_ctx *ctx);
+
+// ---- bh_multigpu.cu ----
+int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total, float theta, float eps,
+                float *d_gathered, float *d_out);
+int partitioned_dev(pcuda_ctx *ctx, const float *d_particles, size_t n, int parts, float theta, float eps,
+                    float *d_out);
+
 constexpr int RB_MAX_LEAF = 32;  // widest leaf window of the one-pass build (== the cap on leaf_size)
 
 // bh_radix_build.cu: one-pass construction of the linear orthtree over t->d_keys() / t->sorted

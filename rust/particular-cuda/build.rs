@@ -5,8 +5,9 @@
 // there is no link-time NCCL dependency.
 use std::{env, path::PathBuf, process::Command};
 
-const UNITS: [&str; 8] = [
-    "context.cu", "bruteforce.cu", "barneshut.cu", "bh_radix_build.cu", "comm.cu", "sim.cu", "custom.cu", "probe.cu",
+const UNITS: [&str; 11] = [
+    "context.cu", "bruteforce.cu", "barneshut.cu", "bh_build.cu", "bh_radix_build.cu", "bh_traverse.cu",
+    "bh_multigpu.cu", "comm.cu", "sim.cu", "custom.cu", "probe.cu",
 ];
 
 fn main() {

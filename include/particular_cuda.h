@@ -76,10 +76,17 @@ typedef struct pcuda_config {
 /* Multi-GPU Barnes-Hut (pcuda_barneshut_f32x3_sharded*): how the tree is built.
  * PARTITIONED: every GPU sorts and builds only the tree of its own key range, the per-GPU trees
  * are exchanged and joined by a small top tree (SURVEY.md 8e "v3").  REPLICATED: every GPU builds
- * the whole tree (8e "v1").  Neither flag: partitioned from 4 GPUs on (measured on 8 B200s,
- * N = 10M: 5.8 ms against 6.4 ms per step; N = 80M: 39.7 against 44.6 ms; equal at 2 GPUs). */
+ * the whole tree (8e "v1").  Neither flag (and too few particles for LET, below): partitioned from
+ * 4 GPUs on (measured on 8 B200s, N = 10M: 5.8 ms against 6.4 ms per step; N = 80M: 39.7 against
+ * 44.6 ms; equal at 2 GPUs). */
 #define PCUDA_FLAG_BH_PARTITIONED_BUILD 2u
 #define PCUDA_FLAG_BH_REPLICATED_BUILD 4u
+/* LET: locally essential trees.  The particles travel once, to the rank that owns their key range; every
+ * rank builds the tree of its range and sends each other rank only the nodes and leaf particles that
+ * rank's walk can open (the rest as stubs); cells that straddle a range boundary are joined by the same
+ * top tree as in the partitioned build.  Nothing is replicated.  Default from 2 GPUs on when every rank
+ * gets at least 65536 particles; the flag forces it. */
+#define PCUDA_FLAG_BH_LET_BUILD 16u
 /* `checked` with zero softening (Acceleration::checked, impls/mod.rs:160-161: a pair at zero distance
  * contributes nothing).  Small f32 brute-force problems (fewer than 2.5e8 pairs) and every f64 path
  * test r^2 == 0 exactly, as the reference does.  Large f32 brute-force problems instead add a floor
@@ -276,6 +283,12 @@ int pcuda_comm_unique_id(pcuda_ctx *ctx, uint8_t id[PCUDA_UNIQUE_ID_BYTES]);
 int pcuda_comm_init(pcuda_ctx *ctx, const uint8_t id[PCUDA_UNIQUE_ID_BYTES], int world_size,
                     int rank);
 int pcuda_comm_destroy(pcuda_ctx *ctx);
+/* In-process communicator for TESTS: binds `world_size` contexts of this process (rank = index; one
+ * host thread drives each; same device, or devices with peer access) so that the sharded entry points
+ * below run all their ranks on a box with a single GPU: the collectives become device-to-device
+ * copies ordered by events behind the same internal calls as NCCL.  Call once, from one thread,
+ * before the rank threads start; every collective is a rendezvous of all ranks. */
+int pcuda_comm_init_local(pcuda_ctx *const *ctxs, int world_size);
 /* All-gather equally sized shards of `bytes_per_rank` bytes (device pointers, context stream). */
 int pcuda_comm_allgather_dev(pcuda_ctx *ctx, const void *d_send, void *d_recv,
                              size_t bytes_per_rank);

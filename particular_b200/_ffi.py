@@ -24,6 +24,7 @@ FLAG_NO_PHASE_TIMINGS = 1
 FLAG_BH_PARTITIONED_BUILD = 2
 FLAG_BH_REPLICATED_BUILD = 4
 FLAG_EXACT_CHECKED = 8
+FLAG_BH_LET_BUILD = 16
 UNIQUE_ID_BYTES = 128
 
 OK = 0
@@ -118,6 +119,7 @@ SIGNATURES = {
     "pcuda_comm_unique_id": (_i, [_vp, C.POINTER(C.c_uint8 * UNIQUE_ID_BYTES)]),
     "pcuda_comm_init": (_i, [_vp, C.POINTER(C.c_uint8 * UNIQUE_ID_BYTES), _i, _i]),
     "pcuda_comm_destroy": (_i, [_vp]),
+    "pcuda_comm_init_local": (_i, [C.POINTER(_vp), _i]),
     "pcuda_comm_allgather_dev": (_i, [_vp, _vp, _vp, _sz]),
     "pcuda_bruteforce_f32x3_sharded": (_i, [_vp, _vp, _sz, _sz, _f, _i, _vp]),
     "pcuda_bruteforce_f32x3_sharded_dev": (_i, [_vp, _vp, _sz, _sz, _f, _i, _vp, _vp]),

@@ -44,7 +44,8 @@ bool g_count = true;              // instrumentation of the traversal (pcuda_tre
 int g_seg_max = 256;              // largest cell (in targets) that is cut into groups
 int g_tpl = 2;                    // targets per lane in the traversal: 1 (groups of 32) or 2 (groups of 64)
 int g_route = 0;                  // accelerations to their owners: 0 = automatic, 1 = all-gather, 2 = all-to-all
-int g_forest = 0;                 // multi-GPU build: 0 = as the context says, 1 = partitioned, 2 = replicated
+int g_forest = 0;                 // multi-GPU build: 0 = as the context says, 1 = partitioned, 2 = replicated,
+                                  // 3 = locally essential trees
 
 // One-shot Barnes-Hut with device pointers: build over `affecting`, traverse for `affected`.
 static int oneshot_dev(pcuda_ctx *ctx, uint32_t dim, const float *d_aff, size_t na, const float *d_src,
@@ -190,7 +191,7 @@ int bh_debug_set(const char *key, int value) {
         bh::g_count = value != 0;
         return PCUDA_OK;
     }
-    if (k == "bh_forest" && value >= 0 && value <= 2) {
+    if (k == "bh_forest" && value >= 0 && value <= 3) {
         bh::g_forest = value;
         return PCUDA_OK;
     }

@@ -122,6 +122,10 @@ template <int DIM>
 void launch_gather64(pcuda_ctx *ctx, const double *d_pos, int stride, bool has_mass, size_t n,
                      const uint32_t *perm, double4 *sorted);
 void launch_narrow(pcuda_ctx *ctx, const double *in, size_t count, float *out);
+// Root cube of a cloud spread over several ranks: {lo[3], hi[3], max|mu|, 0} of the local records, and
+// the frame (into t->d_frame) from the boxes of all ranks; same bits as build_frame over all particles.
+int local_box(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n, float *d_box8);
+int frame_from_boxes(pcuda_ctx *ctx, pcuda_tree *t, const float *d_boxes, int world, size_t n_total);
 
 // ---- bh_traverse.cu ----
 // d_tgt == nullptr: the targets are the tree's own particles (the `&[P]` storage).

@@ -883,6 +883,70 @@ int build64(pcuda_ctx *ctx, pcuda_tree *t, const double *d_particles64, size_t n
 }
 
 
+// ---- root cube of a cloud that is spread over several ranks (bh_multigpu.cu) -------------------------
+// Every rank reduces its own records to {lo[3], hi[3], max|mu|, 0} (local_box); the boxes of all
+// ranks are exchanged; frame_from_boxes folds them — min / max are exact and associative, so the
+// frame has the bits of the single-GPU frame over all particles.
+__global__ void box_kernel(const float *__restrict__ partial, int nblocks, const unsigned *__restrict__ mass_max_bits,
+                           float *__restrict__ box8) {
+    if (threadIdx.x < 6) {
+        const bool is_hi = threadIdx.x >= 3;
+        float v = is_hi ? -INFINITY : INFINITY;
+        for (int j = 0; j < nblocks; ++j) {
+            const float q = partial[j * 6 + threadIdx.x];
+            v = is_hi ? fmaxf(v, q) : fminf(v, q);
+        }
+        box8[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 6) box8[6] = __uint_as_float(*mass_max_bits);
+    if (threadIdx.x == 7) box8[7] = 0.f;
+}
+
+__global__ void frame_from_boxes_kernel(const float *__restrict__ boxes, int world, unsigned long long n_total,
+                                        Frame *out) {
+    if (threadIdx.x != 0) return;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, mmax = 0.f;
+    for (int r = 0; r < world; ++r) {
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], boxes[r * 8 + k]);
+            hi[k] = fmaxf(hi[k], boxes[r * 8 + 3 + k]);
+        }
+        mmax = fmaxf(mmax, boxes[r * 8 + 6]);
+    }
+    float ext = 0.0f;  // same arithmetic as frame_kernel
+    for (int k = 0; k < 3; ++k) {
+        const float e = __fsub_rn(hi[k], lo[k]);
+        ext = e > ext ? e : ext;
+    }
+    const float half = __fdiv_rn(ext, 2.0f);
+    for (int k = 0; k < 3; ++k) out->origin[k] = __fsub_rn(__fdiv_rn(__fadd_rn(lo[k], hi[k]), 2.0f), half);
+    out->ext = ext;
+    out->inv = ext > 0.0f ? __fdiv_rn((float)(1ull << Dims<3>::BITS), ext) : 0.0f;
+    out->mass_bound = (float)n_total * mmax;
+}
+
+int local_box(pcuda_ctx *ctx, pcuda_tree *t, const float *d_particles, size_t n, float *d_box8) {
+    cudaStream_t st = ctx->stream;
+    const int nb = (int)std::max<size_t>(1, std::min<size_t>(ctx->sm_count * 8, (n + 255) / 256));
+    PCUDA_CUDA_TRY(ctx, t->partial.ensure((size_t)nb * 6 * sizeof(float)));
+    PCUDA_CUDA_TRY(ctx, t->d_frame.ensure(sizeof(Frame) + sizeof(unsigned)));
+    unsigned *d_mmax = reinterpret_cast<unsigned *>(t->d_frame.as<Frame>() + 1);
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_mmax, 0, sizeof(unsigned), st));
+    bbox_partial<3><<<nb, 256, 0, st>>>(d_particles, 4, (int)n, t->partial.as<float>(), d_mmax);  // n == 0: +-inf
+    box_kernel<<<1, 32, 0, st>>>(t->partial.as<float>(), nb, d_mmax, d_box8);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return PCUDA_OK;
+}
+
+int frame_from_boxes(pcuda_ctx *ctx, pcuda_tree *t, const float *d_boxes, int world, size_t n_total) {
+    PCUDA_CUDA_TRY(ctx, t->d_frame.ensure(sizeof(Frame) + sizeof(unsigned)));
+    frame_from_boxes_kernel<<<1, 32, 0, ctx->stream>>>(d_boxes, world, (unsigned long long)n_total, t->d_frame.as<Frame>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PCUDA_OK;
+}
+
 // Launchers for the kernels the other translation units need (the kernels themselves stay here).
 template <int DIM>
 void launch_encode(pcuda_ctx *ctx, const float *d_pos, int stride, size_t n, const Frame *d_frame,

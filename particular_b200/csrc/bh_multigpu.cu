@@ -289,6 +289,11 @@ struct pcuda_forest {
     pcuda::bh::PartPack *h_packs = nullptr;        // pinned
     pcuda::bh::BoundaryRec *h_stage = nullptr;     // pinned
     cudaEvent_t ev_stage = nullptr;
+    // locally essential trees (sharded_let_dev)
+    pcuda::DevBuf let_boxes, let_box_all, let_keys[2], let_idx[2], let_send_rec, let_send_gidx, let_recv_rec,
+        let_recv_gidx, let_gidx_sorted, let_cuts, let_cnt_mat, let_dom, let_dom_all, let_open, let_reach, let_parent,
+        let_tile_cnt, let_totals, let_index, let_send_nodes, let_send_src, let_bmap_send, let_bmap_recv, let_gi;
+    uint32_t *h_let = nullptr;  // pinned: count matrices and boundary maps
 };
 
 namespace pcuda {
@@ -300,8 +305,14 @@ void forest_free(pcuda_ctx *ctx) {
     DevBuf *bufs[] = {&f->gkeys, &f->gidx, &f->sample[0], &f->sample[1], &f->split, &f->counts,
                       &f->sel_tmp, &f->sel_count, &f->nodes, &f->sorted, &f->perm, &f->keys, &f->acc,
                       &f->packs, &f->stage, &f->roots, &f->route_cnt, &f->route_pos, &f->route_idx_send,
-                      &f->route_acc_send, &f->route_idx_recv, &f->route_acc_recv};
+                      &f->route_acc_send, &f->route_idx_recv, &f->route_acc_recv, &f->let_boxes, &f->let_box_all,
+                      &f->let_keys[0], &f->let_keys[1], &f->let_idx[0], &f->let_idx[1], &f->let_send_rec,
+                      &f->let_send_gidx, &f->let_recv_rec, &f->let_recv_gidx, &f->let_gidx_sorted, &f->let_cuts,
+                      &f->let_cnt_mat, &f->let_dom, &f->let_dom_all, &f->let_open, &f->let_reach, &f->let_parent,
+                      &f->let_tile_cnt, &f->let_totals, &f->let_index, &f->let_send_nodes, &f->let_send_src,
+                      &f->let_bmap_send, &f->let_bmap_recv, &f->let_gi};
     for (DevBuf *b : bufs) b->release();
+    if (f->h_let) cudaFreeHost(f->h_let);
     if (f->h_route) cudaFreeHost(f->h_route);
     if (f->h_packs) cudaFreeHost(f->h_packs);
     if (f->h_stage) cudaFreeHost(f->h_stage);
@@ -416,9 +427,11 @@ static int forest_build_part(pcuda_ctx *ctx, pcuda_forest *f, const float *d_par
 // Step 5 on the host.  packs / stage: every part's pack and boundary records (stage indexed
 // [part][level][side]); node_base: first node of every part in the joined array; top_base: where
 // the top tree goes.  Out: the top-tree nodes and the start nodes of the walk.
+// gi_table (optional, [part][level][side]): index of every boundary node in the joined array when the
+// parts are not stored with their own numbering (locally essential trees: pruned copies).
 static int merge_top_tree(pcuda_ctx *ctx, int parts, const PartPack *packs, const BoundaryRec *stage,
                           const uint32_t *node_base, uint32_t top_base, std::vector<NodeRec> &top,
-                          std::vector<uint32_t> &roots) {
+                          std::vector<uint32_t> &roots, const uint32_t *gi_table = nullptr) {
     struct Inst {
         int q, l, side;
         uint32_t gi;
@@ -454,7 +467,11 @@ static int merge_top_tree(pcuda_ctx *ctx, int parts, const PartPack *packs, cons
                 in.q = q;
                 in.l = l;
                 in.side = side;
-                in.gi = node_base[q] + (side ? le - 1 : lb);
+                in.gi = gi_table ? gi_table[((size_t)q * TOP_LEVELS + l) * 2 + side]
+                                 : node_base[q] + (side ? le - 1 : lb);
+                // a first / last node of a level that the locally essential tree does not hold lies below a
+                // pruned node: a complete cell nobody will ask for (the chain of partial cells is always sent)
+                if (gi_table && in.gi == 0xffffffffu) continue;
                 in.b = stage + ((size_t)q * TOP_LEVELS + l) * 2 + side;
                 int c = find_cell(l, pk.prefix[l][side]);
                 if (c < 0) {
@@ -874,6 +891,720 @@ static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_tota
     return PCUDA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Locally essential trees (the replicating exchanges of the two builds above are what
+// limits them: every rank receives all N records, all nodes and all accelerations).  Here nothing is
+// replicated:
+//
+//   A. the particles go to the rank that owns their KEY RANGE: common root cube from the ranks' boxes
+//      (all-gather of 32 B), keys of the local block, splitters from an all-gathered key sample, local
+//      sort, one all-to-all of {record, global index} (each record travels once: 20 B x N / world per
+//      rank instead of 16 B x N);
+//   B. every rank sorts what it received (equal keys end up in global-index order, as on one GPU) and
+//      builds the tree of its range in the common cube (one-pass build);
+//   C. every rank tells the others WHERE its targets are — the boxes of LET_BOXES overlapping windows of
+//      its sorted particles; a window overlaps its neighbours by the size of a target group, so every
+//      group of the walk lies inside one window — and sends each of them only what their walk can
+//      touch: node x goes to rank q when all its ancestors are opened by the opening rule against some
+//      window of q (the rule of the walk, made conservative by a margin), the particles of a leaf when
+//      the leaf itself is.  Open flags for every (node, rank) pair, an AND along the ancestors, a
+//      compaction per destination that keeps breadth-first order (children stay contiguous): five small
+//      data-parallel kernels, no work queues.  A pruned node travels as a record without children or
+//      particles, which the walk accepts whatever its own test says;
+//   D. cells that straddle a range boundary are joined into the top tree exactly as in the partitioned
+//      build (merge_top_tree), from the boundary nodes that every locally essential tree always carries;
+//   E. the walk starts at the top root; the accelerations travel back to the owners of the particles
+//      in one all-to-all (16 B x N / world per rank).
+//
+// Exchange per rank at N = 10M on 8 GPUs: 25 + ~25 + 20 MB instead of 140 + 140 + 105 MB.
+constexpr int LET_BOXES = 64;
+constexpr int LET_HALO = 64;      // the largest target group of the walk (two targets per lane)
+constexpr int LET_SAMPLE = 4096;  // key samples per rank
+constexpr int LET_TILE = 1024;    // nodes per block of the compaction kernels
+
+struct LetDomain {  // where the targets of a rank are; entry LET_BOXES is the whole range
+    float lo[LET_BOXES + 1][3];
+    float hi[LET_BOXES + 1][3];
+};
+
+struct LetTotals {  // per destination: counts and send offsets of nodes / particles (device + host copy)
+    uint32_t n_nodes[MAX_PARTS], n_src[MAX_PARTS], off_nodes[MAX_PARTS], off_src[MAX_PARTS];
+};
+
+__global__ void __launch_bounds__(256) let_domain_kernel(const float4 *__restrict__ sorted, uint32_t n,
+                                                         LetDomain *__restrict__ out) {
+    const int j = blockIdx.x;
+    const long m = ((long)n + LET_BOXES - 1) / LET_BOXES;
+    const long begin = max((long)j * m - LET_HALO, 0L), end = min((long)(j + 1) * m + LET_HALO, (long)n);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if ((long)j * m < (long)n) {
+        for (long i = begin + threadIdx.x; i < end; i += 256) {
+            const float4 p = sorted[i];
+            lo[0] = fminf(lo[0], p.x), hi[0] = fmaxf(hi[0], p.x);
+            lo[1] = fminf(lo[1], p.y), hi[1] = fmaxf(hi[1], p.y);
+            lo[2] = fminf(lo[2], p.z), hi[2] = fmaxf(hi[2], p.z);
+        }
+    }
+    __shared__ float s[8][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 3; ++k) {
+            s[threadIdx.x >> 5][k] = lo[k];
+            s[threadIdx.x >> 5][3 + k] = hi[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = s[0][threadIdx.x], b = s[0][3 + threadIdx.x];
+        for (int w = 1; w < 8; ++w) {
+            a = fminf(a, s[w][threadIdx.x]);
+            b = fmaxf(b, s[w][3 + threadIdx.x]);
+        }
+        out->lo[j][threadIdx.x] = a;
+        out->hi[j][threadIdx.x] = b;
+    }
+}
+
+__global__ void let_domain_whole(LetDomain *d) {
+    if (threadIdx.x >= 3) return;
+    float a = INFINITY, b = -INFINITY;
+    for (int j = 0; j < LET_BOXES; ++j) {
+        a = fminf(a, d->lo[j][threadIdx.x]);
+        b = fmaxf(b, d->hi[j][threadIdx.x]);
+    }
+    d->lo[LET_BOXES][threadIdx.x] = a;
+    d->hi[LET_BOXES][threadIdx.x] = b;
+}
+
+// The opening rule of the walk (traverse2_kernel: theta^2 dmin^2 < w^2, dmin = distance from the
+// centre of mass to the box of the targets) against a box that CONTAINS the box of every target group
+// it stands for.  `margin` (a few ulp of the root extent) is taken off every axis distance, so that the
+// different rounding of the walk's centre / half-width form can never make the walk open a node that
+// this test kept closed.
+__device__ __forceinline__ bool let_opens(const float4 cm, float w2, float theta2, const float *lo,
+                                          const float *hi, float margin) {
+    const float dx = fmaxf(fmaxf(lo[0] - cm.x, cm.x - hi[0]) - margin, 0.f);
+    const float dy = fmaxf(fmaxf(lo[1] - cm.y, cm.y - hi[1]) - margin, 0.f);
+    const float dz = fmaxf(fmaxf(lo[2] - cm.z, cm.z - hi[2]) - margin, 0.f);
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    return theta2 * d2 < w2;
+}
+
+// open[x] bit q: rank q's walk may open node x (an internal node: it needs the children; a leaf: it
+// needs the particles).  Boundary nodes (first / last of a level: the only cells that other ranks may
+// hold a share of) are always open: the walk tests the MERGED cell, whose centre of mass this rank
+// does not know.
+__global__ void __launch_bounds__(256) let_open_kernel(const NodeRec *__restrict__ nodes, uint32_t n_nodes,
+                                                       const BuildState *__restrict__ st,
+                                                       const LetDomain *__restrict__ doms, int world, int rank,
+                                                       float theta2, const Frame *__restrict__ frame,
+                                                       uint16_t *__restrict__ open, uint32_t *__restrict__ parent) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    if (x == 0) parent[0] = 0xffffffffu;
+    const NodeRec nd = nodes[x];
+    const uint32_t nc = nd.nchild_level & 0xffu, level = nd.nchild_level >> 8;
+    for (uint32_t j = 0; j < nc; ++j) parent[nd.first_child + j] = x;
+    const float ext = frame->ext;
+    const float w = ext * __int_as_float((127 - (int)level) << 23);
+    const float w2 = w * w, margin = ext * 1e-6f;
+    const bool boundary = nc > 0 && (x == st->level_begin[level] || x + 1 == st->level_begin[level + 1]);
+    uint32_t mask = 0;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        const LetDomain &d = doms[q];
+        bool op = boundary;
+        if (!op && let_opens(nd.cm, w2, theta2, d.lo[LET_BOXES], d.hi[LET_BOXES], margin)) {
+            for (int j = 0; j < LET_BOXES && !op; ++j) op = let_opens(nd.cm, w2, theta2, d.lo[j], d.hi[j], margin);
+        }
+        mask |= (uint32_t)op << q;
+    }
+    open[x] = (uint16_t)mask;
+}
+
+// reach[x] bit q: every ancestor of x is open for q, i.e. x belongs to the tree sent to q.
+__global__ void __launch_bounds__(256) let_reach_kernel(const uint16_t *__restrict__ open,
+                                                        const uint32_t *__restrict__ parent, uint32_t n_nodes,
+                                                        uint32_t all, uint16_t *__restrict__ reach) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    uint32_t m = all, a = parent[x];
+    while (a != 0xffffffffu && m) {
+        m &= open[a];
+        a = parent[a];
+    }
+    reach[x] = (uint16_t)m;
+}
+
+// Per tile and destination: nodes sent, particles sent.  tile_cnt[(2 q + k) * tiles_pad + tile].
+__global__ void __launch_bounds__(256) let_count_kernel(const NodeRec *__restrict__ nodes, uint32_t n_nodes,
+                                                        const uint16_t *__restrict__ open,
+                                                        const uint16_t *__restrict__ reach, int world,
+                                                        uint32_t *__restrict__ tile_cnt, uint32_t tiles_pad) {
+    __shared__ uint32_t s_cnt[2 * MAX_PARTS];
+    if (threadIdx.x < 2 * MAX_PARTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t cn[MAX_PARTS], cp[MAX_PARTS];
+#pragma unroll
+    for (int q = 0; q < MAX_PARTS; ++q) cn[q] = cp[q] = 0;
+    for (int u = 0; u < LET_TILE / 256; ++u) {
+        const uint32_t x = blockIdx.x * LET_TILE + threadIdx.x * (LET_TILE / 256) + u;
+        if (x >= n_nodes) break;
+        const uint32_t r = reach[x];
+        if (!r) continue;
+        const NodeRec nd = nodes[x];
+        const uint32_t send_p = (nd.nchild_level & 0xffu) == 0 ? (r & open[x]) : 0u;
+#pragma unroll
+        for (int q = 0; q < MAX_PARTS; ++q) {
+            cn[q] += (r >> q) & 1u;
+            cp[q] += ((send_p >> q) & 1u) ? nd.count : 0u;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < MAX_PARTS; ++q) {
+        if (q >= world) break;
+        uint32_t a = cn[q], b = cp[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (a) atomicAdd(&s_cnt[2 * q], a);
+            if (b) atomicAdd(&s_cnt[2 * q + 1], b);
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * world) tile_cnt[(size_t)threadIdx.x * tiles_pad + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// Exclusive scan over the tiles of every (destination, kind) row, totals and send offsets.
+__global__ void __launch_bounds__(1024) let_scan_kernel(uint32_t *__restrict__ tile_cnt, uint32_t n_tiles,
+                                                        uint32_t tiles_pad, int world, LetTotals *__restrict__ tot) {
+    __shared__ uint32_t s_total[2 * MAX_PARTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < 2 * world) {
+        uint32_t *row = tile_cnt + (size_t)warp * tiles_pad;
+        uint32_t running = 0;
+        for (uint32_t t0 = 0; t0 < n_tiles; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            const uint32_t v = t < n_tiles ? row[t] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (t < n_tiles) row[t] = running + incl - v;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_total[warp] = running;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t on = 0, os = 0;
+        for (int q = 0; q < MAX_PARTS; ++q) {
+            const uint32_t a = q < world ? s_total[2 * q] : 0u, b = q < world ? s_total[2 * q + 1] : 0u;
+            tot->n_nodes[q] = a;
+            tot->n_src[q] = b;
+            tot->off_nodes[q] = on;
+            tot->off_src[q] = os;
+            on += a;
+            os += b;
+        }
+    }
+}
+
+// Index of every sent node inside the tree of its destination (breadth-first order is kept, so the
+// children of an open node stay contiguous) and first particle slot of every sent leaf.
+// letidx / pidx: [destination][node].
+__global__ void __launch_bounds__(256) let_index_kernel(const NodeRec *__restrict__ nodes, uint32_t n_nodes,
+                                                        const uint16_t *__restrict__ open,
+                                                        const uint16_t *__restrict__ reach, int world, int rank,
+                                                        const uint32_t *__restrict__ tile_base, uint32_t tiles_pad,
+                                                        uint32_t *__restrict__ letidx, uint32_t *__restrict__ pidx) {
+    constexpr int PER = LET_TILE / 256;
+    __shared__ uint32_t s_warp[2][8];
+    const uint32_t x0 = blockIdx.x * LET_TILE + threadIdx.x * PER;
+    uint32_t r[PER], sp[PER], cnt[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const uint32_t x = x0 + u;
+        r[u] = sp[u] = cnt[u] = 0;
+        if (x < n_nodes) {
+            r[u] = reach[x];
+            if (r[u]) {
+                const NodeRec nd = nodes[x];
+                cnt[u] = nd.count;
+                sp[u] = (nd.nchild_level & 0xffu) == 0 ? (r[u] & open[x]) : 0u;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        uint32_t a = 0, b = 0;  // this thread's nodes / particles for q
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            a += (r[u] >> q) & 1u;
+            b += ((sp[u] >> q) & 1u) ? cnt[u] : 0u;
+        }
+        uint32_t ia = a, ib = b;  // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) {
+                ia += ua;
+                ib += ub;
+            }
+        }
+        __syncthreads();
+        if (lane == 31) {
+            s_warp[0][warp] = ia;
+            s_warp[1][warp] = ib;
+        }
+        __syncthreads();
+        uint32_t base_a = tile_base[(size_t)(2 * q) * tiles_pad + blockIdx.x];
+        uint32_t base_b = tile_base[(size_t)(2 * q + 1) * tiles_pad + blockIdx.x];
+        for (int w = 0; w < warp; ++w) {
+            base_a += s_warp[0][w];
+            base_b += s_warp[1][w];
+        }
+        uint32_t ea = base_a + ia - a, eb = base_b + ib - b;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const uint32_t x = x0 + u;
+            if ((r[u] >> q) & 1u) {
+                letidx[(size_t)q * n_nodes + x] = ea++;
+                if ((sp[u] >> q) & 1u) {
+                    pidx[(size_t)q * n_nodes + x] = eb;
+                    eb += cnt[u];
+                }
+            }
+        }
+    }
+}
+
+constexpr uint32_t LET_NO_NODE = 0xffffffffu;
+
+// The records (and the particles of open leaves) into the send buffers; the map of the boundary nodes.
+__global__ void __launch_bounds__(256) let_emit_kernel(const NodeRec *__restrict__ nodes, uint32_t n_nodes,
+                                                       const float4 *__restrict__ sorted,
+                                                       const uint16_t *__restrict__ open,
+                                                       const uint16_t *__restrict__ reach, int world, int rank,
+                                                       const uint32_t *__restrict__ letidx,
+                                                       const uint32_t *__restrict__ pidx,
+                                                       const LetTotals *__restrict__ tot,
+                                                       const BuildState *__restrict__ st,
+                                                       NodeRec *__restrict__ send_nodes, float4 *__restrict__ send_src,
+                                                       uint32_t *__restrict__ bmap) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    const uint32_t r = reach[x];
+    if (!r) return;
+    const NodeRec nd = nodes[x];
+    const uint32_t nc = nd.nchild_level & 0xffu, level = nd.nchild_level >> 8, op = open[x];
+    const bool first = x == st->level_begin[level], last = x + 1 == st->level_begin[level + 1];
+    for (int q = 0; q < world; ++q) {
+        if (q == rank || !((r >> q) & 1u)) continue;
+        const uint32_t me = letidx[(size_t)q * n_nodes + x];
+        NodeRec o;
+        o.cm = nd.cm;
+        o.first_child = 0;
+        o.nchild_level = level << 8;
+        o.begin = 0;
+        o.count = 0;  // no children, no particles: a pruned node, accepted by the walk as it is
+        if ((op >> q) & 1u) {
+            if (nc) {
+                o.first_child = letidx[(size_t)q * n_nodes + nd.first_child];
+                o.nchild_level = nd.nchild_level;
+                o.count = nd.count;
+            } else {
+                const uint32_t p0 = pidx[(size_t)q * n_nodes + x];
+                o.begin = p0;
+                o.count = nd.count;
+                float4 *dst = send_src + tot->off_src[q] + p0;
+                for (uint32_t i = 0; i < nd.count; ++i) dst[i] = sorted[nd.begin + i];
+            }
+        }
+        send_nodes[tot->off_nodes[q] + me] = o;
+        if (first) bmap[((size_t)q * TOP_LEVELS + level) * 2 + 0] = me;
+        if (last) bmap[((size_t)q * TOP_LEVELS + level) * 2 + 1] = me;
+    }
+}
+
+// Received records: links and particle ranges are relative to the sender's block.
+__global__ void __launch_bounds__(256) let_rebase_kernel(NodeRec *__restrict__ nodes, uint32_t n, uint32_t node_base,
+                                                         uint32_t src_base) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NodeRec r = nodes[i];
+    if (r.nchild_level & 0xffu) r.first_child += node_base;
+    else if (r.count) r.begin += src_base;
+    nodes[i] = r;
+}
+
+// collect_boundary for trees that are not stored with their own numbering: gi[part][level][side] is the
+// index of the boundary node in the joined array (LET_NO_NODE: the part has no such level).
+__global__ void __launch_bounds__(2 * TOP_LEVELS * 9) let_collect_boundary(const NodeRec *__restrict__ nodes,
+                                                                           const uint32_t *__restrict__ gi,
+                                                                           BoundaryRec *__restrict__ out) {
+    const int q = blockIdx.x;
+    const int t = threadIdx.x / 9, j = threadIdx.x % 9;
+    const uint32_t g = gi[(size_t)q * TOP_LEVELS * 2 + t];
+    if (g == LET_NO_NODE) return;
+    const NodeRec nd = nodes[g];
+    BoundaryRec *o = out + (size_t)q * TOP_LEVELS * 2 + t;
+    if (j == 0) o->node = nd;
+    else if (j - 1 < (int)(nd.nchild_level & 0xffu)) o->child[j - 1] = nodes[nd.first_child + j - 1];
+}
+
+__global__ void let_cuts_kernel(const uint64_t *__restrict__ keys, uint32_t n, const uint64_t *__restrict__ split,
+                                int world, uint32_t *__restrict__ cuts, uint32_t *__restrict__ cnt_row) {
+    const int q = threadIdx.x;  // cuts[q] = first sorted key >= split[q]; cuts[world] = n
+    if (q > world) return;
+    uint32_t lo = 0, hi = n;
+    if (q == world) lo = n;
+    else
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (keys[mid] < split[q]) lo = mid + 1;
+            else hi = mid;
+        }
+    cuts[q] = q == 0 ? 0u : lo;
+    __syncthreads();
+    if (q < world) cnt_row[q] = cuts[q + 1] - cuts[q];
+}
+
+__global__ void __launch_bounds__(256) let_gidx_kernel(const uint32_t *__restrict__ perm, uint32_t n, uint32_t lo,
+                                                       uint32_t *__restrict__ gidx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gidx[i] = lo + perm[i];
+}
+
+__global__ void __launch_bounds__(256) let_permute_kernel(const uint32_t *__restrict__ in,
+                                                          const uint32_t *__restrict__ perm, uint32_t n,
+                                                          uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+
+__global__ void __launch_bounds__(256) let_sample_kernel(const uint64_t *__restrict__ keys, uint32_t n, int m,
+                                                         uint64_t *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) out[j] = n ? keys[(size_t)j * n / m] : ~0ull;
+}
+
+// One multi-GPU Barnes-Hut step with locally essential trees.  d_local: this rank's block [lo, hi) of
+// the records; d_out: its accelerations.  Collective: every rank of the communicator must call it.
+static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, size_t lo, size_t hi,
+                           float theta, float eps, const float *d_local, float *d_out) {
+    cudaStream_t st = ctx->stream;
+    pcuda_forest *f = nullptr;
+    PCUDA_TRY(forest_of(ctx, &f));
+    pcuda_tree *t = f->local;
+    const size_t n_local = hi - lo;
+    const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
+    if (!f->h_let)
+        PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&f->h_let,
+                                          (2 * MAX_PARTS * MAX_PARTS + MAX_PARTS * TOP_LEVELS * 2) * sizeof(uint32_t) +
+                                              MAX_PARTS * sizeof(LetTotals),
+                                          cudaHostAllocDefault));
+    uint32_t *h_cnt = f->h_let;                                   // world x MAX_PARTS particle counts
+    LetTotals *h_tot = reinterpret_cast<LetTotals *>(f->h_let + 2 * MAX_PARTS * MAX_PARTS);  // per sender
+    uint32_t *h_gi = reinterpret_cast<uint32_t *>(h_tot + MAX_PARTS);  // world x TOP_LEVELS x 2
+
+    // ---- A: particles to the owners of their key ranges ----------------------------------------------
+    phase_begin(ctx, PH_COMM);
+    tree_reset<3>(ctx, t, 0);
+    PCUDA_CUDA_TRY(ctx, f->let_boxes.ensure(8 * sizeof(float)));
+    PCUDA_CUDA_TRY(ctx, f->let_box_all.ensure((size_t)world * 8 * sizeof(float)));
+    PCUDA_TRY(local_box(ctx, t, d_local, n_local, f->let_boxes.as<float>()));
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, f->let_boxes.p, f->let_box_all.p, 8 * sizeof(float)));
+    PCUDA_TRY(frame_from_boxes(ctx, t, f->let_box_all.as<float>(), world, n_total));
+    const Frame *d_frame = t->d_frame.as<Frame>();
+    const size_t nl1 = std::max<size_t>(n_local, 1);
+    for (int i = 0; i < 2; ++i) {
+        PCUDA_CUDA_TRY(ctx, f->let_keys[i].ensure(nl1 * sizeof(uint64_t)));
+        PCUDA_CUDA_TRY(ctx, f->let_idx[i].ensure(nl1 * sizeof(uint32_t)));
+        PCUDA_CUDA_TRY(ctx, f->sample[i].ensure((size_t)world * LET_SAMPLE * sizeof(uint64_t)));
+    }
+    PCUDA_CUDA_TRY(ctx, f->split.ensure((MAX_PARTS + 1) * sizeof(uint64_t)));
+    PCUDA_CUDA_TRY(ctx, f->counts.ensure((MAX_PARTS + 1) * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_cuts.ensure((MAX_PARTS + 2) * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_cnt_mat.ensure((size_t)MAX_PARTS * MAX_PARTS * sizeof(uint32_t)));
+    int cur = 0;
+    size_t tmp = 0;
+    if (n_local) {  // keys of the local block, sorted (stable: equal keys keep global-index order)
+        launch_encode<3>(ctx, d_local, 4, n_local, d_frame, f->let_keys[0].as<uint64_t>(), f->let_idx[0].as<uint32_t>());
+        cub::DoubleBuffer<uint64_t> kb(f->let_keys[0].as<uint64_t>(), f->let_keys[1].as<uint64_t>());
+        cub::DoubleBuffer<uint32_t> vb(f->let_idx[0].as<uint32_t>(), f->let_idx[1].as<uint32_t>());
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)n_local, 0, 63, st));
+        PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(f->sel_tmp.p, tmp, kb, vb, (int)n_local, 0, 63, st));
+        cur = kb.selector;
+        ctx->launches += 10;
+    }
+    const uint64_t *lkeys = f->let_keys[cur].as<uint64_t>();
+    const uint32_t *lperm = f->let_idx[cur].as<uint32_t>();
+    // splitters: the world-quantiles of an all-gathered regular sample of the sorted local keys
+    uint64_t *my_sample = f->sample[0].as<uint64_t>() + (size_t)rank * LET_SAMPLE;
+    let_sample_kernel<<<(LET_SAMPLE + 255) / 256, 256, 0, st>>>(lkeys, (uint32_t)n_local, LET_SAMPLE, my_sample);
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, my_sample, f->sample[0].p, LET_SAMPLE * sizeof(uint64_t)));
+    {
+        const int m = world * LET_SAMPLE;
+        cub::DoubleBuffer<uint64_t> sb(f->sample[0].as<uint64_t>(), f->sample[1].as<uint64_t>());
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, sb, m, 0, 64, st));
+        PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(f->sel_tmp.p, tmp, sb, m, 0, 64, st));
+        pick_splitters<<<1, 32, 0, st>>>(sb.Current(), m, world, f->split.as<uint64_t>(), f->counts.as<uint32_t>());
+        if (sb.selector != 0)  // keep the all-gather buffer in sample[0] for the next call's layout
+            std::swap(f->sample[0], f->sample[1]);
+    }
+    uint32_t *d_mat = f->let_cnt_mat.as<uint32_t>();
+    uint32_t *d_row = d_mat + (size_t)rank * MAX_PARTS;
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_row, 0, MAX_PARTS * sizeof(uint32_t), st));
+    let_cuts_kernel<<<1, 32, 0, st>>>(lkeys, (uint32_t)n_local, f->split.as<uint64_t>(), world, f->let_cuts.as<uint32_t>(),
+                                      d_row);
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 3 + 10;
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_row, d_mat, MAX_PARTS * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_cnt, d_mat, (size_t)world * MAX_PARTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    // records and global indices in local key order: the send buffers (destination ranges are contiguous)
+    PCUDA_CUDA_TRY(ctx, f->let_send_rec.ensure(nl1 * sizeof(float4)));
+    PCUDA_CUDA_TRY(ctx, f->let_send_gidx.ensure(nl1 * sizeof(uint32_t)));
+    if (n_local) {
+        launch_gather<3>(ctx, d_local, 4, true, n_local, lperm, f->let_send_rec.as<float4>());
+        let_gidx_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(lperm, (uint32_t)n_local, (uint32_t)lo,
+                                                                           f->let_send_gidx.as<uint32_t>());
+        ctx->launches++;
+    }
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (1) the count matrix
+    size_t send_off[MAX_PARTS], send_cnt[MAX_PARTS], recv_off[MAX_PARTS], recv_cnt[MAX_PARTS];
+    size_t so[MAX_PARTS], sb_[MAX_PARTS], ro[MAX_PARTS], rb[MAX_PARTS];
+    size_t n_mine = 0, s_off = 0;
+    for (int q = 0; q < world; ++q) {
+        send_off[q] = s_off;
+        send_cnt[q] = h_cnt[(size_t)rank * MAX_PARTS + q];
+        s_off += send_cnt[q];
+        recv_off[q] = n_mine;
+        recv_cnt[q] = h_cnt[(size_t)q * MAX_PARTS + rank];
+        n_mine += recv_cnt[q];
+    }
+    if (s_off != n_local)
+        return fail(ctx, PCUDA_ERR_NCCL, "key ranges do not cover the local block (%zu of %zu particles)", s_off, n_local);
+    const size_t nm1 = std::max<size_t>(n_mine, 1);
+    PCUDA_CUDA_TRY(ctx, f->let_recv_rec.ensure(nm1 * sizeof(float4)));
+    PCUDA_CUDA_TRY(ctx, f->let_recv_gidx.ensure(nm1 * sizeof(uint32_t)));
+    for (int pass = 0; pass < 2; ++pass) {
+        const size_t w = pass == 0 ? sizeof(float4) : sizeof(uint32_t);
+        for (int q = 0; q < world; ++q) {
+            so[q] = send_off[q] * w, sb_[q] = send_cnt[q] * w, ro[q] = recv_off[q] * w, rb[q] = recv_cnt[q] * w;
+        }
+        PCUDA_TRY(nccl_alltoallv(ctx, pass == 0 ? f->let_send_rec.p : f->let_send_gidx.p, so, sb_,
+                                 pass == 0 ? f->let_recv_rec.p : f->let_recv_gidx.p, ro, rb));
+    }
+    phase_end(ctx, PH_COMM);
+
+    // ---- B: the tree of this rank's key range ---------------------------------------------------------
+    phase_begin(ctx, PH_BUILD);
+    tree_reset<3>(ctx, t, n_mine);
+    PCUDA_CUDA_TRY(ctx, t->scan_in.ensure(sizeof(BuildState)));
+    PCUDA_CUDA_TRY(ctx, f->let_gidx_sorted.ensure(nm1 * sizeof(uint32_t)));
+    if (n_mine) {
+        for (int i = 0; i < 2; ++i) {
+            PCUDA_CUDA_TRY(ctx, t->keys[i].ensure(n_mine * sizeof(uint64_t)));
+            PCUDA_CUDA_TRY(ctx, t->perm[i].ensure(n_mine * sizeof(uint32_t)));
+        }
+        const float *recv = f->let_recv_rec.as<float>();
+        launch_encode<3>(ctx, recv, 4, n_mine, d_frame, t->keys[0].as<uint64_t>(), t->perm[0].as<uint32_t>());
+        cub::DoubleBuffer<uint64_t> kb(t->keys[0].as<uint64_t>(), t->keys[1].as<uint64_t>());
+        cub::DoubleBuffer<uint32_t> vb(t->perm[0].as<uint32_t>(), t->perm[1].as<uint32_t>());
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)n_mine, 0, 63, st));
+        PCUDA_CUDA_TRY(ctx, t->cub_tmp.ensure(tmp));
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(t->cub_tmp.p, tmp, kb, vb, (int)n_mine, 0, 63, st));
+        t->cur = kb.selector;
+        PCUDA_CUDA_TRY(ctx, t->sorted.ensure(n_mine * sizeof(float4)));
+        launch_gather<3>(ctx, recv, 4, true, n_mine, t->d_perm(), t->sorted.as<float4>());
+        let_permute_kernel<<<(unsigned)((n_mine + 255) / 256), 256, 0, st>>>(
+            f->let_recv_gidx.as<uint32_t>(), t->d_perm(), (uint32_t)n_mine, f->let_gidx_sorted.as<uint32_t>());
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 11;
+        PCUDA_TRY(build_levels<3>(ctx, t, n_mine));  // (2) synchronises: level table
+    }
+    PartPack *d_packs = f->packs.as<PartPack>();
+    fill_pack<<<1, 64, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(), n_mine ? t->d_keys() : nullptr,
+                                t->scan_in.as<BuildState>(), (uint32_t)t->n_nodes, (uint32_t)t->n_levels, d_packs + rank);
+    // where this rank's targets are
+    PCUDA_CUDA_TRY(ctx, f->let_dom.ensure(sizeof(LetDomain)));
+    PCUDA_CUDA_TRY(ctx, f->let_dom_all.ensure((size_t)world * sizeof(LetDomain)));
+    let_domain_kernel<<<LET_BOXES, 256, 0, st>>>(t->sorted.as<float4>(), (uint32_t)n_mine, f->let_dom.as<LetDomain>());
+    let_domain_whole<<<1, 32, 0, st>>>(f->let_dom.as<LetDomain>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    phase_end(ctx, PH_BUILD);
+
+    // ---- C: locally essential trees ---------------------------------------------------------------------
+    phase_begin(ctx, PH_COMM3);
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_packs + rank, d_packs, sizeof(PartPack)));
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, f->let_dom.p, f->let_dom_all.p, sizeof(LetDomain)));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_packs, d_packs, world * sizeof(PartPack), cudaMemcpyDeviceToHost, st));
+    const uint32_t nn = (uint32_t)t->n_nodes;
+    const uint32_t n_tiles = (nn + LET_TILE - 1) / LET_TILE, tiles_pad = (std::max<uint32_t>(n_tiles, 1) + 31u) & ~31u;
+    const size_t nn1 = std::max<size_t>(nn, 1);
+    PCUDA_CUDA_TRY(ctx, f->let_open.ensure(nn1 * sizeof(uint16_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_reach.ensure(nn1 * sizeof(uint16_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_parent.ensure(nn1 * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_tile_cnt.ensure((size_t)2 * MAX_PARTS * tiles_pad * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_totals.ensure((size_t)MAX_PARTS * sizeof(LetTotals)));
+    PCUDA_CUDA_TRY(ctx, f->let_index.ensure((size_t)2 * world * nn1 * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_bmap_send.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_bmap_recv.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));
+    // worst case: every node and every particle goes to every other rank
+    PCUDA_CUDA_TRY(ctx, f->let_send_nodes.ensure(std::max<size_t>(1, (size_t)(world - 1) * nn) * sizeof(NodeRec)));
+    PCUDA_CUDA_TRY(ctx, f->let_send_src.ensure(std::max<size_t>(1, (size_t)(world - 1) * n_mine) * sizeof(float4)));
+    LetTotals *d_tot_all = f->let_totals.as<LetTotals>();
+    LetTotals *d_tot = d_tot_all + rank;
+    uint32_t *letidx = f->let_index.as<uint32_t>(), *pidx = letidx + (size_t)world * nn1;
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(f->let_bmap_send.p, 0xff, (size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t), st));
+    PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_tot, 0, sizeof(LetTotals), st));
+    if (nn) {
+        const unsigned nb256 = (nn + 255) / 256;
+        const BuildState *d_state = t->scan_in.as<BuildState>();
+        let_open_kernel<<<nb256, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, d_state, f->let_dom_all.as<LetDomain>(), world,
+                                               rank, theta * theta, d_frame, f->let_open.as<uint16_t>(),
+                                               f->let_parent.as<uint32_t>());
+        const uint32_t all = ((1u << world) - 1u) & ~(1u << rank);
+        let_reach_kernel<<<nb256, 256, 0, st>>>(f->let_open.as<uint16_t>(), f->let_parent.as<uint32_t>(), nn, all,
+                                                f->let_reach.as<uint16_t>());
+        let_count_kernel<<<n_tiles, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, f->let_open.as<uint16_t>(),
+                                                  f->let_reach.as<uint16_t>(), world, f->let_tile_cnt.as<uint32_t>(),
+                                                  tiles_pad);
+        let_scan_kernel<<<1, 1024, 0, st>>>(f->let_tile_cnt.as<uint32_t>(), n_tiles, tiles_pad, world, d_tot);
+        let_index_kernel<<<n_tiles, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, f->let_open.as<uint16_t>(),
+                                                  f->let_reach.as<uint16_t>(), world, rank, f->let_tile_cnt.as<uint32_t>(),
+                                                  tiles_pad, letidx, pidx);
+        let_emit_kernel<<<nb256, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, t->sorted.as<float4>(),
+                                               f->let_open.as<uint16_t>(), f->let_reach.as<uint16_t>(), world, rank, letidx,
+                                               pidx, d_tot, d_state, f->let_send_nodes.as<NodeRec>(),
+                                               f->let_send_src.as<float4>(), f->let_bmap_send.as<uint32_t>());
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 6;
+    }
+    PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_tot, d_tot_all, sizeof(LetTotals)));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_tot, d_tot_all, (size_t)world * sizeof(LetTotals), cudaMemcpyDeviceToHost, st));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (3) sizes of the trees on their way
+    // joined arrays: block p = what rank p sent (p == rank: the whole local tree), then the top tree
+    uint32_t node_base[MAX_PARTS], src_base[MAX_PARTS];
+    size_t n_nodes_all = 0, n_src_all = 0;
+    for (int p = 0; p < world; ++p) {
+        node_base[p] = (uint32_t)n_nodes_all;
+        src_base[p] = (uint32_t)n_src_all;
+        n_nodes_all += p == rank ? nn : h_tot[p].n_nodes[rank];
+        n_src_all += p == rank ? n_mine : h_tot[p].n_src[rank];
+    }
+    if (n_nodes_all + TOP_CAP > 0xfffffff0ull || n_src_all > 0xfffffff0ull)
+        return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "joined tree does not fit 32-bit indices");
+    PCUDA_CUDA_TRY(ctx, f->nodes.ensure((n_nodes_all + TOP_CAP) * sizeof(NodeRec)));
+    PCUDA_CUDA_TRY(ctx, f->sorted.ensure(std::max<size_t>(n_src_all, 1) * sizeof(float4)));
+    for (int pass = 0; pass < 3; ++pass) {  // nodes, particles, boundary maps
+        const size_t w = pass == 0 ? sizeof(NodeRec) : pass == 1 ? sizeof(float4) : TOP_LEVELS * 2 * sizeof(uint32_t);
+        for (int q = 0; q < world; ++q) {
+            if (pass == 2) {
+                so[q] = (size_t)q * w, ro[q] = (size_t)q * w;
+                sb_[q] = rb[q] = q == rank ? 0 : w;
+            } else {
+                const uint32_t *soff = pass == 0 ? h_tot[rank].off_nodes : h_tot[rank].off_src;
+                const uint32_t *scnt = pass == 0 ? h_tot[rank].n_nodes : h_tot[rank].n_src;
+                so[q] = (size_t)soff[q] * w;
+                sb_[q] = q == rank ? 0 : (size_t)scnt[q] * w;
+                ro[q] = (size_t)(pass == 0 ? node_base[q] : src_base[q]) * w;
+                rb[q] = q == rank ? 0 : (size_t)(pass == 0 ? h_tot[q].n_nodes[rank] : h_tot[q].n_src[rank]) * w;
+            }
+        }
+        const void *sp = pass == 0 ? f->let_send_nodes.p : pass == 1 ? f->let_send_src.p : f->let_bmap_send.p;
+        void *rp = pass == 0 ? f->nodes.p : pass == 1 ? f->sorted.p : f->let_bmap_recv.p;
+        PCUDA_TRY(nccl_alltoallv(ctx, sp, so, sb_, rp, ro, rb));
+    }
+    NodeRec *fn = f->nodes.as<NodeRec>();
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        const uint32_t cnt = h_tot[p].n_nodes[rank];
+        if (cnt) let_rebase_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(fn + node_base[p], cnt, node_base[p], src_base[p]);
+    }
+    if (nn) {
+        copy_rebase_nodes<<<(nn + 255) / 256, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, node_base[rank], src_base[rank],
+                                                            fn + node_base[rank]);
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->sorted.as<float4>() + src_base[rank], t->sorted.p, n_mine * sizeof(float4),
+                                            cudaMemcpyDeviceToDevice, st));
+    }
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += world;
+
+    // ---- D: the top tree ----------------------------------------------------------------------------------
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_gi, f->let_bmap_recv.p, (size_t)world * TOP_LEVELS * 2 * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, st));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (4a) boundary maps (tiny; the packs are here already)
+    for (int p = 0; p < world; ++p) {
+        const PartPack &pk = f->h_packs[p];
+        for (int l = 0; l < TOP_LEVELS; ++l)
+            for (int side = 0; side < 2; ++side) {
+                uint32_t &g = h_gi[((size_t)p * TOP_LEVELS + l) * 2 + side];
+                if (pk.n_nodes == 0 || l >= (int)pk.n_levels) g = LET_NO_NODE;
+                else if (p == rank) g = node_base[p] + (side ? pk.level_begin[l + 1] - 1 : pk.level_begin[l]);
+                else if (g == LET_NO_NODE)
+                    return fail(ctx, PCUDA_ERR_NCCL, "rank %d sent no boundary node for level %d", p, l);
+                else g += node_base[p];
+            }
+    }
+    PCUDA_CUDA_TRY(ctx, f->let_gi.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->let_gi.p, h_gi, (size_t)world * TOP_LEVELS * 2 * sizeof(uint32_t),
+                                        cudaMemcpyHostToDevice, st));
+    let_collect_boundary<<<world, 2 * TOP_LEVELS * 9, 0, st>>>(fn, f->let_gi.as<uint32_t>(), f->stage.as<BoundaryRec>());
+    PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_stage, f->stage.p, (size_t)world * TOP_LEVELS * 2 * sizeof(BoundaryRec),
+                                        cudaMemcpyDeviceToHost, st));
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (4b) boundary records
+    std::vector<NodeRec> top;
+    std::vector<uint32_t> roots;
+    PCUDA_TRY(merge_top_tree(ctx, world, f->h_packs, f->h_stage, node_base, (uint32_t)n_nodes_all, top, roots, h_gi));
+    if (!top.empty())
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(fn + n_nodes_all, top.data(), top.size() * sizeof(NodeRec),
+                                            cudaMemcpyHostToDevice, st));
+    if (!roots.empty())
+        PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->roots.p, roots.data(), roots.size() * sizeof(uint32_t),
+                                            cudaMemcpyHostToDevice, st));
+    ForestView fv{};
+    fv.nodes = fn;
+    fv.src = f->sorted.as<float4>();
+    fv.d_roots = f->roots.as<uint32_t>();
+    fv.n_roots = (uint32_t)roots.size();
+
+    // ---- E: walk, accelerations back to the owners ----------------------------------------------------
+    RoutePlan plan;
+    PCUDA_TRY(route_plan(ctx, f, n_mine ? f->let_gidx_sorted.as<uint32_t>() : nullptr, n_mine, world, rank, cap, n_local,
+                         &plan));  // (5) synchronises
+    phase_end(ctx, PH_COMM3);
+    phase_begin(ctx, PH_COMPUTE);
+    if (n_mine)
+        PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), plan.d_pos, n_mine, theta, eps,
+                                  plan.d_acc_send, nullptr, &fv));
+    phase_end(ctx, PH_COMPUTE);
+    phase_begin(ctx, PH_COMM2);
+    PCUDA_TRY(route_exchange(ctx, f, plan, world, lo, d_out));
+    phase_end(ctx, PH_COMM2);
+    return PCUDA_OK;
+}
+
 int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total,
                        float theta, float eps, float *d_gathered, float *d_out) {
     int world = 1, rank = 0;
@@ -884,6 +1615,12 @@ int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_t
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
                     "rank %d of %d must own %zu of %zu particles (contiguous blocks of %zu), got %zu",
                     rank, world, hi - lo, n_total, cap, n_local);
+    const int how = g_forest ? g_forest : ctx->bh_build;  // 0 = automatic
+    const bool forest_ok = world > 1 && world <= MAX_PARTS && ctx->order == 1 && g_tpl == 2 && !g_variant;
+    // locally essential trees: nothing is replicated, so they win as soon as there is more than one GPU
+    // and enough particles for every rank to have a range worth a tree
+    if (forest_ok && (how == 3 || (how == 0 && n_total >= (size_t)world * 65536)))
+        return sharded_let_dev(ctx, world, rank, n_total, lo, hi, theta, eps, d_local, d_out);
     float *slot = d_gathered + (size_t)rank * cap * 4;
     phase_begin(ctx, PH_COMM);
     if (n_local)
@@ -891,10 +1628,8 @@ int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_t
                                             ctx->stream));
     if (world > 1) PCUDA_TRY(pcuda_comm_allgather_dev(ctx, slot, d_gathered, cap * 16));
     phase_end(ctx, PH_COMM);
-    const int how = g_forest ? g_forest : ctx->bh_build;  // 0 = automatic: partitioned from 4 GPUs on
     const bool forest = how == 1 || (how == 0 && world >= 4);
-    if (forest && world > 1 && world <= MAX_PARTS && n_total >= (size_t)world && ctx->order == 1 &&
-        g_tpl == 2 && !g_variant)
+    if (forest && forest_ok && n_total >= (size_t)world)
         return sharded_forest_dev(ctx, world, rank, n_total, lo, hi, theta, eps, d_gathered, d_out);
     if (!ctx->call_tree) ctx->call_tree = new pcuda_tree();
     pcuda_tree *t = ctx->call_tree;

@@ -626,7 +626,11 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
             const uint32_t nc = nd.nchild_level & 0xffu;
             const bool open_internal = has && open && nc > 0;
             const bool open_leaf = has && open && nc == 0;
-            const bool accept = has && !open && nd.cm.w != 0.f;
+            // a node without children and without particles is the stub of a subtree that a locally
+            // essential tree left out (bh_multigpu.cu): the sender's test guarantees that no target here
+            // needs it opened, so it is accepted whatever this test says
+            const bool pruned = FOREST && nc == 0 && nd.count == 0;
+            const bool accept = has && (!open || pruned) && nd.cm.w != 0.f;
             if (COUNT) c_test += k;
 
             const int c_child = open_internal ? (int)nc : 0;

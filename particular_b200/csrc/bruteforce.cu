@@ -401,9 +401,16 @@ struct Plan {
 
 static Plan make_plan(int sm_count, size_t na, size_t nb, int force_tp) {
     Plan pl{};
+    // Targets per thread.  Large problems (many sources): 8 targets per thread as soon as there are a
+    // few dozen target tiles — the source splits supply the CTAs — because one LDS.128 then feeds four
+    // packed pairs (B200, 1M sources: 125k targets 0.690 of peak against 0.688 with 2 per thread and a
+    // 1.6 % loss to the last, nearly empty tile that run_f32 now gives to a second launch; 16k targets:
+    // 2 per thread wins, 0.675 against 0.669).  Small problems keep the occupancy-driven choice.
+    const bool large = (double)na * (double)nb >= 2.5e8;
     if (force_tp > 0) pl.tp = force_tp;
-    else if (na >= (size_t)sm_count * 2 * 2048) pl.tp = 4;
-    else if (na >= (size_t)sm_count * 3 * 512) pl.tp = 2;
+    else if (large && na >= 49152) pl.tp = 4;
+    else if (!large && na >= (size_t)sm_count * 2 * 2048) pl.tp = 4;
+    else if (!large && na >= (size_t)sm_count * 3 * 512) pl.tp = 2;
     else pl.tp = 1;
     pl.block = pl.tp == 1 ? 128 : 256;
     pl.minb = pl.tp == 4 ? 2 : (pl.tp == 2 ? 3 : 4);
@@ -462,34 +469,12 @@ static int ensure_tile_tickets(pcuda_ctx *ctx, size_t n_tiles) {
     return PCUDA_OK;
 }
 
-// Enqueues the brute-force evaluation on ctx->stream.  All pointers are device pointers.
-// src4: 16-byte records (DIM 3: {x,y,z,mu}; DIM 2: {x,y,mu,0}); tgt rows have tgt_stride floats.
+// One launch (+ reduction) of the pair kernel over `na` targets with the plan of (na, nb).
 template <int DIM>
-static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na,
-                   const float4 *d_src4, size_t nb, float softening, int checked, float *d_out) {
-    if (na == 0) return PCUDA_OK;
-    if (nb == 0) {
-        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * DIM * sizeof(float), ctx->stream));
-        return PCUDA_OK;
-    }
-    if (na > 0x7fffffffull || nb > 0x7fffffffull)
-        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
-    const float eps2 = softening * softening;
-    int clamp = 0;
-    if (checked && eps2 == 0.0f)
-        clamp = g_clamp_mode ? g_clamp_mode
-                             : ((double)na * (double)nb >= 2.5e8 && !ctx->exact_checked ? 3 : 1);
-    const Plan pl = make_plan(ctx->sm_count, na, nb, g_force_tp);
-    unsigned *mass_max = nullptr;
-    if (clamp >= 2) {
-        PCUDA_CUDA_TRY(ctx, ctx->d_massmax.ensure(sizeof(unsigned)));
-        mass_max = ctx->d_massmax.as<unsigned>();
-        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(mass_max, 0, sizeof(unsigned), ctx->stream));
-        const int blocks = (int)std::min<size_t>((size_t)ctx->sm_count * 4, (nb + 255) / 256);
-        mass_max_kernel<<<blocks, 256, 0, ctx->stream>>>(d_src4, (int)nb, DIM, mass_max);
-        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches++;
-    }
+static int run_f32_part(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na, const float4 *d_src4,
+                        size_t nb, float eps2, int clamp, const unsigned *mass_max, float *d_out,
+                        int force_tp) {
+    const Plan pl = make_plan(ctx->sm_count, na, nb, force_tp);
     const size_t n_pad = (na + 63) & ~size_t(63);
     float *partial = nullptr;
     unsigned *tile_done = nullptr;
@@ -525,6 +510,48 @@ static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na
         ctx->launches++;
     }
     return PCUDA_OK;
+}
+
+// Enqueues the brute-force evaluation on ctx->stream.  All pointers are device pointers.
+// src4: 16-byte records (DIM 3: {x,y,z,mu}; DIM 2: {x,y,mu,0}); tgt rows have tgt_stride floats.
+template <int DIM>
+static int run_f32(pcuda_ctx *ctx, const float *d_tgt, int tgt_stride, size_t na,
+                   const float4 *d_src4, size_t nb, float softening, int checked, float *d_out) {
+    if (na == 0) return PCUDA_OK;
+    if (nb == 0) {
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, na * DIM * sizeof(float), ctx->stream));
+        return PCUDA_OK;
+    }
+    if (na > 0x7fffffffull || nb > 0x7fffffffull)
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "particle count exceeds 2^31-1");
+    const float eps2 = softening * softening;
+    int clamp = 0;
+    if (checked && eps2 == 0.0f)
+        clamp = g_clamp_mode ? g_clamp_mode
+                             : ((double)na * (double)nb >= 2.5e8 && !ctx->exact_checked ? 3 : 1);
+    unsigned *mass_max = nullptr;
+    if (clamp >= 2) {
+        PCUDA_CUDA_TRY(ctx, ctx->d_massmax.ensure(sizeof(unsigned)));
+        mass_max = ctx->d_massmax.as<unsigned>();
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(mass_max, 0, sizeof(unsigned), ctx->stream));
+        const int blocks = (int)std::min<size_t>((size_t)ctx->sm_count * 4, (nb + 255) / 256);
+        mass_max_kernel<<<blocks, 256, 0, ctx->stream>>>(d_src4, (int)nb, DIM, mass_max);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    // The 8-targets-per-thread variant works in tiles of 2048 targets.  A last tile that is mostly
+    // empty costs a full tile's time (125 000 targets = 61.04 tiles: 1.6 % of the launch), so the
+    // remainder goes to a second launch with its own plan (finer tiles, its own source splits).
+    const Plan pl = make_plan(ctx->sm_count, na, nb, g_force_tp);
+    const size_t tile_t = (size_t)pl.block * 2 * pl.tp;
+    const size_t rem = na % tile_t;
+    if (pl.tp == 4 && !pl.small && g_force_tp == 0 && na > tile_t && rem != 0 && rem <= tile_t / 2) {
+        const size_t head = na - rem;
+        PCUDA_TRY(run_f32_part<DIM>(ctx, d_tgt, tgt_stride, head, d_src4, nb, eps2, clamp, mass_max, d_out, 4));
+        return run_f32_part<DIM>(ctx, d_tgt + head * tgt_stride, tgt_stride, rem, d_src4, nb, eps2, clamp,
+                                 mass_max, d_out + head * DIM, 0);
+    }
+    return run_f32_part<DIM>(ctx, d_tgt, tgt_stride, na, d_src4, nb, eps2, clamp, mass_max, d_out, g_force_tp);
 }
 
 template <int DIM = 3>

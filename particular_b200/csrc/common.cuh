@@ -80,7 +80,7 @@ struct pcuda_ctx {
     uint64_t last_counters[5] = {0, 0, 0, 0, 0};
     pcuda_tree *call_tree = nullptr;  // tree reused by the one-shot Barnes-Hut entry points
     pcuda_forest *forest = nullptr;   // partitioned multi-GPU build (PCUDA_FLAG_BH_PARTITIONED_BUILD)
-    int bh_build = 0;                 // multi-GPU tree build: 0 = automatic, 1 = partitioned, 2 = replicated
+    int bh_build = 0;                 // multi-GPU tree build: 0 = automatic, 1 = partitioned, 2 = replicated, 3 = LET
 
     pcuda::Nccl *nccl = nullptr;
     int live_sims = 0;  // pcuda_sim objects created on this context (sim.cu)

@@ -125,6 +125,7 @@ int pcuda_create(const pcuda_config *config, pcuda_ctx **out) {
     ctx->phase_timings = !(config && (config->flags & PCUDA_FLAG_NO_PHASE_TIMINGS));
     ctx->exact_checked = config && (config->flags & PCUDA_FLAG_EXACT_CHECKED);
     ctx->bh_build = !config ? 0
+                    : (config->flags & PCUDA_FLAG_BH_LET_BUILD)         ? 3
                     : (config->flags & PCUDA_FLAG_BH_PARTITIONED_BUILD) ? 1
                     : (config->flags & PCUDA_FLAG_BH_REPLICATED_BUILD)  ? 2
                                                                         : 0;

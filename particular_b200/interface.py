@@ -259,13 +259,16 @@ class CudaContext:
 
     def __init__(self, device: int = 0, leaf_size: int = 0, phase_timings: bool = True,
                  expansion_order: int = 1, partitioned_build: Optional[bool] = None,
-                 exact_checked: bool = False):
+                 exact_checked: bool = False, bh_build: Optional[str] = None):
         """phase_timings=False skips the per-phase CUDA events (PCUDA_FLAG_NO_PHASE_TIMINGS):
         about 10 us less per call; timings() then carries only kernel_launches.
         partitioned_build: multi-GPU Barnes-Hut tree build.  True (PCUDA_FLAG_BH_PARTITIONED_BUILD):
         one tree per GPU over its key range, joined by a top tree; False
         (PCUDA_FLAG_BH_REPLICATED_BUILD): every GPU builds the whole tree; None: partitioned from
-        4 GPUs on.
+        4 GPUs on.  bh_build = "let" (PCUDA_FLAG_BH_LET_BUILD) / "partitioned" / "replicated" names the
+        build instead: "let" = locally essential trees (particles go to the owners of their key ranges,
+        every rank sends the others only what their walks can open), the default from 2 GPUs on when
+        every rank gets at least 65536 particles.
         exact_checked (PCUDA_FLAG_EXACT_CHECKED): the f32 brute-force kernels test r^2 == 0 exactly at
         every problem size instead of adding the floor t ~ 1e-19 to r^2 on large problems (see
         include/particular_cuda.h)."""
@@ -273,6 +276,9 @@ class CudaContext:
             (_ffi.FLAG_EXACT_CHECKED if exact_checked else 0) | \
             (0 if partitioned_build is None else
              _ffi.FLAG_BH_PARTITIONED_BUILD if partitioned_build else _ffi.FLAG_BH_REPLICATED_BUILD)
+        if bh_build is not None:
+            flags |= {"let": _ffi.FLAG_BH_LET_BUILD, "partitioned": _ffi.FLAG_BH_PARTITIONED_BUILD,
+                      "replicated": _ffi.FLAG_BH_REPLICATED_BUILD}[bh_build]
         cfg = _ffi.Config(device, flags, leaf_size, expansion_order)
         h = C.c_void_p()
         check(lib.pcuda_create(C.byref(cfg), C.byref(h)))
@@ -351,6 +357,14 @@ class CudaContext:
     def comm_init(self, unique_id: bytes, world_size: int, rank: int):
         buf = (C.c_uint8 * _ffi.UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         check(lib.pcuda_comm_init(self.handle, C.byref(buf), world_size, rank), self.handle)
+
+    @staticmethod
+    def comm_init_local(contexts) -> None:
+        """In-process communicator for tests (pcuda_comm_init_local): binds the given contexts of this
+        process (rank = position in the list; one host thread must drive each) so that the sharded entry
+        points run all their ranks on a box with a single GPU."""
+        arr = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
+        check(lib.pcuda_comm_init_local(arr, len(contexts)))
 
     def allgather_dev(self, send_ptr: int, recv_ptr: int, bytes_per_rank: int):
         check(lib.pcuda_comm_allgather_dev(self.handle, send_ptr, recv_ptr, bytes_per_rank),

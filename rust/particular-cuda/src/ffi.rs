@@ -26,6 +26,7 @@ pub const PCUDA_FLAG_NO_PHASE_TIMINGS: u32 = 1;
 pub const PCUDA_FLAG_BH_PARTITIONED_BUILD: u32 = 2;
 pub const PCUDA_FLAG_BH_REPLICATED_BUILD: u32 = 4;
 pub const PCUDA_FLAG_EXACT_CHECKED: u32 = 8;
+pub const PCUDA_FLAG_BH_LET_BUILD: u32 = 16;
 
 pub const PCUDA_BRUTE_FORCE: u32 = 0;
 pub const PCUDA_BARNES_HUT: u32 = 1;
@@ -176,6 +177,7 @@ extern "C" {
     pub fn pcuda_comm_unique_id(ctx: *mut pcuda_ctx, id: *mut u8) -> c_int;
     pub fn pcuda_comm_init(ctx: *mut pcuda_ctx, id: *const u8, world_size: c_int, rank: c_int) -> c_int;
     pub fn pcuda_comm_destroy(ctx: *mut pcuda_ctx) -> c_int;
+    pub fn pcuda_comm_init_local(ctxs: *const *mut pcuda_ctx, world_size: c_int) -> c_int;
     pub fn pcuda_comm_allgather_dev(ctx: *mut pcuda_ctx, d_send: *const c_void, d_recv: *mut c_void,
                                     bytes_per_rank: usize) -> c_int;
     pub fn pcuda_bruteforce_f32x3_sharded_dev(ctx: *mut pcuda_ctx, d_local_xyzm: *const f32, n_local: usize,

@@ -146,7 +146,7 @@ def test_theta0_is_brute_force(pb, ctx, dim):
     exact = oracle.brute_force_exact(p[:, :dim], p)
     got = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).compute(p)
     ref32 = oracle.brute_force_parallel(p[:, :dim], p)
-    assert_bruteforce_parity(got, ref32, p[:, :dim], p, aggregate=False)
+    assert_bruteforce_parity(got, ref32, p[:, :dim], p, aggregate=False, plain=False)
     c = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).last_counters()
     assert c["particle_interactions"] == 6000 * 6000 and c["node_interactions"] == 0
 
@@ -176,11 +176,11 @@ def test_f64_theta0_is_f64_brute_force(pb, ctx, dim):
     p[200, :dim] = p[201, :dim] * (1.0 + 1e-12)          # distinct in f64, equal in f32
     got = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).compute(p)
     ref = oracle.brute_force_parallel(p[:, :dim], p)
-    assert_bruteforce_parity(got, ref, p[:, :dim], p, aggregate=False)
+    assert_bruteforce_parity(got, ref, p[:, :dim], p, aggregate=False, plain=False)
     aff = uniform_cloud(777, d=dim, seed=10, dtype=np.float64)[:, :dim]
     got = pb.BarnesHut(ctx, 0.0, pb.AccelerationSoftened.checked(2.0)).compute(pb.Between(aff, p))
     ref = oracle.brute_force_parallel(aff, p, 2.0)
-    assert_bruteforce_parity(got, ref, aff, p, 2.0, aggregate=False)
+    assert_bruteforce_parity(got, ref, aff, p, 2.0, aggregate=False, plain=False)
 
 
 def test_f64_device_api_reference_fixture_and_empty(pb, ctx):
@@ -234,7 +234,7 @@ def test_quadrupole_nodes(pb, ctx, cloud, dim):
         small = p[:3000]
         got = pi.BarnesHut(cq, 0.0, pi.Acceleration.checked()).compute(small)
         assert_bruteforce_parity(got, oracle.brute_force_parallel(small[:, :dim], small), small[:, :dim], small,
-                                 aggregate=False)
+                                 aggregate=False, plain=False)
         # separate targets, softening, tiny inputs, a prebuilt tree
         aff = uniform_cloud(501, d=dim, seed=3)[:, :dim] * 1e-3
         a_q = pi.BarnesHut(cq, 0.5, pi.AccelerationSoftened.checked(0.01)).compute(pi.Between(aff, p))
@@ -436,7 +436,7 @@ def test_partitioned_theta0_is_brute_force(pb, ctx, parts):
     p = uniform_cloud(6000, seed=8)
     got = pb.BarnesHut(ctx, 0.0, pb.Acceleration.checked()).compute_partitioned(p, parts)
     ref32 = oracle.brute_force_parallel(p[:, :3], p)
-    assert_bruteforce_parity(got, ref32, p[:, :3], p, aggregate=False)
+    assert_bruteforce_parity(got, ref32, p[:, :3], p, aggregate=False, plain=False)
 
 
 def test_partitioned_degenerate_inputs(pb, ctx):

@@ -285,6 +285,41 @@ def other_configs(ctx, stream, flush, steps=3):
                                                         "max_rel": float(e2.max())}}
     del d_p, d_o
 
+    # the gravity pair term written as a USER-DEFINED interaction (NVRTC, IEEE sqrt and
+    # division, no fused multiply-add: bit-identical to the CPU fold) next to the hand-written kernel
+    try:
+        nc = 131_072
+        pc = uniform_cloud(nc)
+        custom = pb.CustomInteraction(
+            ctx, CUSTOM_GRAVITY_SRC, np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4")]),
+            np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("mu", "f4")]),
+            np.dtype([("ax", "f4"), ("ay", "f4"), ("az", "f4")]), np.dtype([("softening", "f4")]), push=(0.0,))
+        aff = np.ascontiguousarray(pc[:, :3]).view(custom.affected_dtype).reshape(-1)
+        src = pc.view(custom.affecting_dtype).reshape(-1)
+        custom.brute_force(aff, src)
+        t0 = time.perf_counter()
+        got = custom.brute_force(aff, src)
+        wall = time.perf_counter() - t0
+        k_ms = ctx.timings()["compute_ms"]
+        rows = _sample_rows(nc, 256)
+        refc = oracle.brute_force(pc[rows, :3], pc)
+        gotc = np.stack([got["ax"], got["ay"], got["az"]], axis=1)
+        bf32 = pb.BruteForce(ctx, pb.Acceleration.checked())
+        d_pc = torch.from_numpy(pc).to(dev)
+        d_oc = torch.empty((nc, 3), dtype=torch.float32, device=dev)
+        k1_ms = timed(lambda: bf32.compute_device(None, nc, d_pc.data_ptr(), nc, d_oc.data_ptr()))
+        out["custom_gravity_128k"] = {
+            "config": "pcuda_interaction_* (CustomInteraction): Acceleration::checked written as user source, "
+                      "3-D f32, N=131072; kernel = TMA ring + 2 affected per thread (csrc/custom.cu)",
+            "kernel_ms": k_ms, "value": float(nc) * nc / k_ms / 1e6, "unit": "Gpairs/s",
+            "host_call_ms": 1e3 * wall, "hand_written_kernel_ms": k1_ms,
+            "hand_written_value": float(nc) * nc / k1_ms / 1e6,
+            "bit_identical_to_cpu_fold": bool(np.array_equal(gotc[rows], refc))}
+        custom.close()
+        del d_pc, d_oc
+    except Exception as e:
+        out["custom_gravity_128k"] = {"error": repr(e)}
+
     # device-resident stepping at the reference's criterion size (benches/benchmark.rs: N = 2^k)
     nb = 1024
     pb_small = uniform_cloud(nb)
@@ -322,6 +357,23 @@ def other_configs(ctx, stream, flush, steps=3):
                                       "sequential::BruteForce on one host core",
                             **res}
     return out
+
+
+CUSTOM_GRAVITY_SRC = """
+struct Affected { float x, y, z; };
+struct Affecting { float x, y, z, mu; };
+struct Interaction { float ax, ay, az; };
+struct Push { float softening; };
+__device__ void compute(const Affected &p1, const Affecting &p2, Interaction &out) {
+    const float dx = p2.x - p1.x, dy = p2.y - p1.y, dz = p2.z - p1.z;
+    const float n = dx * dx + dy * dy + dz * dz;
+    if (n != 0.f) {
+        const float ns = n + push.softening * push.softening;
+        const float s = p2.mu / (ns * sqrtf(ns));
+        out.ax += dx * s; out.ay += dy * s; out.az += dz * s;
+    }
+}
+"""
 
 
 # ---- CPU arms ----------------------------------------------------------------------------------------
@@ -402,10 +454,10 @@ def main():
                     help="particle count (default: BASELINE config); use --particles under torchrun, "
                          "whose own parser rejects the abbreviation --n")
     ap.add_argument("--theta", type=float, default=0.5)
-    ap.add_argument("--bh-build", default="auto", choices=["auto", "replicated", "partitioned"],
-                    help="multi-GPU Barnes-Hut: every GPU builds the whole tree, or one tree per GPU "
-                         "over its key range joined by a top tree (PCUDA_FLAG_BH_PARTITIONED_BUILD); "
-                         "auto = the library's default: partitioned from 4 GPUs on")
+    ap.add_argument("--bh-build", default="auto", choices=["auto", "replicated", "partitioned", "let"],
+                    help="multi-GPU Barnes-Hut: every GPU builds the whole tree; one tree per GPU over its "
+                         "key range, all trees all-gathered (PCUDA_FLAG_BH_PARTITIONED_BUILD); or locally "
+                         "essential trees (PCUDA_FLAG_BH_LET_BUILD) — auto = the library's default: LET")
     ap.add_argument("--bh-route", default="auto", choices=["auto", "allgather", "alltoall"],
                     help="multi-GPU Barnes-Hut: how the accelerations reach the ranks that own the "
                          "particles (auto: all-to-all from 4 GPUs and 32M particles on)")
@@ -510,9 +562,12 @@ def split_config(n_massive, n_massless, world):
 
 def barneshut_config(n, theta, world, build="auto"):
     if build == "auto":
-        build = "partitioned" if world >= 4 else "replicated"
-    how = ("tree build replicated" if build == "replicated" else
-           "one tree per GPU over its key range (partitioned build), joined by a top tree")
+        build = "let"
+    how = {"replicated": "particles all-gathered, tree build replicated",
+           "partitioned": "particles all-gathered, one tree per GPU over its key range (partitioned build), "
+                          "trees all-gathered and joined by a top tree",
+           "let": "particles sent to the owners of their key ranges, one tree per GPU, locally essential trees "
+                  "exchanged (all-to-all) and joined by a top tree"}[build]
     return {"workload": f"Barnes-Hut 3-D f32 octree, theta={theta}, N={n} Plummer sphere (a=1, "
                         f"r<50a, equal mu=1/N, seed {SEED}); tree rebuilt every step "
                         f"(BASELINE configs[3]); Acceleration::checked()",
@@ -957,8 +1012,7 @@ def bench_barneshut(args, n, rank, world, local_rank):
     import particular_b200 as pb
     dist = _dist_setup(world, local_rank)
     dev = torch.device("cuda", local_rank)
-    ctx = pb.CudaContext(local_rank, partitioned_build={"auto": None, "partitioned": True,
-                                                        "replicated": False}[args.bh_build])
+    ctx = pb.CudaContext(local_rank, bh_build=None if args.bh_build == "auto" else args.bh_build)
     from particular_b200._ffi import lib as _lib
     assert _lib.pcuda_debug_set(b"bh_route", {"auto": 0, "allgather": 1, "alltoall": 2}[args.bh_route]) == 0
     stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)

@@ -1560,9 +1560,9 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
                 uint32_t &g = h_gi[((size_t)p * TOP_LEVELS + l) * 2 + side];
                 if (pk.n_nodes == 0 || l >= (int)pk.n_levels) g = LET_NO_NODE;
                 else if (p == rank) g = node_base[p] + (side ? pk.level_begin[l + 1] - 1 : pk.level_begin[l]);
-                else if (g == LET_NO_NODE)
-                    return fail(ctx, PCUDA_ERR_NCCL, "rank %d sent no boundary node for level %d", p, l);
-                else g += node_base[p];
+                else if (g != LET_NO_NODE) g += node_base[p];
+                // (LET_NO_NODE: that first / last node of a level lies below a node rank p pruned for us —
+                // a complete cell; the chain of partial cells is always sent.  The merge skips it.)
             }
     }
     PCUDA_CUDA_TRY(ctx, f->let_gi.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));

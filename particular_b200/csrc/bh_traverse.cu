@@ -1269,19 +1269,14 @@ int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na,
 
 // Targets already in key order ({x,y,z,_} records + their keys in the tree's frame); tgt_perm maps
 // traversal order to the output row (nullptr: out row = traversal position).
-int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
-                           const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
-                           float eps, float *d_out, const Ext64 *x64, const ForestView *fv) {
-    const int dim = t->dim;
-    if (fv && (x64 || t->order == 2 || g_tpl != 2 || g_variant))
-        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "a forest is walked by traverse2_kernel only");
-    cudaStream_t st = ctx->stream;
-    const int group_cap = x64 ? 32 : 32 * g_tpl;  // the f64 walk holds one target per lane
-    // K5a: groups from the target keys
-    const int n = (int)na;
+// K5a: the target groups of `n` targets from their keys, into the context's group buffers
+// (ctx->d_stack, ctx->d_counters).  (Running this on a second stream beside the level build — both need
+// only the sorted keys — was tried: build + walk 25.89 ms against 25.90 ms at N = 10M; the kernels of
+// either side already fill the memory system, so nothing is hidden.)
+static int make_groups(pcuda_ctx *ctx, int dim, int bits, const uint64_t *tgt_keys, int n, int group_cap,
+                       cudaStream_t st) {
     PCUDA_CUDA_TRY(ctx, ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
     PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
-    uint32_t *d_work = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 3);
     uint32_t *d_ngroups = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 4);
     // d_stack layout: L (n bytes, padded) | flag (n u32) | pos (n u32) | group_start (n + 1 u32) |
     // hard-boundary bits (one word per 32 targets, padded to whole blocks)
@@ -1297,7 +1292,7 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     if (dim == 3) boundary_levels<3><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
     else boundary_levels<2><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
     const unsigned ngb = (unsigned)((n + GROUP_BLOCK - 1) / GROUP_BLOCK);
-    hard_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_L, n, t->bits, g_seg_max, d_hard);
+    hard_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_L, n, bits, g_seg_max, d_hard);
     group_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_hard, n, g_seg_max, group_cap, d_flag);
     size_t tmp = 0;
     PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_flag, d_pos, n, st));
@@ -1306,6 +1301,23 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     scatter_groups<<<nb256, 256, 0, st>>>(d_flag, d_pos, n, d_gstart, d_ngroups);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 6;
+    return PCUDA_OK;
+}
+
+int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorted,
+                           const uint64_t *tgt_keys, const uint32_t *tgt_perm, size_t na, float theta,
+                           float eps, float *d_out, const Ext64 *x64, const ForestView *fv) {
+    const int dim = t->dim;
+    if (fv && (x64 || t->order == 2 || g_tpl != 2 || g_variant))
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "a forest is walked by traverse2_kernel only");
+    cudaStream_t st = ctx->stream;
+    const int group_cap = x64 ? 32 : 32 * g_tpl;  // the f64 walk holds one target per lane
+    const int n = (int)na;
+    PCUDA_TRY(make_groups(ctx, dim, t->bits, tgt_keys, n, group_cap, st));  // K5a
+    uint32_t *d_work = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 3);
+    uint32_t *d_ngroups = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 4);
+    const size_t n4g = ((size_t)n + 3) & ~size_t(3);
+    uint32_t *d_gstart = reinterpret_cast<uint32_t *>(ctx->d_stack.as<uint8_t>() + n4g) + 2 * (size_t)n;
 
     TravArgs a;
     a.nodes = t->nodes.as<NodeRec>();

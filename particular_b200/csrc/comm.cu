@@ -48,7 +48,7 @@ struct LocalGroup {
             cv.notify_all();
             return true;
         }
-        if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return generation != gen || broken; }) || broken) {
+        if (!cv.wait_for(lk, std::chrono::seconds(30), [&] { return generation != gen || broken; }) || broken) {
             broken = true;  // (a rank that failed before the collective never arrives)
             cv.notify_all();
             return false;

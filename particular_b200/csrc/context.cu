@@ -170,6 +170,7 @@ void pcuda_destroy(pcuda_ctx *ctx) {
     if (ctx->ev_d2h_end) cudaEventDestroy(ctx->ev_d2h_end);
     if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
     if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
+
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -29,8 +29,16 @@
 namespace pcuda {
 namespace custom {
 
-// One thread per affected element; affecting elements staged through shared memory one tile at a
-// time as raw 32-bit words (any trivially copyable struct whose size is a multiple of 4 bytes).
+// The template is the skeleton of the hand-written pair kernel (bruteforce.cu), made generic: the
+// affecting elements stream through a 4-stage shared-memory ring filled by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx; full / empty barrier pairs, one elected producer thread), every
+// thread owns PCUDA_TP affected elements and their accumulators in registers, so one shared-memory read
+// of an affecting element feeds PCUDA_TP calls of compute().  The reference's template is one invocation
+// per affected element with a workgroup-shared tile and two barriers per tile
+// (gpu/bruteforce_shared.wgsl:1-31).  Every accumulator still folds the affecting elements in slice
+// order from `Interaction()` — the order of sequential::BruteForce (sequential.rs:181-194) — which is
+// what makes the gravity term written this way bit-identical to the CPU fold; that is also why the
+// sources are not split over CTAs here as the gravity kernel does.
 static const char *kPrologue = R"PCUDA(
 #define PCUDA_CUSTOM 1
 typedef unsigned int uint32_t;
@@ -45,35 +53,106 @@ static const char *kTemplate = R"PCUDA(
 __constant__ Push push;
 static_assert(sizeof(Affected) % 4 == 0 && sizeof(Affecting) % 4 == 0 && sizeof(Interaction) % 4 == 0,
               "Affected / Affecting / Interaction sizes must be multiples of 4 bytes");
+static_assert(sizeof(Affecting) <= 256, "Affecting must not exceed 256 bytes");
 constexpr int PCUDA_BLOCK = 128;
-constexpr int PCUDA_TILE = (sizeof(Affecting) * 128 <= 16384) ? 128 : 32;
+constexpr int PCUDA_STAGES = 4;
+constexpr int PCUDA_PREFETCH = 2;
+// elements per stage: a multiple of 4 (so that a stage is a multiple of 16 bytes, the TMA granule)
+constexpr int PCUDA_TILE = sizeof(Affecting) <= 64 ? 128 : 32;
+// affected elements per thread: two while their state plausibly stays in registers
+constexpr int PCUDA_TP = (sizeof(Affected) + sizeof(Interaction) <= 64) ? 2 : 1;
 
 __device__ inline void pcuda_compute_fwd(const Affected &p1, const Affecting &p2, Interaction &out) {
     compute(p1, p2, out);
 }
 
+__device__ __forceinline__ unsigned pcuda_smem(const void *p) {
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void pcuda_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pcuda_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void pcuda_mbar_expect(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pcuda_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pcuda_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pcuda_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void pcuda_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PCUDA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PCUDA_DONE;\n"
+        "bra PCUDA_WAIT;\n"
+        "PCUDA_DONE:\n"
+        "}\n" ::"r"(pcuda_smem(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void pcuda_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pcuda_smem(dst)), "l"(src), "r"(bytes), "r"(pcuda_smem(bar)) : "memory");
+}
+
+// `affecting` is padded by the host to a whole number of tiles (the padding is never passed to compute()).
 extern "C" __global__ void __launch_bounds__(PCUDA_BLOCK)
 pcuda_custom_brute_force(const Affected *__restrict__ affected, unsigned n_affected,
                          const Affecting *__restrict__ affecting, unsigned n_affecting,
                          Interaction *__restrict__ interactions) {
-    __shared__ __align__(16) unsigned tile_words[PCUDA_TILE * (sizeof(Affecting) / 4)];
-    const Affecting *tile = reinterpret_cast<const Affecting *>(tile_words);
-    const unsigned i = blockIdx.x * PCUDA_BLOCK + threadIdx.x;
-    const bool live = i < n_affected;
-    Affected p1;
-    if (live) p1 = affected[i];
-    Interaction out = Interaction();
-    constexpr unsigned WORDS = sizeof(Affecting) / 4;
-    for (unsigned first = 0; first < n_affecting; first += PCUDA_TILE) {
-        const unsigned cnt = min((unsigned)PCUDA_TILE, n_affecting - first);
-        const unsigned *src = reinterpret_cast<const unsigned *>(affecting + first);
-        __syncthreads();
-        for (unsigned w = threadIdx.x; w < cnt * WORDS; w += PCUDA_BLOCK) tile_words[w] = src[w];
-        __syncthreads();
-        if (live)
-            for (unsigned j = 0; j < cnt; ++j) pcuda_compute_fwd(p1, tile[j], out);
+    __shared__ __align__(128) unsigned char tile_bytes[PCUDA_STAGES][PCUDA_TILE * sizeof(Affecting)];
+    __shared__ __align__(8) unsigned long long full_bar[PCUDA_STAGES], empty_bar[PCUDA_STAGES];
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    const unsigned base = blockIdx.x * (PCUDA_BLOCK * PCUDA_TP) + tid;
+    Affected p1[PCUDA_TP];
+    Interaction out[PCUDA_TP];
+#pragma unroll
+    for (int p = 0; p < PCUDA_TP; ++p) {
+        const unsigned i = base + p * PCUDA_BLOCK;
+        p1[p] = affected[i < n_affected ? i : n_affected - 1];
+        out[p] = Interaction();
     }
-    if (live) interactions[i] = out;
+    const unsigned ntiles = (n_affecting + PCUDA_TILE - 1) / PCUDA_TILE;
+    constexpr unsigned STAGE_BYTES = PCUDA_TILE * sizeof(Affecting);
+    auto issue = [&](unsigned t) {  // the elected producer: one bulk copy per tile
+        const unsigned st = t % PCUDA_STAGES;
+        pcuda_mbar_expect(&full_bar[st], STAGE_BYTES);
+        pcuda_bulk_g2s(tile_bytes[st], reinterpret_cast<const unsigned char *>(affecting) + (size_t)t * STAGE_BYTES,
+                       STAGE_BYTES, &full_bar[st]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < PCUDA_STAGES; ++s) {
+            pcuda_mbar_init(&full_bar[s], 1);
+            pcuda_mbar_init(&empty_bar[s], PCUDA_BLOCK / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (unsigned t = 0; t < PCUDA_PREFETCH && t < ntiles; ++t) issue(t);
+    for (unsigned t = 0; t < ntiles; ++t) {
+        if (tid == 0 && t + PCUDA_PREFETCH < ntiles) {
+            const unsigned tn = t + PCUDA_PREFETCH;
+            if (tn >= PCUDA_STAGES) pcuda_mbar_wait(&empty_bar[tn % PCUDA_STAGES], ((tn / PCUDA_STAGES) - 1) & 1);
+            issue(tn);
+        }
+        const unsigned st = t % PCUDA_STAGES;
+        pcuda_mbar_wait(&full_bar[st], (t / PCUDA_STAGES) & 1);
+        const Affecting *tile = reinterpret_cast<const Affecting *>(tile_bytes[st]);
+        const unsigned cnt = min((unsigned)PCUDA_TILE, n_affecting - t * PCUDA_TILE);
+        for (unsigned j = 0; j < cnt; ++j) {
+            const Affecting p2 = tile[j];  // one (broadcast) shared-memory read feeds PCUDA_TP interactions
+#pragma unroll
+            for (int p = 0; p < PCUDA_TP; ++p) pcuda_compute_fwd(p1[p], p2, out[p]);
+        }
+        __syncwarp();
+        if (lane == 0) pcuda_mbar_arrive(&empty_bar[st]);
+    }
+#pragma unroll
+    for (int p = 0; p < PCUDA_TP; ++p) {
+        const unsigned i = base + p * PCUDA_BLOCK;
+        if (i < n_affected) interactions[i] = out[p];
+    }
 }
 
 extern "C" __global__ void pcuda_custom_sizes(unsigned *out) {
@@ -81,6 +160,8 @@ extern "C" __global__ void pcuda_custom_sizes(unsigned *out) {
     out[1] = sizeof(Affecting);
     out[2] = sizeof(Interaction);
     out[3] = sizeof(Push);
+    out[4] = PCUDA_TILE;
+    out[5] = PCUDA_TP;
 }
 )PCUDA";
 
@@ -203,7 +284,7 @@ struct pcuda_interaction {
     CUmodule module = nullptr;
     CUfunction kernel = nullptr;
     CUdeviceptr push_ptr = 0;
-    uint32_t sizes[4] = {0, 0, 0, 0};  // Affected, Affecting, Interaction, Push
+    uint32_t sizes[6] = {0, 0, 0, 0, 0, 0};  // Affected, Affecting, Interaction, Push; tile, affected per thread
     pcuda::DevBuf d_affected, d_affecting, d_out;
 };
 
@@ -247,12 +328,12 @@ int pcuda_interaction_create(pcuda_ctx *ctx, const char *source, pcuda_interacti
     CUfunction sizes_fn = nullptr;
     r = custom::g_api.ModuleGetFunction(&sizes_fn, it->module, "pcuda_custom_sizes");
     if (r != CUDA_SUCCESS) return bail(custom::cu_fail(ctx, "cuModuleGetFunction(sizes)", r));
-    if (ctx->d_misc.ensure(16) != cudaSuccess) return bail(fail(ctx, PCUDA_ERR_OUT_OF_MEMORY, "scratch"));
+    if (ctx->d_misc.ensure(32) != cudaSuccess) return bail(fail(ctx, PCUDA_ERR_OUT_OF_MEMORY, "scratch"));
     void *d_sizes = ctx->d_misc.p;
     void *args[] = {&d_sizes};
     r = custom::g_api.LaunchKernel(sizes_fn, 1, 1, 1, 1, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
     if (r != CUDA_SUCCESS) return bail(custom::cu_fail(ctx, "cuLaunchKernel(sizes)", r));
-    if (cudaMemcpyAsync(it->sizes, d_sizes, 16, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+    if (cudaMemcpyAsync(it->sizes, d_sizes, 24, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return bail(fail(ctx, PCUDA_ERR_CUDA, "reading the struct sizes failed"));
     *out = it;
@@ -261,7 +342,7 @@ int pcuda_interaction_create(pcuda_ctx *ctx, const char *source, pcuda_interacti
 
 int pcuda_interaction_sizes(const pcuda_interaction *it, uint32_t sizes[4]) {
     if (!it || !sizes) return PCUDA_ERR_INVALID_ARGUMENT;
-    memcpy(sizes, it->sizes, sizeof it->sizes);
+    memcpy(sizes, it->sizes, 4 * sizeof(uint32_t));
     return PCUDA_OK;
 }
 
@@ -283,11 +364,18 @@ int pcuda_interaction_brute_force(pcuda_ctx *ctx, pcuda_interaction *it, const v
                  o_bytes = n_affected * it->sizes[2];
     phase_begin(ctx, PH_UPLOAD);
     PCUDA_CUDA_TRY(ctx, it->d_affected.ensure(a_bytes));
-    PCUDA_CUDA_TRY(ctx, it->d_affecting.ensure(b_bytes ? b_bytes : 4));
+    // the kernel copies whole tiles (TMA bulk copies): pad the affecting buffer to a tile boundary
+    const size_t tile_bytes = (size_t)it->sizes[4] * it->sizes[1];
+    const size_t b_padded = (b_bytes + tile_bytes - 1) / tile_bytes * tile_bytes;
+    PCUDA_CUDA_TRY(ctx, it->d_affecting.ensure(b_padded ? b_padded : 16));
     PCUDA_CUDA_TRY(ctx, it->d_out.ensure(o_bytes));
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(it->d_affected.p, affected, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (b_bytes)
+    if (b_bytes) {
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(it->d_affecting.p, affecting, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (b_padded > b_bytes)
+            PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(static_cast<char *>(it->d_affecting.p) + b_bytes, 0, b_padded - b_bytes,
+                                                ctx->stream));
+    }
     if (push_bytes)
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<void *>(it->push_ptr), push, push_bytes,
                                             cudaMemcpyHostToDevice, ctx->stream));
@@ -296,7 +384,8 @@ int pcuda_interaction_brute_force(pcuda_ctx *ctx, pcuda_interaction *it, const v
     void *d_a = it->d_affected.p, *d_b = it->d_affecting.p, *d_o = it->d_out.p;
     unsigned na = (unsigned)n_affected, nb = (unsigned)n_affecting;
     void *args[] = {&d_a, &na, &d_b, &nb, &d_o};
-    CUresult r = custom::g_api.LaunchKernel(it->kernel, (na + 127) / 128, 1, 1, 128, 1, 1, 0,
+    const unsigned per_cta = 128 * it->sizes[5];
+    CUresult r = custom::g_api.LaunchKernel(it->kernel, (na + per_cta - 1) / per_cta, 1, 1, 128, 1, 1, 0,
                                             (CUstream)ctx->stream, args, nullptr);
     if (r != CUDA_SUCCESS) return custom::cu_fail(ctx, "cuLaunchKernel", r);
     ctx->launches++;

@@ -42,9 +42,10 @@ class LocalWorld:
             t.start()
         for t in ts:
             t.join()
-        for e in err:
-            if e is not None:
-                raise e
+        errs = [(r, e) for r, e in enumerate(err) if e is not None]
+        if errs:  # the rank that failed first left the others waiting at the next collective: show its error
+            real = [x for x in errs if "did not reach the collective" not in str(x[1])] or errs
+            raise RuntimeError("; ".join(f"rank {r}: {e}" for r, e in real)) from real[0][1]
         return out
 
     # ---- the sharded operators over this world ------------------------------------------------------

@@ -470,6 +470,11 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("PCUDA_DEBUG") and args.impl == "ours":  # tuning hooks, e.g. PCUDA_DEBUG=bh_let_trace=1
+        from particular_b200._ffi import lib as _dbg
+        for kv in os.environ["PCUDA_DEBUG"].split(","):
+            k, v = kv.split("=")
+            assert _dbg.pcuda_debug_set(k.encode(), int(v)) == 0, kv
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n = args.n or {"bruteforce": 1_000_000, "barneshut": 10_000_000, "split": 16_000_000}[args.workload]
 

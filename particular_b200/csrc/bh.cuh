@@ -77,6 +77,7 @@ extern int g_seg_max;
 extern int g_tpl;
 extern int g_route;
 extern int g_forest;
+extern int g_let_trace;
 
 // Double-precision layer of a traversal (tree built by build64).
 struct Ext64 {

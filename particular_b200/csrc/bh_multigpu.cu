@@ -7,9 +7,11 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <string>
 
 #include "bh.cuh"
 
@@ -1311,6 +1313,18 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PCUDA_TRY(forest_of(ctx, &f));
     pcuda_tree *t = f->local;
     const size_t n_local = hi - lo;
+    // tuning hook bh_let_trace: wall-clock time of every stage (the stream is synchronised at each mark)
+    auto t_prev = std::chrono::steady_clock::now();
+    std::string trace;
+    auto mark = [&](const char *what) {
+        if (!g_let_trace) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        char buf[64];
+        snprintf(buf, sizeof buf, " %s %.3f", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        trace += buf;
+        t_prev = now;
+    };
     const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
     if (!f->h_let)
         PCUDA_CUDA_TRY(ctx, cudaHostAlloc((void **)&f->h_let,
@@ -1329,6 +1343,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PCUDA_TRY(local_box(ctx, t, d_local, n_local, f->let_boxes.as<float>()));
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, f->let_boxes.p, f->let_box_all.p, 8 * sizeof(float)));
     PCUDA_TRY(frame_from_boxes(ctx, t, f->let_box_all.as<float>(), world, n_total));
+    mark("frame");
     const Frame *d_frame = t->d_frame.as<Frame>();
     const size_t nl1 = std::max<size_t>(n_local, 1);
     for (int i = 0; i < 2; ++i) {
@@ -1352,6 +1367,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         cur = kb.selector;
         ctx->launches += 10;
     }
+    mark("local_sort");
     const uint64_t *lkeys = f->let_keys[cur].as<uint64_t>();
     const uint32_t *lperm = f->let_idx[cur].as<uint32_t>();
     // splitters: the world-quantiles of an all-gathered regular sample of the sorted local keys
@@ -1388,6 +1404,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     }
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (1) the count matrix
+    mark("splitters+counts");
     size_t send_off[MAX_PARTS], send_cnt[MAX_PARTS], recv_off[MAX_PARTS], recv_cnt[MAX_PARTS];
     size_t so[MAX_PARTS], sb_[MAX_PARTS], ro[MAX_PARTS], rb[MAX_PARTS];
     size_t n_mine = 0, s_off = 0;
@@ -1412,6 +1429,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         PCUDA_TRY(nccl_alltoallv(ctx, pass == 0 ? f->let_send_rec.p : f->let_send_gidx.p, so, sb_,
                                  pass == 0 ? f->let_recv_rec.p : f->let_recv_gidx.p, ro, rb));
     }
+    mark("a2a_particles");
     phase_end(ctx, PH_COMM);
 
     // ---- B: the tree of this rank's key range ---------------------------------------------------------
@@ -1438,7 +1456,9 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
             f->let_recv_gidx.as<uint32_t>(), t->d_perm(), (uint32_t)n_mine, f->let_gidx_sorted.as<uint32_t>());
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches += 11;
+        mark("sort_received");
         PCUDA_TRY(build_levels<3>(ctx, t, n_mine));  // (2) synchronises: level table
+        mark("tree");
     }
     PartPack *d_packs = f->packs.as<PartPack>();
     fill_pack<<<1, 64, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(), n_mine ? t->d_keys() : nullptr,
@@ -1450,6 +1470,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     let_domain_whole<<<1, 32, 0, st>>>(f->let_dom.as<LetDomain>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 3;
+    mark("pack+domain");
     phase_end(ctx, PH_BUILD);
 
     // ---- C: locally essential trees ---------------------------------------------------------------------
@@ -1499,9 +1520,11 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches += 6;
     }
+    mark("let_kernels");
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_tot, d_tot_all, sizeof(LetTotals)));
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_tot, d_tot_all, (size_t)world * sizeof(LetTotals), cudaMemcpyDeviceToHost, st));
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (3) sizes of the trees on their way
+    mark("let_counts");
     // joined arrays: block p = what rank p sent (p == rank: the whole local tree), then the top tree
     uint32_t node_base[MAX_PARTS], src_base[MAX_PARTS];
     size_t n_nodes_all = 0, n_src_all = 0;
@@ -1549,6 +1572,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += world;
 
+    mark("a2a_let+rebase");
     // ---- D: the top tree ----------------------------------------------------------------------------------
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_gi, f->let_bmap_recv.p, (size_t)world * TOP_LEVELS * 2 * sizeof(uint32_t),
                                         cudaMemcpyDeviceToHost, st));
@@ -1589,18 +1613,25 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     fv.d_roots = f->roots.as<uint32_t>();
     fv.n_roots = (uint32_t)roots.size();
 
+    mark("top_tree");
     // ---- E: walk, accelerations back to the owners ----------------------------------------------------
     RoutePlan plan;
     PCUDA_TRY(route_plan(ctx, f, n_mine ? f->let_gidx_sorted.as<uint32_t>() : nullptr, n_mine, world, rank, cap, n_local,
                          &plan));  // (5) synchronises
+    mark("route_plan");
     phase_end(ctx, PH_COMM3);
     phase_begin(ctx, PH_COMPUTE);
     if (n_mine)
         PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), plan.d_pos, n_mine, theta, eps,
                                   plan.d_acc_send, nullptr, &fv));
+    mark("walk");
     phase_end(ctx, PH_COMPUTE);
     phase_begin(ctx, PH_COMM2);
     PCUDA_TRY(route_exchange(ctx, f, plan, world, lo, d_out));
+    mark("route_back");
+    if (g_let_trace)
+        fprintf(stderr, "[let rank %d/%d n_mine %zu nodes %u let_in nodes %zu src %zu]%s\n", rank, world, n_mine, nn,
+                n_nodes_all - nn, n_src_all - n_mine, trace.c_str());
     phase_end(ctx, PH_COMM2);
     return PCUDA_OK;
 }

@@ -3,8 +3,9 @@ has GPUs for is run, the others are skipped): a torchrun-style world of one proc
 collectives issued by the library on its own NCCL communicator, results compared with the restated
 reference algorithms (oracle.*) — sequential::BruteForce for the sharded brute force and the split,
 sequential::BarnesHut at equal theta (error statistics against the extended-precision sum) for every
-multi-GPU Barnes-Hut path: the automatic choice of the world size, the replicated build, the
-partitioned build, and both result routings."""
+multi-GPU Barnes-Hut path: the automatic choice of the world size, locally essential trees, the
+replicated build, the partitioned build, and both result routings; plus locally essential trees at a
+size where they are the automatic choice (N = 1M)."""
 import json
 import os
 import socket
@@ -70,7 +71,7 @@ bh0 = pb.ShardedBarnesHut(ctx, 0.0, pb.Acceleration.checked(), init_comm=False)
 bh0.world, bh0.rank = sh.world, sh.rank
 small_ref = oracle.brute_force_parallel(small[:, :3], small)
 outs = {}
-for name, forest, route in (("auto", 0, 0), ("replicated_allgather", 2, 1), ("replicated_alltoall", 2, 2),
+for name, forest, route in (("auto", 0, 0), ("let", 3, 0), ("replicated_allgather", 2, 1), ("replicated_alltoall", 2, 2),
                             ("partitioned_allgather", 1, 1), ("partitioned_alltoall", 1, 2)):
     assert _ffi.lib.pcuda_debug_set(b"bh_forest", forest) == 0
     assert _ffi.lib.pcuda_debug_set(b"bh_route", route) == 0
@@ -85,6 +86,14 @@ assert _ffi.lib.pcuda_debug_set(b"bh_route", 0) == 0
 # the routing must not change a bit of the result
 res["route_same_replicated"] = bool(np.array_equal(outs["replicated_allgather"], outs["replicated_alltoall"]))
 res["route_same_partitioned"] = bool(np.array_equal(outs["partitioned_allgather"], outs["partitioned_alltoall"]))
+# locally essential trees as the automatic choice: N = 1M Plummer, sampled against the exact sum
+big = plummer_cloud(1_000_000, seed=1808)
+idx = np.sort(np.random.default_rng(1).choice(len(big), 512, replace=False))
+ex_big = oracle.brute_force_exact(big[idx, :3], big)
+got_big = bh.compute(big)
+one_big = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked()).compute(big)
+res["let_1M"] = {"err": stats(rel_err(got_big[idx], ex_big)), "single": stats(rel_err(one_big[idx], ex_big)),
+                 "finite": bool(np.isfinite(got_big).all())}
 res["comm_ms"] = ctx.timings()["comm_ms"]
 if rank == 0:
     print("RESULT " + json.dumps(res), flush=True)
@@ -119,7 +128,7 @@ def test_multi_gpu_matches_oracle(tmp_path, world):
     assert res["split_shape"] == [20011, 3] and res["split_worst"] <= 1.0, res
     # Barnes-Hut: median / p99 / max error no worse than 1.1 x the reference algorithm's at equal theta
     # (SURVEY.md 8c), theta = 0 within the brute-force bound, for every build / routing path
-    for name in ("auto", "replicated_allgather", "replicated_alltoall", "partitioned_allgather",
+    for name in ("auto", "let", "replicated_allgather", "replicated_alltoall", "partitioned_allgather",
                  "partitioned_alltoall"):
         b = res["bh_" + name]
         assert b["shape"] == [40003, 3] and b["finite"], (name, b)
@@ -127,3 +136,6 @@ def test_multi_gpu_matches_oracle(tmp_path, world):
             assert a <= 1.1 * ref + 2e-6, (name, b, res["bh_ref"])
         assert b["theta0_max_rel"] <= 2e-5, (name, b)
     assert res["route_same_replicated"] and res["route_same_partitioned"], res
+    assert res["let_1M"]["finite"]
+    for a, ref in zip(res["let_1M"]["err"], res["let_1M"]["single"]):
+        assert a <= 1.1 * ref + 2e-6, res["let_1M"]

@@ -292,8 +292,8 @@ struct pcuda_forest {
     pcuda::bh::BoundaryRec *h_stage = nullptr;     // pinned
     cudaEvent_t ev_stage = nullptr;
     // locally essential trees (sharded_let_dev)
-    pcuda::DevBuf let_boxes, let_box_all, let_keys[2], let_idx[2], let_send_rec, let_send_gidx, let_recv_rec,
-        let_recv_gidx, let_gidx_sorted, let_cuts, let_cnt_mat, let_dom, let_dom_all, let_open, let_reach, let_parent,
+    pcuda::DevBuf let_boxes, let_box_all, let_keys[2], let_idx[2], let_send_rec, let_recv_rec,
+        let_cuts, let_cnt_mat, let_dom, let_dom_all, let_open, let_reach, let_parent,
         let_tile_cnt, let_totals, let_index, let_send_nodes, let_send_src, let_bmap_send, let_bmap_recv, let_gi;
     uint32_t *h_let = nullptr;  // pinned: count matrices and boundary maps
 };
@@ -309,7 +309,7 @@ void forest_free(pcuda_ctx *ctx) {
                       &f->packs, &f->stage, &f->roots, &f->route_cnt, &f->route_pos, &f->route_idx_send,
                       &f->route_acc_send, &f->route_idx_recv, &f->route_acc_recv, &f->let_boxes, &f->let_box_all,
                       &f->let_keys[0], &f->let_keys[1], &f->let_idx[0], &f->let_idx[1], &f->let_send_rec,
-                      &f->let_send_gidx, &f->let_recv_rec, &f->let_recv_gidx, &f->let_gidx_sorted, &f->let_cuts,
+                      &f->let_recv_rec, &f->let_cuts,
                       &f->let_cnt_mat, &f->let_dom, &f->let_dom_all, &f->let_open, &f->let_reach, &f->let_parent,
                       &f->let_tile_cnt, &f->let_totals, &f->let_index, &f->let_send_nodes, &f->let_send_src,
                       &f->let_bmap_send, &f->let_bmap_recv, &f->let_gi};
@@ -899,90 +899,78 @@ static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_tota
 // replicated:
 //
 //   A. the particles go to the rank that owns their KEY RANGE: common root cube from the ranks' boxes
-//      (all-gather of 32 B), keys of the local block, splitters from an all-gathered key sample, local
-//      sort, one all-to-all of {record, global index} (each record travels once: 20 B x N / world per
-//      rank instead of 16 B x N);
+//      (all-gather of 32 B), keys of the local block, local sort, splitters from an all-gathered sample of
+//      the sorted keys, one all-to-all of the records (each travels once: 16 B x N / world per rank
+//      instead of 16 B x N; no index travels, see E);
 //   B. every rank sorts what it received (equal keys end up in global-index order, as on one GPU) and
 //      builds the tree of its range in the common cube (one-pass build);
-//   C. every rank tells the others WHERE its targets are — the boxes of LET_BOXES overlapping windows of
-//      its sorted particles; a window overlaps its neighbours by the size of a target group, so every
-//      group of the walk lies inside one window — and sends each of them only what their walk can
-//      touch: node x goes to rank q when all its ancestors are opened by the opening rule against some
-//      window of q (the rule of the walk, made conservative by a margin), the particles of a leaf when
-//      the leaf itself is.  Open flags for every (node, rank) pair, an AND along the ancestors, a
+//   C. every rank tells the others WHERE its targets are — the top of its tree as a tree of boxes whose
+//      frontier cells each hold whole target groups of the walk (LetDomain) — and sends each of them
+//      only what their walk can touch: node x goes to rank q when all its ancestors are opened by the
+//      opening rule against some frontier cell of q (the rule of the walk, made conservative by a
+//      margin), the particles of a leaf when the leaf itself is.  Open flags for every (node, rank) pair, an AND along the ancestors, a
 //      compaction per destination that keeps breadth-first order (children stay contiguous): five small
 //      data-parallel kernels, no work queues.  A pruned node travels as a record without children or
 //      particles, which the walk accepts whatever its own test says;
 //   D. cells that straddle a range boundary are joined into the top tree exactly as in the partitioned
 //      build (merge_top_tree), from the boundary nodes that every locally essential tree always carries;
-//   E. the walk starts at the top root; the accelerations travel back to the owners of the particles
-//      in one all-to-all (16 B x N / world per rank).
+//   E. the walk starts at the top root and writes every acceleration where its particle arrived in A;
+//      the blocks return to their senders with the counts of A swapped (12 B x N / world per rank) and
+//      each owner scatters them through its own sort permutation.
 //
 // Exchange per rank at N = 10M on 8 GPUs: 25 + ~25 + 20 MB instead of 140 + 140 + 105 MB.
-constexpr int LET_BOXES = 64;
-constexpr int LET_HALO = 64;      // the largest target group of the walk (two targets per lane)
 constexpr int LET_SAMPLE = 4096;  // key samples per rank
 constexpr int LET_TILE = 1024;    // nodes per block of the compaction kernels
-
-struct LetDomain {  // where the targets of a rank are; entry LET_BOXES is the whole range
-    float lo[LET_BOXES + 1][3];
-    float hi[LET_BOXES + 1][3];
-};
 
 struct LetTotals {  // per destination: counts and send offsets of nodes / particles (device + host copy)
     uint32_t n_nodes[MAX_PARTS], n_src[MAX_PARTS], off_nodes[MAX_PARTS], off_src[MAX_PARTS];
 };
 
-__global__ void __launch_bounds__(256) let_domain_kernel(const float4 *__restrict__ sorted, uint32_t n,
-                                                         LetDomain *__restrict__ out) {
-    const int j = blockIdx.x;
-    const long m = ((long)n + LET_BOXES - 1) / LET_BOXES;
-    const long begin = max((long)j * m - LET_HALO, 0L), end = min((long)(j + 1) * m + LET_HALO, (long)n);
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if ((long)j * m < (long)n) {
-        for (long i = begin + threadIdx.x; i < end; i += 256) {
-            const float4 p = sorted[i];
-            lo[0] = fminf(lo[0], p.x), hi[0] = fmaxf(hi[0], p.x);
-            lo[1] = fminf(lo[1], p.y), hi[1] = fmaxf(hi[1], p.y);
-            lo[2] = fminf(lo[2], p.z), hi[2] = fmaxf(hi[2], p.z);
-        }
-    }
-    __shared__ float s[8][6];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
-        }
-    }
-    if ((threadIdx.x & 31) == 0) {
-        for (int k = 0; k < 3; ++k) {
-            s[threadIdx.x >> 5][k] = lo[k];
-            s[threadIdx.x >> 5][3 + k] = hi[k];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        float a = s[0][threadIdx.x], b = s[0][3 + threadIdx.x];
-        for (int w = 1; w < 8; ++w) {
-            a = fminf(a, s[w][threadIdx.x]);
-            b = fmaxf(b, s[w][3 + threadIdx.x]);
-        }
-        out->lo[j][threadIdx.x] = a;
-        out->hi[j][threadIdx.x] = b;
-    }
-}
+// Where the targets of a rank are: the top of its tree as a tree of boxes.  A FRONTIER cell (nchild == 0)
+// is a cell of the last level that fits, a leaf, or a cell with at most `seg_max` particles — only cells
+// with more than seg_max particles are split, so every boundary between two frontier cells is a "hard"
+// boundary of the target grouping (hard_flags: the smallest cell holding both neighbours has more than
+// seg_max targets) and every target group of the walk lies inside ONE frontier cell.  The box of a cell
+// is its cube (from the key prefix), widened by a margin that covers the rounding of the quantisation.
+// (A first version used the boxes of 64 windows of consecutive particles: a window that straddles a jump
+// of the Z-order curve has a box spanning half the cloud, and one rank received the other's whole tree.)
+constexpr int LET_DOM_MAX = 1024;
+struct LetDomNode {
+    float lo[3], hi[3];
+    uint32_t first_child, nchild;  // nchild == 0: frontier cell
+};
+struct LetDomain {
+    uint32_t n;  // 0: the rank has no targets
+    uint32_t pad[7];
+    LetDomNode node[LET_DOM_MAX];
+};
 
-__global__ void let_domain_whole(LetDomain *d) {
-    if (threadIdx.x >= 3) return;
-    float a = INFINITY, b = -INFINITY;
-    for (int j = 0; j < LET_BOXES; ++j) {
-        a = fminf(a, d->lo[j][threadIdx.x]);
-        b = fmaxf(b, d->hi[j][threadIdx.x]);
+__global__ void __launch_bounds__(256) let_domain_kernel(const NodeRec *__restrict__ nodes,
+                                                         const uint64_t *__restrict__ keys, uint32_t n_dom,
+                                                         uint32_t cut_level, uint32_t seg_max,
+                                                         const Frame *__restrict__ frame, LetDomain *__restrict__ out) {
+    const uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y == 0) out->n = n_dom;
+    if (y >= n_dom) return;
+    const NodeRec nd = nodes[y];
+    const uint32_t nc = nd.nchild_level & 0xffu, level = nd.nchild_level >> 8;
+    const uint64_t pre = level ? keys[nd.begin] >> (3 * (Dims<3>::BITS - level)) : 0ull;
+    uint32_t q[3] = {0, 0, 0};  // cell coordinates: de-interleave the prefix (axis 0 in the lowest bit)
+    for (uint32_t b = 0; b < level; ++b)
+        for (int k = 0; k < 3; ++k) q[k] |= (uint32_t)((pre >> (3 * b + k)) & 1ull) << b;
+    const float ext = frame->ext;
+    const float w = ext * __int_as_float((127 - (int)level) << 23);
+    const float margin = ext * 2e-6f;  // > the rounding of (x - origin) * inv and of the corner below
+    LetDomNode o;
+    for (int k = 0; k < 3; ++k) {
+        const float c = frame->origin[k] + (float)q[k] * w;
+        o.lo[k] = c - margin;
+        o.hi[k] = c + w + margin;
     }
-    d->lo[LET_BOXES][threadIdx.x] = a;
-    d->hi[LET_BOXES][threadIdx.x] = b;
+    const bool frontier = nc == 0 || level >= cut_level || nd.count <= seg_max;
+    o.first_child = frontier ? 0u : nd.first_child;
+    o.nchild = frontier ? 0u : nc;
+    out->node[y] = o;
 }
 
 // The opening rule of the walk (traverse2_kernel: theta^2 dmin^2 < w^2, dmin = distance from the
@@ -1023,8 +1011,17 @@ __global__ void __launch_bounds__(256) let_open_kernel(const NodeRec *__restrict
         if (q == rank) continue;
         const LetDomain &d = doms[q];
         bool op = boundary;
-        if (!op && let_opens(nd.cm, w2, theta2, d.lo[LET_BOXES], d.hi[LET_BOXES], margin)) {
-            for (int j = 0; j < LET_BOXES && !op; ++j) op = let_opens(nd.cm, w2, theta2, d.lo[j], d.hi[j], margin);
+        if (!op && d.n) {  // walk q's domain tree: a box that passes the rule closes its whole branch
+            uint16_t stack[64];
+            int sp = 1;
+            stack[0] = 0;
+            while (sp && !op) {
+                const LetDomNode &y = d.node[stack[--sp]];
+                if (!let_opens(nd.cm, w2, theta2, y.lo, y.hi, margin)) continue;
+                if (y.nchild == 0) op = true;
+                else
+                    for (uint32_t j = 0; j < y.nchild; ++j) stack[sp++] = (uint16_t)(y.first_child + j);
+            }
         }
         mask |= (uint32_t)op << q;
     }
@@ -1268,6 +1265,25 @@ __global__ void __launch_bounds__(2 * TOP_LEVELS * 9) let_collect_boundary(const
     else if (j - 1 < (int)(nd.nchild_level & 0xffu)) o->child[j - 1] = nodes[nd.first_child + j - 1];
 }
 
+// Index of every boundary node in the joined array: what the sender's map says (its tree arrived pruned
+// and renumbered), the level table for this rank's own tree, LET_NO_NODE where the part has no such level
+// or the node was left out (it then lies below a pruned node: a complete cell; the chain of partial cells
+// is always sent).
+__global__ void let_gi_kernel(const uint32_t *__restrict__ bmap_recv, const PartPack *__restrict__ packs,
+                              PartBases bases, int rank, uint32_t *__restrict__ gi) {
+    const int p = blockIdx.x, t = threadIdx.x, l = t >> 1, side = t & 1;
+    const PartPack &pk = packs[p];
+    uint32_t g = LET_NO_NODE;
+    if (pk.n_nodes && l < (int)pk.n_levels) {
+        if (p == rank) g = bases.node_base[p] + (side ? pk.level_begin[l + 1] - 1 : pk.level_begin[l]);
+        else {
+            const uint32_t m = bmap_recv[(size_t)p * TOP_LEVELS * 2 + t];
+            if (m != LET_NO_NODE) g = bases.node_base[p] + m;
+        }
+    }
+    gi[(size_t)p * TOP_LEVELS * 2 + t] = g;
+}
+
 __global__ void let_cuts_kernel(const uint64_t *__restrict__ keys, uint32_t n, const uint64_t *__restrict__ split,
                                 int world, uint32_t *__restrict__ cuts, uint32_t *__restrict__ cnt_row) {
     const int q = threadIdx.x;  // cuts[q] = first sorted key >= split[q]; cuts[world] = n
@@ -1285,17 +1301,34 @@ __global__ void let_cuts_kernel(const uint64_t *__restrict__ keys, uint32_t n, c
     if (q < world) cnt_row[q] = cuts[q + 1] - cuts[q];
 }
 
-__global__ void __launch_bounds__(256) let_gidx_kernel(const uint32_t *__restrict__ perm, uint32_t n, uint32_t lo,
-                                                       uint32_t *__restrict__ gidx) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) gidx[i] = lo + perm[i];
-}
-
-__global__ void __launch_bounds__(256) let_permute_kernel(const uint32_t *__restrict__ in,
-                                                          const uint32_t *__restrict__ perm, uint32_t n,
-                                                          uint32_t *__restrict__ out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[perm[i]];
+// Splitters = the world-quantiles of the union of the ranks' samples.  Every rank's sample is sorted (it
+// was drawn from its sorted keys), so the position of an element in the sorted union is the sum of its
+// lower bounds in the other lists (ties: lower list first, then position): no sort, one launch.
+__global__ void __launch_bounds__(256) let_splitters_kernel(const uint64_t *__restrict__ samples, int world,
+                                                            uint64_t *__restrict__ split) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, m = world * LET_SAMPLE;
+    if (e == 0) {
+        split[0] = 0ull;
+        split[world] = ~0ull;
+    }
+    if (e >= m) return;
+    const int list = e / LET_SAMPLE, pos = e % LET_SAMPLE;
+    const uint64_t key = samples[e];
+    int rank_in_union = pos;
+    for (int l = 0; l < world; ++l) {
+        if (l == list) continue;
+        const uint64_t *a = samples + (size_t)l * LET_SAMPLE;
+        int lo = 0, hi = LET_SAMPLE;  // elements of list l before this one: < key, or == key in a lower list
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const bool before = l < list ? a[mid] <= key : a[mid] < key;
+            if (before) lo = mid + 1;
+            else hi = mid;
+        }
+        rank_in_union += lo;
+    }
+    for (int q = 1; q < world; ++q)
+        if (rank_in_union == (int)((size_t)q * m / world)) split[q] = key;
 }
 
 __global__ void __launch_bounds__(256) let_sample_kernel(const uint64_t *__restrict__ keys, uint32_t n, int m,
@@ -1374,16 +1407,8 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     uint64_t *my_sample = f->sample[0].as<uint64_t>() + (size_t)rank * LET_SAMPLE;
     let_sample_kernel<<<(LET_SAMPLE + 255) / 256, 256, 0, st>>>(lkeys, (uint32_t)n_local, LET_SAMPLE, my_sample);
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, my_sample, f->sample[0].p, LET_SAMPLE * sizeof(uint64_t)));
-    {
-        const int m = world * LET_SAMPLE;
-        cub::DoubleBuffer<uint64_t> sb(f->sample[0].as<uint64_t>(), f->sample[1].as<uint64_t>());
-        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, sb, m, 0, 64, st));
-        PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
-        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(f->sel_tmp.p, tmp, sb, m, 0, 64, st));
-        pick_splitters<<<1, 32, 0, st>>>(sb.Current(), m, world, f->split.as<uint64_t>(), f->counts.as<uint32_t>());
-        if (sb.selector != 0)  // keep the all-gather buffer in sample[0] for the next call's layout
-            std::swap(f->sample[0], f->sample[1]);
-    }
+    let_splitters_kernel<<<(world * LET_SAMPLE + 255) / 256, 256, 0, st>>>(f->sample[0].as<uint64_t>(), world,
+                                                                           f->split.as<uint64_t>());
     uint32_t *d_mat = f->let_cnt_mat.as<uint32_t>();
     uint32_t *d_row = d_mat + (size_t)rank * MAX_PARTS;
     PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_row, 0, MAX_PARTS * sizeof(uint32_t), st));
@@ -1393,15 +1418,10 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     ctx->launches += 3 + 10;
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_row, d_mat, MAX_PARTS * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_cnt, d_mat, (size_t)world * MAX_PARTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    // records and global indices in local key order: the send buffers (destination ranges are contiguous)
+    // records in local key order: the send buffer (destination ranges are contiguous).  No index travels:
+    // the accelerations come back in exactly this order (block by block), and lperm maps it to the rows.
     PCUDA_CUDA_TRY(ctx, f->let_send_rec.ensure(nl1 * sizeof(float4)));
-    PCUDA_CUDA_TRY(ctx, f->let_send_gidx.ensure(nl1 * sizeof(uint32_t)));
-    if (n_local) {
-        launch_gather<3>(ctx, d_local, 4, true, n_local, lperm, f->let_send_rec.as<float4>());
-        let_gidx_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(lperm, (uint32_t)n_local, (uint32_t)lo,
-                                                                           f->let_send_gidx.as<uint32_t>());
-        ctx->launches++;
-    }
+    if (n_local) launch_gather<3>(ctx, d_local, 4, true, n_local, lperm, f->let_send_rec.as<float4>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (1) the count matrix
     mark("splitters+counts");
@@ -1420,15 +1440,11 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         return fail(ctx, PCUDA_ERR_NCCL, "key ranges do not cover the local block (%zu of %zu particles)", s_off, n_local);
     const size_t nm1 = std::max<size_t>(n_mine, 1);
     PCUDA_CUDA_TRY(ctx, f->let_recv_rec.ensure(nm1 * sizeof(float4)));
-    PCUDA_CUDA_TRY(ctx, f->let_recv_gidx.ensure(nm1 * sizeof(uint32_t)));
-    for (int pass = 0; pass < 2; ++pass) {
-        const size_t w = pass == 0 ? sizeof(float4) : sizeof(uint32_t);
-        for (int q = 0; q < world; ++q) {
-            so[q] = send_off[q] * w, sb_[q] = send_cnt[q] * w, ro[q] = recv_off[q] * w, rb[q] = recv_cnt[q] * w;
-        }
-        PCUDA_TRY(nccl_alltoallv(ctx, pass == 0 ? f->let_send_rec.p : f->let_send_gidx.p, so, sb_,
-                                 pass == 0 ? f->let_recv_rec.p : f->let_recv_gidx.p, ro, rb));
+    for (int q = 0; q < world; ++q) {
+        const size_t w = sizeof(float4);
+        so[q] = send_off[q] * w, sb_[q] = send_cnt[q] * w, ro[q] = recv_off[q] * w, rb[q] = recv_cnt[q] * w;
     }
+    PCUDA_TRY(nccl_alltoallv(ctx, f->let_send_rec.p, so, sb_, f->let_recv_rec.p, ro, rb));
     mark("a2a_particles");
     phase_end(ctx, PH_COMM);
 
@@ -1436,7 +1452,6 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     phase_begin(ctx, PH_BUILD);
     tree_reset<3>(ctx, t, n_mine);
     PCUDA_CUDA_TRY(ctx, t->scan_in.ensure(sizeof(BuildState)));
-    PCUDA_CUDA_TRY(ctx, f->let_gidx_sorted.ensure(nm1 * sizeof(uint32_t)));
     if (n_mine) {
         for (int i = 0; i < 2; ++i) {
             PCUDA_CUDA_TRY(ctx, t->keys[i].ensure(n_mine * sizeof(uint64_t)));
@@ -1452,10 +1467,8 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         t->cur = kb.selector;
         PCUDA_CUDA_TRY(ctx, t->sorted.ensure(n_mine * sizeof(float4)));
         launch_gather<3>(ctx, recv, 4, true, n_mine, t->d_perm(), t->sorted.as<float4>());
-        let_permute_kernel<<<(unsigned)((n_mine + 255) / 256), 256, 0, st>>>(
-            f->let_recv_gidx.as<uint32_t>(), t->d_perm(), (uint32_t)n_mine, f->let_gidx_sorted.as<uint32_t>());
         PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches += 11;
+        ctx->launches += 10;
         mark("sort_received");
         PCUDA_TRY(build_levels<3>(ctx, t, n_mine));  // (2) synchronises: level table
         mark("tree");
@@ -1463,13 +1476,19 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PartPack *d_packs = f->packs.as<PartPack>();
     fill_pack<<<1, 64, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(), n_mine ? t->d_keys() : nullptr,
                                 t->scan_in.as<BuildState>(), (uint32_t)t->n_nodes, (uint32_t)t->n_levels, d_packs + rank);
-    // where this rank's targets are
+    // where this rank's targets are: the top of the tree, down to the last level that fits the table
     PCUDA_CUDA_TRY(ctx, f->let_dom.ensure(sizeof(LetDomain)));
     PCUDA_CUDA_TRY(ctx, f->let_dom_all.ensure((size_t)world * sizeof(LetDomain)));
-    let_domain_kernel<<<LET_BOXES, 256, 0, st>>>(t->sorted.as<float4>(), (uint32_t)n_mine, f->let_dom.as<LetDomain>());
-    let_domain_whole<<<1, 32, 0, st>>>(f->let_dom.as<LetDomain>());
+    uint32_t n_dom = 0, cut_level = 0;
+    if (n_mine) {
+        while ((int)cut_level + 1 < t->n_levels && t->level_begin[cut_level + 2] <= (uint32_t)LET_DOM_MAX) ++cut_level;
+        n_dom = t->level_begin[cut_level + 1];
+    }
+    let_domain_kernel<<<(std::max<uint32_t>(n_dom, 1) + 255) / 256, 256, 0, st>>>(
+        t->nodes.as<NodeRec>(), n_mine ? t->d_keys() : nullptr, n_dom, cut_level, (uint32_t)g_seg_max, d_frame,
+        f->let_dom.as<LetDomain>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 2;
     mark("pack+domain");
     phase_end(ctx, PH_BUILD);
 
@@ -1574,30 +1593,19 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
 
     mark("a2a_let+rebase");
     // ---- D: the top tree ----------------------------------------------------------------------------------
-    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_gi, f->let_bmap_recv.p, (size_t)world * TOP_LEVELS * 2 * sizeof(uint32_t),
-                                        cudaMemcpyDeviceToHost, st));
-    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (4a) boundary maps (tiny; the packs are here already)
-    for (int p = 0; p < world; ++p) {
-        const PartPack &pk = f->h_packs[p];
-        for (int l = 0; l < TOP_LEVELS; ++l)
-            for (int side = 0; side < 2; ++side) {
-                uint32_t &g = h_gi[((size_t)p * TOP_LEVELS + l) * 2 + side];
-                if (pk.n_nodes == 0 || l >= (int)pk.n_levels) g = LET_NO_NODE;
-                else if (p == rank) g = node_base[p] + (side ? pk.level_begin[l + 1] - 1 : pk.level_begin[l]);
-                else if (g != LET_NO_NODE) g += node_base[p];
-                // (LET_NO_NODE: that first / last node of a level lies below a node rank p pruned for us —
-                // a complete cell; the chain of partial cells is always sent.  The merge skips it.)
-            }
-    }
+    PartBases bases{};
+    for (int p = 0; p < world; ++p) bases.node_base[p] = node_base[p];
     PCUDA_CUDA_TRY(ctx, f->let_gi.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));
-    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->let_gi.p, h_gi, (size_t)world * TOP_LEVELS * 2 * sizeof(uint32_t),
-                                        cudaMemcpyHostToDevice, st));
+    let_gi_kernel<<<world, 2 * TOP_LEVELS, 0, st>>>(f->let_bmap_recv.as<uint32_t>(), d_packs, bases, rank,
+                                                    f->let_gi.as<uint32_t>());
     let_collect_boundary<<<world, 2 * TOP_LEVELS * 9, 0, st>>>(fn, f->let_gi.as<uint32_t>(), f->stage.as<BoundaryRec>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches++;
+    ctx->launches += 2;
+    PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(h_gi, f->let_gi.p, (size_t)world * TOP_LEVELS * 2 * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, st));
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_stage, f->stage.p, (size_t)world * TOP_LEVELS * 2 * sizeof(BoundaryRec),
                                         cudaMemcpyDeviceToHost, st));
-    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (4b) boundary records
+    PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (4) boundary records and their indices
     std::vector<NodeRec> top;
     std::vector<uint32_t> roots;
     PCUDA_TRY(merge_top_tree(ctx, world, f->h_packs, f->h_stage, node_base, (uint32_t)n_nodes_all, top, roots, h_gi));
@@ -1614,20 +1622,31 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     fv.n_roots = (uint32_t)roots.size();
 
     mark("top_tree");
-    // ---- E: walk, accelerations back to the owners ----------------------------------------------------
-    RoutePlan plan;
-    PCUDA_TRY(route_plan(ctx, f, n_mine ? f->let_gidx_sorted.as<uint32_t>() : nullptr, n_mine, world, rank, cap, n_local,
-                         &plan));  // (5) synchronises
-    mark("route_plan");
+    // ---- E: walk, accelerations back along the path the particles came ------------------------------------
+    // The received records lie block by block in the order their owners sent them, and t->d_perm() maps a
+    // sorted particle to its place there: the walk writes every row straight into that place, the blocks go
+    // back with the counts of step A swapped, and the owner scatters them through its own sort permutation.
+    PCUDA_CUDA_TRY(ctx, f->route_acc_send.ensure(nm1 * 3 * sizeof(float)));
+    PCUDA_CUDA_TRY(ctx, f->route_acc_recv.ensure(nl1 * 3 * sizeof(float)));
     phase_end(ctx, PH_COMM3);
     phase_begin(ctx, PH_COMPUTE);
     if (n_mine)
-        PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), plan.d_pos, n_mine, theta, eps,
-                                  plan.d_acc_send, nullptr, &fv));
+        PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), t->d_perm(), n_mine, theta, eps,
+                                  f->route_acc_send.as<float>(), nullptr, &fv));
     mark("walk");
     phase_end(ctx, PH_COMPUTE);
     phase_begin(ctx, PH_COMM2);
-    PCUDA_TRY(route_exchange(ctx, f, plan, world, lo, d_out));
+    for (int q = 0; q < world; ++q) {
+        const size_t w = 3 * sizeof(float);
+        so[q] = recv_off[q] * w, sb_[q] = recv_cnt[q] * w, ro[q] = send_off[q] * w, rb[q] = send_cnt[q] * w;
+    }
+    PCUDA_TRY(nccl_alltoallv(ctx, f->route_acc_send.p, so, sb_, f->route_acc_recv.p, ro, rb));
+    if (n_local) {
+        scatter_rows<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(f->route_acc_recv.as<float>(), lperm, (int)n_local,
+                                                                        0u, d_out);
+        PCUDA_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     mark("route_back");
     if (g_let_trace)
         fprintf(stderr, "[let rank %d/%d n_mine %zu nodes %u let_in nodes %zu src %zu]%s\n", rank, world, n_mine, nn,

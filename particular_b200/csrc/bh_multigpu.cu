@@ -3,6 +3,7 @@
 // particles, and the single-GPU "virtual rank" test entry.  New functionality: the reference is
 // single-device.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
@@ -926,15 +927,16 @@ struct LetTotals {  // per destination: counts and send offsets of nodes / parti
     uint32_t n_nodes[MAX_PARTS], n_src[MAX_PARTS], off_nodes[MAX_PARTS], off_src[MAX_PARTS];
 };
 
-// Where the targets of a rank are: the top of its tree as a tree of boxes.  A FRONTIER cell (nchild == 0)
-// is a cell of the last level that fits, a leaf, or a cell with at most `seg_max` particles — only cells
-// with more than seg_max particles are split, so every boundary between two frontier cells is a "hard"
+// Where the targets of a rank are: the top of its tree as a tree of boxes, refined while a cell holds more
+// than tau = max(seg_max, 8 n / LET_DOM_MAX) particles.  A FRONTIER cell (nchild == 0) is a leaf or a cell
+// with at most tau particles — only cells with more than seg_max particles are split, so every boundary
+// between two frontier cells is a "hard"
 // boundary of the target grouping (hard_flags: the smallest cell holding both neighbours has more than
 // seg_max targets) and every target group of the walk lies inside ONE frontier cell.  The box of a cell
 // is its cube (from the key prefix), widened by a margin that covers the rounding of the quantisation.
 // (A first version used the boxes of 64 windows of consecutive particles: a window that straddles a jump
 // of the Z-order curve has a box spanning half the cloud, and one rank received the other's whole tree.)
-constexpr int LET_DOM_MAX = 1024;
+constexpr int LET_DOM_MAX = 4096;
 struct LetDomNode {
     float lo[3], hi[3];
     uint32_t first_child, nchild;  // nchild == 0: frontier cell
@@ -945,14 +947,40 @@ struct LetDomain {
     LetDomNode node[LET_DOM_MAX];
 };
 
+// parent[x] of every node (the root: 0xffffffff), from the child ranges.
+__global__ void __launch_bounds__(256) let_parent_kernel(const NodeRec *__restrict__ nodes, uint32_t n_nodes,
+                                                         uint32_t *__restrict__ parent) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    if (x == 0) parent[0] = 0xffffffffu;
+    const NodeRec nd = nodes[x];
+    for (uint32_t j = 0; j < (nd.nchild_level & 0xffu); ++j) parent[nd.first_child + j] = x;
+}
+
+// The domain tree = the nodes whose parent holds more than `tau` particles (the root included): cells are
+// split while they are heavy, so the frontier is fine where the targets are dense.  flag -> (scan) ->
+// idx keeps breadth-first order, hence the children of a split cell stay contiguous.
+__global__ void __launch_bounds__(256) let_dom_flag_kernel(const NodeRec *__restrict__ nodes,
+                                                           const uint32_t *__restrict__ parent, uint32_t n_nodes,
+                                                           uint32_t tau, uint32_t *__restrict__ flag) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    flag[x] = (x == 0 || nodes[parent[x]].count > tau) ? 1u : 0u;
+}
+
 __global__ void __launch_bounds__(256) let_domain_kernel(const NodeRec *__restrict__ nodes,
-                                                         const uint64_t *__restrict__ keys, uint32_t n_dom,
-                                                         uint32_t cut_level, uint32_t seg_max,
-                                                         const Frame *__restrict__ frame, LetDomain *__restrict__ out) {
-    const uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y == 0) out->n = n_dom;
-    if (y >= n_dom) return;
-    const NodeRec nd = nodes[y];
+                                                         const uint64_t *__restrict__ keys,
+                                                         const uint32_t *__restrict__ flag,
+                                                         const uint32_t *__restrict__ idx, uint32_t n_nodes,
+                                                         uint32_t tau, const Frame *__restrict__ frame,
+                                                         LetDomain *__restrict__ out) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    if (x == n_nodes - 1) out->n = min(idx[x] + flag[x], (uint32_t)LET_DOM_MAX);
+    if (!flag[x]) return;
+    const uint32_t y = idx[x];
+    if (y >= (uint32_t)LET_DOM_MAX) return;  // table full: the parent becomes a frontier cell (below)
+    const NodeRec nd = nodes[x];
     const uint32_t nc = nd.nchild_level & 0xffu, level = nd.nchild_level >> 8;
     const uint64_t pre = level ? keys[nd.begin] >> (3 * (Dims<3>::BITS - level)) : 0ull;
     uint32_t q[3] = {0, 0, 0};  // cell coordinates: de-interleave the prefix (axis 0 in the lowest bit)
@@ -967,9 +995,9 @@ __global__ void __launch_bounds__(256) let_domain_kernel(const NodeRec *__restri
         o.lo[k] = c - margin;
         o.hi[k] = c + w + margin;
     }
-    const bool frontier = nc == 0 || level >= cut_level || nd.count <= seg_max;
-    o.first_child = frontier ? 0u : nd.first_child;
-    o.nchild = frontier ? 0u : nc;
+    const bool split = nc > 0 && nd.count > tau && idx[nd.first_child] + nc <= (uint32_t)LET_DOM_MAX;
+    o.first_child = split ? idx[nd.first_child] : 0u;
+    o.nchild = split ? nc : 0u;
     out->node[y] = o;
 }
 
@@ -995,13 +1023,11 @@ __global__ void __launch_bounds__(256) let_open_kernel(const NodeRec *__restrict
                                                        const BuildState *__restrict__ st,
                                                        const LetDomain *__restrict__ doms, int world, int rank,
                                                        float theta2, const Frame *__restrict__ frame,
-                                                       uint16_t *__restrict__ open, uint32_t *__restrict__ parent) {
+                                                       uint16_t *__restrict__ open) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n_nodes) return;
-    if (x == 0) parent[0] = 0xffffffffu;
     const NodeRec nd = nodes[x];
     const uint32_t nc = nd.nchild_level & 0xffu, level = nd.nchild_level >> 8;
-    for (uint32_t j = 0; j < nc; ++j) parent[nd.first_child + j] = x;
     const float ext = frame->ext;
     const float w = ext * __int_as_float((127 - (int)level) << 23);
     const float w2 = w * w, margin = ext * 1e-6f;
@@ -1012,7 +1038,7 @@ __global__ void __launch_bounds__(256) let_open_kernel(const NodeRec *__restrict
         const LetDomain &d = doms[q];
         bool op = boundary;
         if (!op && d.n) {  // walk q's domain tree: a box that passes the rule closes its whole branch
-            uint16_t stack[64];
+            uint16_t stack[192];  // <= 7 siblings per level of the domain tree + 8
             int sp = 1;
             stack[0] = 0;
             while (sp && !op) {
@@ -1476,19 +1502,30 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PartPack *d_packs = f->packs.as<PartPack>();
     fill_pack<<<1, 64, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(), n_mine ? t->d_keys() : nullptr,
                                 t->scan_in.as<BuildState>(), (uint32_t)t->n_nodes, (uint32_t)t->n_levels, d_packs + rank);
-    // where this rank's targets are: the top of the tree, down to the last level that fits the table
+    // where this rank's targets are: the top of the tree, refined while a cell is heavy (LetDomain)
+    const uint32_t nn = (uint32_t)t->n_nodes;
+    const size_t nn1 = std::max<size_t>(nn, 1);
     PCUDA_CUDA_TRY(ctx, f->let_dom.ensure(sizeof(LetDomain)));
     PCUDA_CUDA_TRY(ctx, f->let_dom_all.ensure((size_t)world * sizeof(LetDomain)));
-    uint32_t n_dom = 0, cut_level = 0;
-    if (n_mine) {
-        while ((int)cut_level + 1 < t->n_levels && t->level_begin[cut_level + 2] <= (uint32_t)LET_DOM_MAX) ++cut_level;
-        n_dom = t->level_begin[cut_level + 1];
+    PCUDA_CUDA_TRY(ctx, f->let_parent.ensure(nn1 * sizeof(uint32_t)));
+    PCUDA_CUDA_TRY(ctx, f->let_index.ensure((size_t)2 * world * nn1 * sizeof(uint32_t)));
+    if (nn) {
+        const unsigned nb256 = (nn + 255) / 256;
+        const uint32_t tau = (uint32_t)std::max<size_t>((size_t)g_seg_max, (8 * n_mine + LET_DOM_MAX - 1) / LET_DOM_MAX);
+        uint32_t *d_flag = f->let_index.as<uint32_t>(), *d_idx = d_flag + nn1;  // scratch: free until let_index_kernel
+        let_parent_kernel<<<nb256, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, f->let_parent.as<uint32_t>());
+        let_dom_flag_kernel<<<nb256, 256, 0, st>>>(t->nodes.as<NodeRec>(), f->let_parent.as<uint32_t>(), nn, tau, d_flag);
+        PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_flag, d_idx, (int)nn, st));
+        PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
+        PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(f->sel_tmp.p, tmp, d_flag, d_idx, (int)nn, st));
+        let_domain_kernel<<<nb256, 256, 0, st>>>(t->nodes.as<NodeRec>(), t->d_keys(), d_flag, d_idx, nn, tau, d_frame,
+                                                 f->let_dom.as<LetDomain>());
+        ctx->launches += 5;
+    } else {
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(f->let_dom.p, 0, 32, st));  // n = 0: no targets here
     }
-    let_domain_kernel<<<(std::max<uint32_t>(n_dom, 1) + 255) / 256, 256, 0, st>>>(
-        t->nodes.as<NodeRec>(), n_mine ? t->d_keys() : nullptr, n_dom, cut_level, (uint32_t)g_seg_max, d_frame,
-        f->let_dom.as<LetDomain>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     mark("pack+domain");
     phase_end(ctx, PH_BUILD);
 
@@ -1497,15 +1534,11 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, d_packs + rank, d_packs, sizeof(PartPack)));
     PCUDA_TRY(pcuda_comm_allgather_dev(ctx, f->let_dom.p, f->let_dom_all.p, sizeof(LetDomain)));
     PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->h_packs, d_packs, world * sizeof(PartPack), cudaMemcpyDeviceToHost, st));
-    const uint32_t nn = (uint32_t)t->n_nodes;
     const uint32_t n_tiles = (nn + LET_TILE - 1) / LET_TILE, tiles_pad = (std::max<uint32_t>(n_tiles, 1) + 31u) & ~31u;
-    const size_t nn1 = std::max<size_t>(nn, 1);
     PCUDA_CUDA_TRY(ctx, f->let_open.ensure(nn1 * sizeof(uint16_t)));
     PCUDA_CUDA_TRY(ctx, f->let_reach.ensure(nn1 * sizeof(uint16_t)));
-    PCUDA_CUDA_TRY(ctx, f->let_parent.ensure(nn1 * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, f->let_tile_cnt.ensure((size_t)2 * MAX_PARTS * tiles_pad * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, f->let_totals.ensure((size_t)MAX_PARTS * sizeof(LetTotals)));
-    PCUDA_CUDA_TRY(ctx, f->let_index.ensure((size_t)2 * world * nn1 * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, f->let_bmap_send.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));
     PCUDA_CUDA_TRY(ctx, f->let_bmap_recv.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));
     // worst case: every node and every particle goes to every other rank
@@ -1520,8 +1553,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         const unsigned nb256 = (nn + 255) / 256;
         const BuildState *d_state = t->scan_in.as<BuildState>();
         let_open_kernel<<<nb256, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, d_state, f->let_dom_all.as<LetDomain>(), world,
-                                               rank, theta * theta, d_frame, f->let_open.as<uint16_t>(),
-                                               f->let_parent.as<uint32_t>());
+                                               rank, theta * theta, d_frame, f->let_open.as<uint16_t>());
         const uint32_t all = ((1u << world) - 1u) & ~(1u << rank);
         let_reach_kernel<<<nb256, 256, 0, st>>>(f->let_open.as<uint16_t>(), f->let_parent.as<uint32_t>(), nn, all,
                                                 f->let_reach.as<uint16_t>());

@@ -921,6 +921,7 @@ static int sharded_forest_dev(pcuda_ctx *ctx, int world, int rank, size_t n_tota
 //
 // Exchange per rank at N = 10M on 8 GPUs: 25 + ~25 + 20 MB instead of 140 + 140 + 105 MB.
 constexpr int LET_SAMPLE = 4096;  // key samples per rank
+constexpr int LET_SPLIT_BITS = 32;  // leading key bits that decide the destination of a particle (10.7 levels)
 constexpr int LET_TILE = 1024;    // nodes per block of the compaction kernels
 
 struct LetTotals {  // per destination: counts and send offsets of nodes / particles (device + host copy)
@@ -1319,7 +1320,7 @@ __global__ void let_cuts_kernel(const uint64_t *__restrict__ keys, uint32_t n, c
     else
         while (lo < hi) {
             const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (keys[mid] < split[q]) lo = mid + 1;
+            if (keys[mid] < split[q]) lo = mid + 1;  // split has no low bits: decided by the sorted leading bits
             else hi = mid;
         }
     cuts[q] = q == 0 ? 0u : lo;
@@ -1360,7 +1361,8 @@ __global__ void __launch_bounds__(256) let_splitters_kernel(const uint64_t *__re
 __global__ void __launch_bounds__(256) let_sample_kernel(const uint64_t *__restrict__ keys, uint32_t n, int m,
                                                          uint64_t *__restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < m) out[j] = n ? keys[(size_t)j * n / m] : ~0ull;
+    // (the low bits are cleared: the local keys are sorted by their leading LET_SPLIT_BITS bits only)
+    if (j < m) out[j] = n ? keys[(size_t)j * n / m] & ~((1ull << (63 - LET_SPLIT_BITS)) - 1ull) : ~0ull;
 }
 
 // One multi-GPU Barnes-Hut step with locally essential trees.  d_local: this rank's block [lo, hi) of
@@ -1420,11 +1422,13 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         launch_encode<3>(ctx, d_local, 4, n_local, d_frame, f->let_keys[0].as<uint64_t>(), f->let_idx[0].as<uint32_t>());
         cub::DoubleBuffer<uint64_t> kb(f->let_keys[0].as<uint64_t>(), f->let_keys[1].as<uint64_t>());
         cub::DoubleBuffer<uint32_t> vb(f->let_idx[0].as<uint32_t>(), f->let_idx[1].as<uint32_t>());
-        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)n_local, 0, 63, st));
+        // only the top LET_SPLIT_BITS bits are sorted (4 radix passes instead of 8): the splitters carry no
+        // lower bits, so the destination of a key depends on those bits alone, and the receiver sorts fully
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int)n_local, 63 - LET_SPLIT_BITS, 63, st));
         PCUDA_CUDA_TRY(ctx, f->sel_tmp.ensure(tmp));
-        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(f->sel_tmp.p, tmp, kb, vb, (int)n_local, 0, 63, st));
+        PCUDA_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(f->sel_tmp.p, tmp, kb, vb, (int)n_local, 63 - LET_SPLIT_BITS, 63, st));
         cur = kb.selector;
-        ctx->launches += 10;
+        ctx->launches += 6;
     }
     mark("local_sort");
     const uint64_t *lkeys = f->let_keys[cur].as<uint64_t>();

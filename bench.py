@@ -567,7 +567,7 @@ def split_config(n_massive, n_massless, world):
 
 def barneshut_config(n, theta, world, build="auto"):
     if build == "auto":
-        build = "let"
+        build = "let" if world >= 3 else "replicated"
     how = {"replicated": "particles all-gathered, tree build replicated",
            "partitioned": "particles all-gathered, one tree per GPU over its key range (partitioned build), "
                           "trees all-gathered and joined by a top tree",

@@ -84,8 +84,9 @@ typedef struct pcuda_config {
 /* LET: locally essential trees.  The particles travel once, to the rank that owns their key range; every
  * rank builds the tree of its range and sends each other rank only the nodes and leaf particles that
  * rank's walk can open (the rest as stubs); cells that straddle a range boundary are joined by the same
- * top tree as in the partitioned build.  Nothing is replicated.  Default from 2 GPUs on when every rank
- * gets at least 65536 particles; the flag forces it. */
+ * top tree as in the partitioned build.  Nothing is replicated.  Default from 3 GPUs on when every rank
+ * gets at least 65536 particles (N = 10M, ms per step, LET / partitioned / replicated: 2 GPUs 14.97 / 14.93 /
+ * 14.86, 4 GPUs 8.18 / 8.34 / 8.93, 8 GPUs 5.01 / 5.31 / 6.04); the flag forces it. */
 #define PCUDA_FLAG_BH_LET_BUILD 16u
 /* `checked` with zero softening (Acceleration::checked, impls/mod.rs:160-161: a pair at zero distance
  * contributes nothing).  Small f32 brute-force problems (fewer than 2.5e8 pairs) and every f64 path

@@ -944,7 +944,8 @@ struct LetDomNode {
 };
 struct LetDomain {
     uint32_t n;  // 0: the rank has no targets
-    uint32_t pad[7];
+    uint32_t pad;
+    float lo[3], hi[3];  // box of all frontier cells: one test rules out most nodes of a distant rank
     LetDomNode node[LET_DOM_MAX];
 };
 
@@ -1002,6 +1003,40 @@ __global__ void __launch_bounds__(256) let_domain_kernel(const NodeRec *__restri
     out->node[y] = o;
 }
 
+// Box of the whole domain = union of the cubes of the domain tree's leaves (one block).
+__global__ void __launch_bounds__(256) let_domain_box_kernel(LetDomain *d) {
+    __shared__ float s[8][6];
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t y = threadIdx.x; y < d->n; y += 256) {
+        const LetDomNode &nd = d->node[y];
+        if (nd.nchild) continue;
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], nd.lo[k]);
+            hi[k] = fmaxf(hi[k], nd.hi[k]);
+        }
+    }
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 3; ++k) {
+            s[threadIdx.x >> 5][k] = lo[k];
+            s[threadIdx.x >> 5][3 + k] = hi[k];
+        }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = s[0][threadIdx.x], b = s[0][3 + threadIdx.x];
+        for (int w = 1; w < 8; ++w) {
+            a = fminf(a, s[w][threadIdx.x]);
+            b = fmaxf(b, s[w][3 + threadIdx.x]);
+        }
+        d->lo[threadIdx.x] = a;
+        d->hi[threadIdx.x] = b;
+    }
+}
+
 // The opening rule of the walk (traverse2_kernel: theta^2 dmin^2 < w^2, dmin = distance from the
 // centre of mass to the box of the targets) against a box that CONTAINS the box of every target group
 // it stands for.  `margin` (a few ulp of the root extent) is taken off every axis distance, so that the
@@ -1038,7 +1073,9 @@ __global__ void __launch_bounds__(256) let_open_kernel(const NodeRec *__restrict
         if (q == rank) continue;
         const LetDomain &d = doms[q];
         bool op = boundary;
-        if (!op && d.n) {  // walk q's domain tree: a box that passes the rule closes its whole branch
+        // walk q's domain tree: a box that passes the rule closes its whole branch (first of all the box of
+        // the whole domain)
+        if (!op && d.n && let_opens(nd.cm, w2, theta2, d.lo, d.hi, margin)) {
             uint16_t stack[192];  // <= 7 siblings per level of the domain tree + 8
             int sp = 1;
             stack[0] = 0;
@@ -1524,7 +1561,8 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(f->sel_tmp.p, tmp, d_flag, d_idx, (int)nn, st));
         let_domain_kernel<<<nb256, 256, 0, st>>>(t->nodes.as<NodeRec>(), t->d_keys(), d_flag, d_idx, nn, tau, d_frame,
                                                  f->let_dom.as<LetDomain>());
-        ctx->launches += 5;
+        let_domain_box_kernel<<<1, 256, 0, st>>>(f->let_dom.as<LetDomain>());
+        ctx->launches += 6;
     } else {
         PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(f->let_dom.p, 0, 32, st));  // n = 0: no targets here
     }
@@ -1593,6 +1631,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "joined tree does not fit 32-bit indices");
     PCUDA_CUDA_TRY(ctx, f->nodes.ensure((n_nodes_all + TOP_CAP) * sizeof(NodeRec)));
     PCUDA_CUDA_TRY(ctx, f->sorted.ensure(std::max<size_t>(n_src_all, 1) * sizeof(float4)));
+    PCUDA_TRY(nccl_group_begin(ctx));       // one fused exchange
     for (int pass = 0; pass < 3; ++pass) {  // nodes, particles, boundary maps
         const size_t w = pass == 0 ? sizeof(NodeRec) : pass == 1 ? sizeof(float4) : TOP_LEVELS * 2 * sizeof(uint32_t);
         for (int q = 0; q < world; ++q) {
@@ -1612,6 +1651,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         void *rp = pass == 0 ? f->nodes.p : pass == 1 ? f->sorted.p : f->let_bmap_recv.p;
         PCUDA_TRY(nccl_alltoallv(ctx, sp, so, sb_, rp, ro, rb));
     }
+    PCUDA_TRY(nccl_group_end(ctx));
     NodeRec *fn = f->nodes.as<NodeRec>();
     for (int p = 0; p < world; ++p) {
         if (p == rank) continue;
@@ -1703,9 +1743,10 @@ int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_t
                     rank, world, hi - lo, n_total, cap, n_local);
     const int how = g_forest ? g_forest : ctx->bh_build;  // 0 = automatic
     const bool forest_ok = world > 1 && world <= MAX_PARTS && ctx->order == 1 && g_tpl == 2 && !g_variant;
-    // locally essential trees: nothing is replicated, so they win as soon as there is more than one GPU
-    // and enough particles for every rank to have a range worth a tree
-    if (forest_ok && (how == 3 || (how == 0 && n_total >= (size_t)world * 65536)))
+    // locally essential trees: nothing is replicated.  Measured at N = 10M (r02, ms per step, LET / partitioned /
+    // replicated): 2 GPUs 14.97 / 14.93 / 14.86, 4 GPUs 8.18 / 8.34 / 8.93, 8 GPUs 5.01 / 5.31 / 6.04 — hence
+    // from 3 GPUs on, when every rank has a range worth a tree
+    if (forest_ok && (how == 3 || (how == 0 && world >= 3 && n_total >= (size_t)world * 65536)))
         return sharded_let_dev(ctx, world, rank, n_total, lo, hi, theta, eps, d_local, d_out);
     float *slot = d_gathered + (size_t)rank * cap * 4;
     phase_begin(ctx, PH_COMM);

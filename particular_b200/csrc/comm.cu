@@ -189,6 +189,22 @@ static int local_allgather(pcuda_ctx *ctx, const void *d_send, void *d_recv, siz
     return local_alltoallv(ctx, d_send, zero, cnt, d_recv, roff, cnt);
 }
 
+// Several exchanges as one NCCL group (the calls between begin and end are fused into one launch); nothing
+// to do for the in-process communicator.
+int nccl_group_begin(pcuda_ctx *ctx) {
+    Nccl *n = ctx->nccl;
+    if (!n || n->local || !n->comm || !n->GroupStart) return PCUDA_OK;
+    ncclResult_t rc = n->GroupStart();
+    return rc ? nccl_fail(ctx, "ncclGroupStart", rc) : PCUDA_OK;
+}
+
+int nccl_group_end(pcuda_ctx *ctx) {
+    Nccl *n = ctx->nccl;
+    if (!n || n->local || !n->comm || !n->GroupEnd) return PCUDA_OK;
+    ncclResult_t rc = n->GroupEnd();
+    return rc ? nccl_fail(ctx, "ncclGroupEnd", rc) : PCUDA_OK;
+}
+
 // Variable all-to-all on the context stream: rank o gets send_bytes[o] bytes from d_send +
 // send_off[o] and delivers recv_bytes[o] bytes to d_recv + recv_off[o]; one grouped batch of
 // ncclSend / ncclRecv.  The own share is a device-to-device copy.  Zero-byte pairs are skipped

@@ -267,7 +267,7 @@ class CudaContext:
         (PCUDA_FLAG_BH_REPLICATED_BUILD): every GPU builds the whole tree; None: partitioned from
         4 GPUs on.  bh_build = "let" (PCUDA_FLAG_BH_LET_BUILD) / "partitioned" / "replicated" names the
         build instead: "let" = locally essential trees (particles go to the owners of their key ranges,
-        every rank sends the others only what their walks can open), the default from 2 GPUs on when
+        every rank sends the others only what their walks can open), the default from 3 GPUs on when
         every rank gets at least 65536 particles.
         exact_checked (PCUDA_FLAG_EXACT_CHECKED): the f32 brute-force kernels test r^2 == 0 exactly at
         every problem size instead of adding the floor t ~ 1e-19 to r^2 on large problems (see

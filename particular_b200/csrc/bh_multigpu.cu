@@ -1731,8 +1731,8 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     return PCUDA_OK;
 }
 
-int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total,
-                       float theta, float eps, float *d_gathered, float *d_out) {
+static int sharded_dev_impl(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total,
+                            float theta, float eps, float *d_gathered, float *d_out) {
     int world = 1, rank = 0;
     nccl_world(ctx, &world, &rank);
     const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
@@ -1806,6 +1806,27 @@ int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_t
     return PCUDA_OK;
 }
 
+
+
+// Arguments are validated before the first collective; a failure after it (out of memory, an
+// inconsistent exchange) poisons the communicator (comm.cu: nccl_poison) so that this rank fails fast from
+// then on instead of entering collectives its peers have left.
+int sharded_dev(pcuda_ctx *ctx, const float *d_local, size_t n_local, size_t n_total, float theta, float eps,
+                float *d_gathered, float *d_out) {
+    if (nccl_poisoned(ctx))
+        return fail(ctx, PCUDA_ERR_NCCL, "the communicator is unusable: an earlier multi-GPU step failed on this rank");
+    int world = 1, rank = 0;
+    nccl_world(ctx, &world, &rank);
+    const size_t cap = std::max<size_t>(1, (n_total + world - 1) / world);
+    const size_t lo = std::min(n_total, (size_t)rank * cap), hi = std::min(n_total, lo + cap);
+    if (n_local != hi - lo)  // before any collective: the other ranks are not left waiting
+        return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT,
+                    "rank %d of %d must own %zu of %zu particles (contiguous blocks of %zu), got %zu", rank, world,
+                    hi - lo, n_total, cap, n_local);
+    const int s = sharded_dev_impl(ctx, d_local, n_local, n_total, theta, eps, d_gathered, d_out);
+    if (s != PCUDA_OK && world > 1) nccl_poison(ctx);
+    return s;
+}
 
 }  // namespace bh
 }  // namespace pcuda

@@ -62,6 +62,8 @@ struct Nccl {
     ncclComm_t comm = nullptr;
     LocalGroup *local = nullptr;  // in-process communicator instead of NCCL
     int world = 0, rank = 0;
+    bool poisoned = false;  // a collective call failed half-way on this rank: the communicator is unusable
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -93,6 +95,7 @@ static int nccl_load(pcuda_ctx *ctx) {
     n->Recv = (decltype(n->Recv))dlsym(h, "ncclRecv");
     n->GroupStart = (decltype(n->GroupStart))dlsym(h, "ncclGroupStart");
     n->GroupEnd = (decltype(n->GroupEnd))dlsym(h, "ncclGroupEnd");
+    n->CommAbort = (decltype(n->CommAbort))dlsym(h, "ncclCommAbort");
     if (!n->GetUniqueId || !n->CommInitRank || !n->CommDestroy || !n->AllGather) {
         delete n;
         return fail(ctx, PCUDA_ERR_NCCL, "libnccl.so.2 lacks required symbols");
@@ -122,10 +125,29 @@ void nccl_free(pcuda_ctx *ctx) {
 }
 
 void nccl_world(const pcuda_ctx *ctx, int *world, int *rank) {
-    const bool on = ctx->nccl && (ctx->nccl->comm || ctx->nccl->local);
+    const bool on = ctx->nccl && (ctx->nccl->comm || ctx->nccl->local || ctx->nccl->poisoned);
     *world = on ? ctx->nccl->world : 1;
     *rank = on ? ctx->nccl->rank : 0;
 }
+
+// A multi-rank step that fails on one rank between two collectives leaves the other ranks waiting in the
+// next one; this rank cannot repair that, but it must not add to it: the communicator is aborted (its
+// pending operations are cancelled) and every later call on it fails at once instead of hanging.
+void nccl_poison(pcuda_ctx *ctx) {
+    Nccl *n = ctx->nccl;
+    if (!n || n->poisoned) return;
+    n->poisoned = true;
+    if (n->local) {
+        std::lock_guard<std::mutex> lk(n->local->m);
+        n->local->broken = true;
+        n->local->cv.notify_all();
+    } else if (n->comm && n->CommAbort) {
+        n->CommAbort(n->comm);
+        n->comm = nullptr;
+    }
+}
+
+bool nccl_poisoned(const pcuda_ctx *ctx) { return ctx->nccl && ctx->nccl->poisoned; }
 
 static int nccl_fail(pcuda_ctx *ctx, const char *what, ncclResult_t r) {
     return fail(ctx, PCUDA_ERR_NCCL, "%s failed: %s (%d)", what,

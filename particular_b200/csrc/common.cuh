@@ -129,6 +129,8 @@ void nccl_free(pcuda_ctx *ctx);
 // comm.cu: world size / rank of the context's communicator (1 / 0 when none was initialised).
 void nccl_world(const pcuda_ctx *ctx, int *world, int *rank);
 bool nccl_has_p2p(const pcuda_ctx *ctx);
+void nccl_poison(pcuda_ctx *ctx);  // after a step failed between collectives: abort, fail fast from now on
+bool nccl_poisoned(const pcuda_ctx *ctx);
 int nccl_group_begin(pcuda_ctx *ctx);  // the exchanges up to nccl_group_end() become one NCCL group
 int nccl_group_end(pcuda_ctx *ctx);
 int nccl_alltoallv(pcuda_ctx *ctx, const void *d_send, const size_t *send_off, const size_t *send_bytes,

@@ -253,6 +253,28 @@ def test_quadrupole_nodes(pb, ctx, cloud, dim):
         pi.CudaContext(0, expansion_order=3)
 
 
+def test_two_tight_clusters_beyond_the_key_resolution(pb, ctx):
+    """Depth is limited by the key resolution (extent / 2^21 per axis; the reference subdivides until
+    positions differ, tree/mod.rs:112-134).  Two clumps of 2000 particles, 2e-5 wide, 100 apart: the
+    deepest cells (4.8e-5 wide) hold hundreds of particles each — leaves far beyond leaf_size that are
+    summed directly whenever they are opened.  The result must stay as accurate as the reference's
+    (the cost is the documented O(k^2) per clump, include/particular_cuda.h)."""
+    from particular_b200 import _ffi
+    rng = np.random.default_rng(17)
+    p = uniform_cloud(4000, seed=17)
+    p[:2000, :3] = np.float32(50.0) + rng.normal(scale=2e-5, size=(2000, 3)).astype(np.float32)
+    p[2000:, :3] = np.float32(-50.0) + rng.normal(scale=2e-5, size=(2000, 3)).astype(np.float32)
+    t = pb.RootedOrthtree(ctx, p)
+    leaves = t.read(_ffi.TREE_NODE_NUM_CHILDREN) == 0
+    assert t.n_levels == 22 and t.read(_ffi.TREE_NODE_COUNT)[leaves].max() > 100
+    t.close()
+    exact = oracle.brute_force_exact(p[:, :3], p)
+    got = pb.BarnesHut(ctx, 0.5, pb.Acceleration.checked()).compute(p)
+    ref = oracle.barnes_hut(p[:, :3], p, 0.5, parallel=True)
+    assert np.isfinite(got).all()
+    assert_same_theta_error(got, ref, exact)
+
+
 def test_softened_and_unchecked(pb, ctx):
     p = plummer_cloud(15000, seed=6)
     eps = 0.01

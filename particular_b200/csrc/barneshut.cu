@@ -184,7 +184,7 @@ int bh_debug_set(const char *key, int value) {
         bh::g_level_build = value;
         return PCUDA_OK;
     }
-    if (k == "bh_variant" && value >= 0 && value <= 3) {
+    if (k == "bh_variant" && value >= 0 && value <= 4) {
         bh::g_variant = value;
         return PCUDA_OK;
     }

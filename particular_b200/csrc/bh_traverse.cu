@@ -647,10 +647,30 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
                 const int incl = (int)(packed & 1023u);
                 leaf_incl = (int)(packed >> 10);
                 const int total = __shfl_sync(FULL, incl, 31);
-                const int base = sp + incl - c_child;
+                if (VAR & 4) {
+                    // transposed push: lane f of a round of 32 writes child number `base + f` of the round —
+                    // consecutive words, no bank conflicts (a lane writing its own <= 8 children hits every
+                    // bank incl / 32 times when its neighbours push 8 each) — and finds the parent that owns
+                    // it by a shuffle binary search over the inclusive counts
+                    for (int off = 0; off < total; off += 32) {
+                        const int f = off + lane;
+                        int owner = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j < c_child) stack[base + j] = nd.first_child + j;
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            const int v = __shfl_sync(FULL, incl, (owner + step - 1) & 31);
+                            if (v <= f) owner += step;
+                        }
+                        owner = min(owner, 31);
+                        const uint32_t ofc = __shfl_sync(FULL, nd.first_child, owner);
+                        const int oex = __shfl_sync(FULL, incl - c_child, owner);
+                        if (f < total) stack[sp + f] = ofc + (uint32_t)(f - oex);
+                    }
+                } else {
+                    const int base = sp + incl - c_child;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < c_child) stack[base + j] = nd.first_child + j;
+                }
                 sp += total;
             }
             if (VAR & 2) {  // the next round's nodes are known now: pull them into L1
@@ -1356,7 +1376,8 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     } else if (g_tpl == 2 && g_variant) {
         if (g_variant == 1) traverse2_kernel<false, 1><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else if (g_variant == 2) traverse2_kernel<false, 2><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
-        else traverse2_kernel<false, 3><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+        else if (g_variant == 3) traverse2_kernel<false, 3><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
+        else traverse2_kernel<false, 4><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
     } else if (g_tpl == 2 && fv) {
         if (g_count) traverse2_kernel<true, 0, true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);
         else traverse2_kernel<false, 0, true><<<blocks, TRAV_WARPS * 32, 0, st>>>(a);

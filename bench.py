@@ -673,6 +673,8 @@ def bench_bruteforce(args, n, rank, world, local_rank):
     ms_per_step = total_ms / args.steps
     value = n * float(n) / (ms_per_step * 1e-3) / 1e9
     total_launches = int(_sum_over_ranks(launches, world, dist))
+    spread = {"ms_min": min(times), "ms_median": sorted(times)[len(times) // 2], "ms_max": max(times),
+              "of": "rank 0's timed steps (criterion-style spread; `ms_per_step` is the max-over-ranks mean)"}
 
     # ---- end to end through the public API, host buffers ----
     h_local = ctx.pinned_empty((n_local, 4), np.float32)
@@ -722,7 +724,7 @@ def bench_bruteforce(args, n, rank, world, local_rank):
                     "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(n_local * 12),
                     "bytes_are": "per rank"},
             "gpu_launches": total_launches, "roofline": roofline, "clocks": sampler.summary(),
-            "device": ctx.name}
+            "device": ctx.name, "step_spread": spread}
 
     if rank == 0 and world == 1 and not args.no_extra:
         rate, sample, cores, _ = cpu_bruteforce_rate(P, args.cpu_seconds)

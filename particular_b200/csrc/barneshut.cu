@@ -44,6 +44,7 @@ bool g_count = true;              // instrumentation of the traversal (pcuda_tre
 int g_seg_max = 256;              // largest cell (in targets) that is cut into groups
 int g_tpl = 2;                    // targets per lane in the traversal: 1 (groups of 32) or 2 (groups of 64)
 int g_route = 0;                  // accelerations to their owners: 0 = automatic, 1 = all-gather, 2 = all-to-all
+int g_tree_groups = 1;            // target groups from the tree's nodes when the targets are its own particles
 int g_let_trace = 0;              // locally essential trees: print the wall-clock time of every stage
 int g_forest = 0;                 // multi-GPU build: 0 = as the context says, 1 = partitioned, 2 = replicated,
                                   // 3 = locally essential trees
@@ -194,6 +195,10 @@ int bh_debug_set(const char *key, int value) {
     }
     if (k == "bh_forest" && value >= 0 && value <= 3) {
         bh::g_forest = value;
+        return PCUDA_OK;
+    }
+    if (k == "bh_tree_groups") {
+        bh::g_tree_groups = value;
         return PCUDA_OK;
     }
     if (k == "bh_let_trace") {

@@ -43,6 +43,8 @@ struct pcuda_tree {
     pcuda::DevBuf keys[2], perm[2], sorted, nodes, moments, d_frame, scan_in, scan_out, cub_tmp,
         partial;
     pcuda::DevBuf rb;            // scratch of the one-pass build (bh_radix_build.cu)
+    const uint32_t *d_parent = nullptr;  // parent of every node (inside `rb`); nullptr when the tree was not built
+                                         // by the one-pass build (single-block / level-wise builds)
     pcuda::DevBuf quad64, quad;  // expansion order 2: traceless quadrupole per node, 6 doubles
                                  // (build) and 2 x float4 {xx, xy, xz, yy}{yz, zz, 0, 0} (traversal)
     int order = 1;
@@ -78,6 +80,7 @@ extern int g_tpl;
 extern int g_route;
 extern int g_forest;
 extern int g_let_trace;
+extern int g_tree_groups;
 
 // Double-precision layer of a traversal (tree built by build64).
 struct Ext64 {

@@ -718,6 +718,7 @@ void tree_reset(pcuda_ctx *ctx, pcuda_tree *t, size_t n) {
     t->leaf_size = ctx->leaf_size;
     t->level_begin.clear();
     t->frame = Frame{};
+    t->d_parent = nullptr;
 }
 
 // K2: root cube of `n` particle rows -> t->d_frame (device).

@@ -377,6 +377,7 @@ int radix_build_enqueue(pcuda_ctx *ctx, pcuda_tree *t, size_t n, size_t cap_node
                                            arrive, d_state);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 6;
+    t->d_parent = plink;  // (the root: RB_ROOT = 0xfffffffe)
     return PCUDA_OK;
 }
 

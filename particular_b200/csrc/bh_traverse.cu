@@ -1289,12 +1289,35 @@ int traverse(pcuda_ctx *ctx, const pcuda_tree *t, const float *d_tgt, size_t na,
 
 // Targets already in key order ({x,y,z,_} records + their keys in the tree's frame); tgt_perm maps
 // traversal order to the output row (nullptr: out row = traversal position).
+// K5a from the TREE, when the targets are the tree's own particles and the one-pass build left the parent
+// links: a segment (maximal cell with at most T targets) is then simply a node with at most T particles
+// whose parent has more — every cell with more than T >= leaf_size particles is an internal node, so its
+// children are nodes — and a run of equal keys longer than T is a leaf of the last level.  Same group
+// starts as hard_flags + group_flags (0.41 ms at N = 10M: two neighbourhood searches per target), from
+// one pass over the nodes (3.5M records).
+__global__ void __launch_bounds__(256) group_flags_from_tree(const NodeRec *__restrict__ nodes,
+                                                             const uint32_t *__restrict__ parent, uint32_t n_nodes,
+                                                             uint32_t T, uint32_t gsize, uint32_t *__restrict__ flag) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    const uint4 rec = reinterpret_cast<const uint4 *>(nodes + x)[1];  // first_child, nchild|level, begin, count
+    const uint32_t begin = rec.z, count = rec.w;
+    if (x != 0 && nodes[parent[x]].count <= T) return;  // inside a segment that starts higher up
+    if (count <= T) {
+        for (uint32_t i = begin; i < begin + count; i += gsize) flag[i] = 1u;
+    } else if ((rec.y & 0xffu) == 0) {  // more than T targets with one key: cut at multiples of the group size
+        flag[begin] = 1u;
+        for (uint32_t i = (begin / gsize + 1) * gsize; i < begin + count; i += gsize) flag[i] = 1u;
+    }
+}
+
 // K5a: the target groups of `n` targets from their keys, into the context's group buffers
 // (ctx->d_stack, ctx->d_counters).  (Running this on a second stream beside the level build — both need
 // only the sorted keys — was tried: build + walk 25.89 ms against 25.90 ms at N = 10M; the kernels of
 // either side already fill the memory system, so nothing is hidden.)
+// `own`: the tree whose particles the targets are (flags from its nodes), or nullptr (flags from the keys).
 static int make_groups(pcuda_ctx *ctx, int dim, int bits, const uint64_t *tgt_keys, int n, int group_cap,
-                       cudaStream_t st) {
+                       cudaStream_t st, const pcuda_tree *own = nullptr) {
     PCUDA_CUDA_TRY(ctx, ctx->d_counters.ensure(8 * sizeof(unsigned long long)));
     PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
     uint32_t *d_ngroups = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 4);
@@ -1309,18 +1332,25 @@ static int make_groups(pcuda_ctx *ctx, int dim, int bits, const uint64_t *tgt_ke
     uint32_t *d_gstart = d_pos + n;
     uint32_t *d_hard = d_gstart + n + 1;
     const unsigned nb256 = (unsigned)((n + 255) / 256);
-    if (dim == 3) boundary_levels<3><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
-    else boundary_levels<2><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
-    const unsigned ngb = (unsigned)((n + GROUP_BLOCK - 1) / GROUP_BLOCK);
-    hard_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_L, n, bits, g_seg_max, d_hard);
-    group_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_hard, n, g_seg_max, group_cap, d_flag);
+    if (own) {
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, (size_t)n * sizeof(uint32_t), st));
+        group_flags_from_tree<<<(unsigned)((own->n_nodes + 255) / 256), 256, 0, st>>>(
+            own->nodes.as<NodeRec>(), own->d_parent, (uint32_t)own->n_nodes, (uint32_t)g_seg_max, (uint32_t)group_cap,
+            d_flag);
+    } else {
+        if (dim == 3) boundary_levels<3><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
+        else boundary_levels<2><<<nb256, 256, 0, st>>>(tgt_keys, n, d_L);
+        const unsigned ngb = (unsigned)((n + GROUP_BLOCK - 1) / GROUP_BLOCK);
+        hard_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_L, n, bits, g_seg_max, d_hard);
+        group_flags<<<ngb, GROUP_BLOCK, 0, st>>>(d_hard, n, g_seg_max, group_cap, d_flag);
+    }
     size_t tmp = 0;
     PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_flag, d_pos, n, st));
     PCUDA_CUDA_TRY(ctx, ctx->d_cub_tmp.ensure(tmp));
     PCUDA_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_cub_tmp.p, tmp, d_flag, d_pos, n, st));
     scatter_groups<<<nb256, 256, 0, st>>>(d_flag, d_pos, n, d_gstart, d_ngroups);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 6;
+    ctx->launches += own ? 4 : 6;
     return PCUDA_OK;
 }
 
@@ -1333,7 +1363,10 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     cudaStream_t st = ctx->stream;
     const int group_cap = x64 ? 32 : 32 * g_tpl;  // the f64 walk holds one target per lane
     const int n = (int)na;
-    PCUDA_TRY(make_groups(ctx, dim, t->bits, tgt_keys, n, group_cap, st));  // K5a
+    // K5a: from the tree when the targets are its own particles (tuning hook bh_tree_groups = 0: from the keys)
+    const bool own = g_tree_groups && t->d_parent && tgt_keys == t->d_keys() && na == t->n &&
+                     (uint32_t)g_seg_max >= t->leaf_size;
+    PCUDA_TRY(make_groups(ctx, dim, t->bits, tgt_keys, n, group_cap, st, own ? t : nullptr));
     uint32_t *d_work = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 3);
     uint32_t *d_ngroups = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 4);
     const size_t n4g = ((size_t)n + 3) & ~size_t(3);

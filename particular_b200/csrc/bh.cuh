@@ -43,6 +43,7 @@ struct pcuda_tree {
     pcuda::DevBuf keys[2], perm[2], sorted, nodes, moments, d_frame, scan_in, scan_out, cub_tmp,
         partial;
     pcuda::DevBuf rb;            // scratch of the one-pass build (bh_radix_build.cu)
+    uint32_t *rb_totals = nullptr;       // level totals + ticket of rb_scan (inside `rb`), zeroed when (re)placed
     const uint32_t *d_parent = nullptr;  // parent of every node (inside `rb`); nullptr when the tree was not built
                                          // by the one-pass build (single-block / level-wise builds)
     pcuda::DevBuf quad64, quad;  // expansion order 2: traceless quadrupole per node, 6 doubles

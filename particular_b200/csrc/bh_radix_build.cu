@@ -1,7 +1,7 @@
 // bh_radix_build.cu — K4 in one pass: the linear orthtree over the sorted Morton keys, built from the
 // boundary levels between neighbouring keys instead of level by level (Karras-style: every node is
 // found from the key array alone, and the centres of mass climb bottom-up behind atomic arrival
-// counters).  Six launches whatever the depth of the tree; the level-wise build it replaces
+// counters).  Seven launches whatever the depth of the tree; the level-wise build it replaces
 // (expand_level / moments_kernel in barneshut.cu, kept for leaf sizes above RB_MAX_LEAF) needed
 // 2 x (BITS + 1) dependent launches, each a round of dependent binary searches.
 //
@@ -105,40 +105,64 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_count(const uint8_t *__restrict__
     if (threadIdx.x < RB_LV) tile_cnt[(size_t)threadIdx.x * tiles_pad + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-// Exclusive scan over the tiles of every level (in place) + the level table.  One block; warp w
-// scans levels w and w + 32.
+// Exclusive scan over the tiles of every level (in place) + the level table.  One block per level; the
+// block that finishes last (a ticket) turns the level totals into the level table.  (One block for all
+// levels took 57 us at N = 10M: 4883 tiles x 33 levels behind one another.)
 __global__ void __launch_bounds__(1024) rb_scan(uint32_t *__restrict__ tile_cnt, uint32_t n_tiles,
-                                                uint32_t tiles_pad, BuildState *st, uint32_t capacity) {
-    __shared__ uint32_t s_total[RB_LV];
+                                                uint32_t tiles_pad, BuildState *st, uint32_t capacity,
+                                                uint32_t *__restrict__ totals /* RB_LV + 1: totals, ticket */) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_running;
+    __shared__ bool s_last;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int l = warp; l < RB_LV; l += 32) {
-        uint32_t *row = tile_cnt + (size_t)l * tiles_pad;
-        uint32_t running = 0;
-        for (uint32_t t0 = 0; t0 < n_tiles; t0 += 32) {
-            const uint32_t t = t0 + lane;
-            const uint32_t v = t < n_tiles ? row[t] : 0u;
-            uint32_t incl = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l = blockIdx.x;
+    uint32_t *row = tile_cnt + (size_t)l * tiles_pad;
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint32_t v = t < n_tiles ? row[t] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += u;
+                const uint32_t u = __shfl_up_sync(FULL, w, o);
+                if (lane >= o) w += u;
             }
-            if (t < n_tiles) row[t] = running + incl - v;
-            running += __shfl_sync(FULL, incl, 31);
+            s_warp[lane] = w;  // inclusive over the warps
         }
-        if (lane == 0) s_total[l] = running;
+        __syncthreads();
+        const uint32_t base = s_running + (warp ? s_warp[warp - 1] : 0u);
+        if (t < n_tiles) row[t] = base + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_running += s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        totals[l] = s_running;
+        __threadfence();
+        s_last = atomicAdd(&totals[RB_LV], 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
         unsigned long long b = 0;
-        for (int l = 0; l < 36; ++l) {
-            st->level_begin[l] = b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
-            if (l < RB_LV) b += s_total[l];
+        for (int k = 0; k < 36; ++k) {
+            st->level_begin[k] = b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
+            if (k < RB_LV) b += __ldcg(&totals[k]);
         }
-        for (int l = 0; l < 34; ++l) st->ticket[l] = 0;
+        for (int k = 0; k < 34; ++k) st->ticket[k] = 0;
         st->overflow = b > capacity ? 1u : 0u;
         st->capacity = capacity;
+        totals[RB_LV] = 0;  // ready for the next build
     }
 }
 
@@ -271,20 +295,43 @@ __global__ void __launch_bounds__(256) rb_links(NodeRec *__restrict__ nodes,
 }
 
 // Moments and centres of mass, bottom-up (see the header comment).  Arithmetic and order of
-// node_moments() in barneshut.cu == the CPU statement of the specification.
+// node_moments() in bh_build.cu == the CPU statement of the specification.
 template <int DIM>
-__global__ void __launch_bounds__(128) rb_moments(NodeRec *__restrict__ nodes, double *__restrict__ mom,
-                                                  const float4 *__restrict__ sorted,
-                                                  const uint32_t *__restrict__ plink,
-                                                  uint32_t *__restrict__ arrive,
-                                                  const BuildState *__restrict__ st) {
+__device__ __forceinline__ void rb_store(NodeRec *__restrict__ nodes, double *__restrict__ mom,
+                                         const float4 *__restrict__ sorted, uint32_t x, const double m[4],
+                                         uint32_t beg) {
+    reinterpret_cast<double4 *>(mom)[x] = make_double4(m[0], m[1], m[2], m[3]);
+    float4 cm;
+    if (m[3] == 0.0) {
+        const float4 q = sorted[beg];
+        cm = make_float4(q.x, q.y, DIM == 3 ? q.z : 0.f, 0.f);
+    } else {
+        cm.x = (float)__ddiv_rn(m[0], m[3]);
+        cm.y = (float)__ddiv_rn(m[1], m[3]);
+        cm.z = DIM == 3 ? (float)__ddiv_rn(m[2], m[3]) : 0.f;
+        cm.w = (float)m[3];
+    }
+    nodes[x].cm = cm;
+}
+
+// Pass 1, no synchronisation at all: every leaf sums its particles (key order); every internal node notes
+// whether all its children are leaves.
+template <int DIM>
+__global__ void __launch_bounds__(128) rb_leaf_moments(NodeRec *__restrict__ nodes, double *__restrict__ mom,
+                                                       const float4 *__restrict__ sorted,
+                                                       uint8_t *__restrict__ all_leaf,
+                                                       const BuildState *__restrict__ st) {
     if (st->overflow) return;
     const uint32_t n_nodes = st->level_begin[35];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_nodes; j += gridDim.x * blockDim.x) {
         const uint4 rec = reinterpret_cast<const uint4 *>(nodes + j)[1];
-        if (rec.x != 0) continue;  // internal: computed by the child that arrives last
-        uint32_t x = j, beg = rec.z;
-        const uint32_t end = rec.z + rec.w;
+        if (rec.x != 0) {
+            bool all = true;
+            for (uint32_t c = 0; c < (rec.y & 0xffu); ++c) all &= nodes[rec.x + c].first_child == 0;
+            all_leaf[j] = all ? 1 : 0;
+            continue;
+        }
+        const uint32_t beg = rec.z, end = rec.z + rec.w;
         double m[4] = {0.0, 0.0, 0.0, 0.0};
         for (uint32_t i = beg; i < end; i += 4) {  // four loads in flight, additions in key order
             float4 q[4];
@@ -302,34 +349,58 @@ __global__ void __launch_bounds__(128) rb_moments(NodeRec *__restrict__ nodes, d
                 }
             }
         }
-        for (;;) {
-            const uint32_t p = plink[x];
-            reinterpret_cast<double4 *>(mom)[x] = make_double4(m[0], m[1], m[2], m[3]);
-            float4 cm;
-            if (m[3] == 0.0) {
-                const float4 q = sorted[beg];
-                cm = make_float4(q.x, q.y, DIM == 3 ? q.z : 0.f, 0.f);
-            } else {
-                cm.x = (float)__ddiv_rn(m[0], m[3]);
-                cm.y = (float)__ddiv_rn(m[1], m[3]);
-                cm.z = DIM == 3 ? (float)__ddiv_rn(m[2], m[3]) : 0.f;
-                cm.w = (float)m[3];
+        rb_store<DIM>(nodes, mom, sorted, j, m, beg);
+    }
+}
+
+// Pass 2, the climb.  An internal node whose children are all leaves (most of the internal nodes) sums
+// them directly — their moments were written by pass 1, a kernel ago — so those leaves never touch an
+// arrival counter; the other leaves only count themselves in.  A node that was computed HERE is released
+// before its arrival is counted, and the child that completes a count acquires and reads its siblings from
+// L2 (ld.cg).  (One kernel for everything, every leaf arriving with a fence: 397 us at N = 10M; with
+// __threadfence() pairs and the parent searched in the climb: 491 us.)
+template <int DIM>
+__global__ void __launch_bounds__(128) rb_climb(NodeRec *__restrict__ nodes, double *__restrict__ mom,
+                                                const float4 *__restrict__ sorted,
+                                                const uint32_t *__restrict__ plink, uint32_t *__restrict__ arrive,
+                                                const uint8_t *__restrict__ all_leaf,
+                                                const BuildState *__restrict__ st) {
+    if (st->overflow) return;
+    const uint32_t n_nodes = st->level_begin[35];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_nodes; j += gridDim.x * blockDim.x) {
+        const uint4 rec = reinterpret_cast<const uint4 *>(nodes + j)[1];
+        uint32_t x = j, p = plink[j];
+        bool wrote = false;  // x's data was written by this thread in this kernel: release before arriving
+        if (rec.x == 0) {
+            if (p == RB_ROOT || all_leaf[p]) continue;  // the parent sums this leaf itself
+        } else if (all_leaf[j]) {
+            double m[4] = {0.0, 0.0, 0.0, 0.0};
+            uint32_t total = 0;
+            for (uint32_t c = 0; c < (rec.y & 0xffu); ++c) {
+                const double4 q = reinterpret_cast<const double4 *>(mom)[rec.x + c];
+                m[0] = __dadd_rn(m[0], q.x);
+                m[1] = __dadd_rn(m[1], q.y);
+                if (DIM == 3) m[2] = __dadd_rn(m[2], q.z);
+                m[3] = __dadd_rn(m[3], q.w);
+                total += nodes[rec.x + c].count;
             }
-            nodes[x].cm = cm;
-            if (p == RB_ROOT) break;
-            // release: this node's moments / record are visible before the arrival is counted; the
-            // child that completes the count acquires (one fence for one child in nc) and reads its
-            // siblings' results from L2 (ld.cg).  A __threadfence() pair here costs every node two
-            // MEMBAR.SC + an L1 invalidation, which the particle loop of the next leaf then pays for.
+            rb_store<DIM>(nodes, mom, sorted, j, m, rec.z);
+            nodes[j].count = total;
+            wrote = true;
+        } else {
+            continue;  // completed by the child that arrives last
+        }
+        while (p != RB_ROOT) {
             uint32_t now;
-            asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(now) : "l"(arrive + p) : "memory");
+            if (wrote) asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(now) : "l"(arrive + p) : "memory");
+            else now = atomicAdd(arrive + p, 1u);
             now += 1u;
             if ((now & 0xffu) != (now >> 8)) break;  // siblings still on their way
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
             const uint32_t nc = now >> 8;
             const uint4 prec = reinterpret_cast<const uint4 *>(nodes + p)[1];  // written by earlier kernels
             const uint32_t fc = prec.x;
-            m[0] = m[1] = m[2] = m[3] = 0.0;
+            double m[4] = {0.0, 0.0, 0.0, 0.0};
             uint32_t total = 0;
             for (uint32_t c = 0; c < nc; ++c) {
                 const double2 a = __ldcg(reinterpret_cast<const double2 *>(mom) + 2 * (size_t)(fc + c));
@@ -341,8 +412,10 @@ __global__ void __launch_bounds__(128) rb_moments(NodeRec *__restrict__ nodes, d
                 total += __ldcg(&nodes[fc + c].count);
             }
             x = p;
-            beg = prec.z;
+            rb_store<DIM>(nodes, mom, sorted, x, m, prec.z);
             nodes[x].count = total;
+            wrote = true;
+            p = plink[x];
         }
     }
 }
@@ -356,7 +429,9 @@ int radix_build_enqueue(pcuda_ctx *ctx, pcuda_tree *t, size_t n, size_t cap_node
     const size_t off_L = 0, off_D = up(n + 1 + 4), off_cnt = off_D + up(n),
                  off_parent = off_cnt + up((size_t)RB_LV * tiles_pad * 4),
                  off_plink = off_parent + up(cap_nodes * 4), off_arrive = off_plink + up(cap_nodes * 4),
-                 total = off_arrive + up(cap_nodes * 4);
+                 off_leaf = off_arrive + up(cap_nodes * 4), off_totals = off_leaf + up(cap_nodes),
+                 total = off_totals + up((RB_LV + 1) * 4);
+    const bool fresh = total > t->rb.cap;  // a new allocation: the scan's ticket must start at zero
     PCUDA_CUDA_TRY(ctx, t->rb.ensure(total));
     uint8_t *base = t->rb.as<uint8_t>();
     uint8_t *L = base + off_L, *Dlv = base + off_D;
@@ -364,19 +439,27 @@ int radix_build_enqueue(pcuda_ctx *ctx, pcuda_tree *t, size_t n, size_t cap_node
     uint32_t *parent = reinterpret_cast<uint32_t *>(base + off_parent);
     uint32_t *plink = reinterpret_cast<uint32_t *>(base + off_plink);
     uint32_t *arrive = reinterpret_cast<uint32_t *>(base + off_arrive);
+    uint8_t *all_leaf = base + off_leaf;
+    uint32_t *totals = reinterpret_cast<uint32_t *>(base + off_totals);
+    if (fresh || t->rb_totals != totals) {
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(totals, 0, (RB_LV + 1) * 4, st));
+        t->rb_totals = totals;
+    }
     const int nleaf = (int)t->leaf_size;
     NodeRec *nodes = t->nodes.as<NodeRec>();
     rb_boundaries<DIM><<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(t->d_keys(), (uint32_t)n, L);
     rb_count<DIM><<<n_tiles, RB_BLOCK, 0, st>>>(L, (uint32_t)n, nleaf, Dlv, tile_cnt, tiles_pad);
-    rb_scan<<<1, 1024, 0, st>>>(tile_cnt, n_tiles, tiles_pad, d_state, (uint32_t)cap_nodes);
+    rb_scan<<<RB_LV, 1024, 0, st>>>(tile_cnt, n_tiles, tiles_pad, d_state, (uint32_t)cap_nodes, totals);
     rb_assign<DIM><<<n_tiles, RB_BLOCK, 0, st>>>(L, Dlv, (uint32_t)n, tile_cnt, tiles_pad, d_state, nodes,
                                                  parent, arrive);
     rb_links<<<(unsigned)((cap_nodes + 255) / 256), 256, 0, st>>>(nodes, parent, plink, arrive, d_state);
     const unsigned mgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 16, (cap_nodes + 127) / 128);
-    rb_moments<DIM><<<mgrid, 128, 0, st>>>(nodes, t->moments.as<double>(), t->sorted.as<float4>(), plink,
-                                           arrive, d_state);
+    rb_leaf_moments<DIM><<<mgrid, 128, 0, st>>>(nodes, t->moments.as<double>(), t->sorted.as<float4>(), all_leaf,
+                                                d_state);
+    rb_climb<DIM><<<mgrid, 128, 0, st>>>(nodes, t->moments.as<double>(), t->sorted.as<float4>(), plink, arrive,
+                                         all_leaf, d_state);
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 6;
+    ctx->launches += 7;
     t->d_parent = plink;  // (the root: RB_ROOT = 0xfffffffe)
     return PCUDA_OK;
 }

@@ -297,6 +297,10 @@ struct pcuda_forest {
         let_cuts, let_cnt_mat, let_dom, let_dom_all, let_open, let_reach, let_parent,
         let_tile_cnt, let_totals, let_index, let_send_nodes, let_send_src, let_bmap_send, let_bmap_recv, let_gi;
     uint32_t *h_let = nullptr;  // pinned: count matrices and boundary maps
+    // two-phase walk: the rank's own tree is walked on walk_stream while the others' trees are on their way
+    pcuda::DevBuf let_root0;
+    cudaStream_t walk_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace pcuda {
@@ -313,13 +317,16 @@ void forest_free(pcuda_ctx *ctx) {
                       &f->let_recv_rec, &f->let_cuts,
                       &f->let_cnt_mat, &f->let_dom, &f->let_dom_all, &f->let_open, &f->let_reach, &f->let_parent,
                       &f->let_tile_cnt, &f->let_totals, &f->let_index, &f->let_send_nodes, &f->let_send_src,
-                      &f->let_bmap_send, &f->let_bmap_recv, &f->let_gi};
+                      &f->let_bmap_send, &f->let_bmap_recv, &f->let_gi, &f->let_root0};
     for (DevBuf *b : bufs) b->release();
     if (f->h_let) cudaFreeHost(f->h_let);
     if (f->h_route) cudaFreeHost(f->h_route);
     if (f->h_packs) cudaFreeHost(f->h_packs);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->ev_stage) cudaEventDestroy(f->ev_stage);
+    if (f->ev_fork) cudaEventDestroy(f->ev_fork);
+    if (f->ev_join) cudaEventDestroy(f->ev_join);
+    if (f->walk_stream) cudaStreamDestroy(f->walk_stream);
     delete f;
     ctx->forest = nullptr;
 }
@@ -519,7 +526,7 @@ static int merge_top_tree(pcuda_ctx *ctx, int parts, const PartPack *packs, cons
         if (m[3] == 0.0) r.cm = make_float4(first.cm.x, first.cm.y, first.cm.z, 0.f);
         else r.cm = make_float4((float)(m[0] / m[3]), (float)(m[1] / m[3]), (float)(m[2] / m[3]), (float)m[3]);
         r.first_child = 0;
-        r.nchild_level = (uint32_t)cells[c].l << 8;
+        r.nchild_level = (uint32_t)cells[c].l << 8 | (first.nchild_level & NODE_SHARE);
         r.begin = first.begin;
         r.count = count;
         return r;
@@ -583,7 +590,7 @@ static int merge_top_tree(pcuda_ctx *ctx, int parts, const PartPack *packs, cons
             if (m[3] == 0.0) r.cm = make_float4(rest[0].rec.cm.x, rest[0].rec.cm.y, rest[0].rec.cm.z, 0.f);
             else r.cm = make_float4((float)(m[0] / m[3]), (float)(m[1] / m[3]), (float)(m[2] / m[3]), (float)m[3]);
             r.first_child = 0;
-            r.nchild_level = (uint32_t)cur.level << 8;
+            r.nchild_level = (uint32_t)cur.level << 8 | (top[cur.me].nchild_level & NODE_SHARE);  // a share's rest is a share
             r.begin = rest[0].rec.begin;
             r.count = count;
             cur.kids.push_back({r, -2});
@@ -597,7 +604,7 @@ static int merge_top_tree(pcuda_ctx *ctx, int parts, const PartPack *packs, cons
             else if (k.cell == -2) queue.push_back({idx, cur.level, rest});
         }
         top[cur.me].first_child = top_base + first_child;
-        top[cur.me].nchild_level = (uint32_t)cur.level << 8 | (uint32_t)cur.kids.size();
+        top[cur.me].nchild_level = (top[cur.me].nchild_level & NODE_SHARE) | (uint32_t)cur.level << 8 | (uint32_t)cur.kids.size();
         if (top.size() > TOP_CAP) return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "top tree has %zu nodes", top.size());
     }
     roots.push_back(top_base);
@@ -1334,11 +1341,11 @@ __global__ void __launch_bounds__(2 * TOP_LEVELS * 9) let_collect_boundary(const
 // or the node was left out (it then lies below a pruned node: a complete cell; the chain of partial cells
 // is always sent).
 __global__ void let_gi_kernel(const uint32_t *__restrict__ bmap_recv, const PartPack *__restrict__ packs,
-                              PartBases bases, int rank, uint32_t *__restrict__ gi) {
+                              PartBases bases, int rank, bool without_own, uint32_t *__restrict__ gi) {
     const int p = blockIdx.x, t = threadIdx.x, l = t >> 1, side = t & 1;
     const PartPack &pk = packs[p];
     uint32_t g = LET_NO_NODE;
-    if (pk.n_nodes && l < (int)pk.n_levels) {
+    if (pk.n_nodes && l < (int)pk.n_levels && !(without_own && p == rank)) {
         if (p == rank) g = bases.node_base[p] + (side ? pk.level_begin[l + 1] - 1 : pk.level_begin[l]);
         else {
             const uint32_t m = bmap_recv[(size_t)p * TOP_LEVELS * 2 + t];
@@ -1346,6 +1353,21 @@ __global__ void let_gi_kernel(const uint32_t *__restrict__ bmap_recv, const Part
         }
     }
     gi[(size_t)p * TOP_LEVELS * 2 + t] = g;
+}
+
+// Two-phase walk: the cells that this rank's own tree holds a share of are the first / last cells of its
+// levels; where another rank's tree has the same cell, that node is marked NODE_SHARE (the walk over the
+// others' trees then opens it: a share must not stand in for the whole cell, its centre of mass lies
+// further from this rank's particles than the cell's).
+__global__ void let_mark_shares_kernel(const uint32_t *__restrict__ gi, const PartPack *__restrict__ packs, int rank,
+                                       NodeRec *__restrict__ nodes) {
+    const int p = blockIdx.x, t = threadIdx.x, l = t >> 1, side = t & 1;
+    const PartPack &pk = packs[p], &own = packs[rank];
+    if (p == rank || pk.n_nodes == 0 || own.n_nodes == 0 || l >= (int)pk.n_levels || l >= (int)own.n_levels) return;
+    const uint32_t g = gi[(size_t)p * TOP_LEVELS * 2 + t];
+    if (g == LET_NO_NODE) return;
+    const uint64_t pre = pk.prefix[l][side];
+    if (pre == own.prefix[l][0] || pre == own.prefix[l][1]) nodes[g].nchild_level |= NODE_SHARE;
 }
 
 __global__ void let_cuts_kernel(const uint64_t *__restrict__ keys, uint32_t n, const uint64_t *__restrict__ split,
@@ -1540,6 +1562,46 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         PCUDA_TRY(build_levels<3>(ctx, t, n_mine));  // (2) synchronises: level table
         mark("tree");
     }
+    // Two-phase walk (tuning hook bh_let_overlap = 0: one walk at the end).  The interactions of this rank's
+    // particles with this rank's own tree need nothing from the other ranks: that walk starts now, on a
+    // second stream, and leaves the last SMs to the pruning kernels and the exchanges of stages C and D,
+    // which run beside it.  What arrives is walked afterwards (stage E) and added to the same rows.
+    // A cell that straddles this rank's key range and another's is then seen as two shares: this rank's is an
+    // ordinary node of its tree (its centre of mass is nearer to the targets than the cell's, so it is
+    // opened at least as early), the others' is always opened (let_mark_shares_kernel).
+    const bool overlap = g_let_overlap && n_mine > 0;
+    struct Join {  // no return path leaves the second stream running behind the first
+        pcuda_forest *f;
+        cudaStream_t st;
+        bool armed = false;
+        ~Join() {
+            if (armed) cudaStreamWaitEvent(st, f->ev_join, 0);
+        }
+    } join{f, st};
+    PCUDA_CUDA_TRY(ctx, f->route_acc_send.ensure(std::max<size_t>(n_mine, 1) * 3 * sizeof(float)));
+    if (overlap) {
+        if (!f->walk_stream) {
+            PCUDA_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&f->walk_stream, cudaStreamNonBlocking));
+            PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+            PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+        }
+        PCUDA_CUDA_TRY(ctx, f->let_root0.ensure(sizeof(uint32_t)));
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(f->let_root0.p, 0, sizeof(uint32_t), st));
+        PCUDA_CUDA_TRY(ctx, cudaEventRecord(f->ev_fork, st));
+        PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(f->walk_stream, f->ev_fork, 0));
+        ForestView own{};
+        own.nodes = t->nodes.as<NodeRec>();
+        own.src = t->sorted.as<float4>();
+        own.d_roots = f->let_root0.as<uint32_t>();
+        own.n_roots = 1;
+        own.stream = f->walk_stream;
+        own.reserve_sms = (unsigned)g_let_reserve;
+        const int rc = traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), t->d_perm(), n_mine, theta, eps,
+                                       f->route_acc_send.as<float>(), nullptr, &own);
+        cudaEventRecord(f->ev_join, f->walk_stream);
+        join.armed = true;
+        PCUDA_TRY(rc);
+    }
     PartPack *d_packs = f->packs.as<PartPack>();
     fill_pack<<<1, 64, 0, st>>>(t->nodes.as<NodeRec>(), t->moments.as<double>(), n_mine ? t->d_keys() : nullptr,
                                 t->scan_in.as<BuildState>(), (uint32_t)t->n_nodes, (uint32_t)t->n_levels, d_packs + rank);
@@ -1624,8 +1686,8 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     for (int p = 0; p < world; ++p) {
         node_base[p] = (uint32_t)n_nodes_all;
         src_base[p] = (uint32_t)n_src_all;
-        n_nodes_all += p == rank ? nn : h_tot[p].n_nodes[rank];
-        n_src_all += p == rank ? n_mine : h_tot[p].n_src[rank];
+        n_nodes_all += p == rank ? (overlap ? 0 : nn) : h_tot[p].n_nodes[rank];
+        n_src_all += p == rank ? (overlap ? 0 : n_mine) : h_tot[p].n_src[rank];
     }
     if (n_nodes_all + TOP_CAP > 0xfffffff0ull || n_src_all > 0xfffffff0ull)
         return fail(ctx, PCUDA_ERR_TREE_OVERFLOW, "joined tree does not fit 32-bit indices");
@@ -1658,7 +1720,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         const uint32_t cnt = h_tot[p].n_nodes[rank];
         if (cnt) let_rebase_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(fn + node_base[p], cnt, node_base[p], src_base[p]);
     }
-    if (nn) {
+    if (nn && !overlap) {
         copy_rebase_nodes<<<(nn + 255) / 256, 256, 0, st>>>(t->nodes.as<NodeRec>(), nn, node_base[rank], src_base[rank],
                                                             fn + node_base[rank]);
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(f->sorted.as<float4>() + src_base[rank], t->sorted.p, n_mine * sizeof(float4),
@@ -1672,8 +1734,9 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PartBases bases{};
     for (int p = 0; p < world; ++p) bases.node_base[p] = node_base[p];
     PCUDA_CUDA_TRY(ctx, f->let_gi.ensure((size_t)MAX_PARTS * TOP_LEVELS * 2 * sizeof(uint32_t)));
-    let_gi_kernel<<<world, 2 * TOP_LEVELS, 0, st>>>(f->let_bmap_recv.as<uint32_t>(), d_packs, bases, rank,
+    let_gi_kernel<<<world, 2 * TOP_LEVELS, 0, st>>>(f->let_bmap_recv.as<uint32_t>(), d_packs, bases, rank, overlap,
                                                     f->let_gi.as<uint32_t>());
+    if (overlap) let_mark_shares_kernel<<<world, 2 * TOP_LEVELS, 0, st>>>(f->let_gi.as<uint32_t>(), d_packs, rank, fn);
     let_collect_boundary<<<world, 2 * TOP_LEVELS * 9, 0, st>>>(fn, f->let_gi.as<uint32_t>(), f->stage.as<BoundaryRec>());
     PCUDA_CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches += 2;
@@ -1684,6 +1747,7 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     PCUDA_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // (4) boundary records and their indices
     std::vector<NodeRec> top;
     std::vector<uint32_t> roots;
+    if (overlap) f->h_packs[rank].n_nodes = 0;  // the top tree of the OTHER ranks' trees
     PCUDA_TRY(merge_top_tree(ctx, world, f->h_packs, f->h_stage, node_base, (uint32_t)n_nodes_all, top, roots, h_gi));
     if (!top.empty())
         PCUDA_CUDA_TRY(ctx, cudaMemcpyAsync(fn + n_nodes_all, top.data(), top.size() * sizeof(NodeRec),
@@ -1702,11 +1766,16 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     // The received records lie block by block in the order their owners sent them, and t->d_perm() maps a
     // sorted particle to its place there: the walk writes every row straight into that place, the blocks go
     // back with the counts of step A swapped, and the owner scatters them through its own sort permutation.
-    PCUDA_CUDA_TRY(ctx, f->route_acc_send.ensure(nm1 * 3 * sizeof(float)));
     PCUDA_CUDA_TRY(ctx, f->route_acc_recv.ensure(nl1 * 3 * sizeof(float)));
     phase_end(ctx, PH_COMM3);
-    phase_begin(ctx, PH_COMPUTE);
-    if (n_mine)
+    phase_begin(ctx, PH_COMPUTE);  // (two-phase walk: what is left of the first phase, and the second)
+    if (overlap) {
+        PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(st, f->ev_join, 0));
+        join.armed = false;
+        fv.accumulate = true;
+        fv.reuse_groups = true;
+    }
+    if (n_mine && (!overlap || fv.n_roots))
         PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), t->d_perm(), n_mine, theta, eps,
                                   f->route_acc_send.as<float>(), nullptr, &fv));
     mark("walk");

@@ -204,6 +204,9 @@ struct TravArgs {
     // the loose leaves (partial cells that are leaves in their own part), at most MAX_ROOTS.
     const uint32_t *roots;
     uint32_t n_roots;
+    const uint32_t *n_roots_dev;  // forest walks: the number of start nodes when only the device knows it
+    int accumulate;               // forest walks: add to the output rows (second phase of a two-phase walk)
+    uint32_t reserve_from, reserve_cap;  // forest walks: blocks on SMs >= reserve_from exit (at most reserve_cap)
 };
 
 // The interaction list of a warp lives in shared memory as PAIRS of entries laid out
@@ -503,6 +506,17 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
     __shared__ uint32_t s_stack[TRAV_WARPS][STACK_CAP];
     __shared__ __align__(16) float4 s_list[TRAV_WARPS][LIST_CAP];
 
+    if (FOREST && a.reserve_cap) {
+        // Two-phase walk, first phase: the grid fills the GPU, and the blocks that land on the last SMs
+        // leave at once, so that the kernels of the other stream (tree pruning, NCCL) find free SMs.  The
+        // groups are handed out dynamically, the remaining blocks do all the work; at most reserve_cap
+        // blocks leave, wherever the scheduler puts them.
+        __shared__ int s_quit;
+        if (threadIdx.x == 0)
+            s_quit = ptx::smid() >= a.reserve_from && atomicAdd(a.counters + 6, 1ull) < (unsigned long long)a.reserve_cap;
+        __syncthreads();
+        if (s_quit) return;
+    }
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *stack = s_stack[warp];
@@ -564,7 +578,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
         int fill = 0;  // entries in the ring (uniform), < 32 between steps
         __syncwarp();
         if (FOREST) {
-            sp = (int)a.n_roots;
+            sp = a.n_roots_dev ? (int)*a.n_roots_dev : (int)a.n_roots;
             for (int i = lane; i < sp; i += 32) stack[i] = a.roots[i];
         } else if (lane == 0) {
             stack[0] = 0;
@@ -619,9 +633,11 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
                 const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
                 const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
                 const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                const int level = (int)(nd.nchild_level >> 8);
+                // forest walks: bit 31 marks the others' share of a cell that this rank's own tree holds the
+                // rest of (two-phase walk); a share is never accepted in place of the whole cell
+                const int level = FOREST ? (int)(nd.nchild_level >> 8 & 0xffu) : (int)(nd.nchild_level >> 8);
                 const float w = ext * __int_as_float((127 - level) << 23);
-                open = a.theta2 * d2 < w * w;
+                open = a.theta2 * d2 < w * w || (FOREST && (nd.nchild_level & NODE_SHARE) != 0u);
             }
             const uint32_t nc = nd.nchild_level & 0xffu;
             const bool open_internal = has && open && nc > 0;
@@ -738,19 +754,20 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
             ayb += __shfl_xor_sync(FULL, ayb, o);
             azb += __shfl_xor_sync(FULL, azb, o);
         }
+        const bool acc = FOREST && a.accumulate;  // second phase of a two-phase walk: every row has one writer
         if (slice == 0 && tl < gcnt) {
             const uint32_t row = a.tgt_perm ? a.tgt_perm[ia] : (uint32_t)ia;
             float *o = a.out + (size_t)row * a.dim;
-            o[0] = axa;
-            o[1] = aya;
-            if (a.dim == 3) o[2] = aza;
+            o[0] = acc ? o[0] + axa : axa;
+            o[1] = acc ? o[1] + aya : aya;
+            if (a.dim == 3) o[2] = acc ? o[2] + aza : aza;
         }
         if (slice == 0 && tl + half < gcnt) {
             const uint32_t row = a.tgt_perm ? a.tgt_perm[ib] : (uint32_t)ib;
             float *o = a.out + (size_t)row * a.dim;
-            o[0] = axb;
-            o[1] = ayb;
-            if (a.dim == 3) o[2] = azb;
+            o[0] = acc ? o[0] + axb : axb;
+            o[1] = acc ? o[1] + ayb : ayb;
+            if (a.dim == 3) o[2] = acc ? o[2] + azb : azb;
         }
         if (COUNT) {
             c_node += g_node * gcnt;
@@ -1360,13 +1377,17 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     const int dim = t->dim;
     if (fv && (x64 || t->order == 2 || g_tpl != 2 || g_variant))
         return fail(ctx, PCUDA_ERR_INVALID_ARGUMENT, "a forest is walked by traverse2_kernel only");
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = fv && fv->stream ? fv->stream : ctx->stream;
     const int group_cap = x64 ? 32 : 32 * g_tpl;  // the f64 walk holds one target per lane
     const int n = (int)na;
     // K5a: from the tree when the targets are its own particles (tuning hook bh_tree_groups = 0: from the keys)
     const bool own = g_tree_groups && t->d_parent && tgt_keys == t->d_keys() && na == t->n &&
                      (uint32_t)g_seg_max >= t->leaf_size;
-    PCUDA_TRY(make_groups(ctx, dim, t->bits, tgt_keys, n, group_cap, st, own ? t : nullptr));
+    if (fv && fv->reuse_groups) {  // same targets as the walk before: only the group dispenser starts over
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + 3, 0, sizeof(uint32_t), st));
+    } else {
+        PCUDA_TRY(make_groups(ctx, dim, t->bits, tgt_keys, n, group_cap, st, own ? t : nullptr));
+    }
     uint32_t *d_work = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 3);
     uint32_t *d_ngroups = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 4);
     const size_t n4g = ((size_t)n + 3) & ~size_t(3);
@@ -1389,15 +1410,25 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     a.eps2 = eps * eps;
     a.n_roots = 1;
     a.roots = nullptr;
+    a.n_roots_dev = nullptr;
+    a.accumulate = 0;
+    a.reserve_from = a.reserve_cap = 0;
     if (fv) {
         a.nodes = fv->nodes;
         a.src = fv->src;
         a.n_roots = fv->n_roots;
         a.roots = fv->d_roots;
+        a.n_roots_dev = fv->d_n_roots;
+        a.accumulate = fv->accumulate ? 1 : 0;
+        if (fv->reserve_sms && fv->reserve_sms < (unsigned)ctx->sm_count) {
+            a.reserve_from = (uint32_t)ctx->sm_count - fv->reserve_sms;
+            a.reserve_cap = 4 * fv->reserve_sms;
+        }
     }
     const size_t max_groups = ((size_t)n + 7) / 8;  // enough warps for small inputs, persistent beyond
-    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
-                                                       (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
+    unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4,
+                                                 (max_groups + TRAV_WARPS - 1) / TRAV_WARPS);
+    if (blocks < (unsigned)ctx->sm_count * 4) a.reserve_cap = 0;  // a grid that does not fill the GPU leaves room anyway
     if (!x64 && t->order == 2) {
         const unsigned blocksq = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 6,
                                                            (max_groups + TRAVQ_WARPS - 1) / TRAVQ_WARPS);

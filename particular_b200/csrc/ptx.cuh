@@ -77,6 +77,13 @@ __device__ __forceinline__ float ldg_f32(const float *p) {
     return v;
 }
 
+// The SM this thread runs on.
+__device__ __forceinline__ unsigned smid() {
+    unsigned v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
+
 // Packed FP32 pairs (sm_100+: fma.rn.f32x2 etc.).  One issue slot does two lanes of work, which
 // is what lets MUFU / LDS / loop overhead hide under the FMA pipe in the pair kernel.
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }

@@ -23,7 +23,10 @@ def set_debug(**kv):
         assert lib.pcuda_debug_set(k.encode(), v) == 0, (k, v)
 
 
-BUILDS = {"let": 3, "partitioned": 1, "replicated": 2}
+# "let": the own tree is walked while the others' trees travel (the default); "let_one_walk": one walk at the end
+BUILDS = {"let": dict(bh_forest=3, bh_let_overlap=1), "let_one_walk": dict(bh_forest=3, bh_let_overlap=0),
+          "partitioned": dict(bh_forest=1), "replicated": dict(bh_forest=2)}
+RESET = dict(bh_forest=0, bh_route=0, bh_let_overlap=1)
 
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
@@ -39,7 +42,7 @@ def test_sharded_brute_force_and_split(world):
         assert_bruteforce_parity(gots, oracle.brute_force_parallel(aff, src, 1.0), aff, src, 1.0)
 
 
-@pytest.mark.parametrize("build", ["let", "partitioned", "replicated"])
+@pytest.mark.parametrize("build", list(BUILDS))
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("cloud", ["plummer", "uniform"])
 def test_barnes_hut_same_theta_error_as_reference(world, build, cloud):
@@ -49,7 +52,7 @@ def test_barnes_hut_same_theta_error_as_reference(world, build, cloud):
     for theta in (0.5, 1.0):
         s_ref = stats(rel_err(oracle.barnes_hut(p[:, :3], p, theta, parallel=True), exact))
         try:
-            set_debug(bh_forest=BUILDS[build])
+            set_debug(**BUILDS[build])
             with LocalWorld(world) as w:
                 outs = []
                 for route in (1, 2):
@@ -59,28 +62,29 @@ def test_barnes_hut_same_theta_error_as_reference(world, build, cloud):
                     outs.append(got)
                     s = stats(rel_err(got, exact))
                     assert (s <= 1.1 * s_ref + 2e-6).all(), (build, world, theta, route, s, s_ref)
-                if build != "let":  # (the locally essential trees have one routing)
+                if not build.startswith("let"):  # (the locally essential trees have one routing)
                     assert np.array_equal(outs[0], outs[1])
         finally:
-            set_debug(bh_forest=0, bh_route=0)
+            set_debug(**RESET)
 
 
-@pytest.mark.parametrize("build", ["let", "partitioned", "replicated"])
+@pytest.mark.parametrize("build", list(BUILDS))
 @pytest.mark.parametrize("world", [2, 5, 8])
 def test_barnes_hut_theta0_is_brute_force(world, build):
     p = uniform_cloud(9000, seed=8)
     ref = oracle.brute_force_parallel(p[:, :3], p)
     try:
-        set_debug(bh_forest=BUILDS[build])
+        set_debug(**BUILDS[build])
         with LocalWorld(world) as w:
             got = w.barnes_hut(p, 0.0)
         assert_bruteforce_parity(got, ref, p[:, :3], p, aggregate=False, plain=False)
     finally:
-        set_debug(bh_forest=0)
+        set_debug(**RESET)
 
 
+@pytest.mark.parametrize("overlap", [1, 0])
 @pytest.mark.parametrize("world", [2, 8])
-def test_let_degenerate_inputs(world):
+def test_let_degenerate_inputs(world, overlap):
     """Locally essential trees with inputs that leave ranks empty or put everything into one cell: all
     particles at one point, two tight clumps far apart, fewer distinct keys than ranks, and a block
     order that is already sorted in space (every rank's block goes to one destination)."""
@@ -97,7 +101,7 @@ def test_let_degenerate_inputs(world):
     srt = srt[np.lexsort((srt[:, 2], srt[:, 1], srt[:, 0]))]
     cases["sorted blocks"] = srt
     try:
-        set_debug(bh_forest=3)
+        set_debug(bh_forest=3, bh_let_overlap=overlap)
         with LocalWorld(world) as w:
             for name, p in cases.items():
                 got = w.barnes_hut(p, 0.5)
@@ -107,7 +111,7 @@ def test_let_degenerate_inputs(world):
                 s = stats(rel_err(got, exact))
                 assert (s <= 1.1 * s_ref + 2e-6).all(), (name, s, s_ref)
     finally:
-        set_debug(bh_forest=0)
+        set_debug(**RESET)
 
 
 def test_let_is_the_default_and_matches_one_gpu_at_size():

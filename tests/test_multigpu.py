@@ -3,7 +3,7 @@ has GPUs for is run, the others are skipped): a torchrun-style world of one proc
 collectives issued by the library on its own NCCL communicator, results compared with the restated
 reference algorithms (oracle.*) — sequential::BruteForce for the sharded brute force and the split,
 sequential::BarnesHut at equal theta (error statistics against the extended-precision sum) for every
-multi-GPU Barnes-Hut path: the automatic choice of the world size, locally essential trees, the
+multi-GPU Barnes-Hut path: the automatic choice of the world size, locally essential trees (two-phase walk and one walk), the
 replicated build, the partitioned build, and both result routings; plus locally essential trees at a
 size where they are the automatic choice (N = 1M)."""
 import json
@@ -71,9 +71,10 @@ bh0 = pb.ShardedBarnesHut(ctx, 0.0, pb.Acceleration.checked(), init_comm=False)
 bh0.world, bh0.rank = sh.world, sh.rank
 small_ref = oracle.brute_force_parallel(small[:, :3], small)
 outs = {}
-for name, forest, route in (("auto", 0, 0), ("let", 3, 0), ("replicated_allgather", 2, 1), ("replicated_alltoall", 2, 2),
-                            ("partitioned_allgather", 1, 1), ("partitioned_alltoall", 1, 2)):
+for name, forest, route in (("auto", 0, 0), ("let", 3, 0), ("let_one_walk", 3, 0), ("replicated_allgather", 2, 1),
+                            ("replicated_alltoall", 2, 2), ("partitioned_allgather", 1, 1), ("partitioned_alltoall", 1, 2)):
     assert _ffi.lib.pcuda_debug_set(b"bh_forest", forest) == 0
+    assert _ffi.lib.pcuda_debug_set(b"bh_let_overlap", 0 if name == "let_one_walk" else 1) == 0
     assert _ffi.lib.pcuda_debug_set(b"bh_route", route) == 0
     got = bh.compute(q)
     outs[name] = got
@@ -128,7 +129,7 @@ def test_multi_gpu_matches_oracle(tmp_path, world):
     assert res["split_shape"] == [20011, 3] and res["split_worst"] <= 1.0, res
     # Barnes-Hut: median / p99 / max error no worse than 1.1 x the reference algorithm's at equal theta
     # (SURVEY.md 8c), theta = 0 within the brute-force bound, for every build / routing path
-    for name in ("auto", "let", "replicated_allgather", "replicated_alltoall", "partitioned_allgather",
+    for name in ("auto", "let", "let_one_walk", "replicated_allgather", "replicated_alltoall", "partitioned_allgather",
                  "partitioned_alltoall"):
         b = res["bh_" + name]
         assert b["shape"] == [40003, 3] and b["finite"], (name, b)

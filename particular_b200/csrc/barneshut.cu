@@ -45,8 +45,10 @@ int g_seg_max = 256;              // largest cell (in targets) that is cut into 
 int g_tpl = 2;                    // targets per lane in the traversal: 1 (groups of 32) or 2 (groups of 64)
 int g_route = 0;                  // accelerations to their owners: 0 = automatic, 1 = all-gather, 2 = all-to-all
 int g_tree_groups = 1;            // target groups from the tree's nodes when the targets are its own particles
-int g_let_overlap = 1;            // locally essential trees: walk the own tree while the others' trees travel
-int g_let_reserve = 16;           // ... and the SMs that walk leaves to the kernels beside it
+int g_let_overlap = -1;           // locally essential trees: walk the own tree while the others' trees travel
+                                  // (-1: from 8 ranks on, where it was measured to pay; 0: never; 1: always)
+int g_let_reserve = 16;           // ... the SMs that walk leaves to the kernels beside it
+int g_let_stop = 0;               // ... and whether it stops when the others' trees are here (measured: no gain)
 int g_let_trace = 0;              // locally essential trees: print the wall-clock time of every stage
 int g_forest = 0;                 // multi-GPU build: 0 = as the context says, 1 = partitioned, 2 = replicated,
                                   // 3 = locally essential trees
@@ -203,8 +205,12 @@ int bh_debug_set(const char *key, int value) {
         bh::g_tree_groups = value;
         return PCUDA_OK;
     }
-    if (k == "bh_let_overlap") {
-        bh::g_let_overlap = value != 0;
+    if (k == "bh_let_overlap" && value >= -1 && value <= 1) {
+        bh::g_let_overlap = value;
+        return PCUDA_OK;
+    }
+    if (k == "bh_let_stop") {
+        bh::g_let_stop = value != 0;
         return PCUDA_OK;
     }
     if (k == "bh_let_reserve" && value >= 0 && value <= 64) {

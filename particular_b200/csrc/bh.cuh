@@ -80,7 +80,7 @@ extern int g_seg_max;
 extern int g_tpl;
 extern int g_route;
 extern int g_forest;
-extern int g_let_trace, g_let_overlap, g_let_reserve;
+extern int g_let_trace, g_let_overlap, g_let_reserve, g_let_stop;
 extern int g_tree_groups;
 
 // Double-precision layer of a traversal (tree built by build64).
@@ -95,7 +95,7 @@ struct Ext64 {
 // A forest of trees over the same root cube stored back to back (partitioned build): node and
 // source arrays that replace the tree's own, and the roots the walk starts from.
 // NodeRec::nchild_level, bit 31 (joined trees only): the node is one side's share of a cell whose other
-// share is walked separately; the walk opens it whatever the distance.
+// share is walked separately; the walk accepts it only where it would accept the whole cell.
 constexpr uint32_t NODE_SHARE = 0x80000000u;
 
 struct ForestView {
@@ -105,8 +105,12 @@ struct ForestView {
     uint32_t n_roots;
     // two-phase walks (locally essential trees: own tree while the others' trees are on their way)
     const uint32_t *d_n_roots = nullptr;  // number of start nodes in device memory (overrides n_roots)
+    const uint32_t *d_level_begin = nullptr;  // level table (device) of the walked tree: its first / last nodes
+                                          // of every level may be shares of cells (see NODE_SHARE)
     bool accumulate = false;              // add to the output rows instead of writing them
     bool reuse_groups = false;            // the target groups of the previous walk of the same targets
+    bool continue_groups = false;         // ... and only those the previous walk left when it was stopped
+    const uint32_t *d_stop = nullptr;     // the walk takes no more groups once this device word is non-zero
     unsigned reserve_sms = 0;             // blocks that start on the last reserve_sms SMs give them up (at most
                                           // 4 per SM do): room for the kernels of a concurrent stream
     cudaStream_t stream = nullptr;        // nullptr: the context stream

@@ -1357,7 +1357,7 @@ __global__ void let_gi_kernel(const uint32_t *__restrict__ bmap_recv, const Part
 
 // Two-phase walk: the cells that this rank's own tree holds a share of are the first / last cells of its
 // levels; where another rank's tree has the same cell, that node is marked NODE_SHARE (the walk over the
-// others' trees then opens it: a share must not stand in for the whole cell, its centre of mass lies
+// others' trees then accepts it only where the whole cell would be accepted: a share's centre of mass lies
 // further from this rank's particles than the cell's).
 __global__ void let_mark_shares_kernel(const uint32_t *__restrict__ gi, const PartPack *__restrict__ packs, int rank,
                                        NodeRec *__restrict__ nodes) {
@@ -1562,14 +1562,14 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         PCUDA_TRY(build_levels<3>(ctx, t, n_mine));  // (2) synchronises: level table
         mark("tree");
     }
-    // Two-phase walk (tuning hook bh_let_overlap = 0: one walk at the end).  The interactions of this rank's
+    // Two-phase walk (from 8 ranks on; tuning hook bh_let_overlap = 0 / 1: never / always).  The interactions of this rank's
     // particles with this rank's own tree need nothing from the other ranks: that walk starts now, on a
     // second stream, and leaves the last SMs to the pruning kernels and the exchanges of stages C and D,
     // which run beside it.  What arrives is walked afterwards (stage E) and added to the same rows.
-    // A cell that straddles this rank's key range and another's is then seen as two shares: this rank's is an
-    // ordinary node of its tree (its centre of mass is nearer to the targets than the cell's, so it is
-    // opened at least as early), the others' is always opened (let_mark_shares_kernel).
-    const bool overlap = g_let_overlap && n_mine > 0;
+    // A cell that straddles this rank's key range and another's is then seen as two shares (this rank's: the
+    // first / last node of a level of its tree; the others': let_mark_shares_kernel), and a share is accepted
+    // only where the whole cell would be (traverse2_kernel), so the walk is nowhere coarser than the one walk.
+    const bool overlap = (g_let_overlap < 0 ? world >= 8 : g_let_overlap != 0) && n_mine > 0;
     struct Join {  // no return path leaves the second stream running behind the first
         pcuda_forest *f;
         cudaStream_t st;
@@ -1585,8 +1585,8 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
             PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
             PCUDA_CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
         }
-        PCUDA_CUDA_TRY(ctx, f->let_root0.ensure(sizeof(uint32_t)));
-        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(f->let_root0.p, 0, sizeof(uint32_t), st));
+        PCUDA_CUDA_TRY(ctx, f->let_root0.ensure(2 * sizeof(uint32_t)));  // [0]: the root (node 0); [1]: stop flag
+        PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(f->let_root0.p, 0, 2 * sizeof(uint32_t), st));
         PCUDA_CUDA_TRY(ctx, cudaEventRecord(f->ev_fork, st));
         PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(f->walk_stream, f->ev_fork, 0));
         ForestView own{};
@@ -1594,8 +1594,10 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
         own.src = t->sorted.as<float4>();
         own.d_roots = f->let_root0.as<uint32_t>();
         own.n_roots = 1;
+        own.d_level_begin = t->scan_in.as<BuildState>()->level_begin;
         own.stream = f->walk_stream;
         own.reserve_sms = (unsigned)g_let_reserve;
+        if (g_let_stop) own.d_stop = f->let_root0.as<uint32_t>() + 1;
         const int rc = traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), t->d_perm(), n_mine, theta, eps,
                                        f->route_acc_send.as<float>(), nullptr, &own);
         cudaEventRecord(f->ev_join, f->walk_stream);
@@ -1770,8 +1772,24 @@ static int sharded_let_dev(pcuda_ctx *ctx, int world, int rank, size_t n_total, 
     phase_end(ctx, PH_COMM3);
     phase_begin(ctx, PH_COMPUTE);  // (two-phase walk: what is left of the first phase, and the second)
     if (overlap) {
+        // tuning hook bh_let_stop: the others' trees are here, the first phase stops taking groups (it ran
+        // without the reserved SMs) and what it left is walked on the whole GPU in front of the second phase.
+        // Measured on 4 B200s: 8.51 ms against 8.40 without — a walk ends with a tail of about half a group
+        // time (a group keeps a warp busy for ~0.7 ms), and this makes three tails out of two.
+        if (g_let_stop) PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(f->let_root0.as<uint32_t>() + 1, 1, sizeof(uint32_t), st));
         PCUDA_CUDA_TRY(ctx, cudaStreamWaitEvent(st, f->ev_join, 0));
         join.armed = false;
+        if (g_let_stop) {
+            ForestView rest{};
+            rest.nodes = t->nodes.as<NodeRec>();
+            rest.src = t->sorted.as<float4>();
+            rest.d_roots = f->let_root0.as<uint32_t>();
+            rest.n_roots = 1;
+            rest.d_level_begin = t->scan_in.as<BuildState>()->level_begin;
+            rest.continue_groups = true;
+            PCUDA_TRY(traverse_sorted(ctx, t, t->sorted.as<float4>(), t->d_keys(), t->d_perm(), n_mine, theta, eps,
+                                      f->route_acc_send.as<float>(), nullptr, &rest));
+        }
         fv.accumulate = true;
         fv.reuse_groups = true;
     }

@@ -207,6 +207,9 @@ struct TravArgs {
     const uint32_t *n_roots_dev;  // forest walks: the number of start nodes when only the device knows it
     int accumulate;               // forest walks: add to the output rows (second phase of a two-phase walk)
     uint32_t reserve_from, reserve_cap;  // forest walks: blocks on SMs >= reserve_from exit (at most reserve_cap)
+    const uint32_t *chain;               // forest walks: level table of the tree whose first / last nodes are shares
+    float share_scale;                   // forest walks: 1 + sqrt(3) theta
+    const uint32_t *stop;                // forest walks: no more groups are taken once this word is non-zero
 };
 
 // The interaction list of a warp lives in shared memory as PAIRS of entries laid out
@@ -530,7 +533,11 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
 
     for (;;) {
         uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(a.work, 1u);
+        if (FOREST) {  // (a.stop: the first phase of a two-phase walk ends when the second can begin)
+            if (lane == 0) g = a.stop && *reinterpret_cast<const volatile uint32_t *>(a.stop) ? 0xffffffffu : atomicAdd(a.work, 1u);
+        } else {
+            if (lane == 0) g = atomicAdd(a.work, 1u);
+        }
         g = __shfl_sync(FULL, g, 0);
         if (g >= n_groups) break;
         const int t0 = (int)a.group_start[g];
@@ -613,8 +620,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
             nd.begin = 0;
             nd.count = 0;
             nd.nchild_level = 0;
+            uint32_t id = 0;
             if (has) {
-                const uint32_t id = stack[sp - 1 - lane];
+                id = stack[sp - 1 - lane];
                 const uint4 *q = reinterpret_cast<const uint4 *>(a.nodes + id);
                 const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
                 nd.cm = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y),
@@ -633,11 +641,19 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, 4) traverse2_kernel(TravArgs 
                 const float ddy = fmaxf(fabsf(nd.cm.y - cy) - hy, 0.f);
                 const float ddz = fmaxf(fabsf(nd.cm.z - cz) - hz, 0.f);
                 const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                // forest walks: bit 31 marks the others' share of a cell that this rank's own tree holds the
-                // rest of (two-phase walk); a share is never accepted in place of the whole cell
                 const int level = FOREST ? (int)(nd.nchild_level >> 8 & 0xffu) : (int)(nd.nchild_level >> 8);
-                const float w = ext * __int_as_float((127 - level) << 23);
-                open = a.theta2 * d2 < w * w || (FOREST && (nd.nchild_level & NODE_SHARE) != 0u);
+                float w = ext * __int_as_float((127 - level) << 23);
+                if (FOREST) {
+                    // Two-phase walk: a node that may be one side's share of a cell (the others' share: bit 31;
+                    // this rank's own: the first / last node of a level of its tree, a.chain = the level
+                    // table) is accepted only where the whole cell would be.  The cell's centre of mass lies
+                    // in the same cube, at most sqrt(3) w from the share's, and the distance to a box is
+                    // 1-Lipschitz: theta (d - sqrt(3) w) >= w, i.e. the test with w (1 + sqrt(3) theta).
+                    bool share = (nd.nchild_level & NODE_SHARE) != 0u;
+                    if (a.chain) share |= id == __ldg(a.chain + level) || id + 1u == __ldg(a.chain + level + 1);
+                    if (share) w *= a.share_scale;
+                }
+                open = a.theta2 * d2 < w * w;
             }
             const uint32_t nc = nd.nchild_level & 0xffu;
             const bool open_internal = has && open && nc > 0;
@@ -1383,7 +1399,9 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     // K5a: from the tree when the targets are its own particles (tuning hook bh_tree_groups = 0: from the keys)
     const bool own = g_tree_groups && t->d_parent && tgt_keys == t->d_keys() && na == t->n &&
                      (uint32_t)g_seg_max >= t->leaf_size;
-    if (fv && fv->reuse_groups) {  // same targets as the walk before: only the group dispenser starts over
+    if (fv && fv->continue_groups) {
+        // the groups the walk before did not get to (it was stopped): nothing to prepare
+    } else if (fv && fv->reuse_groups) {  // same targets as the walk before: only the group dispenser starts over
         PCUDA_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + 3, 0, sizeof(uint32_t), st));
     } else {
         PCUDA_TRY(make_groups(ctx, dim, t->bits, tgt_keys, n, group_cap, st, own ? t : nullptr));
@@ -1413,7 +1431,12 @@ int traverse_sorted(pcuda_ctx *ctx, const pcuda_tree *t, const float4 *tgt_sorte
     a.n_roots_dev = nullptr;
     a.accumulate = 0;
     a.reserve_from = a.reserve_cap = 0;
+    a.chain = nullptr;
+    a.stop = nullptr;
+    a.share_scale = 1.f + 1.7320508f * theta;
     if (fv) {
+        a.chain = fv->d_level_begin;
+        a.stop = fv->d_stop;
         a.nodes = fv->nodes;
         a.src = fv->src;
         a.n_roots = fv->n_roots;

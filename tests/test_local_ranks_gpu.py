@@ -23,10 +23,12 @@ def set_debug(**kv):
         assert lib.pcuda_debug_set(k.encode(), v) == 0, (k, v)
 
 
-# "let": the own tree is walked while the others' trees travel (the default); "let_one_walk": one walk at the end
+# "let": the own tree is walked while the others' trees travel (the default from 8 ranks on); "let_one_walk": one
+# walk at the end (the default below 8 ranks); "let_stop": the first phase stops when the others' trees are here
 BUILDS = {"let": dict(bh_forest=3, bh_let_overlap=1), "let_one_walk": dict(bh_forest=3, bh_let_overlap=0),
+          "let_stop": dict(bh_forest=3, bh_let_overlap=1, bh_let_stop=1),
           "partitioned": dict(bh_forest=1), "replicated": dict(bh_forest=2)}
-RESET = dict(bh_forest=0, bh_route=0, bh_let_overlap=1)
+RESET = dict(bh_forest=0, bh_route=0, bh_let_overlap=-1, bh_let_stop=0)
 
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
@@ -114,9 +116,11 @@ def test_let_degenerate_inputs(world, overlap):
         set_debug(**RESET)
 
 
-def test_let_is_the_default_and_matches_one_gpu_at_size():
+@pytest.mark.parametrize("overlap", [-1, 1])
+def test_let_is_the_default_and_matches_one_gpu_at_size(overlap):
     """N = 2M Plummer on 4 ranks, the automatic build (locally essential trees from 65536 particles per
-    rank on): same error statistics as the single tree on one GPU, sampled against the exact sum."""
+    rank on), with the automatic choice of the walk (one walk below 8 ranks) and with the two-phase walk:
+    same error statistics as the single tree on one GPU, sampled against the exact sum."""
     import particular_b200 as pb
     n = 2_000_000
     p = plummer_cloud(n, seed=1808)
@@ -124,9 +128,13 @@ def test_let_is_the_default_and_matches_one_gpu_at_size():
     exact = oracle.brute_force_exact(p[idx, :3], p)
     with pb.CudaContext(0) as c1:
         single = pb.BarnesHut(c1, 0.5, pb.Acceleration.checked()).compute(p)
-    with LocalWorld(4) as w:
-        got = w.barnes_hut(p, 0.5)
-        comm = [c.timings() for c in w.ctxs]
+    try:
+        set_debug(bh_let_overlap=overlap)
+        with LocalWorld(4) as w:
+            got = w.barnes_hut(p, 0.5)
+            comm = [c.timings() for c in w.ctxs]
+    finally:
+        set_debug(**RESET)
     s1, s4 = stats(rel_err(single[idx], exact)), stats(rel_err(got[idx], exact))
     print("one GPU", s1, "4 ranks, locally essential trees", s4, "timings rank 0", comm[0])
     assert (s4 <= 1.1 * s1 + 2e-6).all(), (s4, s1)

@@ -74,7 +74,7 @@ outs = {}
 for name, forest, route in (("auto", 0, 0), ("let", 3, 0), ("let_one_walk", 3, 0), ("replicated_allgather", 2, 1),
                             ("replicated_alltoall", 2, 2), ("partitioned_allgather", 1, 1), ("partitioned_alltoall", 1, 2)):
     assert _ffi.lib.pcuda_debug_set(b"bh_forest", forest) == 0
-    assert _ffi.lib.pcuda_debug_set(b"bh_let_overlap", 0 if name == "let_one_walk" else 1) == 0
+    assert _ffi.lib.pcuda_debug_set(b"bh_let_overlap", 0 if name == "let_one_walk" else 1 if name == "let" else -1) == 0
     assert _ffi.lib.pcuda_debug_set(b"bh_route", route) == 0
     got = bh.compute(q)
     outs[name] = got
@@ -84,6 +84,7 @@ for name, forest, route in (("auto", 0, 0), ("let", 3, 0), ("let_one_walk", 3, 0
                          "theta0_max_rel": float(rel_err(f0, small_ref).max())}
 assert _ffi.lib.pcuda_debug_set(b"bh_forest", 0) == 0
 assert _ffi.lib.pcuda_debug_set(b"bh_route", 0) == 0
+assert _ffi.lib.pcuda_debug_set(b"bh_let_overlap", -1) == 0
 # the routing must not change a bit of the result
 res["route_same_replicated"] = bool(np.array_equal(outs["replicated_allgather"], outs["replicated_alltoall"]))
 res["route_same_partitioned"] = bool(np.array_equal(outs["partitioned_allgather"], outs["partitioned_alltoall"]))

@@ -188,6 +188,90 @@ def test_random_clouds_parts_and_leaf_sizes():
     run()
 
 
+# ---- the top tree of the OTHER parts (two-phase walk of the locally essential trees) --------------------
+SHARE = 0x80000000
+
+
+def stage_of(nodes, node_base, packs):
+    """Boundary records as the device collects them (after the share marks were set in the node array)."""
+    stage = np.zeros((len(packs), LEVELS, 2), BOUND)
+    for q, pk in enumerate(packs):
+        for l in range(int(pk["n_levels"]) if pk["n_nodes"] else 0):
+            lb = pk["level_begin"]
+            for side, j in enumerate((lb[l], lb[l + 1] - 1)):
+                nd = nodes[node_base[q] + j]
+                stage[q, l, side]["node"] = nd
+                nc = int(nd["nchild_level"]) & 0xff
+                stage[q, l, side]["child"][:nc] = nodes[nd["first_child"]: nd["first_child"] + nc]
+    return stage
+
+
+@pytest.mark.parametrize("cloud", ["uniform", "plummer"])
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_top_tree_of_the_other_parts_keeps_the_share_marks(cloud, parts):
+    """bh_multigpu.cu, sharded_let_dev with the two-phase walk: the rank's own part is left out of the merge
+    (its pack says n_nodes = 0) and the other parts' nodes that are shares of a cell the own tree also holds
+    (same level and prefix as a first / last node of an own level: let_mark_shares_kernel) carry bit 31 of
+    nchild_level.  The merged tree must reach every particle of the other parts exactly once, none of the
+    own, and every reachable node of such a cell — merged cells and continuation nodes included — must
+    still carry the mark, with level and child count intact under it."""
+    p = uniform_cloud(5000, seed=21) if cloud == "uniform" else plummer_cloud(5000, seed=21)
+    full, nodes0, keys, node_base, packs0, _ = join(p, parts)
+    part_of_particle = np.zeros(len(p), np.int32)
+    start = 0
+    for q in range(parts):  # particles of part q: the next run of the joined key array
+        cnt = int(nodes0[node_base[q]]["count"]) if packs0[q]["n_nodes"] else 0
+        part_of_particle[start: start + cnt] = q
+        start += cnt
+    assert start == len(p)
+    for own in range(parts):
+        if packs0[own]["n_nodes"] == 0:
+            continue
+        nodes, packs = nodes0.copy(), packs0.copy()
+        own_cells = set()
+        for l in range(int(packs[own]["n_levels"])):
+            own_cells.update({(l, int(packs[own]["prefix"][l][0])), (l, int(packs[own]["prefix"][l][1]))})
+        for q in range(parts):  # let_mark_shares_kernel
+            if q == own or packs[q]["n_nodes"] == 0:
+                continue
+            lb = packs[q]["level_begin"]
+            for l in range(int(packs[q]["n_levels"])):
+                for side, j in enumerate((lb[l], lb[l + 1] - 1)):
+                    if (l, int(packs[q]["prefix"][l][side])) in own_cells:
+                        nodes[node_base[q] + j]["nchild_level"] |= SHARE
+        stage = stage_of(nodes, node_base, packs)
+        packs[own]["n_nodes"] = 0
+        top, roots = merge(parts, packs, stage, node_base, len(nodes))
+        others = int((packs["n_nodes"] > 0).sum())
+        if others == 0:
+            assert len(roots) == 0 and len(top) == 0
+            continue
+        assert len(roots) == 1 and (len(top) == 0) == (others == 1)
+        joined = np.concatenate([nodes, top])
+        covered = np.zeros(len(p), np.int32)
+        stack, marked = [int(roots[0])], 0
+        while stack:
+            i = stack.pop()
+            nd = joined[i]
+            word = int(nd["nchild_level"])
+            nc, lvl = word & 0xff, word >> 8 & 0xff
+            assert nc <= 8 and lvl <= BITS and word & 0x7fff0000 == 0
+            if nd["count"]:
+                cell = (lvl, int(keys[nd["begin"]]) >> (3 * (BITS - lvl)))
+                assert bool(word & SHARE) == (cell in own_cells), (own, i, cell)
+                marked += bool(word & SHARE)
+            if nc == 0:
+                covered[nd["begin"]: nd["begin"] + nd["count"]] += 1
+                continue
+            ch = joined[nd["first_child"]: nd["first_child"] + nc]
+            clv = ch["nchild_level"] >> 8 & 0xff
+            assert ((clv == lvl) | (clv == lvl + 1)).all()
+            assert int(ch["count"].sum()) == int(nd["count"])
+            stack.extend(range(int(nd["first_child"]), int(nd["first_child"]) + nc))
+        assert (covered[part_of_particle != own] == 1).all() and (covered[part_of_particle == own] == 0).all()
+        assert marked >= 1  # the root cell at least is shared
+
+
 # ---- world_size-2 (and 3) gloo run of the partitioned build's exchange + merge on CPU -----------------
 def _free_port():
     import socket
